@@ -1,0 +1,117 @@
+"""ctypes binding of libatlaspatch_b200.so (the C ABI in include/atlaspatch_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot initialise a B200, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libatlaspatch_b200.so"
+
+AP_OK, AP_EINVAL, AP_ECUDA, AP_ENOMEM, AP_ECAPACITY, AP_ESTATE = 0, -1, -2, -3, -4, -5
+EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32, EPI_BIAS_F32 = 0, 1, 2, 3
+
+
+class VitDesc(C.Structure):
+    _fields_ = [("image_size", C.c_int), ("patch", C.c_int), ("layers", C.c_int), ("heads", C.c_int),
+                ("hidden", C.c_int), ("mlp", C.c_int), ("input_patch", C.c_int), ("max_batch", C.c_int),
+                ("ln_eps", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+
+
+_P = C.c_void_p
+_I32P = C.POINTER(C.c_int32)
+_SIGNATURES = {
+    "ap_version": (C.c_int, []),
+    "ap_init": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "ap_destroy": (C.c_int, [_P]),
+    "ap_last_error": (C.c_char_p, [_P]),
+    "ap_launch_count": (C.c_int64, [_P]),
+    "ap_sm_count": (C.c_int, [_P]),
+    "ap_synth_render": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, _P, C.c_int, _P, C.c_int,
+                                  C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "ap_thumbnail_area": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P]),
+    "ap_coords_capacity": (C.c_int64, [_P, _P, C.c_int, C.c_int]),
+    "ap_extract_coords": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    _P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
+    "ap_encoder_create": (C.c_int, [_P, C.POINTER(VitDesc), C.POINTER(_P)]),
+    "ap_encoder_destroy": (C.c_int, [_P]),
+    "ap_encoder_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "ap_encoder_finalize": (C.c_int, [_P]),
+    "ap_encoder_embedding_dim": (C.c_int, [_P]),
+    "ap_encoder_embed_coords": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P, _P]),
+    "ap_encoder_embed_patches_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, _P]),
+    "ap_gemm_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ap_layernorm_f16": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_float, _P, C.c_int, C.c_int, _P]),
+    "ap_attention_f16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class AtlasB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"atlaspatch_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree shared library and bind every symbol the header declares."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(atlaspatch_b200 has no CPU fallback)")
+        lib = C.CDLL(os.fspath(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+class Context:
+    """One per process/GPU (ap_init).  Raises AtlasB200Error when there is no B200."""
+
+    _instances: dict[int, "Context"] = {}
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.device = device
+        h = _P()
+        rc = self.lib.ap_init(device, C.byref(h))
+        if rc != AP_OK:
+            raise AtlasB200Error(rc, self.lib.ap_last_error(None).decode())
+        self.handle = h
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Context":
+        if device not in cls._instances:
+            cls._instances[device] = Context(device)
+        return cls._instances[device]
+
+    def check(self, rc: int) -> None:
+        if rc != AP_OK:
+            raise AtlasB200Error(rc, self.lib.ap_last_error(self.handle).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ap_launch_count(self.handle))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.ap_sm_count(self.handle))
+
+
+def current_stream_ptr() -> int:
+    import torch
+
+    return int(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,79 @@
+// Internal declarations shared by the translation units of libatlaspatch_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "atlaspatch_b200.h"
+
+struct ap_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    char err[1024] = {0};
+    std::atomic<int64_t> launches{0};
+    // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
+    void* encode_tiled = nullptr;
+};
+
+int ap_set_error(ap_ctx* ctx, int code, const char* fmt, ...);
+
+#define AP_CHECK_CUDA(ctx, call)                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return ap_set_error((ctx), AP_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define AP_CHECK_LAUNCH(ctx, what)                                                                 \
+    do {                                                                                           \
+        (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess)                                                                    \
+            return ap_set_error((ctx), AP_ECUDA, "launch of %s failed: %s (%s:%d)", what,          \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+#define AP_REQUIRE(ctx, cond, ...)                                                                 \
+    do {                                                                                           \
+        if (!(cond)) return ap_set_error((ctx), AP_EINVAL, __VA_ARGS__);                           \
+    } while (0)
+
+// ---- TMA descriptor helper (host) --------------------------------------------------------------
+// 2-D row-major fp16 matrix [rows, cols] (cols contiguous), box = box_cols x box_rows, 128B swizzle.
+int ap_make_tmap_f16_2d(ap_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                        uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+
+// ---- kernels' host launchers (internal) --------------------------------------------------------
+struct GemmPlan {
+    CUtensorMap map_a;
+    CUtensorMap map_w;
+    int M, N, K, epilogue;
+    int bn;  // N tile (256 or 128)
+};
+int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue);
+// Patch-embed epilogue parameters: output row remap (b*T + t -> b*(T+1) + 1 + t) and +pos[1+t].
+struct GemmExtra {
+    const float* pos = nullptr;  // [(T+1), N] fp32 or null
+    int tokens_per_image = 0;    // T (0 = no remap)
+    float alpha = 1.0f;          // scale applied to the accumulator before bias
+};
+int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const float* resid, void* out,
+                const GemmExtra* extra, cudaStream_t stream);
+
+int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const float* gamma, const float* beta,
+                     float eps, __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream);
+int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
+int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
+                      int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
+                      cudaStream_t stream);
+int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D,
+                    cudaStream_t stream);

@@ -1,0 +1,369 @@
+// ViT encoder object: weight upload/packing, workspaces, and the forward schedule.
+//
+// Forward = torchvision VisionTransformer with heads -> Identity, as the reference builds it
+// (atlas_patch/models/patch/vit.py:9-38, models/patch/base.py:148-180):
+//   conv_proj (k = s = patch) -> [class_token ; tokens] + pos_embedding
+//   -> layers x [ x += out_proj(MHA(ln_1(x))) ; x += mlp.3(GELU(mlp.0(ln_2(x)))) ] -> ln -> x[:, 0]
+// Residual stream, LayerNorm and softmax are fp32; GEMM operands are fp16 with fp32 accumulation.
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "ap_internal.cuh"
+
+namespace {
+
+struct LayerWeights {
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    __half *w_qkv, *w_o, *w_1, *w_2;
+    float *b_qkv, *b_o, *b_1, *b_2;
+    GemmPlan p_qkv, p_o, p_1, p_2;
+};
+
+}  // namespace
+
+struct ap_encoder {
+    ap_ctx* ctx = nullptr;
+    ap_vit_desc d{};
+    int tokens = 0;   // patches per image (196)
+    int kpe = 0;      // 3 * patch * patch
+    int max_batch = 0;
+    bool finalized = false;
+    std::unordered_map<std::string, std::vector<float>> host;  // staged fp32 tensors until finalize
+    std::vector<void*> allocs;
+    // packed weights
+    __half* w_pe = nullptr;
+    float *b_pe = nullptr, *cls = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+    GemmPlan p_pe;
+    std::vector<LayerWeights> layers;
+    // workspaces
+    __half *a_pe = nullptr, *y1 = nullptr, *y2 = nullptr, *qkv = nullptr, *hbuf = nullptr;
+    float* x = nullptr;
+    // host-patch path
+    uint8_t *pin_in[2] = {nullptr, nullptr}, *dev_patches[2] = {nullptr, nullptr};
+    float *pin_out[2] = {nullptr, nullptr}, *dev_feats[2] = {nullptr, nullptr};
+    int32_t* dev_tall_coords = nullptr;
+    cudaStream_t s_copy = nullptr, s_compute = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+int dev_alloc(ap_encoder* e, void** p, size_t bytes) {
+    cudaError_t err = cudaMalloc(p, bytes);
+    if (err != cudaSuccess) return ap_set_error(e->ctx, AP_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
+    e->allocs.push_back(*p);
+    return AP_OK;
+}
+
+int upload_f32(ap_encoder* e, float** dst, const std::vector<float>& v) {
+    int rc = dev_alloc(e, reinterpret_cast<void**>(dst), v.size() * sizeof(float));
+    if (rc) return rc;
+    AP_CHECK_CUDA(e->ctx, cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return AP_OK;
+}
+
+int upload_f16(ap_encoder* e, __half** dst, const float* src, size_t n) {
+    std::vector<__half> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(src[i]);
+    int rc = dev_alloc(e, reinterpret_cast<void**>(dst), n * sizeof(__half));
+    if (rc) return rc;
+    AP_CHECK_CUDA(e->ctx, cudaMemcpy(*dst, h.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    return AP_OK;
+}
+
+const std::vector<float>* find(ap_encoder* e, const std::string& name, size_t numel) {
+    auto it = e->host.find(name);
+    if (it == e->host.end()) {
+        ap_set_error(e->ctx, AP_ESTATE, "encoder: tensor '%s' was never set", name.c_str());
+        return nullptr;
+    }
+    if (it->second.size() != numel) {
+        ap_set_error(e->ctx, AP_EINVAL, "encoder: tensor '%s' has %zu elements, expected %zu", name.c_str(), it->second.size(), numel);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+// One forward chunk: nb images whose patches are at `coords` (device) inside `slide`.
+int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords, int nb,
+                  float* out_feats, cudaStream_t st) {
+    ap_ctx* ctx = e->ctx;
+    const int D = e->d.hidden, T = e->tokens, T1 = T + 1;
+    const int rows = nb * T1;
+    int rc;
+    if ((rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
+                                e->kpe, st)))
+        return rc;
+    if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, st))) return rc;
+    {
+        GemmPlan p = e->p_pe;
+        p.M = nb * T;
+        GemmExtra ex;
+        ex.pos = e->pos;
+        ex.tokens_per_image = T;
+        if ((rc = ap_gemm_run(ctx, &p, e->b_pe, nullptr, e->x, &ex, st))) return rc;
+    }
+    for (auto& L : e->layers) {
+        GemmPlan p;
+        if ((rc = ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
+        p = L.p_qkv; p.M = rows;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, nullptr, st))) return rc;
+        if ((rc = ap_attention_run(ctx, e->qkv, e->y2, nb, T1, e->d.heads, st))) return rc;
+        p = L.p_o; p.M = rows;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->x, e->x, nullptr, st))) return rc;
+        if ((rc = ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
+        p = L.p_1; p.M = rows;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hbuf, nullptr, st))) return rc;
+        p = L.p_2; p.M = rows;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->x, e->x, nullptr, st))) return rc;
+    }
+    // final LayerNorm on the class-token rows only -> fp32 features
+    return ap_layernorm_run(ctx, e->x, static_cast<int64_t>(T1) * D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
+}
+
+}  // namespace
+
+extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc) {
+    if (!ctx || !desc || !out_enc) return AP_EINVAL;
+    *out_enc = nullptr;
+    AP_REQUIRE(ctx, desc->patch == 16, "encoder: conv patch %d unsupported in this build (16)", desc->patch);
+    AP_REQUIRE(ctx, desc->image_size % desc->patch == 0, "encoder: image %d not a multiple of patch %d", desc->image_size, desc->patch);
+    AP_REQUIRE(ctx, desc->hidden % desc->heads == 0 && desc->hidden / desc->heads == 64,
+               "encoder: head_dim must be 64 (hidden %d, heads %d)", desc->hidden, desc->heads);
+    AP_REQUIRE(ctx, desc->hidden % 128 == 0 && desc->mlp % 128 == 0, "encoder: hidden/mlp must be multiples of 128");
+    AP_REQUIRE(ctx, desc->input_patch >= desc->image_size, "encoder: input_patch %d < image_size %d (needs an up-sampling resize)",
+               desc->input_patch, desc->image_size);
+    AP_REQUIRE(ctx, desc->layers >= 1, "encoder: layers must be >= 1");
+    ap_encoder* e = new ap_encoder();
+    e->ctx = ctx;
+    e->d = *desc;
+    const int g = desc->image_size / desc->patch;
+    e->tokens = g * g;
+    e->kpe = 3 * desc->patch * desc->patch;
+    e->max_batch = desc->max_batch > 0 ? desc->max_batch : 128;
+    if ((e->tokens + 1) > 272) {
+        delete e;
+        return ap_set_error(ctx, AP_EINVAL, "encoder: sequence %d too long (<= 272)", g * g + 1);
+    }
+    *out_enc = e;
+    return AP_OK;
+}
+
+extern "C" int ap_encoder_destroy(ap_encoder* e) {
+    if (!e) return AP_OK;
+    cudaDeviceSynchronize();
+    for (void* p : e->allocs) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (e->pin_in[i]) cudaFreeHost(e->pin_in[i]);
+        if (e->pin_out[i]) cudaFreeHost(e->pin_out[i]);
+        if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    }
+    if (e->s_copy) cudaStreamDestroy(e->s_copy);
+    if (e->s_compute) cudaStreamDestroy(e->s_compute);
+    delete e;
+    return AP_OK;
+}
+
+extern "C" int ap_encoder_embedding_dim(const ap_encoder* e) { return e ? e->d.hidden : 0; }
+
+extern "C" int ap_encoder_set_tensor(ap_encoder* e, const char* name, const float* data_host, int64_t numel) {
+    if (!e || !name || !data_host || numel <= 0) return AP_EINVAL;
+    if (e->finalized) return ap_set_error(e->ctx, AP_ESTATE, "encoder: already finalized");
+    e->host[name].assign(data_host, data_host + numel);
+    return AP_OK;
+}
+
+extern "C" int ap_encoder_finalize(ap_encoder* e) {
+    if (!e) return AP_EINVAL;
+    ap_ctx* ctx = e->ctx;
+    if (e->finalized) return AP_OK;
+    const int D = e->d.hidden, M = e->d.mlp, P = e->d.patch, T = e->tokens, T1 = T + 1, K = e->kpe;
+    const int MB = e->max_batch;
+    int rc;
+#define AP_GET(var, name, n)                                   \
+    const std::vector<float>* var = find(e, (name), (size_t)(n)); \
+    if (!var) return AP_ESTATE;
+    // ---- conv_proj with the preset's normalisation folded in -----------------------------------------
+    // reference preprocess: x = (pixel/255 - mean_c) / std_c   ([tv]transforms/_presets.py:58-64)
+    // kernel input:         a = pixel / 256  (exact in fp16)
+    //   => W'[o,c,ky,kx] = W * 256 / (255 std_c),   b'[o] = b[o] - sum_c mean_c/std_c * sum_{ky,kx} W[o,c,ky,kx]
+    {
+        AP_GET(w, "conv_proj.weight", (size_t)D * K)
+        AP_GET(b, "conv_proj.bias", D)
+        std::vector<float> wf((size_t)D * K), bf(D);
+        for (int o = 0; o < D; ++o) {
+            double acc = (*b)[o];
+            for (int c = 0; c < 3; ++c) {
+                const double sc = 256.0 / (255.0 * e->d.std[c]);
+                double s = 0.0;
+                for (int i = 0; i < P * P; ++i) {
+                    const float v = (*w)[(size_t)o * K + c * P * P + i];
+                    wf[(size_t)o * K + c * P * P + i] = static_cast<float>(v * sc);
+                    s += v;
+                }
+                acc -= s * e->d.mean[c] / e->d.std[c];
+            }
+            bf[o] = static_cast<float>(acc);
+        }
+        if ((rc = upload_f16(e, &e->w_pe, wf.data(), wf.size()))) return rc;
+        if ((rc = upload_f32(e, &e->b_pe, bf))) return rc;
+    }
+    {
+        AP_GET(c, "class_token", D)
+        AP_GET(p, "encoder.pos_embedding", (size_t)T1 * D)
+        AP_GET(g, "encoder.ln.weight", D)
+        AP_GET(b, "encoder.ln.bias", D)
+        if ((rc = upload_f32(e, &e->cls, *c))) return rc;
+        if ((rc = upload_f32(e, &e->pos, *p))) return rc;
+        if ((rc = upload_f32(e, &e->lnf_g, *g))) return rc;
+        if ((rc = upload_f32(e, &e->lnf_b, *b))) return rc;
+    }
+    e->layers.resize(e->d.layers);
+    for (int i = 0; i < e->d.layers; ++i) {
+        const std::string p = "encoder.layers.encoder_layer_" + std::to_string(i) + ".";
+        LayerWeights& L = e->layers[i];
+        AP_GET(ln1g, p + "ln_1.weight", D) AP_GET(ln1b, p + "ln_1.bias", D)
+        AP_GET(ln2g, p + "ln_2.weight", D) AP_GET(ln2b, p + "ln_2.bias", D)
+        AP_GET(wqkv, p + "self_attention.in_proj_weight", (size_t)3 * D * D) AP_GET(bqkv, p + "self_attention.in_proj_bias", 3 * D)
+        AP_GET(wo, p + "self_attention.out_proj.weight", (size_t)D * D) AP_GET(bo, p + "self_attention.out_proj.bias", D)
+        AP_GET(w1, p + "mlp.0.weight", (size_t)M * D) AP_GET(b1, p + "mlp.0.bias", M)
+        AP_GET(w2, p + "mlp.3.weight", (size_t)D * M) AP_GET(b2, p + "mlp.3.bias", D)
+        if ((rc = upload_f32(e, &L.ln1_g, *ln1g)) || (rc = upload_f32(e, &L.ln1_b, *ln1b)) ||
+            (rc = upload_f32(e, &L.ln2_g, *ln2g)) || (rc = upload_f32(e, &L.ln2_b, *ln2b)) ||
+            (rc = upload_f32(e, &L.b_qkv, *bqkv)) || (rc = upload_f32(e, &L.b_o, *bo)) ||
+            (rc = upload_f32(e, &L.b_1, *b1)) || (rc = upload_f32(e, &L.b_2, *b2)) ||
+            (rc = upload_f16(e, &L.w_qkv, wqkv->data(), wqkv->size())) || (rc = upload_f16(e, &L.w_o, wo->data(), wo->size())) ||
+            (rc = upload_f16(e, &L.w_1, w1->data(), w1->size())) || (rc = upload_f16(e, &L.w_2, w2->data(), w2->size())))
+            return rc;
+    }
+#undef AP_GET
+    e->host.clear();
+
+    // ---- workspaces (rows padded to the 128-row GEMM tile so TMA boxes never leave the allocation) ----
+    const size_t rows = ((size_t)MB * T1 + 127) / 128 * 128;
+    const size_t rows_pe = ((size_t)MB * T + 127) / 128 * 128;
+    if ((rc = dev_alloc(e, (void**)&e->a_pe, rows_pe * K * 2)) || (rc = dev_alloc(e, (void**)&e->x, rows * D * 4)) ||
+        (rc = dev_alloc(e, (void**)&e->y1, rows * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2, rows * D * 2)) ||
+        (rc = dev_alloc(e, (void**)&e->qkv, rows * 3 * D * 2)) || (rc = dev_alloc(e, (void**)&e->hbuf, rows * M * 2)))
+        return rc;
+    AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * K * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->y1, 0, rows * D * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->y2, 0, rows * D * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->hbuf, 0, rows * M * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->qkv, 0, rows * 3 * D * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->x, 0, rows * D * 4));
+
+    // ---- GEMM plans (TMA descriptors over the fixed workspaces / weights) ------------------------------
+    if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, K, AP_EPI_BIAS_F32))) return rc;
+    for (auto& L : e->layers) {
+        if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, D, AP_EPI_BIAS_F16)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, D, AP_EPI_BIAS_RESID_F32)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M, D, AP_EPI_BIAS_GELU_F16)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, M, AP_EPI_BIAS_RESID_F32)))
+            return rc;
+    }
+
+    // ---- host-patch path: double-buffered pinned staging + its own streams -------------------------------
+    const size_t IP = e->d.input_patch;
+    const size_t patch_bytes = IP * IP * 3;
+    for (int i = 0; i < 2; ++i) {
+        AP_CHECK_CUDA(ctx, cudaMallocHost((void**)&e->pin_in[i], (size_t)MB * patch_bytes));
+        AP_CHECK_CUDA(ctx, cudaMallocHost((void**)&e->pin_out[i], (size_t)MB * D * 4));
+        if ((rc = dev_alloc(e, (void**)&e->dev_patches[i], (size_t)MB * patch_bytes)) ||
+            (rc = dev_alloc(e, (void**)&e->dev_feats[i], (size_t)MB * D * 4)))
+            return rc;
+        AP_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+        AP_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+    }
+    AP_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+    AP_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+    {
+        std::vector<int32_t> tall((size_t)MB * 5);
+        for (int i = 0; i < MB; ++i) {
+            tall[i * 5 + 0] = 0; tall[i * 5 + 1] = i * (int)IP; tall[i * 5 + 2] = (int)IP; tall[i * 5 + 3] = (int)IP; tall[i * 5 + 4] = 0;
+        }
+        if ((rc = dev_alloc(e, (void**)&e->dev_tall_coords, tall.size() * 4))) return rc;
+        AP_CHECK_CUDA(ctx, cudaMemcpy(e->dev_tall_coords, tall.data(), tall.size() * 4, cudaMemcpyHostToDevice));
+    }
+    AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    e->finalized = true;
+    return AP_OK;
+}
+
+extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
+                                       const int32_t* coords_dev, int64_t n, float* out_features_dev, void* stream) {
+    if (!e) return AP_EINVAL;
+    ap_ctx* ctx = e->ctx;
+    if (!e->finalized) return ap_set_error(ctx, AP_ESTATE, "encoder: ap_encoder_finalize has not been called");
+    AP_REQUIRE(ctx, n >= 0, "embed_coords: n < 0");
+    if (n == 0) return AP_OK;
+    AP_REQUIRE(ctx, slide_dev && coords_dev && out_features_dev, "embed_coords: NULL pointer");
+    AP_REQUIRE(ctx, pitch >= W * 3, "embed_coords: pitch %lld < 3*W", (long long)pitch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int64_t s = 0; s < n; s += e->max_batch) {
+        const int nb = static_cast<int>(n - s < e->max_batch ? n - s : e->max_batch);
+        int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, out_features_dev + s * e->d.hidden, st);
+        if (rc) return rc;
+    }
+    return AP_OK;
+}
+
+extern "C" int ap_encoder_embed_patches_host(ap_encoder* e, const uint8_t* const* patches_host, int64_t n,
+                                             float* out_features_host) {
+    if (!e) return AP_EINVAL;
+    ap_ctx* ctx = e->ctx;
+    if (!e->finalized) return ap_set_error(ctx, AP_ESTATE, "encoder: ap_encoder_finalize has not been called");
+    AP_REQUIRE(ctx, n >= 0, "embed_patches_host: n < 0");
+    if (n == 0) return AP_OK;
+    AP_REQUIRE(ctx, patches_host && out_features_host, "embed_patches_host: NULL pointer");
+    const int MB = e->max_batch, D = e->d.hidden;
+    const size_t IP = e->d.input_patch, patch_bytes = IP * IP * 3;
+    const int64_t n_chunks = (n + MB - 1) / MB;
+    // Pipeline over chunks with two buffers: host gather (CPU threads) | H2D (copy stream) | forward (compute stream)
+    // | D2H (copy stream).  Buffer i%2 is reused only after chunk i-2's features have been copied out.
+    for (int64_t c = 0; c < n_chunks + 1; ++c) {
+        if (c < n_chunks) {
+            const int buf = static_cast<int>(c & 1);
+            const int64_t s = c * MB;
+            const int nb = static_cast<int>(n - s < MB ? n - s : MB);
+            if (c >= 2) AP_CHECK_CUDA(ctx, cudaEventSynchronize(e->ev_done[buf]));  // chunk c-2 fully drained
+            if (c >= 2) {
+                const int64_t ps = (c - 2) * MB;
+                const int pnb = static_cast<int>(n - ps < MB ? n - ps : MB);
+                memcpy(out_features_host + ps * D, e->pin_out[buf], (size_t)pnb * D * 4);
+            }
+            {   // gather the (possibly scattered) host patches into pinned memory
+                const int nthreads = nb >= 32 ? 4 : 1;
+                auto work = [&](int t) {
+                    for (int i = t; i < nb; i += nthreads) memcpy(e->pin_in[buf] + (size_t)i * patch_bytes, patches_host[s + i], patch_bytes);
+                };
+                if (nthreads == 1) work(0);
+                else {
+                    std::vector<std::thread> th;
+                    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+                    for (auto& t : th) t.join();
+                }
+            }
+            AP_CHECK_CUDA(ctx, cudaMemcpyAsync(e->dev_patches[buf], e->pin_in[buf], (size_t)nb * patch_bytes, cudaMemcpyHostToDevice, e->s_copy));
+            AP_CHECK_CUDA(ctx, cudaEventRecord(e->ev_h2d[buf], e->s_copy));
+            AP_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->s_compute, e->ev_h2d[buf], 0));
+            int rc = forward_chunk(e, e->dev_patches[buf], (int64_t)IP, (int64_t)IP * nb, (int64_t)IP * 3, e->dev_tall_coords, nb,
+                                   e->dev_feats[buf], e->s_compute);
+            if (rc) return rc;
+            AP_CHECK_CUDA(ctx, cudaMemcpyAsync(e->pin_out[buf], e->dev_feats[buf], (size_t)nb * D * 4, cudaMemcpyDeviceToHost, e->s_compute));
+            AP_CHECK_CUDA(ctx, cudaEventRecord(e->ev_done[buf], e->s_compute));
+        }
+    }
+    // drain the last (up to) two chunks in order
+    for (int64_t c = (n_chunks >= 2 ? n_chunks - 2 : 0); c < n_chunks; ++c) {
+        const int buf = static_cast<int>(c & 1);
+        AP_CHECK_CUDA(ctx, cudaEventSynchronize(e->ev_done[buf]));
+        const int64_t ps = c * MB;
+        const int pnb = static_cast<int>(n - ps < MB ? n - ps : MB);
+        memcpy(out_features_host + ps * D, e->pin_out[buf], (size_t)pnb * D * 4);
+    }
+    return AP_OK;
+}

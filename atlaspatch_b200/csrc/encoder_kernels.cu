@@ -1,0 +1,344 @@
+// Non-GEMM kernels of the encoder forward: patch crop -> fp16 im2col (preprocess), class-token rows,
+// LayerNorm, multi-head attention.  All fp32 statistics / softmax; fp16 only as tensor-core operands.
+#include "ap_internal.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+// =====================================================================================================
+// a11 + a12: patch read + encoder preprocess, fused with the im2col of conv_proj.
+//   reference: feature_embedding.py:81-96 (wsi.extract at coords), models/patch/base.py:42-45 +
+//   torchvision ImageClassification preset (centre crop `image` out of `input_patch`, /255, normalise).
+//   Normalisation is folded into the conv_proj weights at ap_encoder_finalize, so this kernel is a pure
+//   byte gather: out[(b*g*g + ty*g + tx), c*p*p + ky*p + kx] = fp16(pixel / 256)   (exact in fp16).
+//   Pixels outside the slide read as 0 (reference backends pad with black, openslide_wsi.py:198).
+// One CTA per (patch b, token row ty): stages p image rows x (image*3) bytes in smem with coalesced
+// byte loads, then writes g token rows of 3*p*p halfs with 16-byte stores.
+// =====================================================================================================
+template <int P>  // conv patch edge (16)
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64_t pitch,
+                  const int32_t* __restrict__ coords, int input_patch, int image, __half* __restrict__ out,
+                  int64_t out_row_stride) {
+    extern __shared__ uint8_t s_rows[];  // [P][image*3]
+    const int g = image / P;
+    const int b = blockIdx.x / g;
+    const int ty = blockIdx.x % g;
+    const int off = (input_patch - image) / 2;  // centre crop: int(round((256-224)/2)) = 16
+    const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + off;
+    const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + off + ty * P;
+    const int row_bytes = image * 3;
+    for (int i = threadIdx.x; i < P * row_bytes; i += blockDim.x) {
+        const int r = i / row_bytes;
+        const int bx = i - r * row_bytes;
+        const int64_t y = y0 + r;
+        const int64_t x = x0 + bx / 3;
+        uint8_t v = 0;
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(slide + y * pitch + x0 * 3 + bx);
+        s_rows[i] = v;
+    }
+    __syncthreads();
+    // output: g tokens x (3*P*P) halfs; each thread produces 8 consecutive kx (16 B)
+    const int kdim = 3 * P * P;
+    const int chunks_per_token = kdim / 8;
+    for (int i = threadIdx.x; i < g * chunks_per_token; i += blockDim.x) {
+        const int tx = i / chunks_per_token;
+        const int ch = i - tx * chunks_per_token;
+        const int k0 = ch * 8;
+        const int c = k0 / (P * P);
+        const int ky = (k0 - c * P * P) / P;
+        const int kx0 = k0 % P;
+        const uint8_t* src = s_rows + ky * row_bytes + (tx * P + kx0) * 3 + c;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half2 hh = __floats2half2_rn(src[(2 * j) * 3] * (1.0f / 256.0f), src[(2 * j + 1) * 3] * (1.0f / 256.0f));
+            w[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        const int64_t orow = static_cast<int64_t>(b) * g * g + ty * g + tx;
+        *reinterpret_cast<uint4*>(out + orow * out_row_stride + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// x[b*tokens + 0, :] = class_token + pos[0, :]
+__global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                                int n_images, int tokens, int D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_images * D) return;
+    const int b = i / D, d = i - b * D;
+    x[static_cast<int64_t>(b) * tokens * D + d] = cls[d] + pos[d];
+}
+
+// =====================================================================================================
+// LayerNorm over the last dim (biased variance, eps inside the sqrt: torch.nn.LayerNorm, eps 1e-6 in
+// torchvision's EncoderBlock).  One warp per row, the row lives in registers, two-pass mean / variance.
+// =====================================================================================================
+template <int VEC>  // D = VEC * 128
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int64_t x_row_stride, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __half* __restrict__ y16, float* __restrict__ y32, int rows) {
+    constexpr int D = VEC * 128;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(warp) * x_row_stride);
+    float4 v[VEC];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        v[i] = xr[lane + 32 * i];
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float4 g = __ldg(g4 + lane + 32 * i);
+        const float4 bb = __ldg(b4 + lane + 32 * i);
+        const float o0 = (v[i].x - mean) * rstd * g.x + bb.x;
+        const float o1 = (v[i].y - mean) * rstd * g.y + bb.y;
+        const float o2 = (v[i].z - mean) * rstd * g.z + bb.z;
+        const float o3 = (v[i].w - mean) * rstd * g.w + bb.w;
+        if (y16) {
+            __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            reinterpret_cast<uint2*>(y16 + static_cast<int64_t>(warp) * D)[lane + 32 * i] = u;
+        } else {
+            reinterpret_cast<float4*>(y32 + static_cast<int64_t>(warp) * D)[lane + 32 * i] = make_float4(o0, o1, o2, o3);
+        }
+    }
+}
+
+// =====================================================================================================
+// Multi-head self-attention, head_dim 64, sequence S <= 272 (197 for ViT/16@224, 257 for ViT/14@224).
+// nn.MultiheadAttention semantics (torchvision EncoderBlock.self_attention): softmax((q/sqrt(d)) k^T) v.
+// One CTA per (head, image): Q, K, V head slices staged once in (XOR-swizzled) smem with cp.async,
+// each warp owns 16-query tiles and streams keys in chunks of 64 with an online softmax (fp32).
+// v1 uses warp-level mma.sync m16n8k16 (4 % of the model FLOPs); the tcgen05 version is the next step.
+// =====================================================================================================
+constexpr int HD = 64;
+constexpr int ATT_WARPS = 7;
+constexpr int ATT_THREADS = ATT_WARPS * 32;
+constexpr int KCHUNK = 64;
+
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk16) {  // byte offset in a [rows][128 B] tile
+    return static_cast<uint32_t>(row * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int S_pad, int heads) {
+    extern __shared__ __align__(128) uint8_t smem_att[];
+    const int D = heads * HD;
+    const int h = blockIdx.x;
+    const int b = blockIdx.y;
+    uint8_t* sQ = smem_att;
+    uint8_t* sK = sQ + S_pad * 128;
+    uint8_t* sV = sK + S_pad * 128;
+    const uint32_t sQ_u = ptx::smem_u32(sQ), sK_u = ptx::smem_u32(sK), sV_u = ptx::smem_u32(sV);
+
+    // ---- stage Q, K, V (zero-filled beyond S) ----
+    const __half* base = qkv + static_cast<int64_t>(b) * S * 3 * D + h * HD;
+    for (int i = threadIdx.x; i < S_pad * 8 * 3; i += ATT_THREADS) {
+        const int mat = i / (S_pad * 8);
+        const int rem = i - mat * (S_pad * 8);
+        const int row = rem >> 3, ch = rem & 7;
+        const uint32_t dst = (mat == 0 ? sQ_u : (mat == 1 ? sK_u : sV_u)) + swz_off(row, ch);
+        const int srow = row < S ? row : S - 1;
+        const __half* src = base + static_cast<int64_t>(srow) * 3 * D + mat * D + ch * 8;
+        ptx::cp_async_16(dst, src, row < S ? 16u : 0u);
+    }
+    ptx::cp_async_commit();
+    ptx::cp_async_wait_all();
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const float scale_log2 = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e)
+    const int n_qtiles = S_pad / 16;
+
+    for (int qt = warp; qt < n_qtiles; qt += ATT_WARPS) {
+        const int q0 = qt * 16;
+        uint32_t qf[4][4];  // A fragments for the 4 k-steps of head_dim 64
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int row = q0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int ch = ks * 2 + (lane >> 4);
+            ptx::ldmatrix_x4(sQ_u + swz_off(row, ch), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        }
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+        for (int kc = 0; kc < S_pad; kc += KCHUNK) {
+            float s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+            // ---- S = Q K^T for up to 64 keys (8 n-tiles), two n-tiles per ldmatrix.x4 ----
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                const int key0 = kc + np * 16;
+                if (key0 < S_pad) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        uint32_t b0, b1, b2, b3;
+                        const int row = key0 + (lane & 7) + (lane >> 4) * 8;
+                        const int ch = ks * 2 + ((lane >> 3) & 1);
+                        ptx::ldmatrix_x4(sK_u + swz_off(row, ch), b0, b1, b2, b3);
+                        ptx::mma_m16n8k16_f16(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
+                        ptx::mma_m16n8k16_f16(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+                    }
+                }
+            }
+            // ---- mask keys >= S, chunk max ----
+            float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int key = kc + i * 8 + 2 * t;
+                if (key >= S) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
+                if (key + 1 >= S) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+                cm0 = fmaxf(cm0, fmaxf(s[i][0], s[i][1]));
+                cm1 = fmaxf(cm1, fmaxf(s[i][2], s[i][3]));
+            }
+            cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+            cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+            cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+            cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+            const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);  // finite: every chunk holds >= 1 valid key
+            const float corr0 = exp2f((m0 - nm0) * scale_log2), corr1 = exp2f((m1 - nm1) * scale_log2);
+            m0 = nm0; m1 = nm1;
+            l0 *= corr0; l1 *= corr1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o[i][0] *= corr0; o[i][1] *= corr0; o[i][2] *= corr1; o[i][3] *= corr1; }
+            // ---- P = exp2((s - m) * scale), row sums, pack to fp16 A fragments ----
+            uint32_t pf[4][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float p0 = exp2f((s[i][0] - m0) * scale_log2), p1 = exp2f((s[i][1] - m0) * scale_log2);
+                const float p2 = exp2f((s[i][2] - m1) * scale_log2), p3 = exp2f((s[i][3] - m1) * scale_log2);
+                l0 += p0 + p1; l1 += p2 + p3;
+                __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+                pf[i >> 1][(i & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
+                pf[i >> 1][(i & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&h23);
+            }
+            // ---- O += P V ----
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int key0 = kc + ks * 16;
+                if (key0 < S_pad) {
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {
+                        uint32_t b0, b1, b2, b3;
+                        const int row = key0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                        const int ch = np * 2 + (lane >> 4);
+                        ptx::ldmatrix_x4_trans(sV_u + swz_off(row, ch), b0, b1, b2, b3);
+                        ptx::mma_m16n8k16_f16(o[2 * np], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b0, b1);
+                        ptx::mma_m16n8k16_f16(o[2 * np + 1], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b2, b3);
+                    }
+                }
+            }
+        }
+        // ---- finalise: O / l, store fp16 ----
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+        const int r0 = q0 + g, r1 = q0 + g + 8;
+        __half* obase = out + static_cast<int64_t>(b) * S * D + h * HD;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int col = i * 8 + 2 * t;
+            if (r0 < S) *reinterpret_cast<__half2*>(obase + static_cast<int64_t>(r0) * D + col) = __floats2half2_rn(o[i][0] * inv0, o[i][1] * inv0);
+            if (r1 < S) *reinterpret_cast<__half2*>(obase + static_cast<int64_t>(r1) * D + col) = __floats2half2_rn(o[i][2] * inv1, o[i][3] * inv1);
+        }
+    }
+}
+
+}  // namespace
+
+int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
+                      int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
+                      cudaStream_t stream) {
+    AP_REQUIRE(ctx, patch == 16, "preprocess: conv patch %d unsupported (16 only)", patch);
+    AP_REQUIRE(ctx, image % patch == 0 && input_patch >= image, "preprocess: bad geometry input %d image %d patch %d",
+               input_patch, image, patch);
+    if (n == 0) return AP_OK;
+    const int g = image / patch;
+    const size_t smem = static_cast<size_t>(patch) * image * 3;
+    preprocess_kernel<16><<<static_cast<unsigned>(n * g), 256, smem, stream>>>(slide, W, H, pitch, coords, input_patch, image,
+                                                                               out, out_row_stride);
+    AP_CHECK_LAUNCH(ctx, "preprocess_kernel");
+    return AP_OK;
+}
+
+int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D,
+                    cudaStream_t stream) {
+    if (n_images == 0) return AP_OK;
+    const int total = n_images * D;
+    cls_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(x, cls, pos, n_images, tokens, D);
+    AP_CHECK_LAUNCH(ctx, "cls_rows_kernel");
+    return AP_OK;
+}
+
+int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
+                     __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream) {
+    AP_REQUIRE(ctx, D % 128 == 0 && D <= 1536, "layernorm: D=%d unsupported (multiple of 128, <= 1536)", D);
+    AP_REQUIRE(ctx, x_row_stride % 4 == 0, "layernorm: row stride %lld not a multiple of 4", (long long)x_row_stride);
+    if (rows == 0) return AP_OK;
+    const int blocks = (rows + 7) / 8;
+#define AP_LN_CASE(V)                                                                                               \
+    case V:                                                                                                         \
+        layernorm_kernel<V><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, y_f16, y_f32, rows);       \
+        break;
+    switch (D / 128) {
+        AP_LN_CASE(1) AP_LN_CASE(2) AP_LN_CASE(3) AP_LN_CASE(4) AP_LN_CASE(5) AP_LN_CASE(6) AP_LN_CASE(8) AP_LN_CASE(10)
+        AP_LN_CASE(12)
+        default: return ap_set_error(ctx, AP_EINVAL, "layernorm: D=%d not instantiated", D);
+    }
+#undef AP_LN_CASE
+    AP_CHECK_LAUNCH(ctx, "layernorm_kernel");
+    return AP_OK;
+}
+
+int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream) {
+    AP_REQUIRE(ctx, S >= 1 && S <= 272, "attention: S=%d unsupported (<= 272)", S);
+    if (B == 0) return AP_OK;
+    const int S_pad = (S + 15) / 16 * 16;
+    const size_t smem = static_cast<size_t>(S_pad) * 128 * 3;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 272 * 128 * 3));
+        attr_set = true;
+    }
+    attention_kernel<<<dim3(heads, B), ATT_THREADS, smem, stream>>>(qkv, out, S, S_pad, heads);
+    AP_CHECK_LAUNCH(ctx, "attention_kernel");
+    return AP_OK;
+}
+
+extern "C" int ap_layernorm_f16(ap_ctx* ctx, const float* x_dev, int64_t x_row_stride, const float* gamma_dev,
+                                const float* beta_dev, float eps, void* y_dev, int rows, int D, void* stream) {
+    if (!ctx) return AP_EINVAL;
+    return ap_layernorm_run(ctx, x_dev, x_row_stride, gamma_dev, beta_dev, eps, static_cast<__half*>(y_dev), nullptr, rows, D,
+                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ap_attention_f16(ap_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int S, int heads, void* stream) {
+    if (!ctx) return AP_EINVAL;
+    return ap_attention_run(ctx, static_cast<const __half*>(qkv_dev), static_cast<__half*>(out_dev), B, S, heads,
+                            static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,113 @@
+"""Encoder plug-in (seam #2 of SURVEY.md section 8b): the reference's FeatureExtractor contract on the B200 engine.
+
+reference interface: atlas_patch/models/patch/base.py:15-29 (name, embedding_dim, extract_batch, cleanup);
+extract_batch(patches: Sequence[np.ndarray (P,P,3) uint8], *, batch_size) -> np.ndarray (len, D) float32, rows in
+input order, (0, D) for empty input (base.py:76-107).  `embed_coords` is the zero-copy fast path that reads patches
+straight out of a device-resident slide.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Mapping, Sequence
+
+import numpy as np
+
+from atlaspatch_b200._lib import Context, VitDesc, current_stream_ptr
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+# name -> (patch, layers, heads, hidden, mlp); the torchvision ViTs the reference registers (models/patch/vit.py:9-15)
+VIT_CONFIGS = {
+    "vit_b_16": (16, 12, 12, 768, 3072),
+    "vit_l_16": (16, 24, 16, 1024, 4096),
+    "vit_test_tiny": (16, 2, 4, 256, 512),
+}
+
+
+def vit_state_dict_names(layers: int) -> list[str]:
+    names = ["conv_proj.weight", "conv_proj.bias", "class_token", "encoder.pos_embedding", "encoder.ln.weight", "encoder.ln.bias"]
+    for i in range(layers):
+        p = f"encoder.layers.encoder_layer_{i}."
+        names += [p + s for s in ("ln_1.weight", "ln_1.bias", "self_attention.in_proj_weight", "self_attention.in_proj_bias",
+                                  "self_attention.out_proj.weight", "self_attention.out_proj.bias", "ln_2.weight", "ln_2.bias",
+                                  "mlp.0.weight", "mlp.0.bias", "mlp.3.weight", "mlp.3.bias")]
+    return names
+
+
+class B200FeatureExtractor:
+    """ViT encoder forward on hand-written sm_100a kernels behind the reference's FeatureExtractor interface."""
+
+    def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int = 256, image_size: int = 224,
+                 max_batch: int = 128, device: int = 0, config: tuple | None = None, registry_name: str | None = None):
+        cfg = config or VIT_CONFIGS.get(name)
+        if cfg is None:
+            raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS)}")
+        patch, layers, heads, hidden, mlp = cfg
+        self.name = registry_name or name   # H5 dataset name: features/<name> (services/storage.py:250-337)
+        self.embedding_dim = int(hidden)
+        self.input_patch = int(input_patch)
+        self.max_batch = int(max_batch)
+        self.ctx = Context.get(device)
+        lib = self.ctx.lib
+        desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
+                       input_patch=input_patch, max_batch=max_batch, ln_eps=1e-6,
+                       mean=(C.c_float * 3)(*IMAGENET_MEAN), std=(C.c_float * 3)(*IMAGENET_STD))
+        h = C.c_void_p()
+        self.ctx.check(lib.ap_encoder_create(self.ctx.handle, C.byref(desc), C.byref(h)))
+        self._h = h
+        try:
+            for key in vit_state_dict_names(layers):
+                if key not in state_dict:
+                    raise KeyError(f"state_dict is missing '{key}'")
+                t = state_dict[key]
+                a = t.detach().to("cpu").float().contiguous().numpy() if hasattr(t, "detach") else np.ascontiguousarray(t, np.float32)
+                self.ctx.check(lib.ap_encoder_set_tensor(h, key.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+            self.ctx.check(lib.ap_encoder_finalize(h))
+        except Exception:
+            lib.ap_encoder_destroy(h)
+            self._h = None
+            raise
+
+    # ---- reference contract ------------------------------------------------------------------------
+    def extract_batch(self, patches: Sequence[np.ndarray], *, batch_size: int | None = None) -> np.ndarray:
+        n = len(patches)
+        out = np.empty((n, self.embedding_dim), dtype=np.float32)
+        if n == 0:
+            return out
+        P = self.input_patch
+        keep = []  # keep converted arrays alive while the C call runs
+        ptrs = (C.c_void_p * n)()
+        for i, p in enumerate(patches):
+            a = np.asarray(p)
+            if a.shape != (P, P, 3) or a.dtype != np.uint8:
+                raise ValueError(f"patch {i}: expected uint8 array of shape ({P},{P},3), got {a.dtype} {a.shape}")
+            if not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a)
+            keep.append(a)
+            ptrs[i] = a.ctypes.data
+        self.ctx.check(self.ctx.lib.ap_encoder_embed_patches_host(self._h, ptrs, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def cleanup(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            self.ctx.lib.ap_encoder_destroy(self._h)
+            self._h = None
+
+    __del__ = cleanup
+
+    # ---- device-resident fast path -----------------------------------------------------------------
+    def embed_coords(self, image, W: int, H: int, pitch: int, coords_dev, out=None):
+        """image: uint8 CUDA tensor (level-0 RGB rows, `pitch` bytes/row); coords_dev: int32 CUDA (n,5) -> (n,D) fp32 CUDA."""
+        import torch
+
+        n = int(coords_dev.shape[0])
+        if out is None:
+            out = torch.empty((n, self.embedding_dim), dtype=torch.float32, device="cuda")
+        if n == 0:
+            return out
+        assert coords_dev.dtype == torch.int32 and coords_dev.is_contiguous() and coords_dev.is_cuda
+        self.ctx.check(self.ctx.lib.ap_encoder_embed_coords(
+            self._h, C.c_void_p(image.data_ptr()), W, H, pitch, C.c_void_p(coords_dev.data_ptr()), n,
+            C.c_void_p(out.data_ptr()), C.c_void_p(current_stream_ptr())))
+        return out

@@ -1,0 +1,33 @@
+"""`--feature-plugin` entry point for the reference CLI (atlas_patch/cli.py:182-191,621-628).
+
+    atlaspatch process slide.svs -o out --feature-plugin /path/to/atlaspatch_b200/plugin.py \
+        --feature-extractors b200_vit_b_16
+
+The hook signature is the reference's CustomRegistryHook (atlas_patch/models/patch/custom.py:92-146).  Weights come
+from torchvision exactly as the reference's own `vit_b_16` builder resolves them (models/patch/base.py:126-180); the
+forward runs on the sm_100a kernels.  A CUDA device is mandatory: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from atlaspatch_b200.encoder import B200FeatureExtractor
+
+_TORCHVISION = {"vit_b_16": ("vit_b_16", "ViT_B_16_Weights"), "vit_l_16": ("vit_l_16", "ViT_L_16_Weights")}
+
+
+def _build(name: str, device) -> B200FeatureExtractor:
+    import torch
+    from torchvision import models
+
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("atlaspatch_b200 encoders need a CUDA device (B200); no CPU fallback exists")
+    ctor_name, enum_name = _TORCHVISION[name]
+    weights_enum = getattr(models, enum_name)
+    weights = getattr(weights_enum, "IMAGENET1K_V1", None) or weights_enum.DEFAULT
+    model = getattr(models, ctor_name)(weights=weights)
+    idx = torch.device(device).index or 0
+    return B200FeatureExtractor(name, model.state_dict(), device=idx, registry_name=f"b200_{name}")
+
+
+def register_feature_extractors(registry, device, dtype, num_workers) -> None:
+    for name in _TORCHVISION:
+        registry.register(f"b200_{name}", lambda n=name: _build(n, device))

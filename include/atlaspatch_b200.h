@@ -1,0 +1,139 @@
+/*
+ * atlaspatch_b200 -- C ABI of the B200-native AtlasPatch hot path (libatlaspatch_b200.so).
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Every entry point returns 0 on
+ * success or a negative AP_E* code; the message is available from ap_last_error().  Device
+ * pointers are ordinary CUDA device pointers of the ctx's device (e.g. torch `tensor.data_ptr()`),
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  The library owns
+ * only encoder weights and workspaces; all inputs/outputs are caller-allocated.
+ *
+ * Each entry cites the reference interface it replaces (paths under the AtlasPatch repo).
+ * The reference is pure Python and has no FFI of its own; INTEGRATION.md shows the ctypes
+ * binding a maintainer adds at each of these seams.
+ */
+#ifndef ATLASPATCH_B200_H
+#define ATLASPATCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AP_OK 0
+#define AP_EINVAL (-1)      /* bad argument / unsupported configuration */
+#define AP_ECUDA (-2)       /* CUDA runtime or driver error */
+#define AP_ENOMEM (-3)      /* allocation failed */
+#define AP_ECAPACITY (-4)   /* caller-provided output buffer too small */
+#define AP_ESTATE (-5)      /* object not ready (e.g. encoder weights missing) */
+
+typedef struct ap_ctx ap_ctx;
+typedef struct ap_encoder ap_encoder;
+
+/* ---- context ------------------------------------------------------------------------- */
+int ap_version(void);
+/* One ctx per GPU/process (SURVEY.md section 8b "Threading").  Fails (AP_ECUDA) when no sm_100 device. */
+int ap_init(int device, ap_ctx** out_ctx);
+int ap_destroy(ap_ctx* ctx);
+/* Last error text for this ctx (ctx==NULL: last error of a failed ap_init).  Never NULL. */
+const char* ap_last_error(const ap_ctx* ctx);
+/* Number of kernels this library has launched on ctx since ap_init (bench.py "gpu_launches"). */
+int64_t ap_launch_count(const ap_ctx* ctx);
+int ap_sm_count(const ap_ctx* ctx);
+
+/* ---- synthetic slide (benchmark input) ---------------------------------
+ * Renders the region [x0,x0+w) x [y0,y0+h) of the synthetic slide (W x H, seed, blobs, holes)
+ * into `out` (RGB uint8, HWC, row pitch `pitch` bytes).  blobs: n_blobs x 6 int32
+ * (cx,cy,a,b,c,s), holes: n_holes x 3 int32 (cx,cy,r) -- HOST pointers.  Pixels outside the
+ * slide are 0.  Same integer function as atlaspatch_b200/synthetic.py:render_region_host. */
+int ap_synth_render(ap_ctx* ctx, uint8_t* out_dev, int64_t pitch, int64_t W, int64_t H, uint32_t seed,
+                    const int32_t* blobs_host, int n_blobs, const int32_t* holes_host, int n_holes,
+                    int64_t x0, int64_t y0, int64_t w, int64_t h, void* stream);
+
+/* ---- a1: whole-level thumbnail -------------------------------------------------------------
+ * Replaces IWSI.get_thumbnail_at_power's whole-level read + cv2.resize(INTER_AREA)
+ * (atlas_patch/core/wsi/iwsi.py:293-321) for an integer factor f = base_mag/power with
+ * W % f == H % f == 0: out[(H/f),(W/f),3] = round-half-even(mean of f x f block).  out is tightly
+ * packed RGB.  One pass over W*H*3 bytes: the HBM-roofline kernel of the path. */
+int ap_thumbnail_area(ap_ctx* ctx, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
+                      int factor, uint8_t* out_dev, void* stream);
+
+/* ---- a9: patch-coordinate extraction -------------------------------------------------------
+ * Replaces PatchExtractionService._iter_patch_entries (fast mode) + _in_tissue +
+ * FourPointContainment (atlas_patch/services/extraction.py:67-103, utils/contours.py:22-38).
+ * Inputs are the level-0 contours produced by _prepare_contours (extraction.py:30-42), flattened:
+ *   contour_xy      int32 (sum K_c) x 2         vertices of all tissue contours, in order
+ *   contour_offsets int32 n_contours+1          vertex ranges
+ *   hole_xy         int32 (sum K_h) x 2         vertices of all hole contours
+ *   hole_offsets    int32 n_holes+1             vertex ranges
+ *   hole_first      int32 n_contours+1          holes of contour c are [hole_first[c], hole_first[c+1])
+ * (all HOST pointers; they are a few KB).  patch_src/step_src/read_w/read_h/level come from
+ * _prepare_geometry (extraction.py:44-64).
+ * Output rows (x, y, read_w, read_h, level) int32, in the reference's order (contour-major, y, x),
+ * are written to out_rows_dev (device, capacity rows) and/or out_rows_host (host, capacity rows);
+ * either may be NULL.  *out_count receives N.  Synchronous on `stream`. */
+int64_t ap_coords_capacity(const int32_t* contour_xy, const int32_t* contour_offsets, int n_contours,
+                           int step_src);
+int ap_extract_coords(ap_ctx* ctx, const int32_t* contour_xy, const int32_t* contour_offsets, int n_contours,
+                      const int32_t* hole_xy, const int32_t* hole_offsets, const int32_t* hole_first,
+                      int patch_src, int step_src, int read_w, int read_h, int level,
+                      int32_t* out_rows_dev, int32_t* out_rows_host, int64_t capacity,
+                      int64_t* out_count, void* stream);
+
+/* ---- a11-a13: patch read -> preprocess -> encoder forward ------------------------------------
+ * Replaces PatchFeatureEmbeddingService._iter_patch_entries_coords + PatchDataset/preprocess +
+ * PatchFeatureExtractor.extract_batch + the torchvision VisionTransformer forward
+ * (atlas_patch/services/feature_embedding.py:81-96, models/patch/base.py:32-107,
+ *  models/patch/vit.py:9-38).  fp16 operands, fp32 accumulation / residual / LayerNorm / softmax. */
+typedef struct ap_vit_desc {
+    int image_size;   /* 224 */
+    int patch;        /* 16  */
+    int layers;       /* 12  */
+    int heads;        /* 12  */
+    int hidden;       /* 768 */
+    int mlp;          /* 3072 */
+    int input_patch;  /* edge of the RGB patches fed in (256): centre crop to image_size */
+    int max_batch;    /* patches per forward chunk (workspace size); 0 = default 128 */
+    float ln_eps;     /* 1e-6 */
+    float mean[3];    /* ImageNet mean / std of the torchvision preset */
+    float std[3];
+} ap_vit_desc;
+
+int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc);
+int ap_encoder_destroy(ap_encoder* enc);
+/* Upload one fp32 tensor by its torchvision state_dict name (HOST pointer), e.g.
+ * "conv_proj.weight", "encoder.layers.encoder_layer_3.self_attention.in_proj_weight". */
+int ap_encoder_set_tensor(ap_encoder* enc, const char* name, const float* data_host, int64_t numel);
+/* Pack weights (fp16, normalisation folded into conv_proj), build TMA descriptors.
+ * AP_ESTATE if a tensor is missing. */
+int ap_encoder_finalize(ap_encoder* enc);
+int ap_encoder_embedding_dim(const ap_encoder* enc);
+/* Device-resident fast path: patches are cut straight out of the level-0 slide in HBM at
+ * coords_dev rows (x, y, read_w, read_h, level) [int32, n x 5]; features (n x D fp32) to
+ * out_features_dev.  Asynchronous on `stream`.  read_w/read_h must equal input_patch. */
+int ap_encoder_embed_coords(ap_encoder* enc, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
+                            const int32_t* coords_dev, int64_t n, float* out_features_dev, void* stream);
+/* extract_batch-compatible path: n HOST patches (each input_patch x input_patch x 3 uint8,
+ * contiguous) given by pointer; features (n x D fp32) to HOST.  Includes H2D / D2H; synchronous. */
+int ap_encoder_embed_patches_host(ap_encoder* enc, const uint8_t* const* patches_host, int64_t n,
+                                  float* out_features_host);
+
+/* ---- building-block ops (kernel-level parity tests; also what the encoder is made of) -------- */
+#define AP_EPI_BIAS_F16 0        /* out fp16 = acc + bias                          */
+#define AP_EPI_BIAS_GELU_F16 1   /* out fp16 = gelu_erf(acc + bias)                */
+#define AP_EPI_BIAS_RESID_F32 2  /* out fp32 = resid + acc + bias (resid may == out) */
+#define AP_EPI_BIAS_F32 3        /* out fp32 = acc + bias                          */
+/* out[M,N] = epilogue(A[M,K] (fp16, row-major) x W[N,K]^T (fp16, row-major)); tcgen05/TMEM/TMA.
+ * K % 64 == 0, N % 128 == 0. */
+int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,
+                const float* resid_dev, void* out_dev, int M, int N, int K, int epilogue, void* stream);
+/* y fp16 [rows, D] = LayerNorm(x fp32 [rows, D]; gamma, beta, eps), x row stride in elements. */
+int ap_layernorm_f16(ap_ctx* ctx, const float* x_dev, int64_t x_row_stride, const float* gamma_dev,
+                     const float* beta_dev, float eps, void* y_dev, int rows, int D, void* stream);
+/* Multi-head self-attention on packed QKV fp16 [B*S, 3*D] -> out fp16 [B*S, D]; head_dim 64. */
+int ap_attention_f16(ap_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int S, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATLASPATCH_B200_H */

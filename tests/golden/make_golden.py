@@ -1,0 +1,141 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the reference through oracle/refimport.py (stubbed optional deps), plugs a
+synthetic-slide backend into the reference's own IWSI ABC (core/wsi/iwsi.py:9-124), and
+records what the reference's functions return:
+
+* coords_<case>.npz  -- PatchExtractionService._prepare_contours + _iter_patch_entries
+                        (services/extraction.py:30-42,83-128) -> int32 (N,5) rows
+* thumb_<case>.npz   -- IWSI.get_thumbnail_at_power(1.25) (core/wsi/iwsi.py:246-323)
+* vit_b_16_feats.npz -- PatchFeatureExtractor.extract_batch (models/patch/base.py:76-107)
+                        on torchvision vit_b_16 + its ImageClassification preset, fp32 CPU,
+                        seeded weights from oracle/weights.py
+* library versions the vectors were made with (versions.json)
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from oracle.refimport import import_reference  # noqa: E402
+
+import_reference()
+
+import cv2  # noqa: E402
+import PIL  # noqa: E402
+import torch  # noqa: E402
+import torchvision  # noqa: E402
+from PIL import Image  # noqa: E402
+
+from atlas_patch.core.config import ExtractionConfig, OutputConfig  # noqa: E402
+from atlas_patch.core.wsi.iwsi import IWSI  # noqa: E402
+from atlas_patch.services.extraction import PatchExtractionService  # noqa: E402
+
+from atlaspatch_b200.synthetic import make_spec, render_region_host, truth_mask  # noqa: E402
+from tests.cases import COORD_CASES, THUMB_CASES, build_mask  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+class RefSyntheticWSI(IWSI):
+    """Synthetic slide behind the reference's own IWSI ABC (single level, ds=[1.0])."""
+
+    def __init__(self, spec):
+        super().__init__(path=f"synthetic_{spec.width}x{spec.height}_s{spec.seed}.synth", mpp=spec.mpp)
+        self.spec = spec
+        self._ensure_loaded()
+
+    def _setup(self):
+        self.w, self.h = self.spec.width, self.spec.height
+        self.nlvl, self.ds, self.dims = 1, [1.0], [(self.w, self.h)]
+        self.meta = {}
+        self.mpp = self._extract_mpp()
+        self.mag = self._extract_mag()
+
+    def _extract_mpp(self):
+        return self.validate_mpp(float(self._mpp_manual), source="manual")
+
+    def _extract_mag(self):
+        return self._infer_mag(self.mpp)
+
+    def extract(self, xy, lv, wh, *, mode="array"):
+        arr = render_region_host(self.spec, int(xy[0]), int(xy[1]), int(wh[0]), int(wh[1]))
+        return arr if mode == "array" else Image.fromarray(arr)
+
+    def get_size(self, lv=0):
+        return self.w, self.h
+
+    def get_thumb(self, max_hw):
+        t = self.get_thumbnail_at_power(power=1.25)
+        t.thumbnail(max_hw)
+        return t
+
+    def cleanup(self):
+        pass
+
+
+def reference_coords(case) -> np.ndarray:
+    spec = make_spec(case["width"], case["height"], case["seed"], mpp=case["mpp"])
+    wsi = RefSyntheticWSI(spec)
+    mask = build_mask(case, spec)
+    with tempfile.TemporaryDirectory() as td:
+        svc = PatchExtractionService(
+            ExtractionConfig(patch_size=case["patch"], target_magnification=case["target_mag"],
+                             step_size=case["step"], tissue_threshold=case["tissue_thresh"]),
+            OutputConfig(output_root=Path(td)),
+        )
+        tissue, holes = svc._prepare_contours(mask, wsi)
+        rows = [e[:5] for e in svc._iter_patch_entries(wsi, tissue, holes, include_patch=False)]
+    return np.asarray(rows, dtype=np.int32).reshape(-1, 5)
+
+
+def main() -> None:
+    versions = {"cv2": cv2.__version__, "numpy": np.__version__, "PIL": PIL.__version__,
+                "torch": torch.__version__, "torchvision": torchvision.__version__}
+    for case in COORD_CASES:
+        coords = reference_coords(case)
+        np.savez_compressed(OUT / f"coords_{case['name']}.npz", coords=coords)
+        print(f"coords_{case['name']}: N={coords.shape[0]} first={coords[0].tolist() if len(coords) else None}")
+
+    for case in THUMB_CASES:
+        spec = make_spec(case["width"], case["height"], case["seed"], mpp=case["mpp"])
+        thumb = np.asarray(RefSyntheticWSI(spec).get_thumbnail_at_power(power=1.25))
+        np.savez_compressed(OUT / f"thumb_{case['name']}.npz", thumb=thumb)
+        print(f"thumb_{case['name']}: {thumb.shape}")
+
+    # ---- encoder features through the reference's own extractor class -------------------
+    from atlas_patch.models.patch.base import PatchFeatureExtractor
+    from torchvision import models as tvm
+
+    from oracle.weights import vit_state_dict
+    from tests.cases import FEATURE_CASE, feature_patches
+
+    model = tvm.vit_b_16(weights=None)
+    model.heads = torch.nn.Identity()
+    model.load_state_dict(vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"]), strict=True)
+    preprocess = tvm.ViT_B_16_Weights.IMAGENET1K_V1.transforms()
+    ext = PatchFeatureExtractor(name="vit_b_16", model=model, embedding_dim=768, preprocess=preprocess,
+                                device=torch.device("cpu"), dtype=torch.float32, num_workers=0)
+    patches = feature_patches()
+    feats = ext.extract_batch(patches, batch_size=8)
+    np.savez_compressed(OUT / "vit_b_16_feats.npz", feats=feats.astype(np.float32))
+    print("vit_b_16_feats:", feats.shape, float(np.abs(feats).mean()))
+
+    (OUT / "versions.json").write_text(json.dumps(versions, indent=1) + "\n")
+
+
+if __name__ == "__main__":
+    os.environ.setdefault("OMP_NUM_THREADS", "8")
+    main()

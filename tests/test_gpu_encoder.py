@@ -1,0 +1,85 @@
+"""GPU parity tests: preprocess + ViT forward (a11-a13) against the CPU oracle and the reference golden features."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit as ov
+from oracle.weights import vit_state_dict
+from tests.cases import FEATURE_CASE, feature_patches
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3   # BASELINE.json north_star: encoder features within 1e-3 relative of the fp32 CPU path
+
+
+def _rel(got, want):
+    return np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+
+
+def test_tiny_vit_matches_oracle():
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+
+    sd = vit_state_dict("vit_test_tiny", seed=3)
+    patches = feature_patches()[:6]
+    want = ov.extract_features(patches, sd, "vit_test_tiny")
+    ext = B200FeatureExtractor("vit_test_tiny", sd, max_batch=4)   # 6 patches -> two chunks (4 + 2)
+    got = ext.extract_batch(patches, batch_size=32)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert _rel(got, want).max() < REL_TOL, _rel(got, want)
+    assert ext.extract_batch([]).shape == (0, 256)
+    with pytest.raises(ValueError):
+        ext.extract_batch([np.zeros((224, 224, 3), np.uint8)])
+    ext.cleanup()
+
+
+def test_vit_b_16_matches_reference_golden(golden_dir):
+    """Golden rows were produced by the reference's PatchFeatureExtractor on torchvision vit_b_16 (fp32, CPU)."""
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+
+    gold = np.load(golden_dir / "vit_b_16_feats.npz")["feats"]
+    sd = vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"])
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=128)
+    patches = feature_patches()
+    got = ext.extract_batch(patches, batch_size=32)
+    rel = _rel(got, gold)
+    print("vit_b_16 rel err per row:", rel)
+    assert rel.max() < REL_TOL, rel
+
+    # device-resident fast path on the same pixels must give the same rows as the host-patch path
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec
+
+    s = FEATURE_CASE["slide"]
+    wsi = SyntheticWSI(make_spec(s["width"], s["height"], s["seed"], mpp=s["mpp"]))
+    rng = np.random.default_rng(77)
+    xy = [(int(rng.integers(0, wsi.w - 256)), int(rng.integers(0, wsi.h - 256))) for _ in range(FEATURE_CASE["n"])]
+    coords = torch.tensor([[x, y, 256, 256, 0] for x, y in xy], dtype=torch.int32, device="cuda")
+    feats_dev = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords).cpu().numpy()
+    assert np.array_equal(feats_dev, got)
+    assert _rel(feats_dev, gold).max() < REL_TOL
+    ext.cleanup()
+
+
+def test_vit_b_16_many_patches_ragged_and_overhang():
+    """300 patches (chunks 128+128+44), some overhanging the slide edge (zero padding like the reference backends)."""
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec, render_region_host
+
+    sd = vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"])
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=128)
+    spec = make_spec(3000, 2000, seed=21)
+    wsi = SyntheticWSI(spec)
+    rng = np.random.default_rng(5)
+    xy = [(int(rng.integers(-100, spec.width - 100)), int(rng.integers(-100, spec.height - 100))) for _ in range(300)]
+    coords = torch.tensor([[x, y, 256, 256, 0] for x, y in xy], dtype=torch.int32, device="cuda")
+    feats = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords).cpu().numpy()
+    assert np.isfinite(feats).all()
+    idx = [0, 1, 127, 128, 255, 256, 299] + [i for i, (x, y) in enumerate(xy) if x < 0 or y < 0 or x + 256 > spec.width][:3]
+    want = ov.extract_features([render_region_host(spec, *xy[i], 256, 256) for i in idx], sd, "vit_b_16")
+    assert _rel(feats[idx], want).max() < REL_TOL
+    # order / batching invariance: same rows when embedded in another order
+    perm = torch.randperm(300, generator=torch.Generator().manual_seed(0))
+    feats_p = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords[perm.cuda()].contiguous()).cpu().numpy()
+    assert np.array_equal(feats_p, feats[perm.numpy()])
+    ext.cleanup()

@@ -1,0 +1,95 @@
+"""GPU parity tests of the building-block kernels, called through the C ABI (ctypes)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from atlaspatch_b200._lib import Context
+
+    return Context.get(0)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+GEMM_CASES = [
+    # M, N, K, epilogue
+    (128, 256, 64, 0), (128, 256, 128, 0), (256, 256, 768, 0), (200, 512, 256, 0),
+    (197 * 4, 2304, 768, 0), (197 * 4, 3072, 768, 1), (197 * 4, 768, 3072, 2), (196 * 4, 768, 768, 3),
+    (1000, 128, 192, 0), (77, 384, 64, 2), (25216, 768, 768, 2), (5000, 2304, 768, 0),
+]
+
+
+@pytest.mark.parametrize("M,N,K,epi", GEMM_CASES)
+def test_gemm_tcgen05(ctx, M, N, K, epi):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    ref = A.float() @ W.float().T + bias
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi == 2:
+        ref = ref + resid
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16 if epi in (0, 1) else torch.float32)
+    ctx.check(ctx.lib.ap_gemm_f16(ctx.handle, _p(A), _p(W), _p(bias), _p(resid) if epi == 2 else None, _p(out), M, N, K, epi, _stream()))
+    torch.cuda.synchronize()
+    got = out.float()
+    assert torch.isfinite(got).all()
+    tol = 2e-3 if epi in (0, 1) else 2e-5   # fp16 output rounding vs fp32 output
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * max(scale, 1.0), f"max abs err {err} (scale {scale})"
+
+
+def test_gemm_rejects_bad_shapes(ctx):
+    from atlaspatch_b200._lib import AtlasB200Error
+
+    A = torch.zeros(128, 100, device="cuda", dtype=torch.float16)
+    W = torch.zeros(256, 100, device="cuda", dtype=torch.float16)
+    b = torch.zeros(256, device="cuda")
+    o = torch.zeros(128, 256, device="cuda", dtype=torch.float16)
+    with pytest.raises(AtlasB200Error):
+        ctx.check(ctx.lib.ap_gemm_f16(ctx.handle, _p(A), _p(W), _p(b), None, _p(o), 128, 256, 100, 0, _stream()))
+
+
+@pytest.mark.parametrize("rows,D", [(1, 256), (197 * 3, 768), (1000, 1024), (37, 1536), (5, 128)])
+def test_layernorm(ctx, rows, D):
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 3 + 1.5
+    gamma = torch.randn(D, device="cuda", generator=g)
+    beta = torch.randn(D, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps=1e-6)
+    out = torch.empty(rows, D, device="cuda", dtype=torch.float16)
+    ctx.check(ctx.lib.ap_layernorm_f16(ctx.handle, _p(x), D, _p(gamma), _p(beta), 1e-6, _p(out), rows, D, _stream()))
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,S,heads", [(1, 197, 12), (3, 197, 4), (2, 257, 16), (2, 16, 2), (1, 1, 1), (2, 64, 3), (1, 272, 2)])
+def test_attention(ctx, B, S, heads):
+    D = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + S + heads)
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 1.5).half()
+    out = torch.full((B * S, D), float("nan"), device="cuda", dtype=torch.float16)
+    ctx.check(ctx.lib.ap_attention_f16(ctx.handle, _p(qkv), _p(out), B, S, heads, _stream()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1) @ v          # (B, heads, S, 64)
+    ref = ref.permute(0, 2, 1, 3).reshape(B * S, D)
+    got = out.float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())

@@ -1,0 +1,59 @@
+"""CPU tests: oracle/vit.py and oracle/thumbnail.py against the golden vectors produced by the
+unmodified reference, and against the libraries the reference calls."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import thumbnail as ot
+from oracle import vit as ov
+from oracle.weights import vit_state_dict
+from tests.cases import FEATURE_CASE, THUMB_CASES, case_spec, feature_patches
+from atlaspatch_b200.synthetic import render_region_host
+
+
+def test_vit_oracle_matches_reference_golden(golden_dir):
+    gold = np.load(golden_dir / "vit_b_16_feats.npz")["feats"]
+    sd = vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"])
+    got = ov.extract_features(feature_patches(), sd, "vit_b_16", batch_size=8)
+    assert got.shape == gold.shape == (16, 768)
+    rel = np.linalg.norm(got - gold, axis=1) / np.linalg.norm(gold, axis=1)
+    assert rel.max() < 2e-5, rel.max()   # same fp32 arithmetic, different op order only
+
+
+def test_vit_oracle_matches_torchvision_tiny():
+    from torchvision.models.vision_transformer import VisionTransformer
+
+    sd = vit_state_dict("vit_test_tiny", seed=3)
+    m = VisionTransformer(image_size=224, patch_size=16, num_layers=2, num_heads=4, hidden_dim=256, mlp_dim=512)
+    m.heads = torch.nn.Identity()
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = ov.preprocess(feature_patches()[:4])
+    with torch.inference_mode():
+        want = m(x)
+    got = ov.forward(x, sd, "vit_test_tiny")
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_preprocess_is_crop_scale_normalize():
+    p = feature_patches()[:2]
+    x = ov.preprocess(p)
+    from torchvision.models import ViT_B_16_Weights
+    from PIL import Image
+
+    tf = ViT_B_16_Weights.IMAGENET1K_V1.transforms()
+    want = torch.stack([tf(Image.fromarray(a)) for a in p])
+    assert torch.equal(x, want)
+    assert ov.extract_features([], vit_state_dict("vit_test_tiny", 0), "vit_test_tiny").shape == (0, 256)
+
+
+@pytest.mark.parametrize("case", THUMB_CASES, ids=[c["name"] for c in THUMB_CASES])
+def test_thumbnail_oracle_matches_reference_golden(case, golden_dir):
+    gold = np.load(golden_dir / f"thumb_{case['name']}.npz")["thumb"]
+    spec = case_spec(case)
+    mag = {0.5: 20, 0.25: 40, 1.0: 10}[case["mpp"]]
+    f = ot.thumbnail_factor(mag)
+    assert f == int(f)
+    lvl0 = render_region_host(spec, 0, 0, spec.width, spec.height)
+    got = ot.area_reduce(lvl0, int(f))
+    assert np.array_equal(got, gold)
