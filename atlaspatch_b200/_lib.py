@@ -31,6 +31,8 @@ _SIGNATURES = {
     "ap_last_error": (C.c_char_p, [_P]),
     "ap_launch_count": (C.c_int64, [_P]),
     "ap_sm_count": (C.c_int, [_P]),
+    "ap_profile_enable": (C.c_int, [_P, C.c_int]),
+    "ap_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "ap_synth_render": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, _P, C.c_int, _P, C.c_int,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "ap_thumbnail_area": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P]),
@@ -109,6 +111,19 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(self.lib.ap_sm_count(self.handle))
+
+    KERNEL_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "coords", "thumbnail", "other")
+
+    def profile(self, on: bool) -> None:
+        self.check(self.lib.ap_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self) -> dict[str, tuple[float, int]]:
+        """{kernel class: (total ms, launches)} measured with CUDA events since the last read."""
+        n = len(self.KERNEL_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self.check(self.lib.ap_profile_read(self.handle, ms, cnt, n))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
 
 def current_stream_ptr() -> int:

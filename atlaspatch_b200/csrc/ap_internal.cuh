@@ -7,6 +7,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -21,6 +23,22 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    // optional per-launch CUDA-event timing (ap_profile_*): bench.py's live roofline measurement
+    bool profiling = false;
+    std::mutex prof_mu;
+    struct ProfRec { cudaEvent_t start, stop; int cls; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+};
+
+enum ApKernelClass { AP_K_GEMM = 0, AP_K_ATTENTION = 1, AP_K_LAYERNORM = 2, AP_K_PREPROCESS = 3, AP_K_COORDS = 4,
+                     AP_K_THUMBNAIL = 5, AP_K_OTHER = 6, AP_K_NUM = 7 };
+
+// Records a CUDA-event pair around the launches issued in its scope when profiling is on (same stream as the kernel).
+struct ProfScope {
+    ap_ctx* ctx; cudaStream_t st; cudaEvent_t stop = nullptr;
+    ProfScope(ap_ctx* c, cudaStream_t s, int cls);
+    ~ProfScope();
 };
 
 int ap_set_error(ap_ctx* ctx, int code, const char* fmt, ...);
@@ -74,6 +92,6 @@ int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const fl
 int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
-                      cudaStream_t stream);
+                      const int* centre, int dup, cudaStream_t stream);
 int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D,
                     cudaStream_t stream);

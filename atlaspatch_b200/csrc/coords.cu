@@ -268,6 +268,7 @@ extern "C" int ap_extract_coords(ap_ctx* ctx, const int32_t* contour_xy, const i
     AP_TRY(cudaMemcpyAsync(scratch + o_bd, plan.blocks.data(), (size_t)nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
     int32_t* rows_dev = own_rows ? reinterpret_cast<int32_t*>(scratch + o_rows) : out_rows_dev;
 
+    ProfScope prof(ctx, st, AP_K_COORDS);
     coords_flags_kernel<<<nb, CB, 0, st>>>(reinterpret_cast<const int2*>(scratch + o_cv), reinterpret_cast<const int2*>(scratch + o_hv),
                                            reinterpret_cast<const int*>(scratch + o_ho),
                                            reinterpret_cast<const ContourDesc*>(scratch + o_cd),

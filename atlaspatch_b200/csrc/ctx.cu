@@ -54,7 +54,57 @@ extern "C" int ap_init(int device, ap_ctx** out_ctx) {
 }
 
 extern "C" int ap_destroy(ap_ctx* ctx) {
+    if (ctx) {
+        for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+        for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+    }
     delete ctx;
+    return AP_OK;
+}
+
+// ---- per-launch event timing -----------------------------------------------------------------------
+static cudaEvent_t prof_get_event(ap_ctx* ctx) {
+    if (!ctx->prof_pool.empty()) {
+        cudaEvent_t e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(ap_ctx* c, cudaStream_t s, int cls) : ctx(c), st(s) {
+    if (!ctx || !ctx->profiling) return;
+    std::lock_guard<std::mutex> lk(ctx->prof_mu);
+    cudaEvent_t start = prof_get_event(ctx);
+    stop = prof_get_event(ctx);
+    cudaEventRecord(start, st);
+    ctx->prof_recs.push_back({start, stop, cls});
+}
+ProfScope::~ProfScope() {
+    if (stop) cudaEventRecord(stop, st);
+}
+
+extern "C" int ap_profile_enable(ap_ctx* ctx, int on) {
+    if (!ctx) return AP_EINVAL;
+    ctx->profiling = on != 0;
+    return AP_OK;
+}
+
+// Sums (and clears) the recorded event pairs: total_ms[AP_K_NUM], counts[AP_K_NUM].  Synchronises the device.
+extern "C" int ap_profile_read(ap_ctx* ctx, double* total_ms, int64_t* counts, int n_classes) {
+    if (!ctx || !total_ms || !counts || n_classes < AP_K_NUM) return AP_EINVAL;
+    AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(ctx->prof_mu);
+    for (int i = 0; i < n_classes; ++i) { total_ms[i] = 0.0; counts[i] = 0; }
+    for (auto& r : ctx->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) { total_ms[r.cls] += ms; counts[r.cls] += 1; }
+        ctx->prof_pool.push_back(r.start);
+        ctx->prof_pool.push_back(r.stop);
+    }
+    ctx->prof_recs.clear();
     return AP_OK;
 }
 

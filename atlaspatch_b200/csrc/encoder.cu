@@ -28,6 +28,7 @@ struct ap_encoder {
     ap_vit_desc d{};
     int tokens = 0;   // patches per image (196)
     int kpe = 0;      // 3 * patch * patch
+    int centre[3] = {0, 0, 0};  // integer pixel centre per channel = round(255 * mean_c)
     int max_batch = 0;
     bool finalized = false;
     std::unordered_map<std::string, std::vector<float>> host;  // staged fp32 tensors until finalize
@@ -94,7 +95,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     const int rows = nb * T1;
     int rc;
     if ((rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
-                                e->kpe, st)))
+                                2 * e->kpe, e->centre, 1, st)))
         return rc;
     if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, st))) return rc;
     {
@@ -188,12 +189,17 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     if (!var) return AP_ESTATE;
     // ---- conv_proj with the preset's normalisation folded in -----------------------------------------
     // reference preprocess: x = (pixel/255 - mean_c) / std_c   ([tv]transforms/_presets.py:58-64)
-    // kernel input:         a = pixel / 256  (exact in fp16)
-    //   => W'[o,c,ky,kx] = W * 256 / (255 std_c),   b'[o] = b[o] - sum_c mean_c/std_c * sum_{ky,kx} W[o,c,ky,kx]
+    // kernel input:         a = (pixel - centre_c) / 256, centre_c = round(255 mean_c)   (exact in fp16)
+    //   => W'[o,c,ky,kx] = W * 256 / (255 std_c)
+    //      b'[o] = b[o] + sum_c (centre_c - 255 mean_c) / (255 std_c) * sum_{ky,kx} W[o,c,ky,kx]
+    // conv_proj sees raw pixels, whose common mode is large against the signal, so fp16 rounding of W' alone costs
+    // ~5.7e-4 of the 1e-3 feature budget (measured on the CPU simulation in DESIGN.md).  It is 0.7 % of the FLOPs,
+    // so W' is kept as an fp16 hi/lo pair and the GEMM runs over K = [A | A] x [W_hi | W_lo]: ~22-bit weights.
     {
         AP_GET(w, "conv_proj.weight", (size_t)D * K)
         AP_GET(b, "conv_proj.bias", D)
-        std::vector<float> wf((size_t)D * K), bf(D);
+        std::vector<float> wcat((size_t)D * 2 * K), bf(D);
+        for (int c = 0; c < 3; ++c) e->centre[c] = static_cast<int>(lrint(255.0 * e->d.mean[c]));
         for (int o = 0; o < D; ++o) {
             double acc = (*b)[o];
             for (int c = 0; c < 3; ++c) {
@@ -201,14 +207,17 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
                 double s = 0.0;
                 for (int i = 0; i < P * P; ++i) {
                     const float v = (*w)[(size_t)o * K + c * P * P + i];
-                    wf[(size_t)o * K + c * P * P + i] = static_cast<float>(v * sc);
+                    const float wf = static_cast<float>(v * sc);
+                    const float hi = __half2float(__float2half_rn(wf));
+                    wcat[(size_t)o * 2 * K + c * P * P + i] = hi;
+                    wcat[(size_t)o * 2 * K + K + c * P * P + i] = wf - hi;
                     s += v;
                 }
-                acc -= s * e->d.mean[c] / e->d.std[c];
+                acc += s * (e->centre[c] - 255.0 * e->d.mean[c]) / (255.0 * e->d.std[c]);
             }
             bf[o] = static_cast<float>(acc);
         }
-        if ((rc = upload_f16(e, &e->w_pe, wf.data(), wf.size()))) return rc;
+        if ((rc = upload_f16(e, &e->w_pe, wcat.data(), wcat.size()))) return rc;
         if ((rc = upload_f32(e, &e->b_pe, bf))) return rc;
     }
     {
@@ -245,11 +254,11 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     // ---- workspaces (rows padded to the 128-row GEMM tile so TMA boxes never leave the allocation) ----
     const size_t rows = ((size_t)MB * T1 + 127) / 128 * 128;
     const size_t rows_pe = ((size_t)MB * T + 127) / 128 * 128;
-    if ((rc = dev_alloc(e, (void**)&e->a_pe, rows_pe * K * 2)) || (rc = dev_alloc(e, (void**)&e->x, rows * D * 4)) ||
+    if ((rc = dev_alloc(e, (void**)&e->a_pe, rows_pe * 2 * K * 2)) || (rc = dev_alloc(e, (void**)&e->x, rows * D * 4)) ||
         (rc = dev_alloc(e, (void**)&e->y1, rows * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2, rows * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->qkv, rows * 3 * D * 2)) || (rc = dev_alloc(e, (void**)&e->hbuf, rows * M * 2)))
         return rc;
-    AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * K * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * 2 * K * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y1, 0, rows * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y2, 0, rows * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->hbuf, 0, rows * M * 2));
@@ -257,7 +266,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     AP_CHECK_CUDA(ctx, cudaMemset(e->x, 0, rows * D * 4));
 
     // ---- GEMM plans (TMA descriptors over the fixed workspaces / weights) ------------------------------
-    if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, K, AP_EPI_BIAS_F32))) return rc;
+    if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, 2 * K, AP_EPI_BIAS_F32))) return rc;
     for (auto& L : e->layers) {
         if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, D, AP_EPI_BIAS_F16)) ||
             (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, D, AP_EPI_BIAS_RESID_F32)) ||

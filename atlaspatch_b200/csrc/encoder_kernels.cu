@@ -10,7 +10,9 @@ namespace {
 //   reference: feature_embedding.py:81-96 (wsi.extract at coords), models/patch/base.py:42-45 +
 //   torchvision ImageClassification preset (centre crop `image` out of `input_patch`, /255, normalise).
 //   Normalisation is folded into the conv_proj weights at ap_encoder_finalize, so this kernel is a pure
-//   byte gather: out[(b*g*g + ty*g + tx), c*p*p + ky*p + kx] = fp16(pixel / 256)   (exact in fp16).
+//   byte gather: out[(b*g*g + ty*g + tx), c*p*p + ky*p + kx] = fp16((pixel - centre_c) / 256)  (exact in fp16;
+//   centre_c = round(255 mean_c) keeps the operand small so weight rounding does not see the common mode).
+//   With `dup` the row is written twice ([A | A], K = 2*3*p*p) to meet the hi/lo split conv_proj weights.
 //   Pixels outside the slide read as 0 (reference backends pad with black, openslide_wsi.py:198).
 // One CTA per (patch b, token row ty): stages p image rows x (image*3) bytes in smem with coalesced
 // byte loads, then writes g token rows of 3*p*p halfs with 16-byte stores.
@@ -19,7 +21,7 @@ template <int P>  // conv patch edge (16)
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64_t pitch,
                   const int32_t* __restrict__ coords, int input_patch, int image, __half* __restrict__ out,
-                  int64_t out_row_stride) {
+                  int64_t out_row_stride, int3 centre, int dup) {
     extern __shared__ uint8_t s_rows[];  // [P][image*3]
     const int g = image / P;
     const int b = blockIdx.x / g;
@@ -49,14 +51,18 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
         const int ky = (k0 - c * P * P) / P;
         const int kx0 = k0 % P;
         const uint8_t* src = s_rows + ky * row_bytes + (tx * P + kx0) * 3 + c;
+        const int cen = c == 0 ? centre.x : (c == 1 ? centre.y : centre.z);
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const __half2 hh = __floats2half2_rn(src[(2 * j) * 3] * (1.0f / 256.0f), src[(2 * j + 1) * 3] * (1.0f / 256.0f));
+            const __half2 hh = __floats2half2_rn(static_cast<float>(static_cast<int>(src[(2 * j) * 3]) - cen) * (1.0f / 256.0f),
+                                                 static_cast<float>(static_cast<int>(src[(2 * j + 1) * 3]) - cen) * (1.0f / 256.0f));
             w[j] = *reinterpret_cast<const uint32_t*>(&hh);
         }
         const int64_t orow = static_cast<int64_t>(b) * g * g + ty * g + tx;
-        *reinterpret_cast<uint4*>(out + orow * out_row_stride + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+        const uint4 u = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(out + orow * out_row_stride + k0) = u;
+        if (dup) *reinterpret_cast<uint4*>(out + orow * out_row_stride + kdim + k0) = u;
     }
 }
 
@@ -273,15 +279,16 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S
 
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
-                      cudaStream_t stream) {
+                      const int* centre, int dup, cudaStream_t stream) {
     AP_REQUIRE(ctx, patch == 16, "preprocess: conv patch %d unsupported (16 only)", patch);
     AP_REQUIRE(ctx, image % patch == 0 && input_patch >= image, "preprocess: bad geometry input %d image %d patch %d",
                input_patch, image, patch);
     if (n == 0) return AP_OK;
     const int g = image / patch;
     const size_t smem = static_cast<size_t>(patch) * image * 3;
-    preprocess_kernel<16><<<static_cast<unsigned>(n * g), 256, smem, stream>>>(slide, W, H, pitch, coords, input_patch, image,
-                                                                               out, out_row_stride);
+    ProfScope prof(ctx, stream, AP_K_PREPROCESS);
+    preprocess_kernel<16><<<static_cast<unsigned>(n * g), 256, smem, stream>>>(
+        slide, W, H, pitch, coords, input_patch, image, out, out_row_stride, make_int3(centre[0], centre[1], centre[2]), dup);
     AP_CHECK_LAUNCH(ctx, "preprocess_kernel");
     return AP_OK;
 }
@@ -290,6 +297,7 @@ int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, i
                     cudaStream_t stream) {
     if (n_images == 0) return AP_OK;
     const int total = n_images * D;
+    ProfScope prof(ctx, stream, AP_K_OTHER);
     cls_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(x, cls, pos, n_images, tokens, D);
     AP_CHECK_LAUNCH(ctx, "cls_rows_kernel");
     return AP_OK;
@@ -301,6 +309,7 @@ int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const fl
     AP_REQUIRE(ctx, x_row_stride % 4 == 0, "layernorm: row stride %lld not a multiple of 4", (long long)x_row_stride);
     if (rows == 0) return AP_OK;
     const int blocks = (rows + 7) / 8;
+    ProfScope prof(ctx, stream, AP_K_LAYERNORM);
 #define AP_LN_CASE(V)                                                                                               \
     case V:                                                                                                         \
         layernorm_kernel<V><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, y_f16, y_f32, rows);       \
@@ -325,6 +334,7 @@ int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, 
         AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 272 * 128 * 3));
         attr_set = true;
     }
+    ProfScope prof(ctx, stream, AP_K_ATTENTION);
     attention_kernel<<<dim3(heads, B), ATT_THREADS, smem, stream>>>(qkv, out, S, S_pad, heads);
     AP_CHECK_LAUNCH(ctx, "attention_kernel");
     return AP_OK;

@@ -251,6 +251,7 @@ int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t str
     }
     const int tiles = ((p->M + BM - 1) / BM) * (p->N / BN);
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    ProfScope prof(ctx, stream, AP_K_GEMM);
     kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(p->map_a, p->map_w, p->M, p->N, p->K, ep);
     AP_CHECK_LAUNCH(ctx, "gemm_tcgen05_kernel");
     return AP_OK;

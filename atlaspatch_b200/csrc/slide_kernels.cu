@@ -177,6 +177,7 @@ extern "C" int ap_thumbnail_area(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
     AP_REQUIRE(ctx, out_h <= 65535, "thumbnail_area: output height %d > 65535", out_h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((out_w + 127) / 128, out_h);
+    ProfScope prof(ctx, st, AP_K_THUMBNAIL);
     const bool vec_ok = (pitch % 16 == 0) && ((reinterpret_cast<uintptr_t>(slide_dev) & 15) == 0);
     if (vec_ok && factor == 16) thumb_vec_kernel<16><<<grid, 128, 0, st>>>(slide_dev, pitch, out_w, out_h, out_dev);
     else if (vec_ok && factor == 32) thumb_vec_kernel<32><<<grid, 128, 0, st>>>(slide_dev, pitch, out_w, out_h, out_dev);

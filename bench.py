@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- patches/s embedded (256 px, ViT-B/16) on synthetic 80000x60000 slides, one slide per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this framework (B200, CUDA path)
+    python bench.py --impl reference --steps 3 --warmup 1          # the reference's CPU pipeline (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                     # N slides on N GPUs (weak scaling)
+
+A step = one pass of the hot path over one batch of `--batch` patch coordinates of the slide resident in HBM:
+fused crop/centre/im2col -> ViT-B/16 forward -> (batch, 768) fp32 features.  Successive steps walk through the
+slide's coordinate list, so every step reads different pixels (batch * 150 KB >> L2).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "patches/sec embedded (256px, ViT-B/16)"
+UNIT = "patches/s"
+WEIGHT_SEED = 1234
+# algorithmic FLOPs per 256-px patch, ViT-B/16 @224, 197 tokens: 2 x MAC
+GEMM_MAC_PER_TOKEN_LAYER = 768 * 2304 + 768 * 768 + 2 * 768 * 3072
+GEMM_FLOP_PER_PATCH = 2 * (197 * GEMM_MAC_PER_TOKEN_LAYER * 12 + 196 * 768 * 768)
+ATTN_FLOP_PER_PATCH = 2 * 12 * 12 * 2 * 197 * 197 * 64
+MODEL_FLOP_PER_PATCH = GEMM_FLOP_PER_PATCH + ATTN_FLOP_PER_PATCH  # 35.13 GFLOP
+PATCH_BYTES = 256 * 256 * 3
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=2048, help="patches per step (b200 arm)")
+    ap.add_argument("--width", type=int, default=80000)
+    ap.add_argument("--height", type=int, default=60000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=96, help="patches timed for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=32, help="patches per step of the reference arm")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def slide_mask_coords_cpu(width, height, seed):
+    """Mask the segmentation service would hand to extraction: truth lattice resampled to the <=1024 thumbnail."""
+    from PIL import Image
+
+    from atlaspatch_b200.synthetic import make_spec, truth_mask
+
+    spec = make_spec(width, height, seed)
+    t = (truth_mask(spec) * 255).astype(np.uint8)
+    th, tw = t.shape
+    s = min(1.0, 1024.0 / max(th, tw))
+    mh, mw = max(1, int(round(th * s))), max(1, int(round(tw * s)))
+    if (mh, mw) != (th, tw):
+        t = np.asarray(Image.fromarray(t).resize((mw, mh), Image.Resampling.NEAREST))
+    return spec, t.astype(np.float32) / 255.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        # "under load" = upper half of the samples (idle samples before/after the region would bias the median)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU pipeline (oracle port; /root/reference is absent on the GPU box)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_pipeline_setup(width, height, seed):
+    import torch
+
+    from atlaspatch_b200.synthetic import render_region_host
+    from oracle import reference_loop as rl
+    from oracle.weights import vit_state_dict
+
+    spec, mask = slide_mask_coords_cpu(width, height, seed)
+    gold = ROOT / "tests" / "golden" / "coords_c1_80000x60000_p256.npz"
+    if (width, height, seed) == (80000, 60000, 0) and gold.exists():
+        coords = np.load(gold)["coords"]     # produced by the reference itself on this exact slide / mask
+    else:
+        from oracle import coords as oc
+
+        coords = oc.coords_from_mask(mask, level0_wh=(width, height), src_mag=20, target_mag=20, patch_size=256,
+                                     step_size=256, tissue_thresh=0.0)
+    model, preprocess = rl.build_vit_b_16(vit_state_dict("vit_b_16", seed=WEIGHT_SEED))
+    read = lambda x, y, w, h: render_region_host(spec, x, y, w, h)  # noqa: E731
+    return spec, coords, model, preprocess, read, torch.get_num_threads()
+
+
+def run_cpu_sample(coords, model, preprocess, read, start, n):
+    from oracle import reference_loop as rl
+
+    rows = coords[start:start + n]
+    t0 = time.perf_counter()
+    feats = rl.embed_slide_rows(model, preprocess, read, rows, patch_size=256, feature_batch=32, num_workers=4)
+    dt = time.perf_counter() - t0
+    assert feats.shape == (rows.shape[0], 768)
+    return dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    spec, coords, model, preprocess, read, threads = cpu_pipeline_setup(args.width, args.height, 0)
+    n = args.ref_sample
+    for i in range(args.warmup):
+        run_cpu_sample(coords, model, preprocess, read, (i * n) % max(1, len(coords) - n), n)
+    t = 0.0
+    for i in range(args.steps):
+        t += run_cpu_sample(coords, model, preprocess, read, ((args.warmup + i) * n) % max(1, len(coords) - n), n)
+    value = args.steps * n / t
+    sample = (f"{args.steps} steps x {n} consecutive coordinate rows of the {args.width}x{args.height} slide "
+              f"({len(coords)} patches total), batch 32, DataLoader num_workers=4, fp32")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"single synthetic {args.width}x{args.height} RGB slide, 256px patches stride 256, ViT-B/16 "
+                               "random-init (seeded), reference CPU pipeline port (oracle/reference_loop.py)",
+                   "patches_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU pipeline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as ge
+
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+
+    from atlaspatch_b200._lib import Context
+    from atlaspatch_b200.encoder import B200FeatureExtractor, vit_state_dict_names
+    from atlaspatch_b200.extraction import extract_coords
+    from atlaspatch_b200.slide import SyntheticWSI
+
+    ctx = Context.get(local_rank)
+    peaks = measured_peaks()
+
+    # ---- slide resident in HBM, thumbnail, coords (one slide per rank, seed = rank) ----------------------
+    spec, mask = slide_mask_coords_cpu(args.width, args.height, rank)
+    wsi = SyntheticWSI(spec, ctx=ctx)
+    image = wsi.device_image
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wsi.thumbnail_at_power_device(1.25)  # warm
+    ev0.record()
+    thumb = wsi.thumbnail_at_power_device(1.25)
+    ev1.record()
+    torch.cuda.synchronize()
+    thumb_ms = ev0.elapsed_time(ev1)
+    thumb_bytes = args.width * args.height * 3 + thumb.numel()
+    t0 = time.perf_counter()
+    coords_np, coords_dev = extract_coords(mask, level0_wh=(args.width, args.height), src_mag=20, target_mag=20, patch_size=256,
+                                           step_size=256, tissue_thresh=0.0, ctx=ctx, return_device=True)
+    coords_ms = 1000 * (time.perf_counter() - t0)
+    n_coords = int(coords_np.shape[0])
+    assert n_coords > 0
+
+    # ---- encoder weights: rank 0 builds the seeded state_dict, NCCL broadcast to the other ranks ----------
+    names = vit_state_dict_names(12)
+    if rank == 0:
+        from oracle.weights import vit_state_dict  # seeded random weights shared with the CPU arm
+
+        sd = vit_state_dict("vit_b_16", seed=WEIGHT_SEED)
+    else:
+        from oracle.weights import VIT_SPECS  # noqa: F401  (shapes only)
+
+        sd = None
+    if world > 1:
+        shapes = [None]
+        if rank == 0:
+            shapes = [{k: tuple(sd[k].shape) for k in names}]
+        dist.broadcast_object_list(shapes, src=0)
+        out = {}
+        for k in names:
+            t = sd[k].cuda() if rank == 0 else torch.empty(shapes[0][k], dtype=torch.float32, device="cuda")
+            dist.broadcast(t, src=0)
+            out[k] = t.cpu()
+        sd = out
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=128, device=local_rank)
+    del sd
+
+    B = args.batch
+    reps = (B + n_coords - 1) // n_coords + 1
+    coords_ring = coords_dev.repeat(reps + 1, 1).contiguous() if n_coords < 2 * B else coords_dev
+    n_ring = int(coords_ring.shape[0])
+    feats = torch.empty((B, 768), dtype=torch.float32, device="cuda")
+
+    def step(i):
+        s = (i * B) % (n_ring - B + 1)
+        ext.embed_coords(image, wsi.w, wsi.h, wsi.pitch, coords_ring[s:s + B], out=feats)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count
+    ctx.profile(True)
+    ctx.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * args.steps * B / (ms_max / 1000.0)
+
+    # ---- e2e: the reference-facing plug-in call with HOST patches (H2D + D2H inside the timed region) -----
+    n_e2e = B
+    host_rows = coords_np[:n_e2e] if n_coords >= n_e2e else np.concatenate([coords_np] * (n_e2e // n_coords + 1))[:n_e2e]
+    host_patches = []
+    img3 = image  # (H, pitch) uint8
+    for (x, y, _rw, _rh, _lv) in host_rows.tolist():     # patches a caller would have read from the slide (not timed)
+        host_patches.append(wsi.extract((x, y), 0, (256, 256)))
+    ext.extract_batch(host_patches[:256], batch_size=32)  # warm
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        f_host = ext.extract_batch(host_patches, batch_size=32)
+    e2e_s = time.perf_counter() - t0
+    assert f_host.shape == (n_e2e, 768)
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.e2e_steps * n_e2e / float(t_e2e.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    gemm_ms, gemm_n = prof["gemm"]
+    patches_timed = args.steps * B
+    achieved_tflops = (patches_timed * GEMM_FLOP_PER_PATCH) / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all 49 launches per 128-patch chunk: conv_proj, in_proj, out_proj, mlp.0, mlp.3)",
+        "achieved": achieved_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+        "frac": (achieved_tflops / peaks["tflops_sustained"]) if achieved_tflops else None, "traffic": None,
+        "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
+        "algorithmic_flop_per_launch": GEMM_FLOP_PER_PATCH * patches_timed / max(gemm_n, 1),
+        "avg_launch_ms": gemm_ms / max(gemm_n, 1), "launches_timed": gemm_n,
+        "kernel_share_of_step": gemm_ms / ms if ms > 0 else None,
+        "per_class_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+        "whole_model": {"tflops": value / world * MODEL_FLOP_PER_PATCH / 1e12,
+                        "frac_of_sustained_peak": value / world * MODEL_FLOP_PER_PATCH / 1e12 / peaks["tflops_sustained"]},
+        "thumbnail_hbm": {"bound": "hbm", "achieved": thumb_bytes / (thumb_ms / 1000.0) / 1e9, "peak": peaks["hbm_gbs"],
+                          "unit": "GB/s", "frac": thumb_bytes / (thumb_ms / 1000.0) / 1e9 / peaks["hbm_gbs"], "ms": thumb_ms},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        _spec, c_coords, model, preprocess, read, threads = cpu_pipeline_setup(args.width, args.height, 0)
+        run_cpu_sample(c_coords, model, preprocess, read, 0, 32)  # warm
+        dt = run_cpu_sample(c_coords, model, preprocess, read, 32, args.cpu_sample)
+        cpu_baseline = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{args.cpu_sample} consecutive coordinate rows (after a 32-patch warm-up) of the same slide through "
+                                  "oracle/reference_loop.py: per-row read, new DataLoader(num_workers=4) per 32 patches, "
+                                  "torchvision vit_b_16 fp32 on the host cores"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate/residual/LayerNorm/softmax", "data": "synthetic",
+        "config": {"workload": f"single synthetic {args.width}x{args.height} RGB slide per GPU resident in HBM, 256px patches "
+                               f"stride 256 ({n_coords} coords on rank 0), ViT-B/16 random-init (seeded)",
+                   "patches_per_step": B, "forward_chunk": 128, "l2": "inputs larger than L2 (each step reads a different "
+                   f"{B * 150528 / 1e6:.0f} MB of the 14.4 GB slide)", "parallelism": f"slides sharded 1 per GPU x{world}, no steady-state collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * PATCH_BYTES, "d2h_bytes_per_step": n_e2e * 768 * 4,
+                "api": "B200FeatureExtractor.extract_batch(list of host uint8 patches) -> host float32 features",
+                "patches_per_step": n_e2e, "steps": args.e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "aux": {"coords": n_coords, "coords_ms_incl_host_contours": coords_ms, "thumbnail_ms": thumb_ms},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

@@ -40,6 +40,11 @@ const char* ap_last_error(const ap_ctx* ctx);
 /* Number of kernels this library has launched on ctx since ap_init (bench.py "gpu_launches"). */
 int64_t ap_launch_count(const ap_ctx* ctx);
 int ap_sm_count(const ap_ctx* ctx);
+/* Optional per-launch timing with CUDA events recorded on the launching stream (bench.py's live roofline
+ * numbers).  Kernel classes: 0 gemm, 1 attention, 2 layernorm, 3 preprocess, 4 coords, 5 thumbnail, 6 other.
+ * ap_profile_read sums and clears the records into total_ms[n_classes] / counts[n_classes] (n_classes >= 7). */
+int ap_profile_enable(ap_ctx* ctx, int on);
+int ap_profile_read(ap_ctx* ctx, double* total_ms, int64_t* counts, int n_classes);
 
 /* ---- synthetic slide (benchmark input) ---------------------------------
  * Renders the region [x0,x0+w) x [y0,y0+h) of the synthetic slide (W x H, seed, blobs, holes)

@@ -57,3 +57,13 @@ def test_thumbnail_oracle_matches_reference_golden(case, golden_dir):
     lvl0 = render_region_host(spec, 0, 0, spec.width, spec.height)
     got = ot.area_reduce(lvl0, int(f))
     assert np.array_equal(got, gold)
+
+
+def test_reference_loop_port_matches_golden(golden_dir):
+    """oracle/reference_loop.py (the timed CPU baseline) reproduces the reference's extractor output."""
+    from oracle import reference_loop as rl
+
+    gold = np.load(golden_dir / "vit_b_16_feats.npz")["feats"]
+    model, preprocess = rl.build_vit_b_16(vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"]))
+    got = rl.extract_batch(model, preprocess, feature_patches()[:8], batch_size=8, num_workers=0)
+    assert np.allclose(got, gold[:8], rtol=1e-4, atol=1e-5)
