@@ -31,6 +31,7 @@ _SIGNATURES = {
     "ap_last_error": (C.c_char_p, [_P]),
     "ap_launch_count": (C.c_int64, [_P]),
     "ap_sm_count": (C.c_int, [_P]),
+    "ap_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ap_profile_enable": (C.c_int, [_P, C.c_int]),
     "ap_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "ap_synth_render": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, _P, C.c_int, _P, C.c_int,
@@ -113,6 +114,9 @@ class Context:
         return int(self.lib.ap_sm_count(self.handle))
 
     KERNEL_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "coords", "thumbnail", "other")
+
+    def set_option(self, key: str, value: int) -> None:
+        self.check(self.lib.ap_set_option(self.handle, key.encode(), int(value)))
 
     def profile(self, on: bool) -> None:
         self.check(self.lib.ap_profile_enable(self.handle, 1 if on else 0))

@@ -23,6 +23,8 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    int gemm_debug = 0;      // diagnostics: see EpiParams::debug
+    int gemm_cta_group = 2;  // default GEMM flavour (ap_set_option "gemm_cta_group"; env AP_GEMM_CTA_GROUP)
     // optional per-launch CUDA-event timing (ap_profile_*): bench.py's live roofline measurement
     bool profiling = false;
     std::mutex prof_mu;
@@ -73,9 +75,11 @@ int ap_make_tmap_f16_2d(ap_ctx* ctx, CUtensorMap* map, const void* base, uint64_
 // ---- kernels' host launchers (internal) --------------------------------------------------------
 struct GemmPlan {
     CUtensorMap map_a;
-    CUtensorMap map_w;
+    CUtensorMap map_w;       // box = bn rows of W (single-CTA tiles)
+    CUtensorMap map_w_half;  // box = bn/2 rows of W (each CTA of a cta_group::2 pair loads half)
     int M, N, K, epilogue;
-    int bn;  // N tile (256 or 128)
+    int bn;         // N tile (256 or 128)
+    int cta_group;  // 2: CTA pair owns a 256 x 256 tile; 1: one CTA owns a 128 x bn tile
 };
 int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue);
 // Patch-embed epilogue parameters: output row remap (b*T + t -> b*(T+1) + 1 + t) and +pos[1+t].

@@ -1,4 +1,6 @@
 // Context, error reporting and the TMA descriptor helper.
+#include <cstdlib>
+
 #include "ap_internal.cuh"
 
 static thread_local char g_init_error[1024] = "no error";
@@ -49,8 +51,23 @@ extern "C" int ap_init(int device, ap_ctx** out_ctx) {
         delete ctx;
         return ap_set_error(nullptr, AP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
     }
+    if (const char* env = getenv("AP_GEMM_CTA_GROUP")) ctx->gemm_cta_group = atoi(env) == 1 ? 1 : 2;
     *out_ctx = ctx;
     return AP_OK;
+}
+
+extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return AP_EINVAL;
+    if (!strcmp(key, "gemm_cta_group")) {
+        AP_REQUIRE(ctx, value == 1 || value == 2, "gemm_cta_group must be 1 or 2");
+        ctx->gemm_cta_group = value;
+        return AP_OK;
+    }
+    if (!strcmp(key, "gemm_debug")) {
+        ctx->gemm_debug = value;
+        return AP_OK;
+    }
+    return ap_set_error(ctx, AP_EINVAL, "unknown option '%s'", key);
 }
 
 extern "C" int ap_destroy(ap_ctx* ctx) {

@@ -6,35 +6,43 @@
 // torch (atlas_patch/models/patch/base.py:100 -> torchvision VisionTransformer): conv_proj (as an
 // im2col GEMM), in_proj (QKV), out_proj, mlp.0 (+GELU), mlp.3 (+residual).
 //
-// CTA = 384 threads, one CTA per SM, persistent over 128 x BN output tiles (static round-robin):
-//   warp 0     TMA producer: A (128x64) and W (BNx64) boxes, 128B swizzle, 4-stage mbarrier ring
-//   warp 1     MMA issuer:   one thread issues tcgen05.mma 128xBNx16 (4 per 64-wide K block),
-//                            tcgen05.commit frees the smem stage / publishes the accumulator
+// Two instantiations of one kernel:
+//   CG = 2 (default when N % 256 == 0): a CTA PAIR (cluster 2x1x1, tcgen05 cta_group::2) owns a 256 x 256 output tile.
+//       Each CTA TMA-loads its 128 rows of A and its 128 rows of W per 64-wide K block (32 KB / stage, 6 stages); the
+//       leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16) which reads both
+//       CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  L2 -> SM operand traffic per FLOP
+//       is 1.5x lower than with 128 x 256 single-CTA tiles, which is what bounded the first version.
+//   CG = 1: one CTA owns a 128 x BN tile (BN = 256 or 128), 4 stages.  Used when N % 256 != 0.
+// CTA = 384 threads, one CTA per SM, persistent over tiles (static round-robin over CTAs / CTA pairs):
+//   warp 0     TMA producer (128B-swizzled boxes, mbarrier ring)
+//   warp 1     MMA issuer: one thread; tcgen05.commit frees the smem stage / publishes the accumulator
 //   warp 2     TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
-//   warps 4-11 epilogue:     tcgen05.ld 32 lanes x 32 columns -> registers -> bias / GELU / residual /
-//                            positional embedding -> vectorised global stores; overlaps the next tile's MMAs
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns (software-pipelined) -> bias / GELU / residual /
+//              positional embedding -> vectorised global stores; overlaps the next tile's MMAs
 #include "ap_internal.cuh"
 #include "ptx.cuh"
 
 namespace {
 
-constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
-constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 384;
 constexpr int NUM_EPI_WARPS = 8;
 
-template <int BN>
+template <int CG, int BN>
 struct SmemLayout {
-    static constexpr int A_STAGE = BM * BK * 2;  // 16 KB
-    static constexpr int B_STAGE = BN * BK * 2;  // 32 KB (BN=256)
+    static constexpr int STAGES = CG == 2 ? 6 : 4;
+    static constexpr int A_STAGE = 128 * BK * 2;        // 16 KB: this CTA's 128 rows of A
+    static constexpr int B_ROWS = BN / CG;              // rows of W this CTA loads
+    static constexpr int B_STAGE = B_ROWS * BK * 2;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE;
     static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE;
     static constexpr int NUM_BARS = 2 * STAGES + 4;
     static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
-    static constexpr int TOTAL = TMEM_PTR_OFF + 16;
+    static constexpr int STAGING_OFF = (TMEM_PTR_OFF + 16 + 255) / 256 * 256;  // 8 epilogue warps x (32 rows x 128 B)
+    static constexpr int STAGING_BYTES = 8 * 32 * 128;
+    static constexpr int TOTAL = STAGING_OFF + STAGING_BYTES;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
 };
 
@@ -45,33 +53,183 @@ struct EpiParams {
     const float* pos;
     int tokens_per_image;
     float alpha;
+    int debug;  // diagnostics only (ap_set_option "gemm_debug"): 1 = no epilogue math/stores, 2 = no MMA issue, 4 = no TMA loads
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): halves the issue slots of the epilogue math ----------------
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Exact-erf GELU (torch.nn.GELU() default, as in torchvision's MLPBlock) for two values at once.
+//   gelu(x) = x Phi(x),  Phi(x) = 1 - t for x >= 0,  t for x < 0,  t = 0.5 erfc(|x| / sqrt 2)
+//           = max(x, 0) - |x| t
+//   t = 2^Q(|x|): Q = degree-6 polynomial fit of log2(0.5 erfc(|x|/sqrt 2)) on [0, 6] (|x| clamped to 6, t(6) = 1e-9),
+//   weighted by the sensitivity |x| t of the result.  Evaluated in fp32 against float64 erf on [-6, 6] (fit script in
+//   DESIGN.md): max abs error of gelu 9.2e-8, never more than 0.11 of an fp16 half-ulp of the result (+1e-7).
+// Cost per element: 7 FMA-pipe ops (packed as FFMA2) + 1 MUFU.EX2 + 4 ALU-pipe ops, against ~30 issue slots for libdevice
+// erff, which made the mlp.0 GEMM epilogue-bound (166 us with erff, 110 us with an A&S 7.1.28 variant, 75 us without
+// any epilogue).
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const float a0 = __uint_as_float(__float_as_uint(x0) & 0x7fffffffu), a1 = __uint_as_float(__float_as_uint(x1) & 0x7fffffffu);
+    const uint64_t z = pk2(fminf(a0, 6.0f), fminf(a1, 6.0f));
+    uint64_t q = fma2(pk2(3.4089207474607974e-05f, 3.4089207474607974e-05f), z, pk2(-0.0007762229652144015f, -0.0007762229652144015f));
+    q = fma2(q, z, pk2(0.008098662830889225f, 0.008098662830889225f));
+    q = fma2(q, z, pk2(-0.05343286693096161f, -0.05343286693096161f));
+    q = fma2(q, z, pk2(-0.4587600827217102f, -0.4587600827217102f));
+    q = fma2(q, z, pk2(-1.151203989982605f, -1.151203989982605f));
+    q = fma2(q, z, pk2(-0.9999929070472717f, -0.9999929070472717f));
+    float q0, q1;
+    upk2(q, q0, q1);
+    const uint64_t nabs = pk2(__uint_as_float(__float_as_uint(x0) | 0x80000000u), __uint_as_float(__float_as_uint(x1) | 0x80000000u));
+    upk2(fma2(nabs, pk2(ex2_approx(q0), ex2_approx(q1)), pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), x0, x1);
+}
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, int EPI>
+// Epilogue of one warp = 32 accumulator rows x (BN/2) columns, processed in 128-byte-per-row groups.
+// tcgen05.ld hands every lane ONE ROW (32 consecutive fp32 columns); storing that directly would make each warp
+// store instruction touch 32 different 128 B lines (the first version did, and ncu showed the GEMMs epilogue-bound:
+// tensor pipe 20-54 % active).  So each group is transposed through a per-warp 4 KB shared-memory tile
+// (32 rows x 128 B, 16-byte pieces XOR-swizzled by row -> conflict-free both ways) and written / residual-read with
+// fully coalesced accesses: 8 lanes cover one 128 B row segment, one warp instruction covers 4 rows.
+__device__ __forceinline__ uint32_t stg_off(int row, int piece) { return static_cast<uint32_t>(row * 128 + ((piece ^ (row & 7)) << 4)); }
+
+// fp32 output (residual add / positional embedding): one 32-column chunk = 128 B per row.
+// The residual rows are fetched (coalesced) one chunk AHEAD -- the first chunk even before the accumulator is ready, i.e.
+// under the tile's MMAs -- because the epilogue of out_proj / mlp.3 is bound by the latency of these loads, not by
+// bandwidth.  In-place use (resid == out) is fine: every element is read and written by the same lane, reads first.
+template <int EPI>
+__device__ __forceinline__ void resid_prefetch(float4 (&rr)[8], const EpiParams& ep, int M, int N, int row_base, int col0, int lane) {
+    if (EPI != AP_EPI_BIAS_RESID_F32) return;
+    const int p = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = row_base + it * 4 + (lane >> 3);
+        rr[it] = row < M ? *(reinterpret_cast<const float4*>(ep.resid + static_cast<int64_t>(row) * N + col0) + p)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], const float4 (&rr)[8], uint8_t* stg, const EpiParams& ep,
+                                                   int M, int N, int row_base, int col0, int lane) {
+    const int p = lane & 7;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(stg + stg_off(lane, q)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    __syncwarp();
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + p);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + (lane >> 3);
+        const int row = row_base + rl;
+        const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(rl, p));
+        float4 v = make_float4(a.x * ep.alpha + bb.x, a.y * ep.alpha + bb.y, a.z * ep.alpha + bb.z, a.w * ep.alpha + bb.w);
+        if (row < M) {
+            int64_t out_row = row;
+            if (EPI == AP_EPI_BIAS_RESID_F32) {
+                v.x += rr[it].x; v.y += rr[it].y; v.z += rr[it].z; v.w += rr[it].w;
+            } else if (ep.tokens_per_image > 0) {   // conv_proj: token row -> sequence row (+1 class token per image), + pos
+                const int b = row / ep.tokens_per_image;
+                const int tk = row - b * ep.tokens_per_image;
+                out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + 1) + 1 + tk;
+                if (ep.pos != nullptr) {
+                    const float4 pp = __ldg(reinterpret_cast<const float4*>(ep.pos + static_cast<int64_t>(1 + tk) * N + col0) + p);
+                    v.x += pp.x; v.y += pp.y; v.z += pp.z; v.w += pp.w;
+                }
+            }
+            *(reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * N + col0) + p) = v;
+        }
+    }
+    __syncwarp();
+}
+
+// fp16 output: bias (+GELU) in the row-per-lane layout, packed halves staged; `half_sel` = which 64 B half of the
+// 128 B row this 32-column chunk fills.  Call flush after both halves.
+template <int EPI>
+__device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int col0, int lane,
+                                                   int half_sel) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+    const uint64_t alpha2 = pk2(ep.alpha, ep.alpha);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
+        float v[8];
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), alpha2, pk2(b0.x, b0.y)), v[0], v[1]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), alpha2, pk2(b0.z, b0.w)), v[2], v[3]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), alpha2, pk2(b1.x, b1.y)), v[4], v[5]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), alpha2, pk2(b1.z, b1.w)), v[6], v[7]);
+        if (EPI == AP_EPI_BIAS_GELU_F16) {
+            gelu_erf2(v[0], v[1]); gelu_erf2(v[2], v[3]); gelu_erf2(v[4], v[5]); gelu_erf2(v[6], v[7]);
+        }
+        *reinterpret_cast<uint4*>(stg + stg_off(lane, half_sel * 4 + j)) =
+            make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+    }
+}
+__device__ __forceinline__ void epilogue_flush_f16(uint8_t* stg, const EpiParams& ep, int M, int N, int row_base, int col0, int lane) {
+    __syncwarp();
+    const int p = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + (lane >> 3);
+        const int row = row_base + rl;
+        const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(rl, p));
+        if (row < M) *(reinterpret_cast<uint4*>(static_cast<__half*>(ep.out) + static_cast<int64_t>(row) * N + col0) + p) = u;
+    }
+    __syncwarp();
+}
+
+template <int CG, int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
                     int K, EpiParams ep) {
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<CG, BN>;
+    constexpr int STAGES = L::STAGES;
+    constexpr int TILE_M = 128 * CG;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
-    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
+    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA      (CG=2: the leader CTA's copy is used)
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA      (CG=2: multicast commit to both CTAs)
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue (CG=2: multicast commit to both CTAs)
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA (CG=2: both CTAs arrive on the leader's)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::TMEM_PTR_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int cta_rank = CG == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+    const int worker = blockIdx.x / CG;
+    const int num_workers = gridDim.x / CG;
     const int tiles_n = N / BN;
-    const int tiles_m = (M + BM - 1) / BM;
+    const int tiles_m = (M + TILE_M - 1) / TILE_M;
     const int num_tiles = tiles_m * tiles_n;
     const int k_blocks = K / BK;
 
@@ -86,45 +244,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+            ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS * CG);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_ptr_smem, 2 * BN);
-        ptx::tmem_relinquish();
+        ptx::tmem_alloc<CG>(tmem_ptr_smem, 2 * BN);
+        ptx::tmem_relinquish<CG>();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (every CTA loads its own 128 rows of A and BN/CG rows of W) =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM;
-                const int n0 = (tile % tiles_n) * BN;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m0 = (tile / tiles_n) * TILE_M + cta_rank * 128;
+                const int n0 = (tile % tiles_n) * BN + cta_rank * L::B_ROWS;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], L::A_STAGE + L::B_STAGE);
-                    ptx::tma_load_2d(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], kb * BK, m0);
-                    ptx::tma_load_2d(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kb * BK, n0);
+                    if (ep.debug & 4) {
+                        if (cta_rank == 0) ptx::mbar_arrive(&full_bar[stage]);
+                    } else if (CG == 1) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], L::A_STAGE + L::B_STAGE);
+                        ptx::tma_load_2d(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kb * BK, n0);
+                    } else {
+                        // both CTAs' bytes are accounted on the leader's barrier (peer bit cleared in the address)
+                        if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (L::A_STAGE + L::B_STAGE));
+                        ptx::tma_load_2d_2sm(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d_2sm(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kb * BK, n0);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN);
+        // ================= MMA issuer (leader CTA only) =================
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(TILE_M, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, 2);
@@ -138,132 +305,124 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 B (16 fp16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                        ptx::tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(ep.debug & 2)) ptx::tc_mma_f16<CG>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::tc_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+                    ptx::tc_commit<CG>(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::tc_commit(&tfull_bar[as]);  // accumulator complete
+                ptx::tc_commit<CG>(&tfull_bar[as]);  // accumulator complete
             }
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ================= epilogue =================
+        // ================= epilogue (each CTA drains its own 128 accumulator rows) =================
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int half_idx = (warp - 4) >> 2;    // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
+        constexpr int NCH = COLS_PER_WARP / 32;
+        uint8_t* stg = smem + L::STAGING_OFF + (warp - 4) * 4096;
+        uint32_t tempty_remote[2] = {0, 0};
+        if (CG == 2 && cta_rank != 0) {
+            tempty_remote[0] = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0);
+            tempty_remote[1] = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[1]), 0);
+        }
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (tile / tiles_n) * BM;
+            const int m0 = (tile / tiles_n) * TILE_M + cta_rank * 128;
             const int n0 = (tile % tiles_n) * BN;
-            ptx::mbar_wait(&tfull_bar[as], aphase, 4);
-            ptx::tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
-            int64_t out_row = row;
-            int pos_row = 0;
-            if (EPI == AP_EPI_BIAS_F32 && ep.tokens_per_image > 0) {
-                const int b = row / ep.tokens_per_image;
-                const int t = row - b * ep.tokens_per_image;
-                out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + 1) + 1 + t;
-                pos_row = 1 + t;
-            }
-#pragma unroll 1
-            for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-                const int col_local = half_idx * COLS_PER_WARP + c * 32;
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_local;
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr, r);
-                ptx::tc_wait_ld();
-                const int col0 = n0 + col_local;
-                float v[32];
-                const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bb = __ldg(b4 + j);
-                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) * ep.alpha + bb.x;
-                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) * ep.alpha + bb.y;
-                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) * ep.alpha + bb.z;
-                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) * ep.alpha + bb.w;
+            const int row_base = m0 + q * 32;
+            const int col_base = n0 + half_idx * COLS_PER_WARP;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half_idx * COLS_PER_WARP;
+            auto release_tmem = [&]() {  // all of this warp's accumulator reads are complete: hand the TMEM stage back early
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_remote(tempty_remote[as]);
+                    else ptx::mbar_arrive(&tempty_bar[as]);
                 }
-                if (row_ok) {
-                    if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16) {
-                        if (EPI == AP_EPI_BIAS_GELU_F16) {
+            };
+            if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16) {
+                ptx::mbar_wait(&tfull_bar[as], aphase, 4);
+                ptx::tc_fence_after();
+                uint32_t r[2][32];
+                ptx::tmem_ld_32x32(taddr0, r[0]);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                        }
-                        uint4* o = reinterpret_cast<uint4*>(static_cast<__half*>(ep.out) + out_row * N + col0);
+                for (int c = 0; c < NCH; ++c) {
+                    ptx::tc_wait_ld();
+                    if (c + 1 < NCH) ptx::tmem_ld_32x32(taddr0 + (c + 1) * 32, r[(c + 1) & 1]);  // overlaps the math below
+                    else release_tmem();
+                    if (ep.debug & 1) continue;
+                    epilogue_stage_f16<EPI>(r[c & 1], stg, ep, col_base + c * 32, lane, c & 1);
+                    if (c & 1) epilogue_flush_f16(stg, ep, M, N, row_base, col_base + (c - 1) * 32, lane);
+                }
+            } else {
+                float4 rr[2][8];
+                resid_prefetch<EPI>(rr[0], ep, M, N, row_base, col_base, lane);  // in flight while the MMAs of this tile run
+                ptx::mbar_wait(&tfull_bar[as], aphase, 4);
+                ptx::tc_fence_after();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-                            u.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-                            u.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-                            u.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-                            o[j] = u;
-                        }
-                    } else {
-                        if (EPI == AP_EPI_BIAS_RESID_F32) {
-                            const float4* r4 = reinterpret_cast<const float4*>(ep.resid + out_row * N + col0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 rr = r4[j];
-                                v[4 * j + 0] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
-                            }
-                        } else if (ep.pos != nullptr) {
-                            const float4* p4 = reinterpret_cast<const float4*>(ep.pos + static_cast<int64_t>(pos_row) * N + col0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 pp = __ldg(p4 + j);
-                                v[4 * j + 0] += pp.x; v[4 * j + 1] += pp.y; v[4 * j + 2] += pp.z; v[4 * j + 3] += pp.w;
-                            }
-                        }
-                        float4* o = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * N + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(taddr0 + c * 32, r);
+                    if (c + 1 < NCH) resid_prefetch<EPI>(rr[(c + 1) & 1], ep, M, N, row_base, col_base + (c + 1) * 32, lane);
+                    ptx::tc_wait_ld();
+                    if (c + 1 == NCH) release_tmem();
+                    if (ep.debug & 1) continue;
+                    epilogue_group_f32<EPI>(r, rr[c & 1], stg, ep, M, N, row_base, col_base + c * 32, lane);
                 }
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
         }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 2 * BN);
+        ptx::tmem_dealloc<CG>(tmem_base, 2 * BN);
     }
 }
 
-template <int BN, int EPI>
+template <int CG, int BN, int EPI>
 int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t stream) {
-    using L = SmemLayout<BN>;
-    auto kern = gemm_tcgen05_kernel<BN, EPI>;
-    static bool attr_set = false;  // per (BN, EPI) instantiation
+    using L = SmemLayout<CG, BN>;
+    auto kern = gemm_tcgen05_kernel<CG, BN, EPI>;
+    static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
         attr_set = true;
     }
-    const int tiles = ((p->M + BM - 1) / BM) * (p->N / BN);
-    const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    const int tile_m = 128 * CG;
+    const int tiles = ((p->M + tile_m - 1) / tile_m) * (p->N / BN);
+    const int max_workers = ctx->sm_count / CG;
+    const int workers = tiles < max_workers ? tiles : max_workers;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(workers * CG);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::DYN_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = CG;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
     ProfScope prof(ctx, stream, AP_K_GEMM);
-    kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(p->map_a, p->map_w, p->M, p->N, p->K, ep);
+    const CUtensorMap& mw = CG == 2 ? p->map_w_half : p->map_w;
+    AP_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, p->map_a, mw, p->M, p->N, p->K, ep));
     AP_CHECK_LAUNCH(ctx, "gemm_tcgen05_kernel");
     return AP_OK;
 }
 
-template <int BN>
+template <int CG, int BN>
 int dispatch_epi(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t stream) {
     switch (p->epilogue) {
-        case AP_EPI_BIAS_F16: return launch<BN, AP_EPI_BIAS_F16>(ctx, p, ep, stream);
-        case AP_EPI_BIAS_GELU_F16: return launch<BN, AP_EPI_BIAS_GELU_F16>(ctx, p, ep, stream);
-        case AP_EPI_BIAS_RESID_F32: return launch<BN, AP_EPI_BIAS_RESID_F32>(ctx, p, ep, stream);
-        case AP_EPI_BIAS_F32: return launch<BN, AP_EPI_BIAS_F32>(ctx, p, ep, stream);
+        case AP_EPI_BIAS_F16: return launch<CG, BN, AP_EPI_BIAS_F16>(ctx, p, ep, stream);
+        case AP_EPI_BIAS_GELU_F16: return launch<CG, BN, AP_EPI_BIAS_GELU_F16>(ctx, p, ep, stream);
+        case AP_EPI_BIAS_RESID_F32: return launch<CG, BN, AP_EPI_BIAS_RESID_F32>(ctx, p, ep, stream);
+        case AP_EPI_BIAS_F32: return launch<CG, BN, AP_EPI_BIAS_F32>(ctx, p, ep, stream);
     }
     return ap_set_error(ctx, AP_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
 }
@@ -277,9 +436,12 @@ int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int 
     AP_REQUIRE(ctx, epilogue >= 0 && epilogue <= 3, "gemm: unknown epilogue %d", epilogue);
     plan->M = M; plan->N = N; plan->K = K; plan->epilogue = epilogue;
     plan->bn = (N % 256 == 0) ? 256 : 128;
-    int rc = ap_make_tmap_f16_2d(ctx, &plan->map_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK);
+    plan->cta_group = (plan->bn == 256 && ctx->gemm_cta_group == 2) ? 2 : 1;
+    int rc = ap_make_tmap_f16_2d(ctx, &plan->map_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, BK);
     if (rc) return rc;
-    return ap_make_tmap_f16_2d(ctx, &plan->map_w, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, plan->bn, BK);
+    rc = ap_make_tmap_f16_2d(ctx, &plan->map_w, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, plan->bn, BK);
+    if (rc) return rc;
+    return ap_make_tmap_f16_2d(ctx, &plan->map_w_half, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, plan->bn / 2, BK);
 }
 
 int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const float* resid, void* out,
@@ -291,8 +453,10 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
     ep.pos = extra ? extra->pos : nullptr;
     ep.tokens_per_image = extra ? extra->tokens_per_image : 0;
     ep.alpha = extra ? extra->alpha : 1.0f;
-    if (plan->bn == 256) return dispatch_epi<256>(ctx, plan, ep, stream);
-    return dispatch_epi<128>(ctx, plan, ep, stream);
+    ep.debug = ctx->gemm_debug;
+    if (plan->cta_group == 2) return dispatch_epi<2, 256>(ctx, plan, ep, stream);
+    if (plan->bn == 256) return dispatch_epi<1, 256>(ctx, plan, ep, stream);
+    return dispatch_epi<1, 128>(ctx, plan, ep, stream);
 }
 
 extern "C" int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,

@@ -39,7 +39,7 @@ class B200FeatureExtractor:
     """ViT encoder forward on hand-written sm_100a kernels behind the reference's FeatureExtractor interface."""
 
     def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int = 256, image_size: int = 224,
-                 max_batch: int = 128, device: int = 0, config: tuple | None = None, registry_name: str | None = None):
+                 max_batch: int = 127, device: int = 0, config: tuple | None = None, registry_name: str | None = None):
         cfg = config or VIT_CONFIGS.get(name)
         if cfg is None:
             raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS)}")

@@ -35,6 +35,8 @@ GEMM_FLOP_PER_PATCH = 2 * (197 * GEMM_MAC_PER_TOKEN_LAYER * 12 + 196 * 768 * 768
 ATTN_FLOP_PER_PATCH = 2 * 12 * 12 * 2 * 197 * 197 * 64
 MODEL_FLOP_PER_PATCH = GEMM_FLOP_PER_PATCH + ATTN_FLOP_PER_PATCH  # 35.13 GFLOP
 PATCH_BYTES = 256 * 256 * 3
+# patches per forward chunk: 127 x 197 tokens = 98 CTA-pair row tiles -> 294 / 882 / 1176 tiles = 3.97 / 11.9 / 15.9 waves of 74 pairs
+CHUNK = 127
 
 
 def parse_args():
@@ -43,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--batch", type=int, default=2048, help="patches per step (b200 arm)")
+    ap.add_argument("--batch", type=int, default=2032, help="patches per step (b200 arm); 16 forward chunks of 127")
     ap.add_argument("--width", type=int, default=80000)
     ap.add_argument("--height", type=int, default=60000)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -258,7 +260,7 @@ def main_b200(args):
             dist.broadcast(t, src=0)
             out[k] = t.cpu()
         sd = out
-    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=128, device=local_rank)
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=CHUNK, device=local_rank)
     del sd
 
     B = args.batch
@@ -329,7 +331,7 @@ def main_b200(args):
     patches_timed = args.steps * B
     achieved_tflops = (patches_timed * GEMM_FLOP_PER_PATCH) / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all 49 launches per 128-patch chunk: conv_proj, in_proj, out_proj, mlp.0, mlp.3)",
+        "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all 49 launches per 127-patch chunk: conv_proj, in_proj, out_proj, mlp.0, mlp.3)",
         "achieved": achieved_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": (achieved_tflops / peaks["tflops_sustained"]) if achieved_tflops else None, "traffic": None,
         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
@@ -359,7 +361,7 @@ def main_b200(args):
         "dtype": "f16 operands, f32 accumulate/residual/LayerNorm/softmax", "data": "synthetic",
         "config": {"workload": f"single synthetic {args.width}x{args.height} RGB slide per GPU resident in HBM, 256px patches "
                                f"stride 256 ({n_coords} coords on rank 0), ViT-B/16 random-init (seeded)",
-                   "patches_per_step": B, "forward_chunk": 128, "l2": "inputs larger than L2 (each step reads a different "
+                   "patches_per_step": B, "forward_chunk": CHUNK, "l2": "inputs larger than L2 (each step reads a different "
                    f"{B * 150528 / 1e6:.0f} MB of the 14.4 GB slide)", "parallelism": f"slides sharded 1 per GPU x{world}, no steady-state collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * PATCH_BYTES, "d2h_bytes_per_step": n_e2e * 768 * 4,

@@ -40,6 +40,9 @@ const char* ap_last_error(const ap_ctx* ctx);
 /* Number of kernels this library has launched on ctx since ap_init (bench.py "gpu_launches"). */
 int64_t ap_launch_count(const ap_ctx* ctx);
 int ap_sm_count(const ap_ctx* ctx);
+/* Tuning knobs.  "gemm_cta_group": 2 (default; CTA-pair 256x256 tiles, tcgen05 cta_group::2) or 1 (128x256 tiles).
+ * Affects GEMM plans created afterwards. */
+int ap_set_option(ap_ctx* ctx, const char* key, int value);
 /* Optional per-launch timing with CUDA events recorded on the launching stream (bench.py's live roofline
  * numbers).  Kernel classes: 0 gemm, 1 attention, 2 layernorm, 3 preprocess, 4 coords, 5 thumbnail, 6 other.
  * ap_profile_read sums and clears the records into total_ms[n_classes] / counts[n_classes] (n_classes >= 7). */

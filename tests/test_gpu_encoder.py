@@ -38,7 +38,7 @@ def test_vit_b_16_matches_reference_golden(golden_dir):
 
     gold = np.load(golden_dir / "vit_b_16_feats.npz")["feats"]
     sd = vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"])
-    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=128)
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=127)
     patches = feature_patches()
     got = ext.extract_batch(patches, batch_size=32)
     rel = _rel(got, gold)
@@ -61,13 +61,13 @@ def test_vit_b_16_matches_reference_golden(golden_dir):
 
 
 def test_vit_b_16_many_patches_ragged_and_overhang():
-    """300 patches (chunks 128+128+44), some overhanging the slide edge (zero padding like the reference backends)."""
+    """300 patches (chunks 127+127+46), some overhanging the slide edge (zero padding like the reference backends)."""
     from atlaspatch_b200.encoder import B200FeatureExtractor
     from atlaspatch_b200.slide import SyntheticWSI
     from atlaspatch_b200.synthetic import make_spec, render_region_host
 
     sd = vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"])
-    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=128)
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=127)
     spec = make_spec(3000, 2000, seed=21)
     wsi = SyntheticWSI(spec)
     rng = np.random.default_rng(5)
@@ -75,7 +75,7 @@ def test_vit_b_16_many_patches_ragged_and_overhang():
     coords = torch.tensor([[x, y, 256, 256, 0] for x, y in xy], dtype=torch.int32, device="cuda")
     feats = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords).cpu().numpy()
     assert np.isfinite(feats).all()
-    idx = [0, 1, 127, 128, 255, 256, 299] + [i for i, (x, y) in enumerate(xy) if x < 0 or y < 0 or x + 256 > spec.width][:3]
+    idx = [0, 1, 126, 127, 253, 254, 299] + [i for i, (x, y) in enumerate(xy) if x < 0 or y < 0 or x + 256 > spec.width][:3]
     want = ov.extract_features([render_region_host(spec, *xy[i], 256, 256) for i in idx], sd, "vit_b_16")
     assert _rel(feats[idx], want).max() < REL_TOL
     # order / batching invariance: same rows when embedded in another order

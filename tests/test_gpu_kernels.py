@@ -32,8 +32,10 @@ GEMM_CASES = [
 ]
 
 
+@pytest.mark.parametrize("cg", [2, 1])
 @pytest.mark.parametrize("M,N,K,epi", GEMM_CASES)
-def test_gemm_tcgen05(ctx, M, N, K, epi):
+def test_gemm_tcgen05(ctx, M, N, K, epi, cg):
+    ctx.set_option("gemm_cta_group", cg)   # 2: CTA-pair 256x256 tiles (cta_group::2), 1: 128xBN tiles
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
     W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
@@ -52,6 +54,7 @@ def test_gemm_tcgen05(ctx, M, N, K, epi):
     tol = 2e-3 if epi in (0, 1) else 2e-5   # fp16 output rounding vs fp32 output
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
+    ctx.set_option("gemm_cta_group", 2)
     assert err <= tol * max(scale, 1.0), f"max abs err {err} (scale {scale})"
 
 
