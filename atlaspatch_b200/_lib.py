@@ -18,7 +18,7 @@ EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32, EPI_BIAS_F32 = 0, 1, 2, 3
 
 class VitDesc(C.Structure):
     _fields_ = [("image_size", C.c_int), ("patch", C.c_int), ("layers", C.c_int), ("heads", C.c_int),
-                ("hidden", C.c_int), ("mlp", C.c_int), ("input_patch", C.c_int), ("max_batch", C.c_int),
+                ("hidden", C.c_int), ("mlp", C.c_int), ("input_patch", C.c_int), ("max_batch", C.c_int), ("precise_layers", C.c_int),
                 ("ln_eps", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
 
 

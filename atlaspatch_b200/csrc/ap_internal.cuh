@@ -78,10 +78,11 @@ struct GemmPlan {
     CUtensorMap map_w;       // box = bn rows of W (single-CTA tiles)
     CUtensorMap map_w_half;  // box = bn/2 rows of W (each CTA of a cta_group::2 pair loads half)
     int M, N, K, epilogue;
+    int Ka;         // width of A in memory (K % Ka == 0; K > Ka when W holds hi/lo split weights)
     int bn;         // N tile (256 or 128)
     int cta_group;  // 2: CTA pair owns a 256 x 256 tile; 1: one CTA owns a 128 x bn tile
 };
-int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue);
+int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue, int Ka = 0);
 // Patch-embed epilogue parameters: output row remap (b*T + t -> b*(T+1) + 1 + t) and +pos[1+t].
 struct GemmExtra {
     const float* pos = nullptr;  // [(T+1), N] fp32 or null

@@ -19,6 +19,7 @@ struct LayerWeights {
     __half *w_qkv, *w_o, *w_1, *w_2;
     float *b_qkv, *b_o, *b_1, *b_2;
     GemmPlan p_qkv, p_o, p_1, p_2;
+    bool split = false;  // weights stored as [hi | lo] fp16 pairs (K doubled)
 };
 
 }  // namespace
@@ -30,6 +31,7 @@ struct ap_encoder {
     int kpe = 0;      // 3 * patch * patch
     int centre[3] = {0, 0, 0};  // integer pixel centre per channel = round(255 * mean_c)
     int max_batch = 0;
+    int precise_layers = 1;
     bool finalized = false;
     std::unordered_map<std::string, std::vector<float>> host;  // staged fp32 tensors until finalize
     std::vector<void*> allocs;
@@ -65,6 +67,22 @@ int upload_f32(ap_encoder* e, float** dst, const std::vector<float>& v) {
     return AP_OK;
 }
 
+// [rows, K] fp32 -> [rows, 2K] fp16 = [hi | lo] with hi = fp16(w), lo = fp16(w - hi)
+int upload_f16_split(ap_encoder* e, __half** dst, const float* src, size_t rows, size_t K) {
+    std::vector<__half> h(rows * 2 * K);
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t k = 0; k < K; ++k) {
+            const float w = src[r * K + k];
+            const __half hi = __float2half_rn(w);
+            h[r * 2 * K + k] = hi;
+            h[r * 2 * K + K + k] = __float2half_rn(w - __half2float(hi));
+        }
+    int rc = dev_alloc(e, reinterpret_cast<void**>(dst), h.size() * sizeof(__half));
+    if (rc) return rc;
+    AP_CHECK_CUDA(e->ctx, cudaMemcpy(*dst, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return AP_OK;
+}
+
 int upload_f16(ap_encoder* e, __half** dst, const float* src, size_t n) {
     std::vector<__half> h(n);
     for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(src[i]);
@@ -95,7 +113,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     const int rows = nb * T1;
     int rc;
     if ((rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
-                                2 * e->kpe, e->centre, 1, st)))
+                                e->kpe, e->centre, 0, st)))
         return rc;
     if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, st))) return rc;
     {
@@ -143,7 +161,8 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     const int g = desc->image_size / desc->patch;
     e->tokens = g * g;
     e->kpe = 3 * desc->patch * desc->patch;
-    e->max_batch = desc->max_batch > 0 ? desc->max_batch : 128;
+    e->max_batch = desc->max_batch > 0 ? desc->max_batch : 127;
+    e->precise_layers = desc->precise_layers < 0 ? 1 : (desc->precise_layers > desc->layers ? desc->layers : desc->precise_layers);
     if ((e->tokens + 1) > 272) {
         delete e;
         return ap_set_error(ctx, AP_EINVAL, "encoder: sequence %d too long (<= 272)", g * g + 1);
@@ -194,7 +213,8 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     //      b'[o] = b[o] + sum_c (centre_c - 255 mean_c) / (255 std_c) * sum_{ky,kx} W[o,c,ky,kx]
     // conv_proj sees raw pixels, whose common mode is large against the signal, so fp16 rounding of W' alone costs
     // ~5.7e-4 of the 1e-3 feature budget (measured on the CPU simulation in DESIGN.md).  It is 0.7 % of the FLOPs,
-    // so W' is kept as an fp16 hi/lo pair and the GEMM runs over K = [A | A] x [W_hi | W_lo]: ~22-bit weights.
+    // so W' is kept as an fp16 hi/lo pair and the GEMM contracts over 2K = [W_hi | W_lo] while re-reading the same A
+    // blocks (GemmPlan::Ka): ~22-bit weights.
     {
         AP_GET(w, "conv_proj.weight", (size_t)D * K)
         AP_GET(b, "conv_proj.bias", D)
@@ -243,9 +263,15 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         if ((rc = upload_f32(e, &L.ln1_g, *ln1g)) || (rc = upload_f32(e, &L.ln1_b, *ln1b)) ||
             (rc = upload_f32(e, &L.ln2_g, *ln2g)) || (rc = upload_f32(e, &L.ln2_b, *ln2b)) ||
             (rc = upload_f32(e, &L.b_qkv, *bqkv)) || (rc = upload_f32(e, &L.b_o, *bo)) ||
-            (rc = upload_f32(e, &L.b_1, *b1)) || (rc = upload_f32(e, &L.b_2, *b2)) ||
-            (rc = upload_f16(e, &L.w_qkv, wqkv->data(), wqkv->size())) || (rc = upload_f16(e, &L.w_o, wo->data(), wo->size())) ||
-            (rc = upload_f16(e, &L.w_1, w1->data(), w1->size())) || (rc = upload_f16(e, &L.w_2, w2->data(), w2->size())))
+            (rc = upload_f32(e, &L.b_1, *b1)) || (rc = upload_f32(e, &L.b_2, *b2)))
+            return rc;
+        L.split = i < e->precise_layers;
+        if (L.split) {
+            if ((rc = upload_f16_split(e, &L.w_qkv, wqkv->data(), 3 * D, D)) || (rc = upload_f16_split(e, &L.w_o, wo->data(), D, D)) ||
+                (rc = upload_f16_split(e, &L.w_1, w1->data(), M, D)) || (rc = upload_f16_split(e, &L.w_2, w2->data(), D, M)))
+                return rc;
+        } else if ((rc = upload_f16(e, &L.w_qkv, wqkv->data(), wqkv->size())) || (rc = upload_f16(e, &L.w_o, wo->data(), wo->size())) ||
+                   (rc = upload_f16(e, &L.w_1, w1->data(), w1->size())) || (rc = upload_f16(e, &L.w_2, w2->data(), w2->size())))
             return rc;
     }
 #undef AP_GET
@@ -254,11 +280,11 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     // ---- workspaces (rows padded to the 128-row GEMM tile so TMA boxes never leave the allocation) ----
     const size_t rows = ((size_t)MB * T1 + 127) / 128 * 128;
     const size_t rows_pe = ((size_t)MB * T + 127) / 128 * 128;
-    if ((rc = dev_alloc(e, (void**)&e->a_pe, rows_pe * 2 * K * 2)) || (rc = dev_alloc(e, (void**)&e->x, rows * D * 4)) ||
+    if ((rc = dev_alloc(e, (void**)&e->a_pe, rows_pe * K * 2)) || (rc = dev_alloc(e, (void**)&e->x, rows * D * 4)) ||
         (rc = dev_alloc(e, (void**)&e->y1, rows * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2, rows * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->qkv, rows * 3 * D * 2)) || (rc = dev_alloc(e, (void**)&e->hbuf, rows * M * 2)))
         return rc;
-    AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * 2 * K * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * K * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y1, 0, rows * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y2, 0, rows * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->hbuf, 0, rows * M * 2));
@@ -266,12 +292,13 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     AP_CHECK_CUDA(ctx, cudaMemset(e->x, 0, rows * D * 4));
 
     // ---- GEMM plans (TMA descriptors over the fixed workspaces / weights) ------------------------------
-    if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, 2 * K, AP_EPI_BIAS_F32))) return rc;
+    if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, 2 * K, AP_EPI_BIAS_F32, K))) return rc;
     for (auto& L : e->layers) {
-        if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, D, AP_EPI_BIAS_F16)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, D, AP_EPI_BIAS_RESID_F32)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M, D, AP_EPI_BIAS_GELU_F16)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, M, AP_EPI_BIAS_RESID_F32)))
+        const int s = L.split ? 2 : 1;
+        if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, s * D, AP_EPI_BIAS_F16, D)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, s * D, AP_EPI_BIAS_RESID_F32, D)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M, s * D, AP_EPI_BIAS_GELU_F16, D)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, s * M, AP_EPI_BIAS_RESID_F32, M)))
             return rc;
     }
 

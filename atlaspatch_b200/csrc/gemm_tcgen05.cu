@@ -53,6 +53,8 @@ struct EpiParams {
     const float* pos;
     int tokens_per_image;
     float alpha;
+    int a_k_blocks;  // A has this many 64-wide K blocks; block kb of the contraction reads A block kb % a_k_blocks
+                     // (hi/lo split weights: W = [W_hi | W_lo] over 2K while A is stored once)
     int debug;  // diagnostics only (ap_set_option "gemm_debug"): 1 = no epilogue math/stores, 2 = no MMA issue, 4 = no TMA loads
 };
 
@@ -271,12 +273,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         if (cta_rank == 0) ptx::mbar_arrive(&full_bar[stage]);
                     } else if (CG == 1) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], L::A_STAGE + L::B_STAGE);
-                        ptx::tma_load_2d(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], (kb % ep.a_k_blocks) * BK, m0);
                         ptx::tma_load_2d(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kb * BK, n0);
                     } else {
                         // both CTAs' bytes are accounted on the leader's barrier (peer bit cleared in the address)
                         if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (L::A_STAGE + L::B_STAGE));
-                        ptx::tma_load_2d_2sm(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d_2sm(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], (kb % ep.a_k_blocks) * BK, m0);
                         ptx::tma_load_2d_2sm(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kb * BK, n0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -429,15 +431,16 @@ int dispatch_epi(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream
 
 }  // namespace
 
-int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue) {
+int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue, int Ka) {
+    if (Ka <= 0) Ka = K;
     AP_REQUIRE(ctx, M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
-    AP_REQUIRE(ctx, K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
+    AP_REQUIRE(ctx, K % BK == 0 && Ka % BK == 0 && K % Ka == 0, "gemm: K=%d (A width %d) must be multiples of %d, K %% Ka == 0", K, Ka, BK);
     AP_REQUIRE(ctx, N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
     AP_REQUIRE(ctx, epilogue >= 0 && epilogue <= 3, "gemm: unknown epilogue %d", epilogue);
-    plan->M = M; plan->N = N; plan->K = K; plan->epilogue = epilogue;
+    plan->M = M; plan->N = N; plan->K = K; plan->Ka = Ka; plan->epilogue = epilogue;
     plan->bn = (N % 256 == 0) ? 256 : 128;
     plan->cta_group = (plan->bn == 256 && ctx->gemm_cta_group == 2) ? 2 : 1;
-    int rc = ap_make_tmap_f16_2d(ctx, &plan->map_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, BK);
+    int rc = ap_make_tmap_f16_2d(ctx, &plan->map_a, A, (uint64_t)M, (uint64_t)Ka, (uint64_t)Ka, 128, BK);
     if (rc) return rc;
     rc = ap_make_tmap_f16_2d(ctx, &plan->map_w, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, plan->bn, BK);
     if (rc) return rc;
@@ -454,6 +457,7 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
     ep.tokens_per_image = extra ? extra->tokens_per_image : 0;
     ep.alpha = extra ? extra->alpha : 1.0f;
     ep.debug = ctx->gemm_debug;
+    ep.a_k_blocks = plan->Ka / BK;
     if (plan->cta_group == 2) return dispatch_epi<2, 256>(ctx, plan, ep, stream);
     if (plan->bn == 256) return dispatch_epi<1, 256>(ctx, plan, ep, stream);
     return dispatch_epi<1, 128>(ctx, plan, ep, stream);
@@ -463,7 +467,7 @@ extern "C" int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, co
                            const float* resid_dev, void* out_dev, int M, int N, int K, int epilogue, void* stream) {
     if (!ctx) return AP_EINVAL;
     GemmPlan plan;
-    int rc = ap_gemm_plan(ctx, &plan, A_dev, W_dev, M, N, K, epilogue);
+    int rc = ap_gemm_plan(ctx, &plan, A_dev, W_dev, M, N, K, epilogue, K);
     if (rc) return rc;
     return ap_gemm_run(ctx, &plan, bias_dev, resid_dev, out_dev, nullptr, static_cast<cudaStream_t>(stream));
 }

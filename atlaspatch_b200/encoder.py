@@ -39,7 +39,8 @@ class B200FeatureExtractor:
     """ViT encoder forward on hand-written sm_100a kernels behind the reference's FeatureExtractor interface."""
 
     def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int = 256, image_size: int = 224,
-                 max_batch: int = 127, device: int = 0, config: tuple | None = None, registry_name: str | None = None):
+                 max_batch: int = 127, device: int = 0, config: tuple | None = None, registry_name: str | None = None,
+                 precise_layers: int = -1):
         cfg = config or VIT_CONFIGS.get(name)
         if cfg is None:
             raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS)}")
@@ -51,7 +52,7 @@ class B200FeatureExtractor:
         self.ctx = Context.get(device)
         lib = self.ctx.lib
         desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
-                       input_patch=input_patch, max_batch=max_batch, ln_eps=1e-6,
+                       input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=1e-6,
                        mean=(C.c_float * 3)(*IMAGENET_MEAN), std=(C.c_float * 3)(*IMAGENET_STD))
         h = C.c_void_p()
         self.ctx.check(lib.ap_encoder_create(self.ctx.handle, C.byref(desc), C.byref(h)))
