@@ -23,6 +23,8 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    int attn_mode = 2;       // 2: tcgen05 attention when 16 <= S_pad <= 256, 1: warp-MMA (mma.sync) kernel
+    int attn_variant = 0;    // diagnostics
     int gemm_debug = 0;      // diagnostics: see EpiParams::debug
     int gemm_cta_group = 2;  // default GEMM flavour (ap_set_option "gemm_cta_group"; env AP_GEMM_CTA_GROUP)
     // optional per-launch CUDA-event timing (ap_profile_*): bench.py's live roofline measurement
@@ -95,6 +97,14 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
 int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const float* gamma, const float* beta,
                      float eps, __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream);
 int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
+// tcgen05 attention (16 <= S_pad <= 256): TMA descriptors over the packed QKV buffer [rows, 3 * heads * 64]
+struct AttnPlan {
+    CUtensorMap map_q;   // box 128 rows x 64
+    CUtensorMap map_kv;  // box S_pad rows x 64
+    int S_pad;
+};
+int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int rows, int S, int heads);
+int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream);
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
                       const int* centre, int dup, cudaStream_t stream);

@@ -63,6 +63,15 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         ctx->gemm_cta_group = value;
         return AP_OK;
     }
+    if (!strcmp(key, "attn_mode")) {
+        AP_REQUIRE(ctx, value == 1 || value == 2, "attn_mode must be 1 or 2");
+        ctx->attn_mode = value;
+        return AP_OK;
+    }
+    if (!strcmp(key, "attn_variant")) {
+        ctx->attn_variant = value;
+        return AP_OK;
+    }
     if (!strcmp(key, "gemm_debug")) {
         ctx->gemm_debug = value;
         return AP_OK;

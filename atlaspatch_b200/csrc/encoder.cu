@@ -39,6 +39,8 @@ struct ap_encoder {
     __half* w_pe = nullptr;
     float *b_pe = nullptr, *cls = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
     GemmPlan p_pe;
+    AttnPlan p_attn;
+    bool attn_tc = false;
     std::vector<LayerWeights> layers;
     // workspaces
     __half *a_pe = nullptr, *y1 = nullptr, *y2 = nullptr, *qkv = nullptr, *hbuf = nullptr;
@@ -129,7 +131,9 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         if ((rc = ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
         p = L.p_qkv; p.M = rows;
         if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, nullptr, st))) return rc;
-        if ((rc = ap_attention_run(ctx, e->qkv, e->y2, nb, T1, e->d.heads, st))) return rc;
+        if (e->attn_tc && ctx->attn_mode == 2) {
+            if ((rc = ap_attention_tc_run(ctx, &e->p_attn, e->y2, nb, T1, e->d.heads, st))) return rc;
+        } else if ((rc = ap_attention_run(ctx, e->qkv, e->y2, nb, T1, e->d.heads, st))) return rc;
         p = L.p_o; p.M = rows;
         if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->x, e->x, nullptr, st))) return rc;
         if ((rc = ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
@@ -300,6 +304,12 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
             (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M, s * D, AP_EPI_BIAS_GELU_F16, D)) ||
             (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, s * M, AP_EPI_BIAS_RESID_F32, M)))
             return rc;
+    }
+
+    {
+        const int S_pad = (T1 + 15) / 16 * 16;
+        e->attn_tc = S_pad <= 256;
+        if (e->attn_tc && (rc = ap_attention_tc_plan(ctx, &e->p_attn, e->qkv, (int)rows, T1, e->d.heads))) return rc;
     }
 
     // ---- host-patch path: double-buffered pinned staging + its own streams -------------------------------

@@ -349,6 +349,13 @@ extern "C" int ap_layernorm_f16(ap_ctx* ctx, const float* x_dev, int64_t x_row_s
 
 extern "C" int ap_attention_f16(ap_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int S, int heads, void* stream) {
     if (!ctx) return AP_EINVAL;
+    const int S_pad = (S + 15) / 16 * 16;
+    if (ctx->attn_mode == 2 && S_pad >= 16 && S_pad <= 256 && B > 0) {
+        AttnPlan plan;
+        int rc = ap_attention_tc_plan(ctx, &plan, static_cast<const __half*>(qkv_dev), B * S, S, heads);
+        if (rc) return rc;
+        return ap_attention_tc_run(ctx, &plan, static_cast<__half*>(out_dev), B, S, heads, static_cast<cudaStream_t>(stream));
+    }
     return ap_attention_run(ctx, static_cast<const __half*>(qkv_dev), static_cast<__half*>(out_dev), B, S, heads,
                             static_cast<cudaStream_t>(stream));
 }

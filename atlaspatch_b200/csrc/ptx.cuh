@@ -170,15 +170,51 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 16 (or 8) consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A operand read from tensor memory (lane = row, 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand tile stored as [rows][64 fp16] (128 B rows) with the
 // 128-byte swizzle TMA applies (8-row x 128 B atoms, 1024 B apart):
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)
 //   bits [32,46) stride byte offset >> 4 (1024 B between 8-row groups = 64)
 //   bits [46,48) descriptor version = 1 (Blackwell)      bits [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+// MN-major operand (rows = K index, 128 B = 64 contiguous M/N elements per row, same 128B swizzle): 8-row K groups are
+// again 1024 B apart (stride field); with a single 64-wide M/N atom the leading field is unused (set lbo16 = 64 as well).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo16 = 1) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(lbo16 & 0x3FFF) << 16;
     d |= static_cast<uint64_t>(1024 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(2) << 61;
@@ -186,9 +222,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 }
 // Instruction descriptor, kind::f16: c_format F32 (bits[4,6)=1), a/b format F16 (0) or BF16 (1) at bits [7,10)/[10,13),
 // a/b K-major (bits 15,16 = 0), N>>3 at bits [17,23), M>>4 at bits [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool bf16 = false) {
-    return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-           (static_cast<uint32_t>(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool bf16 = false, bool b_mn_major = false) {
+    return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((b_mn_major ? 1u : 0u) << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---- legacy warp MMA (attention v1) ------------------------------------------------------------
