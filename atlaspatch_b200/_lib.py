@@ -118,8 +118,12 @@ class Context:
     def set_option(self, key: str, value: int) -> None:
         self.check(self.lib.ap_set_option(self.handle, key.encode(), int(value)))
 
-    def profile(self, on: bool) -> None:
-        self.check(self.lib.ap_profile_enable(self.handle, 1 if on else 0))
+    def profile(self, on, classes=None) -> None:
+        """on=False: off; on=True: time every kernel class, or only `classes` (names from KERNEL_CLASSES)."""
+        mask = 0
+        if on:
+            mask = -1 if classes is None else sum(1 << self.KERNEL_CLASSES.index(c) for c in classes)
+        self.check(self.lib.ap_profile_enable(self.handle, mask))
 
     def profile_read(self) -> dict[str, tuple[float, int]]:
         """{kernel class: (total ms, launches)} measured with CUDA events since the last read."""

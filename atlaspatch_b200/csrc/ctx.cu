@@ -68,6 +68,10 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         ctx->attn_mode = value;
         return AP_OK;
     }
+    if (!strcmp(key, "cls_only_last_layer")) {
+        ctx->cls_only_last_layer = value != 0;
+        return AP_OK;
+    }
     if (!strcmp(key, "attn_variant")) {
         ctx->attn_variant = value;
         return AP_OK;
@@ -101,7 +105,7 @@ static cudaEvent_t prof_get_event(ap_ctx* ctx) {
 }
 
 ProfScope::ProfScope(ap_ctx* c, cudaStream_t s, int cls) : ctx(c), st(s) {
-    if (!ctx || !ctx->profiling) return;
+    if (!ctx || !((ctx->profiling >> cls) & 1u)) return;
     std::lock_guard<std::mutex> lk(ctx->prof_mu);
     cudaEvent_t start = prof_get_event(ctx);
     stop = prof_get_event(ctx);
@@ -114,7 +118,7 @@ ProfScope::~ProfScope() {
 
 extern "C" int ap_profile_enable(ap_ctx* ctx, int on) {
     if (!ctx) return AP_EINVAL;
-    ctx->profiling = on != 0;
+    ctx->profiling = on < 0 ? 0xFFFFFFFFu : static_cast<unsigned>(on);  // -1 (or 1 | 2 | 4 ...): bit c = time kernel class c
     return AP_OK;
 }
 

@@ -19,6 +19,7 @@ struct LayerWeights {
     __half *w_qkv, *w_o, *w_1, *w_2;
     float *b_qkv, *b_o, *b_1, *b_2;
     GemmPlan p_qkv, p_o, p_1, p_2;
+    GemmPlan pc_o, pc_1, pc_2;  // last layer only: class-token rows (M = images)
     bool split = false;  // weights stored as [hi | lo] fp16 pairs (K doubled)
 };
 
@@ -45,6 +46,9 @@ struct ap_encoder {
     // workspaces
     __half *a_pe = nullptr, *y1 = nullptr, *y2 = nullptr, *qkv = nullptr, *hbuf = nullptr;
     float* x = nullptr;
+    // class-token-only tail of the last layer
+    __half *yc_attn = nullptr, *yc_ln = nullptr, *hc = nullptr;
+    float* xc = nullptr;
     // host-patch path
     uint8_t *pin_in[2] = {nullptr, nullptr}, *dev_patches[2] = {nullptr, nullptr};
     float *pin_out[2] = {nullptr, nullptr}, *dev_feats[2] = {nullptr, nullptr};
@@ -126,11 +130,26 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         ex.tokens_per_image = T;
         if ((rc = ap_gemm_run(ctx, &p, e->b_pe, nullptr, e->x, &ex, st))) return rc;
     }
-    for (auto& L : e->layers) {
+    for (size_t li = 0; li < e->layers.size(); ++li) {
+        auto& L = e->layers[li];
         GemmPlan p;
         if ((rc = ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
         p = L.p_qkv; p.M = rows;
         if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, nullptr, st))) return rc;
+        if (li + 1 == e->layers.size() && ctx->cls_only_last_layer) {
+            // Only x[:, 0] survives the final LayerNorm (models/patch/base.py:100 -> torchvision forward `x[:, 0]`): the last
+            // layer's attention needs every token's K/V but only the class-token query, and out_proj / MLP only that row.
+            if ((rc = ap_cls_attention_run(ctx, e->qkv, e->yc_attn, nb, T1, e->d.heads, st))) return rc;
+            if ((rc = ap_gather_rows_run(ctx, e->x, e->xc, nb, static_cast<int64_t>(T1) * D, D, st))) return rc;
+            p = L.pc_o; p.M = nb;
+            if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->xc, e->xc, nullptr, st))) return rc;
+            if ((rc = ap_layernorm_run(ctx, e->xc, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->yc_ln, nullptr, nb, D, st))) return rc;
+            p = L.pc_1; p.M = nb;
+            if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hc, nullptr, st))) return rc;
+            p = L.pc_2; p.M = nb;
+            if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->xc, e->xc, nullptr, st))) return rc;
+            return ap_layernorm_run(ctx, e->xc, D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
+        }
         if (e->attn_tc && ctx->attn_mode == 2) {
             if ((rc = ap_attention_tc_run(ctx, &e->p_attn, e->y2, nb, T1, e->d.heads, st))) return rc;
         } else if ((rc = ap_attention_run(ctx, e->qkv, e->y2, nb, T1, e->d.heads, st))) return rc;
@@ -288,6 +307,14 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         (rc = dev_alloc(e, (void**)&e->y1, rows * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2, rows * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->qkv, rows * 3 * D * 2)) || (rc = dev_alloc(e, (void**)&e->hbuf, rows * M * 2)))
         return rc;
+    const size_t rows_c = ((size_t)MB + 127) / 128 * 128;
+    if ((rc = dev_alloc(e, (void**)&e->yc_attn, rows_c * D * 2)) || (rc = dev_alloc(e, (void**)&e->yc_ln, rows_c * D * 2)) ||
+        (rc = dev_alloc(e, (void**)&e->hc, rows_c * M * 2)) || (rc = dev_alloc(e, (void**)&e->xc, rows_c * D * 4)))
+        return rc;
+    AP_CHECK_CUDA(ctx, cudaMemset(e->yc_attn, 0, rows_c * D * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->yc_ln, 0, rows_c * D * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->hc, 0, rows_c * M * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->xc, 0, rows_c * D * 4));
     AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * K * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y1, 0, rows * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y2, 0, rows * D * 2));
@@ -303,6 +330,11 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
             (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, s * D, AP_EPI_BIAS_RESID_F32, D)) ||
             (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M, s * D, AP_EPI_BIAS_GELU_F16, D)) ||
             (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, s * M, AP_EPI_BIAS_RESID_F32, M)))
+            return rc;
+        if (&L == &e->layers.back() &&
+            ((rc = ap_gemm_plan(ctx, &L.pc_o, e->yc_attn, L.w_o, MB, D, s * D, AP_EPI_BIAS_RESID_F32, D)) ||
+             (rc = ap_gemm_plan(ctx, &L.pc_1, e->yc_ln, L.w_1, MB, M, s * D, AP_EPI_BIAS_GELU_F16, D)) ||
+             (rc = ap_gemm_plan(ctx, &L.pc_2, e->hc, L.w_2, MB, D, s * M, AP_EPI_BIAS_RESID_F32, M))))
             return rc;
     }
 

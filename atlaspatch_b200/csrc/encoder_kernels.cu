@@ -275,7 +275,111 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S
     }
 }
 
+// =====================================================================================================
+// Last encoder layer: only the class-token row feeds the output (x[:, 0] after the final LayerNorm), so attention is
+// evaluated for that single query per (image, head) and out_proj / MLP run on B rows instead of B * S.
+// One warp per (image, head): lane j scores keys j, j+32, ...; softmax over the warp; lane pair d accumulates P.V.
+// =====================================================================================================
+__global__ void __launch_bounds__(384)
+cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int heads) {
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int D = heads * HD;
+    __shared__ float s_p[12][288];
+    for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
+        float* sp = s_p[threadIdx.x >> 5];
+        const __half* base = qkv + static_cast<int64_t>(b) * S * 3 * D + h * HD;
+        // q (class-token row) -> every lane holds all 64 values as 32 half2
+        __half2 q2[32];
+        const uint4* qv = reinterpret_cast<const uint4*>(base);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 u = __ldg(qv + i);
+            q2[4 * i + 0] = *reinterpret_cast<const __half2*>(&u.x); q2[4 * i + 1] = *reinterpret_cast<const __half2*>(&u.y);
+            q2[4 * i + 2] = *reinterpret_cast<const __half2*>(&u.z); q2[4 * i + 3] = *reinterpret_cast<const __half2*>(&u.w);
+        }
+        float sc[9];
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int key = lane + 32 * i;
+            float acc = -INFINITY;
+            if (key < S) {
+                const uint4* kv = reinterpret_cast<const uint4*>(base + static_cast<int64_t>(key) * 3 * D + D);
+                acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 u = __ldg(kv + c);
+                    const __half2 k0 = *reinterpret_cast<const __half2*>(&u.x), k1 = *reinterpret_cast<const __half2*>(&u.y);
+                    const __half2 k2 = *reinterpret_cast<const __half2*>(&u.z), k3 = *reinterpret_cast<const __half2*>(&u.w);
+                    const float2 a0 = __half22float2(q2[4 * c]), b0 = __half22float2(k0);
+                    const float2 a1 = __half22float2(q2[4 * c + 1]), b1 = __half22float2(k1);
+                    const float2 a2 = __half22float2(q2[4 * c + 2]), b2 = __half22float2(k2);
+                    const float2 a3 = __half22float2(q2[4 * c + 3]), b3 = __half22float2(k3);
+                    acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+                }
+            }
+            sc[i] = acc;
+            m = fmaxf(m, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float scale_log2 = 0.125f * 1.44269504088896340736f;
+        float l = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int key = lane + 32 * i;
+            // P is rounded to fp16 before P.V exactly like the tensor-core kernels do
+            const float p = key < S ? __half2float(__float2half_rn(exp2f((sc[i] - m) * scale_log2))) : 0.f;
+            const float pe = key < S ? exp2f((sc[i] - m) * scale_log2) : 0.f;
+            l += pe;
+            if (key < 288) sp[key] = p;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        __syncwarp();
+        // O[d] = sum_j p_j V[j][d]; lane owns d = 2 lane, 2 lane + 1
+        float o0 = 0.f, o1 = 0.f;
+        const __half* vbase = base + 2 * D + 2 * lane;
+        for (int key = 0; key < S; ++key) {
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(vbase + static_cast<int64_t>(key) * 3 * D));
+            const float p = sp[key];
+            o0 = fmaf(p, v.x, o0);
+            o1 = fmaf(p, v.y, o1);
+        }
+        const float inv = 1.0f / l;
+        *reinterpret_cast<__half2*>(out + static_cast<int64_t>(b) * D + h * HD + 2 * lane) = __floats2half2_rn(o0 * inv, o1 * inv);
+        __syncwarp();
+    }
+}
+
+// dst[b, :] = src[b * row_stride_rows, :]   (fp32 rows of D floats; picks the class-token row of every image)
+__global__ void gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_rows, int64_t src_row_stride, int D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * (D / 4)) return;
+    const int b = i / (D / 4), c = i - b * (D / 4);
+    reinterpret_cast<float4*>(dst + static_cast<int64_t>(b) * D)[c] = reinterpret_cast<const float4*>(src + b * src_row_stride)[c];
+}
+
 }  // namespace
+
+int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream) {
+    AP_REQUIRE(ctx, S >= 1 && S <= 288 && heads <= 24, "cls attention: S=%d heads=%d unsupported", S, heads);
+    if (B == 0) return AP_OK;
+    ProfScope prof(ctx, stream, AP_K_ATTENTION);
+    cls_attention_kernel<<<B, 384, 0, stream>>>(qkv, out, S, heads);
+    AP_CHECK_LAUNCH(ctx, "cls_attention_kernel");
+    return AP_OK;
+}
+
+int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, int64_t src_row_stride, int D, cudaStream_t stream) {
+    if (n_rows == 0) return AP_OK;
+    const int total = n_rows * (D / 4);
+    ProfScope prof(ctx, stream, AP_K_OTHER);
+    gather_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, dst, n_rows, src_row_stride, D);
+    AP_CHECK_LAUNCH(ctx, "gather_rows_kernel");
+    return AP_OK;
+}
 
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,

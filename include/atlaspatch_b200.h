@@ -45,6 +45,7 @@ int ap_sm_count(const ap_ctx* ctx);
 int ap_set_option(ap_ctx* ctx, const char* key, int value);
 /* Optional per-launch timing with CUDA events recorded on the launching stream (bench.py's live roofline
  * numbers).  Kernel classes: 0 gemm, 1 attention, 2 layernorm, 3 preprocess, 4 coords, 5 thumbnail, 6 other.
+ * ap_profile_enable: on = 0 off, -1 all classes, else a bit mask (bit c = class c).
  * ap_profile_read sums and clears the records into total_ms[n_classes] / counts[n_classes] (n_classes >= 7). */
 int ap_profile_enable(ap_ctx* ctx, int on);
 int ap_profile_read(ap_ctx* ctx, double* total_ms, int64_t* counts, int n_classes);

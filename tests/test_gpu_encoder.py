@@ -83,3 +83,31 @@ def test_vit_b_16_many_patches_ragged_and_overhang():
     feats_p = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords[perm.cuda()].contiguous()).cpu().numpy()
     assert np.array_equal(feats_p, feats[perm.numpy()])
     ext.cleanup()
+
+
+def test_cls_only_last_layer_and_attention_flavours_agree():
+    """Algorithmic shortcuts must not change results: class-token-only last layer vs full last layer, and
+    tcgen05 attention vs the warp-MMA attention kernel."""
+    from atlaspatch_b200._lib import Context
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+
+    ctx = Context.get(0)
+    sd = vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"])
+    patches = feature_patches()
+    want = ov.extract_features(patches, sd, "vit_b_16")
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=127)
+    base = ext.extract_batch(patches)
+    try:
+        ctx.set_option("cls_only_last_layer", 0)
+        full = ext.extract_batch(patches)
+        ctx.set_option("attn_mode", 1)
+        full_mma = ext.extract_batch(patches)
+    finally:
+        ctx.set_option("cls_only_last_layer", 1)
+        ctx.set_option("attn_mode", 2)
+    # same attention flavour, class-token-only last layer vs full last layer: only accumulation order differs
+    assert _rel(full, base).max() < 1e-4
+    # the two attention kernels round P against different row maxima: independent fp16-level noise, both within tolerance
+    for f in (base, full, full_mma):
+        assert _rel(f, want).max() < REL_TOL
+    ext.cleanup()
