@@ -113,13 +113,13 @@ const std::vector<float>* find(ap_encoder* e, const std::string& name, size_t nu
 
 // One forward chunk: nb images whose patches are at `coords` (device) inside `slide`.
 int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords, int nb,
-                  float* out_feats, cudaStream_t st) {
+                  int read_scale, float* out_feats, cudaStream_t st) {
     ap_ctx* ctx = e->ctx;
     const int D = e->d.hidden, T = e->tokens, T1 = T + 1;
     const int rows = nb * T1;
     int rc;
     if ((rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
-                                e->kpe, e->centre, 0, st)))
+                                e->kpe, e->centre, 0, read_scale, st)))
         return rc;
     if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, st))) return rc;
     {
@@ -372,7 +372,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
 }
 
 extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
-                                       const int32_t* coords_dev, int64_t n, float* out_features_dev, void* stream) {
+                                       const int32_t* coords_dev, int64_t n, int read_size, float* out_features_dev, void* stream) {
     if (!e) return AP_EINVAL;
     ap_ctx* ctx = e->ctx;
     if (!e->finalized) return ap_set_error(ctx, AP_ESTATE, "encoder: ap_encoder_finalize has not been called");
@@ -380,10 +380,14 @@ extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, 
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, slide_dev && coords_dev && out_features_dev, "embed_coords: NULL pointer");
     AP_REQUIRE(ctx, pitch >= W * 3, "embed_coords: pitch %lld < 3*W", (long long)pitch);
+    AP_REQUIRE(ctx, read_size == e->d.input_patch || read_size == 2 * e->d.input_patch,
+               "embed_coords: read size %d with patch size %d needs a resize that is not implemented (1x and exact 2x only)", read_size,
+               e->d.input_patch);
+    const int read_scale = read_size / e->d.input_patch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int64_t s = 0; s < n; s += e->max_batch) {
         const int nb = static_cast<int>(n - s < e->max_batch ? n - s : e->max_batch);
-        int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, out_features_dev + s * e->d.hidden, st);
+        int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, read_scale, out_features_dev + s * e->d.hidden, st);
         if (rc) return rc;
     }
     return AP_OK;
@@ -428,7 +432,7 @@ extern "C" int ap_encoder_embed_patches_host(ap_encoder* e, const uint8_t* const
             AP_CHECK_CUDA(ctx, cudaMemcpyAsync(e->dev_patches[buf], e->pin_in[buf], (size_t)nb * patch_bytes, cudaMemcpyHostToDevice, e->s_copy));
             AP_CHECK_CUDA(ctx, cudaEventRecord(e->ev_h2d[buf], e->s_copy));
             AP_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->s_compute, e->ev_h2d[buf], 0));
-            int rc = forward_chunk(e, e->dev_patches[buf], (int64_t)IP, (int64_t)IP * nb, (int64_t)IP * 3, e->dev_tall_coords, nb,
+            int rc = forward_chunk(e, e->dev_patches[buf], (int64_t)IP, (int64_t)IP * nb, (int64_t)IP * 3, e->dev_tall_coords, nb, 1,
                                    e->dev_feats[buf], e->s_compute);
             if (rc) return rc;
             AP_CHECK_CUDA(ctx, cudaMemcpyAsync(e->pin_out[buf], e->dev_feats[buf], (size_t)nb * D * 4, cudaMemcpyDeviceToHost, e->s_compute));

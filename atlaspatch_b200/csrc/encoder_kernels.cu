@@ -21,23 +21,45 @@ template <int P>  // conv patch edge (16)
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64_t pitch,
                   const int32_t* __restrict__ coords, int input_patch, int image, __half* __restrict__ out,
-                  int64_t out_row_stride, int3 centre, int dup) {
+                  int64_t out_row_stride, int3 centre, int dup, int read_scale) {
     extern __shared__ uint8_t s_rows[];  // [P][image*3]
     const int g = image / P;
     const int b = blockIdx.x / g;
     const int ty = blockIdx.x % g;
     const int off = (input_patch - image) / 2;  // centre crop: int(round((256-224)/2)) = 16
-    const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + off;
-    const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + off + ty * P;
     const int row_bytes = image * 3;
-    for (int i = threadIdx.x; i < P * row_bytes; i += blockDim.x) {
-        const int r = i / row_bytes;
-        const int bx = i - r * row_bytes;
-        const int64_t y = y0 + r;
-        const int64_t x = x0 + bx / 3;
-        uint8_t v = 0;
-        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(slide + y * pitch + x0 * 3 + bx);
-        s_rows[i] = v;
+    if (read_scale == 1) {
+        const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + off;
+        const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + off + ty * P;
+        for (int i = threadIdx.x; i < P * row_bytes; i += blockDim.x) {
+            const int r = i / row_bytes;
+            const int bx = i - r * row_bytes;
+            const int64_t y = y0 + r;
+            const int64_t x = x0 + bx / 3;
+            uint8_t v = 0;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(slide + y * pitch + x0 * 3 + bx);
+            s_rows[i] = v;
+        }
+    } else {
+        // read size = 2 x patch size (e.g. a 40x slide read for 20x patches): the reference resizes the 2P x 2P read with
+        // cv2.resize(patch, (P, P)) (feature_embedding.py:93-95), whose exact-2x uint8 path is the 2x2 box mean
+        // (a + b + c + d + 2) >> 2; pixels outside the slide count as 0 (the read is zero-padded before the resize).
+        const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + 2 * off;
+        const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + 2 * (off + ty * P);
+        for (int i = threadIdx.x; i < P * row_bytes; i += blockDim.x) {
+            const int r = i / row_bytes;
+            const int bx = i - r * row_bytes;
+            const int px = bx / 3, c = bx - px * 3;
+            unsigned s = 2;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int64_t y = y0 + 2 * r + dy, x = x0 + 2 * px + dx;
+                    if (y >= 0 && y < H && x >= 0 && x < W) s += __ldg(slide + y * pitch + x * 3 + c);
+                }
+            s_rows[i] = static_cast<uint8_t>(s >> 2);
+        }
     }
     __syncthreads();
     // output: g tokens x (3*P*P) halfs; each thread produces 8 consecutive kx (16 B)
@@ -383,7 +405,8 @@ int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, in
 
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
-                      const int* centre, int dup, cudaStream_t stream) {
+                      const int* centre, int dup, int read_scale, cudaStream_t stream) {
+    AP_REQUIRE(ctx, read_scale == 1 || read_scale == 2, "preprocess: read size must be 1x or 2x the patch size (got %dx)", read_scale);
     AP_REQUIRE(ctx, patch == 16, "preprocess: conv patch %d unsupported (16 only)", patch);
     AP_REQUIRE(ctx, image % patch == 0 && input_patch >= image, "preprocess: bad geometry input %d image %d patch %d",
                input_patch, image, patch);
@@ -392,7 +415,7 @@ int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, i
     const size_t smem = static_cast<size_t>(patch) * image * 3;
     ProfScope prof(ctx, stream, AP_K_PREPROCESS);
     preprocess_kernel<16><<<static_cast<unsigned>(n * g), 256, smem, stream>>>(
-        slide, W, H, pitch, coords, input_patch, image, out, out_row_stride, make_int3(centre[0], centre[1], centre[2]), dup);
+        slide, W, H, pitch, coords, input_patch, image, out, out_row_stride, make_int3(centre[0], centre[1], centre[2]), dup, read_scale);
     AP_CHECK_LAUNCH(ctx, "preprocess_kernel");
     return AP_OK;
 }

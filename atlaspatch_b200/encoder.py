@@ -98,8 +98,9 @@ class B200FeatureExtractor:
     __del__ = cleanup
 
     # ---- device-resident fast path -----------------------------------------------------------------
-    def embed_coords(self, image, W: int, H: int, pitch: int, coords_dev, out=None):
-        """image: uint8 CUDA tensor (level-0 RGB rows, `pitch` bytes/row); coords_dev: int32 CUDA (n,5) -> (n,D) fp32 CUDA."""
+    def embed_coords(self, image, W: int, H: int, pitch: int, coords_dev, out=None, read_size: int | None = None):
+        """image: uint8 CUDA tensor (level-0 RGB rows, `pitch` bytes/row); coords_dev: int32 CUDA (n,5) -> (n,D) fp32 CUDA.
+        read_size: the rows' read_w (= read_h); defaults to the patch size (no resize), 2x the patch size is supported."""
         import torch
 
         n = int(coords_dev.shape[0])
@@ -110,5 +111,5 @@ class B200FeatureExtractor:
         assert coords_dev.dtype == torch.int32 and coords_dev.is_contiguous() and coords_dev.is_cuda
         self.ctx.check(self.ctx.lib.ap_encoder_embed_coords(
             self._h, C.c_void_p(image.data_ptr()), W, H, pitch, C.c_void_p(coords_dev.data_ptr()), n,
-            C.c_void_p(out.data_ptr()), C.c_void_p(current_stream_ptr())))
+            int(read_size or self.input_patch), C.c_void_p(out.data_ptr()), C.c_void_p(current_stream_ptr())))
         return out

@@ -1,0 +1,110 @@
+"""Service adapters with the reference's seam-#1 signatures (atlas_patch/services/interfaces.py:12-32).
+
+`B200PatchExtractionService.extract(wsi, mask, *, slide)` replaces PatchExtractionService.extract
+(services/extraction.py:131-197) for the fast-mode coordinate path: same contours / geometry / order, coordinates
+computed by the CUDA kernels.  `B200FeatureEmbeddingService.embed_features(result, *, wsi)` replaces
+PatchFeatureEmbeddingService._embed_with_extractor (services/feature_embedding.py:179-249) with the zero-copy path
+when the slide is resident in HBM.  The H5 container (services/storage.py) is not written by this round's build
+(no h5py / libhdf5 in the image): results are returned in memory and can be saved as .npz.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+
+from atlaspatch_b200.extraction import extract_coords_from_contours, flatten_contours, mask_to_contours, scale_contours
+from atlaspatch_b200.geometry import prepare_geometry
+
+
+@dataclass(frozen=True)
+class Slide:  # core/models.py:10-18
+    path: Path
+    mpp: float | None = None
+    backend: str | None = None
+
+    @property
+    def stem(self) -> str:
+        return Path(self.path).stem
+
+
+@dataclass
+class ExtractionResult:  # core/models.py:27-36 (h5_path is None until the H5 writer lands)
+    slide: Slide
+    h5_path: Path | None
+    num_patches: int
+    image_dir: Path | None = None
+    visualizations: dict[str, Path] = field(default_factory=dict)
+    metadata: dict[str, Any] = field(default_factory=dict)
+    coords: np.ndarray | None = None
+    patch_size_level0: int | None = None
+    coords_device: Any = None          # int32 (N, 5) CUDA tensor for the embed step
+    features: dict[str, np.ndarray] = field(default_factory=dict)
+
+
+@dataclass
+class ExtractionConfig:  # core/config.py:62-89 (fields used on the path; CLI default tissue_threshold is 0.0, cli.py:85-91)
+    patch_size: int
+    target_magnification: int
+    step_size: int | None = None
+    tissue_threshold: float = 0.0
+    fast_mode: bool = True
+
+    def validated(self) -> "ExtractionConfig":
+        if self.patch_size <= 0 or self.target_magnification <= 0:
+            raise ValueError("patch_size and target_magnification must be > 0")
+        if self.step_size is None:
+            self.step_size = self.patch_size
+        if self.step_size <= 0:
+            raise ValueError("step_size must be > 0")
+        if not (0 <= self.tissue_threshold <= 1):
+            raise ValueError("tissue_threshold must be between 0 and 1")
+        if not self.fast_mode:
+            raise NotImplementedError("--no-fast-mode (black/white patch filter) is not built yet (SURVEY.md section 8f rank 2)")
+        return self
+
+
+class B200PatchExtractionService:
+    def __init__(self, extraction_cfg: ExtractionConfig):
+        self.cfg = extraction_cfg.validated()
+
+    def _prepare_contours(self, mask: np.ndarray, wsi):  # services/extraction.py:30-42
+        tissue_t, holes_t = mask_to_contours(mask, tissue_area_thresh=self.cfg.tissue_threshold)
+        W, H = wsi.get_size(lv=0)
+        mh, mw = mask.shape[:2]
+        sx, sy = W / float(mw), H / float(mh)
+        return scale_contours(tissue_t, sx, sy), [scale_contours(hs, sx, sy) for hs in holes_t]
+
+    def _prepare_geometry(self, wsi):  # services/extraction.py:44-64
+        return prepare_geometry(src_mag=wsi.mag, target_mag=self.cfg.target_magnification, patch_size=self.cfg.patch_size,
+                                step_size=self.cfg.step_size, downsamples=wsi.ds or [1.0])
+
+    def extract(self, wsi, mask: np.ndarray, *, slide: Slide) -> ExtractionResult:
+        tissue, holes = self._prepare_contours(np.asarray(mask), wsi)
+        geo = self._prepare_geometry(wsi)
+        coords, coords_dev = extract_coords_from_contours(flatten_contours(tissue, holes), geo, return_device=True)
+        return ExtractionResult(slide=slide, h5_path=None, num_patches=int(coords.shape[0]), coords=coords,
+                                patch_size_level0=geo.patch_size_level0, coords_device=coords_dev)
+
+
+class B200FeatureEmbeddingService:
+    """One extractor at a time, like embed_all (services/feature_embedding.py:251-316)."""
+
+    def __init__(self, extractor):
+        self.extractor = extractor
+
+    def embed_features(self, result: ExtractionResult, *, wsi) -> ExtractionResult:
+        name = self.extractor.name
+        if result.num_patches == 0:
+            result.features[name] = np.empty((0, self.extractor.embedding_dim), dtype=np.float32)
+        elif hasattr(wsi, "device_image") and result.coords_device is not None:
+            feats = self.extractor.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, result.coords_device.contiguous(),
+                                                read_size=int(result.coords[0, 2]))
+            result.features[name] = feats.cpu().numpy()
+        else:  # reference-style host reads (feature_embedding.py:81-96)
+            patches = [wsi.extract((int(x), int(y)), int(lv), (int(rw), int(rh))) for x, y, rw, rh, lv in result.coords.tolist()]
+            result.features[name] = self.extractor.extract_batch(patches, batch_size=32)
+        result.metadata.setdefault("feature_sets", []).append(name)
+        return result

@@ -121,9 +121,11 @@ int ap_encoder_finalize(ap_encoder* enc);
 int ap_encoder_embedding_dim(const ap_encoder* enc);
 /* Device-resident fast path: patches are cut straight out of the level-0 slide in HBM at
  * coords_dev rows (x, y, read_w, read_h, level) [int32, n x 5]; features (n x D fp32) to
- * out_features_dev.  Asynchronous on `stream`.  read_w/read_h must equal input_patch. */
+ * out_features_dev.  Asynchronous on `stream`.  read_size = the rows' read_w = read_h: input_patch (no resize) or
+ * 2 * input_patch (the reference's cv2.resize to patch size, feature_embedding.py:93-95, whose exact-2x uint8 path
+ * is the 2x2 box mean (a+b+c+d+2)>>2); other ratios -> AP_EINVAL (not implemented). */
 int ap_encoder_embed_coords(ap_encoder* enc, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
-                            const int32_t* coords_dev, int64_t n, float* out_features_dev, void* stream);
+                            const int32_t* coords_dev, int64_t n, int read_size, float* out_features_dev, void* stream);
 /* extract_batch-compatible path: n HOST patches (each input_patch x input_patch x 3 uint8,
  * contiguous) given by pointer; features (n x D fp32) to HOST.  Includes H2D / D2H; synchronous. */
 int ap_encoder_embed_patches_host(ap_encoder* enc, const uint8_t* const* patches_host, int64_t n,

@@ -111,3 +111,45 @@ def test_cls_only_last_layer_and_attention_flavours_agree():
     for f in (base, full, full_mma):
         assert _rel(f, want).max() < REL_TOL
     ext.cleanup()
+
+
+def test_vit_l_16_matches_oracle():
+    """Same kernels, larger shape (24 layers, 1024 hidden, 16 heads, mlp 4096): the reference's `vit_l_16` entry."""
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+
+    sd = vit_state_dict("vit_l_16", seed=7)
+    patches = feature_patches()[:3]
+    want = ov.extract_features(patches, sd, "vit_l_16")
+    ext = B200FeatureExtractor("vit_l_16", sd, max_batch=32)
+    got = ext.extract_batch(patches)
+    assert got.shape == (3, 1024)
+    rel = _rel(got, want)
+    print("vit_l_16 rel err per row:", rel)
+    assert rel.max() < REL_TOL, rel
+    ext.cleanup()
+
+
+def test_mag40_read_2x_box_resize_matches_oracle():
+    """a11 with read size = 2 x patch size (40x slide, 20x patches): coords rows carry read_w = 512; the reference reads
+    512 x 512 and cv2.resize()s to 256 (feature_embedding.py:88-95).  Oracle: cv2 itself + the fp32 ViT."""
+    import cv2
+
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec, render_region_host
+
+    sd = vit_state_dict("vit_test_tiny", seed=9)
+    ext = B200FeatureExtractor("vit_test_tiny", sd, max_batch=8)
+    spec = make_spec(4096, 4096, seed=31, mpp=0.25)
+    wsi = SyntheticWSI(spec)
+    xy = [(0, 0), (1000, 2000), (3700, 3800), (-100, 512), (2048, 1024)]     # incl. overhang (zero padded before the resize)
+    coords = torch.tensor([[x, y, 512, 512, 0] for x, y in xy], dtype=torch.int32, device="cuda")
+    got = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords, read_size=512).cpu().numpy()
+    patches = [cv2.resize(render_region_host(spec, x, y, 512, 512), (256, 256)) for x, y in xy]
+    want = ov.extract_features(patches, sd, "vit_test_tiny")
+    assert _rel(got, want).max() < REL_TOL
+    from atlaspatch_b200._lib import AtlasB200Error
+
+    with pytest.raises(AtlasB200Error):
+        ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords, read_size=384)
+    ext.cleanup()

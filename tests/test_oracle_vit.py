@@ -67,3 +67,15 @@ def test_reference_loop_port_matches_golden(golden_dir):
     model, preprocess = rl.build_vit_b_16(vit_state_dict("vit_b_16", seed=FEATURE_CASE["weight_seed"]))
     got = rl.extract_batch(model, preprocess, feature_patches()[:8], batch_size=8, num_workers=0)
     assert np.allclose(got, gold[:8], rtol=1e-4, atol=1e-5)
+
+
+def test_cv2_exact_2x_resize_is_box_mean():
+    """T9: cv2.resize(patch, (P, P)) on a 2P x 2P uint8 read = (a+b+c+d+2)>>2, what the CUDA preprocess implements."""
+    import cv2
+
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (512, 512, 3), dtype=np.uint8)
+    got = cv2.resize(a, (256, 256))
+    s = a.astype(np.uint32)
+    want = ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    assert np.array_equal(got, want)
