@@ -23,6 +23,7 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    int pdl = 1;                  // programmatic dependent launch for the encoder kernel chain (ap_set_option "pdl")
     int cls_only_last_layer = 1;  // last layer: attention / out_proj / MLP only for the class-token row (ap_set_option)
     int attn_mode = 2;       // 2: tcgen05 attention when 16 <= S_pad <= 256, 1: warp-MMA (mma.sync) kernel
     int attn_variant = 0;    // diagnostics
@@ -69,6 +70,36 @@ int ap_set_error(ap_ctx* ctx, int code, const char* fmt, ...);
     do {                                                                                           \
         if (!(cond)) return ap_set_error((ctx), AP_EINVAL, __VA_ARGS__);                           \
     } while (0)
+
+// Launch with the programmatic-stream-serialization attribute (PDL): every kernel of the encoder chain starts with
+// griddepcontrol.wait, so its prologue (barrier init, TMEM allocation, descriptor prefetch, index math) overlaps the tail
+// of its predecessor.  cluster_x > 1 adds the thread-block-cluster dimension.
+template <typename... KArgs, typename... Args>
+inline cudaError_t ap_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                 bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attrs[n].id = cudaLaunchAttributeClusterDimension;
+        attrs[n].val.clusterDim.x = cluster_x;
+        attrs[n].val.clusterDim.y = 1;
+        attrs[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl) {
+        attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- TMA descriptor helper (host) --------------------------------------------------------------
 // 2-D row-major fp16 matrix [rows, cols] (cols contiguous), box = box_cols x box_rows, 128B swizzle.

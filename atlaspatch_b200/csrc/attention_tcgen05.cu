@@ -83,6 +83,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
 
     if (warp < 4) {
       if (warp == 0 || warp == 3) {
@@ -396,9 +398,11 @@ int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, i
     const int grid = jobs < ctx->sm_count ? jobs : ctx->sm_count;
     ProfScope prof(ctx, stream, AP_K_ATTENTION);
     if (S_pad == 208 && !(ctx->attn_variant & 16))   // 197 tokens (ViT/16 @ 224): register-resident single-pass softmax
-        attention_tc_kernel<13><<<grid, ATC_THREADS, smem, stream>>>(plan->map_q, plan->map_kv, out, B, S, S_pad, heads, ctx->attn_variant);
+        AP_CHECK_CUDA(ctx, ap_launch_pdl(attention_tc_kernel<13>, dim3(grid), dim3(ATC_THREADS), smem, stream, 1, ctx->pdl != 0, plan->map_q,
+                                         plan->map_kv, out, B, S, S_pad, heads, ctx->attn_variant));
     else
-        attention_tc_kernel<0><<<grid, ATC_THREADS, smem, stream>>>(plan->map_q, plan->map_kv, out, B, S, S_pad, heads, ctx->attn_variant);
+        AP_CHECK_CUDA(ctx, ap_launch_pdl(attention_tc_kernel<0>, dim3(grid), dim3(ATC_THREADS), smem, stream, 1, ctx->pdl != 0, plan->map_q,
+                                         plan->map_kv, out, B, S, S_pad, heads, ctx->attn_variant));
     AP_CHECK_LAUNCH(ctx, "attention_tc_kernel");
     return AP_OK;
 }

@@ -68,6 +68,10 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         ctx->attn_mode = value;
         return AP_OK;
     }
+    if (!strcmp(key, "pdl")) {
+        ctx->pdl = value != 0;
+        return AP_OK;
+    }
     if (!strcmp(key, "cls_only_last_layer")) {
         ctx->cls_only_last_layer = value != 0;
         return AP_OK;

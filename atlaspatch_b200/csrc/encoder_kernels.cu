@@ -23,6 +23,8 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
                   const int32_t* __restrict__ coords, int input_patch, int image, __half* __restrict__ out,
                   int64_t out_row_stride, int3 centre, int dup, int read_scale) {
     extern __shared__ uint8_t s_rows[];  // [P][image*3]
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int g = image / P;
     const int b = blockIdx.x / g;
     const int ty = blockIdx.x % g;
@@ -91,6 +93,8 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
 // x[b*tokens + 0, :] = class_token + pos[0, :]
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                 int n_images, int tokens, int D) {
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_images * D) return;
     const int b = i / D, d = i - b * D;
@@ -106,6 +110,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t x_row_stride, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ y16, float* __restrict__ y32, int rows) {
     constexpr int D = VEC * 128;
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -170,6 +176,8 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk16) {  // byte off
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int S_pad, int heads) {
     extern __shared__ __align__(128) uint8_t smem_att[];
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int D = heads * HD;
     const int h = blockIdx.x;
     const int b = blockIdx.y;
@@ -304,6 +312,8 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S
 // =====================================================================================================
 __global__ void __launch_bounds__(384)
 cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int heads) {
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const int D = heads * HD;
@@ -377,6 +387,8 @@ cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
 // dst[b, :] = src[b * row_stride_rows, :]   (fp32 rows of D floats; picks the class-token row of every image)
 __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_rows, int64_t src_row_stride, int D) {
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows * (D / 4)) return;
     const int b = i / (D / 4), c = i - b * (D / 4);
@@ -389,7 +401,7 @@ int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int
     AP_REQUIRE(ctx, S >= 1 && S <= 288 && heads <= 24, "cls attention: S=%d heads=%d unsupported", S, heads);
     if (B == 0) return AP_OK;
     ProfScope prof(ctx, stream, AP_K_ATTENTION);
-    cls_attention_kernel<<<B, 384, 0, stream>>>(qkv, out, S, heads);
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_attention_kernel, dim3(B), dim3(384), 0, stream, 1, ctx->pdl != 0, qkv, out, S, heads));
     AP_CHECK_LAUNCH(ctx, "cls_attention_kernel");
     return AP_OK;
 }
@@ -398,7 +410,8 @@ int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, in
     if (n_rows == 0) return AP_OK;
     const int total = n_rows * (D / 4);
     ProfScope prof(ctx, stream, AP_K_OTHER);
-    gather_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, dst, n_rows, src_row_stride, D);
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(gather_rows_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, 1, ctx->pdl != 0, src, dst, n_rows,
+                                     src_row_stride, D));
     AP_CHECK_LAUNCH(ctx, "gather_rows_kernel");
     return AP_OK;
 }
@@ -414,8 +427,9 @@ int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, i
     const int g = image / patch;
     const size_t smem = static_cast<size_t>(patch) * image * 3;
     ProfScope prof(ctx, stream, AP_K_PREPROCESS);
-    preprocess_kernel<16><<<static_cast<unsigned>(n * g), 256, smem, stream>>>(
-        slide, W, H, pitch, coords, input_patch, image, out, out_row_stride, make_int3(centre[0], centre[1], centre[2]), dup, read_scale);
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(preprocess_kernel<16>, dim3(static_cast<unsigned>(n * g)), dim3(256), smem, stream, 1, ctx->pdl != 0, slide, W,
+                                     H, pitch, coords, input_patch, image, out, out_row_stride, make_int3(centre[0], centre[1], centre[2]), dup,
+                                     read_scale));
     AP_CHECK_LAUNCH(ctx, "preprocess_kernel");
     return AP_OK;
 }
@@ -425,7 +439,8 @@ int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, i
     if (n_images == 0) return AP_OK;
     const int total = n_images * D;
     ProfScope prof(ctx, stream, AP_K_OTHER);
-    cls_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(x, cls, pos, n_images, tokens, D);
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_rows_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, 1, ctx->pdl != 0, x, cls, pos, n_images,
+                                     tokens, D));
     AP_CHECK_LAUNCH(ctx, "cls_rows_kernel");
     return AP_OK;
 }
@@ -439,7 +454,8 @@ int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const fl
     ProfScope prof(ctx, stream, AP_K_LAYERNORM);
 #define AP_LN_CASE(V)                                                                                               \
     case V:                                                                                                         \
-        layernorm_kernel<V><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, y_f16, y_f32, rows);       \
+        AP_CHECK_CUDA(ctx, ap_launch_pdl(layernorm_kernel<V>, dim3(blocks), dim3(256), 0, stream, 1, ctx->pdl != 0, x, x_row_stride, gamma, \
+                                         beta, eps, y_f16, y_f32, rows));                                                  \
         break;
     switch (D / 128) {
         AP_LN_CASE(1) AP_LN_CASE(2) AP_LN_CASE(3) AP_LN_CASE(4) AP_LN_CASE(5) AP_LN_CASE(6) AP_LN_CASE(8) AP_LN_CASE(10)
@@ -462,7 +478,8 @@ int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, 
         attr_set = true;
     }
     ProfScope prof(ctx, stream, AP_K_ATTENTION);
-    attention_kernel<<<dim3(heads, B), ATT_THREADS, smem, stream>>>(qkv, out, S, S_pad, heads);
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(attention_kernel, dim3(heads, B), dim3(ATT_THREADS), smem, stream, 1, ctx->pdl != 0, qkv, out, S, S_pad,
+                                     heads));
     AP_CHECK_LAUNCH(ctx, "attention_kernel");
     return AP_OK;
 }

@@ -258,6 +258,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (CG == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    ptx::pdl_wait();                 // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+    ptx::pdl_launch_dependents();
 
     if (warp == 0) {
         // ================= TMA producer (every CTA loads its own 128 rows of A and BN/CG rows of W) =================
@@ -399,21 +401,10 @@ int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t str
     const int tiles = ((p->M + tile_m - 1) / tile_m) * (p->N / BN);
     const int max_workers = ctx->sm_count / CG;
     const int workers = tiles < max_workers ? tiles : max_workers;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(workers * CG);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = L::DYN_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = CG;
-    attrs[0].val.clusterDim.y = 1;
-    attrs[0].val.clusterDim.z = 1;
-    cfg.attrs = attrs;
-    cfg.numAttrs = 1;
     ProfScope prof(ctx, stream, AP_K_GEMM);
     const CUtensorMap& mw = CG == 2 ? p->map_w_half : p->map_w;
-    AP_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, p->map_a, mw, p->M, p->N, p->K, ep));
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(kern, dim3(workers * CG), dim3(NUM_THREADS), L::DYN_BYTES, stream, CG, ctx->pdl != 0, p->map_a, mw,
+                                     p->M, p->N, p->K, ep));
     AP_CHECK_LAUNCH(ctx, "gemm_tcgen05_kernel");
     return AP_OK;
 }
