@@ -22,6 +22,11 @@ class VitDesc(C.Structure):
                 ("ln_eps", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
 
 
+class Sam2Desc(C.Structure):
+    _fields_ = [("embed_dim", C.c_int), ("blocks_per_stage", C.c_int * 4), ("heads_per_stage", C.c_int * 4),
+                ("window_per_stage", C.c_int * 4), ("n_global", C.c_int), ("global_blocks", C.c_int * 8)]
+
+
 _P = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
 _SIGNATURES = {
@@ -47,6 +52,13 @@ _SIGNATURES = {
     "ap_encoder_embedding_dim": (C.c_int, [_P]),
     "ap_encoder_embed_coords": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int, _P, _P]),
     "ap_encoder_embed_patches_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, _P]),
+    "ap_sam2_create": (C.c_int, [_P, C.POINTER(Sam2Desc), C.POINTER(_P)]),
+    "ap_sam2_destroy": (C.c_int, [_P]),
+    "ap_sam2_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "ap_sam2_finalize": (C.c_int, [_P]),
+    "ap_sam2_forward": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ap_sam2_predict_host": (C.c_int, [_P, _P, _P, _P]),
+    "ap_sam2_debug_copy": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "ap_gemm_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ap_layernorm_f16": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_float, _P, C.c_int, C.c_int, _P]),
     "ap_attention_f16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

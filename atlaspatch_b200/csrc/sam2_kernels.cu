@@ -1,0 +1,397 @@
+// fp32 building blocks of the SAM2 image path (a4): correctness-first SIMT kernels.  The SAM2 forward runs once per slide on a
+// 1024 x 1024 thumbnail (~210 GFLOP for Hiera-T, against ~900 TFLOP for embedding a slide), so round 1 keeps it in exact fp32
+// -- which also makes parity with the fp32 oracle tight -- and leaves the tcgen05 port of its GEMMs / attention to a later round.
+// Layout everywhere: tokens x channels, row-major ("NHWC").
+#include "ap_internal.cuh"
+#include "sam2_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C[M,N] = act(A[M,K] W[N,K]^T + bias[N]) (+ C if accumulate).  64x64 tile, BK = 16, 256 threads, 4x4 micro-tile.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LT = 64, LK = 16;
+__global__ void __launch_bounds__(256)
+sam_linear_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ C,
+                  int ldc, int M, int N, int K, int act, int accumulate) {
+    __shared__ float sA[LK][LT + 4];
+    __shared__ float sW[LK][LT + 4];
+    const int m0 = blockIdx.y * LT, n0 = blockIdx.x * LT;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += LK) {
+        for (int i = threadIdx.x; i < LT * LK; i += 256) {
+            const int r = i / LK, c = i - r * LK;
+            const int k = k0 + c;
+            sA[c][r] = (m0 + r < M && k < K) ? A[static_cast<int64_t>(m0 + r) * lda + k] : 0.f;
+            sW[c][r] = (n0 + r < N && k < K) ? W[static_cast<int64_t>(n0 + r) * K + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; b[i] = sW[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            if (act == SAM_ACT_GELU) v = gelu_exact(v);
+            else if (act == SAM_ACT_RELU) v = fmaxf(v, 0.f);
+            float* dst = C + static_cast<int64_t>(m) * ldc + n;
+            *dst = accumulate ? *dst + v : v;
+        }
+    }
+}
+
+// LayerNorm over the last dim (any D), one warp per row, optional GELU afterwards.
+__global__ void __launch_bounds__(256)
+sam_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ y, int rows,
+                     int D, float eps, int act) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + static_cast<int64_t>(row) * D;
+    float s = 0.f;
+    for (int i = lane; i < D; i += 32) s += xr[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / D;
+    float q = 0.f;
+    for (int i = lane; i < D; i += 32) { const float d = xr[i] - mean; q += d * d; }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / D + eps);
+    float* yr = y + static_cast<int64_t>(row) * D;
+    for (int i = lane; i < D; i += 32) {
+        float v = (xr[i] - mean) * rstd * g[i] + b[i];
+        if (act == SAM_ACT_GELU) v = gelu_exact(v);
+        yr[i] = v;
+    }
+}
+
+// 7x7 stride-4 pad-3 patch embedding on a uint8 HWC image with the ImageNet normalisation applied on the fly, + positional
+// embedding.  One thread per (output pixel, output channel).
+__global__ void __launch_bounds__(256)
+sam_patch_embed_kernel(const uint8_t* __restrict__ img, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ pos, float* __restrict__ out, int C, float3 mean, float3 inv_std) {
+    const int Ho = H / 4, Wo = W / 4;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(Ho) * Wo * C) return;
+    const int c = static_cast<int>(idx % C);
+    const int p = static_cast<int>(idx / C);
+    const int oy = p / Wo, ox = p - oy * Wo;
+    float acc = bias[c];
+    const float mu[3] = {mean.x, mean.y, mean.z}, is[3] = {inv_std.x, inv_std.y, inv_std.z};
+    for (int ky = 0; ky < 7; ++ky) {
+        const int y = oy * 4 - 3 + ky;
+        if (y < 0 || y >= H) continue;
+        for (int kx = 0; kx < 7; ++kx) {
+            const int x = ox * 4 - 3 + kx;
+            if (x < 0 || x >= W) continue;
+            const uint8_t* px = img + (static_cast<int64_t>(y) * W + x) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float v = (static_cast<float>(px[ci]) * (1.0f / 255.0f) - mu[ci]) * is[ci];
+                acc = fmaf(v, w[((c * 3 + ci) * 7 + ky) * 7 + kx], acc);
+            }
+        }
+    }
+    out[idx] = acc + pos[idx];
+}
+
+// [H, W, C] -> windows [nWy * nWx, ws * ws, C], zero padded at the bottom / right (window_partition).
+__global__ void sam_window_gather_kernel(const float* __restrict__ x, float* __restrict__ win, int H, int W, int C, int ws, int nWy, int nWx) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = static_cast<int64_t>(nWy) * nWx * ws * ws * C;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % C);
+    int64_t t = idx / C;
+    const int ix = static_cast<int>(t % ws); t /= ws;
+    const int iy = static_cast<int>(t % ws); t /= ws;
+    const int wx = static_cast<int>(t % nWx);
+    const int wy = static_cast<int>(t / nWx);
+    const int y = wy * ws + iy, xx = wx * ws + ix;
+    win[idx] = (y < H && xx < W) ? x[(static_cast<int64_t>(y) * W + xx) * C + c] : 0.f;
+}
+
+// out[H, W, C] = res[H, W, C] + windows (window_unpartition, padding dropped)
+__global__ void sam_window_scatter_add_kernel(const float* __restrict__ win, const float* __restrict__ res, float* __restrict__ out, int H, int W,
+                                              int C, int ws, int nWx) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(H) * W * C) return;
+    const int c = static_cast<int>(idx % C);
+    const int p = static_cast<int>(idx / C);
+    const int y = p / W, x = p - y * W;
+    const int wy = y / ws, wx = x / ws, iy = y - wy * ws, ix = x - wx * ws;
+    out[idx] = res[idx] + win[((static_cast<int64_t>(wy) * nWx + wx) * ws * ws + iy * ws + ix) * C + c];
+}
+
+// 2x2 max pool over [nB, H, W, (row stride ld)] taking C channels -> [nB, H/2, W/2, C] dense
+__global__ void sam_maxpool2_kernel(const float* __restrict__ x, int ld, float* __restrict__ y, int nB, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(nB) * Ho * Wo * C) return;
+    const int c = static_cast<int>(idx % C);
+    int64_t t = idx / C;
+    const int ox = static_cast<int>(t % Wo); t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    const float* base = x + (static_cast<int64_t>(b) * H * W) * ld + c;
+    const float a0 = base[(static_cast<int64_t>(2 * oy) * W + 2 * ox) * ld], a1 = base[(static_cast<int64_t>(2 * oy) * W + 2 * ox + 1) * ld];
+    const float a2 = base[(static_cast<int64_t>(2 * oy + 1) * W + 2 * ox) * ld], a3 = base[(static_cast<int64_t>(2 * oy + 1) * W + 2 * ox + 1) * ld];
+    y[idx] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention, fp32, any head_dim <= 128, any Lq / Lk: CTA = 64 queries of one (batch, head); keys streamed in tiles of 64 with an
+// online softmax.  q/k/v are addressed as base + (b * L + i) * tok_stride + h * hd.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int AQ = 64, AK = 64;
+__global__ void __launch_bounds__(256)
+sam_attention_kernel(const float* __restrict__ q, int q_stride, const float* __restrict__ k, const float* __restrict__ v, int kv_stride,
+                     float* __restrict__ out, int out_stride, int Lq, int Lk, int heads, int hd, float scale) {
+    extern __shared__ float smf[];
+    const int hdp = hd + 1;
+    float* sQ = smf;                 // [AQ][hdp]
+    float* sK = sQ + AQ * hdp;       // [AK][hdp]
+    float* sV = sK + AK * hdp;       // [AK][hdp]
+    float* sS = sV + AK * hdp;       // [AQ][AK + 1]
+    float* sM = sS + AQ * (AK + 1);  // [AQ] running max
+    float* sL = sM + AQ;             // [AQ] running sum
+    float* sAl = sL + AQ;            // [AQ] rescale factor of this tile
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
+    const int tid = threadIdx.x;
+    const float* qb = q + static_cast<int64_t>(b) * Lq * q_stride + h * hd;
+    const float* kb = k + static_cast<int64_t>(b) * Lk * kv_stride + h * hd;
+    const float* vb = v + static_cast<int64_t>(b) * Lk * kv_stride + h * hd;
+    for (int i = tid; i < AQ * hd; i += 256) {
+        const int r = i / hd, c = i - r * hd;
+        sQ[r * hdp + c] = (q0 + r < Lq) ? qb[static_cast<int64_t>(q0 + r) * q_stride + c] * scale : 0.f;
+    }
+    if (tid < AQ) { sM[tid] = -INFINITY; sL[tid] = 0.f; }
+    // O accumulators: thread (ty, tx) owns rows ty*4..+3 and columns tx + 16 j  (j < 8 -> hd <= 128)
+    const int ty = tid >> 4, tx = tid & 15;
+    float o[4][8] = {};
+    __syncthreads();
+    for (int k0 = 0; k0 < Lk; k0 += AK) {
+        for (int i = tid; i < AK * hd; i += 256) {
+            const int r = i / hd, c = i - r * hd;
+            const bool ok = k0 + r < Lk;
+            sK[r * hdp + c] = ok ? kb[static_cast<int64_t>(k0 + r) * kv_stride + c] : 0.f;
+            sV[r * hdp + c] = ok ? vb[static_cast<int64_t>(k0 + r) * kv_stride + c] : 0.f;
+        }
+        __syncthreads();
+        {   // S tile: thread owns a 4x4 patch (rows ty*4.., cols tx*4..)
+            float s[4][4] = {};
+            for (int d = 0; d < hd; ++d) {
+                float a[4], bb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = sQ[(ty * 4 + i) * hdp + d]; bb[i] = sK[(tx * 4 + i) * hdp + d]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) s[i][j] = fmaf(a[i], bb[j], s[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sS[(ty * 4 + i) * (AK + 1) + tx * 4 + j] = (k0 + tx * 4 + j < Lk) ? s[i][j] : -INFINITY;
+        }
+        __syncthreads();
+        {   // online softmax: 4 threads per row
+            const int r = tid >> 2, part = tid & 3;
+            float mx = -INFINITY;
+            for (int j = part; j < AK; j += 4) mx = fmaxf(mx, sS[r * (AK + 1) + j]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_old = sM[r];
+            const float m_new = fmaxf(m_old, mx);
+            float sum = 0.f;
+            for (int j = part; j < AK; j += 4) {
+                const float p = __expf(sS[r * (AK + 1) + j] - m_new);
+                sS[r * (AK + 1) + j] = p;
+                sum += p;
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            __syncwarp();
+            if (part == 0) {
+                const float al = __expf(m_old - m_new);   // m_old = -inf on the first tile -> 0
+                sAl[r] = al;
+                sL[r] = sL[r] * al + sum;
+                sM[r] = m_new;
+            }
+        }
+        __syncthreads();
+        {   // O = alpha * O + P V
+            float al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) al[i] = sAl[ty * 4 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[i][j] *= al[i];
+            for (int kk = 0; kk < AK; ++kk) {
+                float p[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) p[i] = sS[(ty * 4 + i) * (AK + 1) + kk];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = tx + 16 * j;
+                    if (c < hd) {
+                        const float vv = sV[kk * hdp + c];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) o[i][j] = fmaf(p[i], vv, o[i][j]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = q0 + ty * 4 + i;
+        if (r >= Lq) continue;
+        const float inv = 1.0f / sL[ty * 4 + i];
+        float* orow = out + (static_cast<int64_t>(b) * Lq + r) * out_stride + h * hd;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = tx + 16 * j;
+            if (c < hd) orow[c] = o[i][j] * inv;
+        }
+    }
+}
+
+// y = a + b (b broadcast over rows when b_rows == 1)
+__global__ void sam_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n, int D, int b_rows) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = a[i] + (b_rows == 1 ? b[i % D] : b[i]);
+}
+
+// dst[2y+dy, 2x+dx, co] = lin[(y*W + x), (dy*2+dx)*Co + co] + skip[...]   (ConvTranspose2d k=2 s=2 as a GEMM + pixel shuffle), optional GELU
+__global__ void sam_pixel_shuffle_add_kernel(const float* __restrict__ lin, const float* __restrict__ skip, float* __restrict__ dst, int H, int W,
+                                             int Co, int act) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(4) * H * W * Co) return;
+    const int co = static_cast<int>(idx % Co);
+    const int p = static_cast<int>(idx / Co);
+    const int oy = p / (2 * W), ox = p - oy * (2 * W);
+    const int y = oy >> 1, dy = oy & 1, x = ox >> 1, dx = ox & 1;
+    float v = lin[(static_cast<int64_t>(y) * W + x) * (4 * Co) + (dy * 2 + dx) * Co + co] + (skip ? skip[idx] : 0.f);
+    if (act == SAM_ACT_GELU) v = gelu_exact(v);
+    dst[idx] = v;
+}
+
+// dst[2y.., 2x.., :] += src[y, x, :]  (nearest x2 top-down path of the FPN)
+__global__ void sam_upsample2_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int C) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(4) * H * W * C) return;
+    const int c = static_cast<int>(idx % C);
+    const int p = static_cast<int>(idx / C);
+    const int oy = p / (2 * W), ox = p - oy * (2 * W);
+    dst[idx] += src[(static_cast<int64_t>(oy >> 1) * W + (ox >> 1)) * C + c];
+}
+
+// bilinear resize (align_corners = False, no antialias) of a single-channel map: torch F.interpolate semantics
+__global__ void sam_bilinear_kernel(const float* __restrict__ src, int Hs, int Ws, float* __restrict__ dst, int Hd, int Wd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Hd * Wd) return;
+    const int oy = idx / Wd, ox = idx - oy * Wd;
+    const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(Hs) / Hd) - 0.5f, 0.f);
+    const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(Ws) / Wd) - 0.5f, 0.f);
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float v = (1.f - ly) * ((1.f - lx) * src[y0 * Ws + x0] + lx * src[y0 * Ws + x1]) + ly * ((1.f - lx) * src[y1 * Ws + x0] + lx * src[y1 * Ws + x1]);
+    dst[idx] = v;
+}
+
+inline unsigned blocks_for(int64_t n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
+
+}  // namespace
+
+#define SAM_LAUNCH_CHECK(ctx, what) AP_CHECK_LAUNCH(ctx, what)
+
+int sam_linear(ap_ctx* ctx, const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, int act,
+               int accumulate, cudaStream_t st) {
+    if (M == 0) return AP_OK;
+    dim3 grid((N + LT - 1) / LT, (M + LT - 1) / LT);
+    sam_linear_kernel<<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K, act, accumulate);
+    SAM_LAUNCH_CHECK(ctx, "sam_linear_kernel");
+    return AP_OK;
+}
+int sam_layernorm(ap_ctx* ctx, const float* x, const float* g, const float* b, float* y, int rows, int D, float eps, int act, cudaStream_t st) {
+    sam_layernorm_kernel<<<blocks_for(static_cast<int64_t>(rows) * 32), 256, 0, st>>>(x, g, b, y, rows, D, eps, act);
+    SAM_LAUNCH_CHECK(ctx, "sam_layernorm_kernel");
+    return AP_OK;
+}
+int sam_patch_embed(ap_ctx* ctx, const uint8_t* img, int H, int W, const float* w, const float* bias, const float* pos, float* out, int C,
+                    const float* mean, const float* stdv, cudaStream_t st) {
+    sam_patch_embed_kernel<<<blocks_for(static_cast<int64_t>(H / 4) * (W / 4) * C), 256, 0, st>>>(
+        img, H, W, w, bias, pos, out, C, make_float3(mean[0], mean[1], mean[2]), make_float3(1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]));
+    SAM_LAUNCH_CHECK(ctx, "sam_patch_embed_kernel");
+    return AP_OK;
+}
+int sam_window_gather(ap_ctx* ctx, const float* x, float* win, int H, int W, int C, int ws, int nWy, int nWx, cudaStream_t st) {
+    sam_window_gather_kernel<<<blocks_for(static_cast<int64_t>(nWy) * nWx * ws * ws * C), 256, 0, st>>>(x, win, H, W, C, ws, nWy, nWx);
+    SAM_LAUNCH_CHECK(ctx, "sam_window_gather_kernel");
+    return AP_OK;
+}
+int sam_window_scatter_add(ap_ctx* ctx, const float* win, const float* res, float* out, int H, int W, int C, int ws, int nWx, cudaStream_t st) {
+    sam_window_scatter_add_kernel<<<blocks_for(static_cast<int64_t>(H) * W * C), 256, 0, st>>>(win, res, out, H, W, C, ws, nWx);
+    SAM_LAUNCH_CHECK(ctx, "sam_window_scatter_add_kernel");
+    return AP_OK;
+}
+int sam_maxpool2(ap_ctx* ctx, const float* x, int ld, float* y, int nB, int H, int W, int C, cudaStream_t st) {
+    sam_maxpool2_kernel<<<blocks_for(static_cast<int64_t>(nB) * (H / 2) * (W / 2) * C), 256, 0, st>>>(x, ld, y, nB, H, W, C);
+    SAM_LAUNCH_CHECK(ctx, "sam_maxpool2_kernel");
+    return AP_OK;
+}
+int sam_attention(ap_ctx* ctx, const float* q, int q_stride, const float* k, const float* v, int kv_stride, float* out, int out_stride, int nB,
+                  int Lq, int Lk, int heads, int hd, float scale, cudaStream_t st) {
+    AP_REQUIRE(ctx, hd >= 1 && hd <= 128, "sam attention: head_dim %d unsupported", hd);
+    const size_t smem = sizeof(float) * (static_cast<size_t>(AQ + 2 * AK) * (hd + 1) + AQ * (AK + 1) + 3 * AQ);
+    static bool attr_set = false;
+    if (!attr_set) {
+        AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(sizeof(float) * ((AQ + 2 * AK) * 129 + AQ * (AK + 1) + 3 * AQ))));
+        attr_set = true;
+    }
+    dim3 grid((Lq + AQ - 1) / AQ, heads, nB);
+    sam_attention_kernel<<<grid, 256, smem, st>>>(q, q_stride, k, v, kv_stride, out, out_stride, Lq, Lk, heads, hd, scale);
+    SAM_LAUNCH_CHECK(ctx, "sam_attention_kernel");
+    return AP_OK;
+}
+int sam_add(ap_ctx* ctx, const float* a, const float* b, float* y, int64_t n, int D, int b_rows, cudaStream_t st) {
+    sam_add_kernel<<<blocks_for(n), 256, 0, st>>>(a, b, y, n, D, b_rows);
+    SAM_LAUNCH_CHECK(ctx, "sam_add_kernel");
+    return AP_OK;
+}
+int sam_pixel_shuffle_add(ap_ctx* ctx, const float* lin, const float* skip, float* dst, int H, int W, int Co, int act, cudaStream_t st) {
+    sam_pixel_shuffle_add_kernel<<<blocks_for(static_cast<int64_t>(4) * H * W * Co), 256, 0, st>>>(lin, skip, dst, H, W, Co, act);
+    SAM_LAUNCH_CHECK(ctx, "sam_pixel_shuffle_add_kernel");
+    return AP_OK;
+}
+int sam_upsample2_add(ap_ctx* ctx, const float* src, float* dst, int H, int W, int C, cudaStream_t st) {
+    sam_upsample2_add_kernel<<<blocks_for(static_cast<int64_t>(4) * H * W * C), 256, 0, st>>>(src, dst, H, W, C);
+    SAM_LAUNCH_CHECK(ctx, "sam_upsample2_add_kernel");
+    return AP_OK;
+}
+int sam_bilinear(ap_ctx* ctx, const float* src, int Hs, int Ws, float* dst, int Hd, int Wd, cudaStream_t st) {
+    sam_bilinear_kernel<<<blocks_for(static_cast<int64_t>(Hd) * Wd), 256, 0, st>>>(src, Hs, Ws, dst, Hd, Wd);
+    SAM_LAUNCH_CHECK(ctx, "sam_bilinear_kernel");
+    return AP_OK;
+}

@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=2032, help="patches per step (b200 arm); 16 forward chunks of 127")
+    ap.add_argument("--chunk", type=int, default=CHUNK, help="patches per forward chunk (workspace size)")
     ap.add_argument("--width", type=int, default=80000)
     ap.add_argument("--height", type=int, default=60000)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -260,7 +261,7 @@ def main_b200(args):
             dist.broadcast(t, src=0)
             out[k] = t.cpu()
         sd = out
-    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=CHUNK, device=local_rank)
+    ext = B200FeatureExtractor("vit_b_16", sd, max_batch=args.chunk, device=local_rank)
     del sd
 
     B = args.batch
@@ -367,7 +368,7 @@ def main_b200(args):
         "dtype": "f16 operands, f32 accumulate/residual/LayerNorm/softmax", "data": "synthetic",
         "config": {"workload": f"single synthetic {args.width}x{args.height} RGB slide per GPU resident in HBM, 256px patches "
                                f"stride 256 ({n_coords} coords on rank 0), ViT-B/16 random-init (seeded)",
-                   "patches_per_step": B, "forward_chunk": CHUNK, "l2": "inputs larger than L2 (each step reads a different "
+                   "patches_per_step": B, "forward_chunk": args.chunk, "l2": "inputs larger than L2 (each step reads a different "
                    f"{B * 150528 / 1e6:.0f} MB of the 14.4 GB slide)", "parallelism": f"slides sharded 1 per GPU x{world}, no steady-state collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * PATCH_BYTES, "d2h_bytes_per_step": n_e2e * 768 * 4,

@@ -131,6 +131,33 @@ int ap_encoder_embed_coords(ap_encoder* enc, const uint8_t* slide_dev, int64_t W
 int ap_encoder_embed_patches_host(ap_encoder* enc, const uint8_t* const* patches_host, int64_t n,
                                   float* out_features_host);
 
+/* ---- a4: SAM2 box-prompted tissue mask on the 1024 x 1024 thumbnail ---------------------------------------------------
+ * Replaces the model calls of _SAM2Predictor.predict_image (atlas_patch/services/segmentation.py:127-136):
+ * SAM2ImagePredictor.set_image + predict(box = whole image, multimask_output = False) -> mask logits.  The caller keeps the
+ * reference's host steps around it (PIL resize to 1024^2, `> mask_threshold`, NEAREST back to the thumbnail).
+ * Hyper-parameters: atlas_patch/configs/sam2.1_hiera_t.yaml (Hiera-T: embed_dim 96, blocks {1,2,7,2}, heads {1,2,4,8},
+ * windows {8,4,14,7}, global attention in blocks {5,7,9}).  Parameter names: transformers' Sam2Model state_dict.  fp32. */
+typedef struct ap_sam2 ap_sam2;
+typedef struct ap_sam2_desc {
+    int embed_dim;
+    int blocks_per_stage[4];
+    int heads_per_stage[4];
+    int window_per_stage[4];
+    int n_global;
+    int global_blocks[8];
+} ap_sam2_desc;
+int ap_sam2_create(ap_ctx* ctx, const ap_sam2_desc* desc, ap_sam2** out);
+int ap_sam2_destroy(ap_sam2* s);
+int ap_sam2_set_tensor(ap_sam2* s, const char* name, const float* data_host, int64_t numel);
+int ap_sam2_finalize(ap_sam2* s);
+/* image_dev: uint8 RGB [1024,1024,3] (device); logits_dev: float [1024,1024]; lowres_dev: float [256,256] or NULL. */
+int ap_sam2_forward(ap_sam2* s, const uint8_t* image_dev, float* logits_dev, float* lowres_dev, void* stream);
+/* Same with host buffers (synchronous). */
+int ap_sam2_predict_host(ap_sam2* s, const uint8_t* image_host, float* logits_host, float* lowres_host);
+/* Parity tests: copy a named intermediate activation ("patch_embed", "blk0".."blk11", "fpn0".."fpn2", "feat_s0", "feat_s1",
+ * "keys", "queries", "upscaled", "low_res") to the host. */
+int ap_sam2_debug_copy(ap_sam2* s, const char* buffer_name, float* host_out, int64_t numel);
+
 /* ---- building-block ops (kernel-level parity tests; also what the encoder is made of) -------- */
 #define AP_EPI_BIAS_F16 0        /* out fp16 = acc + bias                          */
 #define AP_EPI_BIAS_GELU_F16 1   /* out fp16 = gelu_erf(acc + bias)                */

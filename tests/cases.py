@@ -98,3 +98,15 @@ def feature_patches() -> list[np.ndarray]:
         x, y = int(rng.integers(0, spec.width - 256)), int(rng.integers(0, spec.height - 256))
         out.append(render_region_host(spec, x, y, 256, 256))
     return out
+
+
+def sam2_input_image() -> np.ndarray:
+    """The 1024 x 1024 uint8 image the segmentation service would hand to SAM2 for the 8192^2 synthetic slide (seed 0):
+    1.25x thumbnail (512^2, exact area mean) -> PIL BILINEAR to 1024^2 (services/segmentation.py:104-110)."""
+    from PIL import Image
+
+    spec = make_spec(8192, 8192, 0)
+    lvl0 = render_region_host(spec, 0, 0, 8192, 8192)
+    s = lvl0.reshape(512, 16, 512, 16, 3).astype(np.uint32).sum(axis=(1, 3))
+    thumb = np.clip(np.rint(s.astype(np.float32) * np.float32(1 / 256.0)), 0, 255).astype(np.uint8)
+    return np.array(Image.fromarray(thumb).resize((1024, 1024), Image.Resampling.BILINEAR))

@@ -136,6 +136,22 @@ def main() -> None:
     (OUT / "versions.json").write_text(json.dumps(versions, indent=1) + "\n")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--sam2" not in sys.argv:
     os.environ.setdefault("OMP_NUM_THREADS", "8")
     main()
+
+
+def make_sam2_golden() -> None:
+    """a4 has no runnable reference here (no `sam2` package / checkpoint): the golden logits come from transformers' Sam2Model
+    (an independent restatement of the same architecture) with the seeded weights of oracle/sam2_hf.py."""
+    from oracle import sam2_hf
+    from tests.cases import sam2_input_image
+
+    model = sam2_hf.build_model(sam2_hf.sam2_state_dict(0))
+    up, low = sam2_hf.predict_logits(model, sam2_input_image())
+    np.savez_compressed(OUT / "sam2_hiera_t_lowres.npz", low=low.astype(np.float16), positives=np.int64((up > 0).sum()))
+    print("sam2 golden:", low.shape, float(low.std()), int((up > 0).sum()))
+
+
+if __name__ == "__main__" and "--sam2" in sys.argv:
+    make_sam2_golden()
