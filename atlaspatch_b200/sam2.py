@@ -59,3 +59,61 @@ class B200Sam2Predictor:
             self._h = None
 
     __del__ = close
+
+
+HIERA_L = dict(embed_dim=144, blocks=(2, 6, 36, 4), heads=(2, 4, 8, 16), windows=(8, 4, 16, 8), global_blocks=(23, 33, 43))
+
+_UPSTREAM_RULES = [   # (upstream substring, HF substring); applied in order to every key of checkpoint["model"]
+    ("image_encoder.trunk.patch_embed.proj.", "vision_encoder.backbone.patch_embed.projection."),
+    ("image_encoder.trunk.", "vision_encoder.backbone."),
+    ("image_encoder.neck.", "vision_encoder.neck."),
+    (".conv.weight", ".weight"), (".conv.bias", ".bias"),                    # neck.convs.N.conv.* -> neck.convs.N.*
+    (".norm1.", ".layer_norm1."), (".norm2.", ".layer_norm2."), (".norm3.", ".layer_norm3."), (".norm4.", ".layer_norm4."),
+    ("sam_mask_decoder.", "mask_decoder."), ("sam_prompt_encoder.", "prompt_encoder."),
+    (".out_proj.", ".o_proj."), ("norm_final_attn", "layer_norm_final_attn"),
+    ("output_upscaling.0.", "upscale_conv1."), ("output_upscaling.1.", "upscale_layer_norm."), ("output_upscaling.3.", "upscale_conv2."),
+    ("pe_layer.positional_encoding_gaussian_matrix", "shared_embedding.positional_embedding"),
+    ("mask_downscaling.0.", "mask_embed.conv1."), ("mask_downscaling.1.", "mask_embed.layer_norm1."),
+    ("mask_downscaling.3.", "mask_embed.conv2."), ("mask_downscaling.4.", "mask_embed.layer_norm2."),
+    ("mask_downscaling.6.", "mask_embed.conv3."),
+    ("no_mem_embed", "no_memory_embedding"),
+]
+
+
+def convert_upstream_state_dict(model_sd: Mapping[str, object]) -> dict:
+    """facebookresearch/sam2 parameter names (what the reference loads: `torch.load(model.pth)["model"]`,
+    atlas_patch/services/segmentation.py:66-67) -> transformers' Sam2Model names used by this engine.
+
+    NOTE: written from the published module layout; neither the `sam2` package nor a checkpoint is available offline, so this
+    map is exercised only by a round-trip test on synthetic keys.  Memory-attention / memory-encoder tensors (instantiated
+    by the reference but never executed on the image path, configs/sam2.1_hiera_t.yaml:30-86) are dropped.
+    """
+    import numpy as np
+
+    out: dict = {}
+    points: dict[int, object] = {}
+    for key, val in model_sd.items():
+        if key.startswith(("memory_attention.", "memory_encoder.", "obj_ptr", "mask_downsample", "maskmem_tpos_enc",
+                           "no_mem_pos_enc", "no_obj_ptr", "no_obj_embed_spatial")):
+            continue
+        k = key
+        for a, b in _UPSTREAM_RULES:
+            k = k.replace(a, b)
+        if ".mlp.layers." in k or "_head.layers." in k or "hypernetworks_mlps" in k:
+            # MLP(layers=[Linear...]) -> proj_in / layers.{i-1} / proj_out
+            head, idx_rest = k.rsplit(".layers.", 1)
+            idx, rest = idx_rest.split(".", 1)
+            n_layers = 2 if ".mlp" in head and "transformer" in head or ".blocks." in head else 3
+            i = int(idx)
+            k = f"{head}.proj_in.{rest}" if i == 0 else (f"{head}.proj_out.{rest}" if i == n_layers - 1 else f"{head}.layers.{i - 1}.{rest}")
+        if "prompt_encoder.point_embeddings." in k:
+            points[int(k.split("point_embeddings.")[1].split(".")[0])] = val
+            continue
+        out[k] = val
+    if points:
+        to_np = lambda t: t.detach().cpu().float().numpy() if hasattr(t, "detach") else np.asarray(t, np.float32)
+        out["prompt_encoder.point_embed.weight"] = np.concatenate([to_np(points[i]).reshape(1, -1) for i in sorted(points)], axis=0)
+    g = out.get("prompt_encoder.shared_embedding.positional_embedding")
+    if g is not None:
+        out["shared_image_embedding.positional_embedding"] = g
+    return out

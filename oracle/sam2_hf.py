@@ -21,20 +21,29 @@ MEAN = (0.485, 0.456, 0.406)
 STD = (0.229, 0.224, 0.225)
 
 
-def make_config():
-    from transformers import Sam2Config
+def make_config(variant: str = "tiny"):
+    """'tiny' = the model the reference ships (configs/sam2.1_hiera_t.yaml); 'large' = BASELINE.json configs[2] (Hiera-L)."""
+    from transformers import Sam2Config, Sam2HieraDetConfig, Sam2VisionConfig
 
-    cfg = Sam2Config()
+    if variant == "tiny":
+        cfg = Sam2Config()
+    elif variant == "large":
+        bb = Sam2HieraDetConfig(hidden_size=144, num_attention_heads=2, blocks_per_stage=[2, 6, 36, 4],
+                                embed_dim_per_stage=[144, 288, 576, 1152], num_attention_heads_per_stage=[2, 4, 8, 16],
+                                window_size_per_stage=[8, 4, 16, 8], global_attention_blocks=[23, 33, 43])
+        cfg = Sam2Config(vision_config=Sam2VisionConfig(backbone_config=bb, backbone_channel_list=[1152, 576, 288, 144]))
+    else:
+        raise ValueError(variant)
     cfg.mask_decoder_config.dynamic_multimask_via_stability = False
     return cfg
 
 
-def sam2_state_dict(seed: int = 0) -> dict[str, torch.Tensor]:
-    """Seeded random parameters in transformers' Sam2Model (Hiera-T) naming."""
+def sam2_state_dict(seed: int = 0, variant: str = "tiny") -> dict[str, torch.Tensor]:
+    """Seeded random parameters in transformers' Sam2Model naming."""
     from transformers import Sam2Model
 
     with torch.device("meta"):
-        shapes = {k: tuple(v.shape) for k, v in Sam2Model(make_config()).state_dict().items()}
+        shapes = {k: tuple(v.shape) for k, v in Sam2Model(make_config(variant)).state_dict().items()}
     rng = np.random.default_rng(seed)
     sd = {}
     for k, shp in shapes.items():
@@ -58,10 +67,10 @@ def sam2_state_dict(seed: int = 0) -> dict[str, torch.Tensor]:
     return sd
 
 
-def build_model(sd):
+def build_model(sd, variant: str = "tiny"):
     from transformers import Sam2Model
 
-    m = Sam2Model(make_config())
+    m = Sam2Model(make_config(variant))
     m.load_state_dict(sd, strict=True)
     return m.eval()
 

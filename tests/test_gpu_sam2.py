@@ -70,3 +70,22 @@ def test_segmentation_service_end_to_end(predictor):
     kw = dict(level0_wh=(spec.width, spec.height), src_mag=20, target_mag=20, patch_size=256, step_size=256, tissue_thresh=0.01)
     got = extract_coords(mask.data, **kw)
     assert np.array_equal(got, oc.coords_from_mask(mask.data, **kw))
+
+
+def test_hiera_large_matches_live_hf_model():
+    """BASELINE.json configs[2]: SAM2 Hiera-L (embed 144, blocks 2/6/36/4, windows 8/4/16/8, global blocks 23/33/43) on the
+    1024 x 1024 thumbnail, mask IoU against the fp32 restatement."""
+    from atlaspatch_b200.sam2 import HIERA_L, B200Sam2Predictor
+    from oracle import sam2_hf
+
+    sd = sam2_hf.sam2_state_dict(1, "large")
+    model = sam2_hf.build_model(sd, "large")
+    img = sam2_input_image()
+    up_ref, low_ref = sam2_hf.predict_logits(model, img)
+    pred = B200Sam2Predictor(sd, config=HIERA_L)
+    up, low = pred.predict_logits(img, return_lowres=True)
+    pred.close()
+    rel = np.linalg.norm(low - low_ref) / np.linalg.norm(low_ref)
+    print("hiera-L low-res rel-l2", rel, "IoU", _iou(up > 0, up_ref > 0))
+    assert rel < 5e-3
+    assert _iou(up > 0, up_ref > 0) > 0.998
