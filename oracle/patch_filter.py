@@ -1,0 +1,79 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for the --no-fast-mode content filter.
+
+Restates, in numpy integer arithmetic, what the reference does per candidate patch when ``fast_mode`` is off
+(atlas_patch/services/extraction.py:105-119):
+
+    patch = wsi.extract((x, y), lv, (read_w, read_h))              # extraction.py:105
+    patch = cv2.resize(patch, (patch_size, patch_size))            # extraction.py:109-113 (bilinear) when read != patch
+    drop if is_black_patch(patch, rgb_thresh=black_threshold)      # utils/image.py:7-18
+    drop if is_white_patch(patch, sat_thresh=white_threshold)      # utils/image.py:21-41
+
+The OpenCV pieces are restated from its published 8-bit fixed-point definitions and pinned EXHAUSTIVELY (all 2^24 colours)
+against the cv2 build recorded in tests/golden/versions.json by tests/test_oracle_filter.py:
+
+* COLOR_RGB2GRAY (8u):  gray = (9798 R + 19235 G + 3735 B + 2^14) >> 15
+* COLOR_RGB2HSV  (8u):  v = max(R,G,B);  s = ((v - min) * sdiv[v] + 2^11) >> 12,  sdiv[v] = round((255 << 12) / v), sdiv[0] = 0
+* cv2.resize INTER_LINEAR at exactly 2:1 (8u): out = (a + b + c + d + 2) >> 2 over each 2 x 2 block (both taps weigh 1024/2048;
+  the vertical pass's ((b*(S>>4))>>16 ... +2)>>2 collapses to this)
+
+Pinned against the reference itself by tests/golden/filter_*.npz (make_golden.py --filter runs the reference's
+_iter_patch_entries with fast_mode=False on the synthetic slides).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GRAY_R, GRAY_G, GRAY_B, GRAY_SHIFT = 9798, 19235, 3735, 15
+HSV_SHIFT = 12
+SDIV = np.zeros(256, dtype=np.int64)
+SDIV[1:] = np.rint((255 << HSV_SHIFT) / np.arange(1, 256, dtype=np.float64)).astype(np.int64)
+
+
+def rgb_to_gray(rgb: np.ndarray) -> np.ndarray:
+    p = rgb.astype(np.int64)
+    return (p[..., 0] * GRAY_R + p[..., 1] * GRAY_G + p[..., 2] * GRAY_B + (1 << (GRAY_SHIFT - 1))) >> GRAY_SHIFT
+
+
+def rgb_to_sv(rgb: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    p = rgb.astype(np.int64)
+    v = p.max(axis=-1)
+    mn = p.min(axis=-1)
+    s = ((v - mn) * SDIV[v] + (1 << (HSV_SHIFT - 1))) >> HSV_SHIFT
+    return s, v
+
+
+def halve_bilinear(rgb: np.ndarray) -> np.ndarray:
+    a = rgb.astype(np.int64)
+    return ((a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
+
+def patch_counts(patch: np.ndarray, black_thresh: int, white_thresh: int, value_thresh: int = 200) -> tuple[int, int]:
+    """(# pixels with gray < black_thresh, # pixels with s < white_thresh and v >= value_thresh)."""
+    gray = rgb_to_gray(patch)
+    s, v = rgb_to_sv(patch)
+    return int((gray < black_thresh).sum()), int(((s < white_thresh) & (v >= value_thresh)).sum())
+
+
+def keep_patch(patch: np.ndarray, black_thresh: int, white_thresh: int, min_fraction: float = 0.7) -> bool:
+    nb, nw = patch_counts(patch, black_thresh, white_thresh)
+    n = patch.shape[0] * patch.shape[1]
+    # numpy's bool mean is an exact integer sum divided once in float64 (utils/image.py:17,39)
+    return not (nb / n >= float(min_fraction) or nw / n >= float(min_fraction))
+
+
+def filter_rows(read_region, rows: np.ndarray, patch_size: int, black_thresh: int, white_thresh: int,
+                min_fraction: float = 0.7) -> tuple[np.ndarray, np.ndarray]:
+    """rows: int32 (N, 5) candidates (x, y, read_w, read_h, level); read_region(x, y, w, h) -> uint8 (h, w, 3).
+    Returns (kept rows, counts (N, 2))."""
+    keep = np.zeros(len(rows), dtype=bool)
+    counts = np.zeros((len(rows), 2), dtype=np.int32)
+    for i, (x, y, rw, rh, _lv) in enumerate(rows.tolist()):
+        patch = read_region(x, y, rw, rh)
+        if rw != patch_size:
+            if rw != 2 * patch_size:
+                raise ValueError("oracle restates cv2.resize only for the exact 2:1 read")
+            patch = halve_bilinear(patch)
+        counts[i] = patch_counts(patch, black_thresh, white_thresh)
+        n = patch_size * patch_size
+        keep[i] = not (counts[i, 0] / n >= float(min_fraction) or counts[i, 1] / n >= float(min_fraction))
+    return rows[keep], counts

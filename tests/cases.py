@@ -47,6 +47,16 @@ THUMB_CASES = [
     dict(name="2000x3008_mag10", width=2000, height=3008, seed=2, mpp=1.0),   # f = 8
 ]
 
+# --no-fast-mode content filter (services/extraction.py:105-119): geometry from COORD_CASES + thresholds.  The synthetic
+# tissue's gray level straddles 142 (about 70 % of a tissue patch below it) and the background's saturation straddles 6, so
+# the non-default thresholds put hundreds of patches right at the 0.7 decision fraction.
+FILTER_CASES = [
+    dict(name="noisy_default", coords="noisy_10000x7000", black=50, white=15),      # config defaults (core/config.py:69-70)
+    dict(name="truth_b142_w6", coords="c0_8192_p256_s128", black=142, white=6),
+    dict(name="mag40_b142_w6", coords="mag40_8192_p256", black=142, white=6),       # 512 px read -> cv2.resize 2:1
+    dict(name="p224_b143_w5", coords="p224_12000x9008", black=143, white=5),
+]
+
 FEATURE_CASE = dict(weight_seed=1234, slide=dict(width=4096, height=4096, seed=11, mpp=0.5), n=16)
 
 

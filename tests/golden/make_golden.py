@@ -136,7 +136,7 @@ def main() -> None:
     (OUT / "versions.json").write_text(json.dumps(versions, indent=1) + "\n")
 
 
-if __name__ == "__main__" and "--sam2" not in sys.argv:
+if __name__ == "__main__" and "--sam2" not in sys.argv and "--filter" not in sys.argv:
     os.environ.setdefault("OMP_NUM_THREADS", "8")
     main()
 
@@ -155,3 +155,33 @@ def make_sam2_golden() -> None:
 
 if __name__ == "__main__" and "--sam2" in sys.argv:
     make_sam2_golden()
+
+
+def make_filter_golden() -> None:
+    """filter_<case>.npz: rows the reference keeps with fast_mode=False (services/extraction.py:105-119; every candidate is
+    read through IWSI.extract on the host, resized by cv2.resize when read != patch, and tested by utils/image.py)."""
+    from tests.cases import FILTER_CASES
+
+    by_name = {c["name"]: c for c in COORD_CASES}
+    for fc in FILTER_CASES:
+        case = by_name[fc["coords"]]
+        spec = make_spec(case["width"], case["height"], case["seed"], mpp=case["mpp"])
+        wsi = RefSyntheticWSI(spec)
+        mask = build_mask(case, spec)
+        with tempfile.TemporaryDirectory() as td:
+            svc = PatchExtractionService(
+                ExtractionConfig(patch_size=case["patch"], target_magnification=case["target_mag"], step_size=case["step"],
+                                 tissue_threshold=case["tissue_thresh"], fast_mode=False,
+                                 white_threshold=fc["white"], black_threshold=fc["black"]),
+                OutputConfig(output_root=Path(td)),
+            )
+            tissue, holes = svc._prepare_contours(mask, wsi)
+            rows = [e[:5] for e in svc._iter_patch_entries(wsi, tissue, holes, include_patch=False)]
+        rows = np.asarray(rows, dtype=np.int32).reshape(-1, 5)
+        cand = np.load(OUT / f"coords_{case['name']}.npz")["coords"]
+        np.savez_compressed(OUT / f"filter_{fc['name']}.npz", coords=rows)
+        print(f"filter_{fc['name']}: kept {rows.shape[0]} of {cand.shape[0]} candidates")
+
+
+if __name__ == "__main__" and "--filter" in sys.argv:
+    make_filter_golden()
