@@ -45,6 +45,8 @@ _SIGNATURES = {
     "ap_coords_capacity": (C.c_int64, [_P, _P, C.c_int, C.c_int]),
     "ap_extract_coords": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     _P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
+    "ap_filter_patches": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_double, _P, _P, C.POINTER(C.c_int64), _P, _P]),
     "ap_encoder_create": (C.c_int, [_P, C.POINTER(VitDesc), C.POINTER(_P)]),
     "ap_encoder_destroy": (C.c_int, [_P]),
     "ap_encoder_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),

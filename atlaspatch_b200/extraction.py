@@ -134,3 +134,30 @@ def extract_coords(mask: np.ndarray, *, level0_wh: tuple[int, int], src_mag: int
     tissue = scale_contours(tissue_t, sx, sy)
     holes = [scale_contours(hs, sx, sy) for hs in holes_t]
     return extract_coords_from_contours(flatten_contours(tissue, holes), geo, ctx=ctx, return_device=return_device)
+
+
+def filter_patches(slide_dev, W: int, H: int, pitch: int, rows_dev, *, patch_size: int, black_threshold: int = 50,
+                   white_threshold: int = 15, min_fraction: float = 0.7, ctx: Context | None = None, return_counts: bool = False):
+    """The --no-fast-mode content filter (services/extraction.py:105-119, utils/image.py:7-41) on a slide resident in HBM.
+
+    rows_dev: int32 (N, 5) CUDA tensor of candidates from extract_coords_from_contours.  Returns (kept rows as numpy,
+    kept rows as a CUDA tensor[, per-candidate (black, white) pixel counts as numpy])."""
+    import torch
+
+    ctx = ctx or Context.get(torch.cuda.current_device())
+    n = int(rows_dev.shape[0])
+    out_dev = torch.empty((max(n, 1), 5), dtype=torch.int32, device="cuda")
+    out_host = np.empty((max(n, 1), 5), dtype=np.int32)
+    counts = torch.zeros((max(n, 1), 2), dtype=torch.int32, device="cuda") if return_counts else None
+    count = C.c_int64(0)
+    if n:
+        rows_dev = rows_dev.contiguous()
+        read_size = int(rows_dev[0, 2].item())
+        ctx.check(ctx.lib.ap_filter_patches(
+            ctx.handle, C.c_void_p(slide_dev.data_ptr()), W, H, pitch, C.c_void_p(rows_dev.data_ptr()), n, read_size,
+            int(patch_size), int(black_threshold), int(white_threshold), float(min_fraction), C.c_void_p(out_dev.data_ptr()),
+            _ptr(out_host), C.byref(count), C.c_void_p(counts.data_ptr()) if counts is not None else None,
+            C.c_void_p(current_stream_ptr())))
+    k = int(count.value)
+    res = (out_host[:k].copy(), out_dev[:k])
+    return res + (counts[:n].cpu().numpy(),) if return_counts else res

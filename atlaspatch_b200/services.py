@@ -1,8 +1,8 @@
 """Service adapters with the reference's seam-#1 signatures (atlas_patch/services/interfaces.py:12-32).
 
 `B200PatchExtractionService.extract(wsi, mask, *, slide)` replaces PatchExtractionService.extract
-(services/extraction.py:131-197) for the fast-mode coordinate path: same contours / geometry / order, coordinates
-computed by the CUDA kernels.  `B200FeatureEmbeddingService.embed_features(result, *, wsi)` replaces
+(services/extraction.py:131-197) for the coordinate path (fast mode, and the black/white content filter of --no-fast-mode on an HBM-resident slide):
+same contours / geometry / order, coordinates computed by the CUDA kernels.  `B200FeatureEmbeddingService.embed_features(result, *, wsi)` replaces
 PatchFeatureEmbeddingService._embed_with_extractor (services/feature_embedding.py:179-249) with the zero-copy path
 when the slide is resident in HBM.  The H5 container (services/storage.py) is not written by this round's build
 (no h5py / libhdf5 in the image): results are returned in memory and can be saved as .npz.
@@ -15,7 +15,8 @@ from typing import Any
 
 import numpy as np
 
-from atlaspatch_b200.extraction import extract_coords_from_contours, flatten_contours, mask_to_contours, scale_contours
+from atlaspatch_b200.extraction import (extract_coords_from_contours, filter_patches, flatten_contours, mask_to_contours,
+                                        scale_contours)
 from atlaspatch_b200.geometry import prepare_geometry
 
 
@@ -50,6 +51,8 @@ class ExtractionConfig:  # core/config.py:62-89 (fields used on the path; CLI de
     target_magnification: int
     step_size: int | None = None
     tissue_threshold: float = 0.0
+    white_threshold: int = 15
+    black_threshold: int = 50
     fast_mode: bool = True
 
     def validated(self) -> "ExtractionConfig":
@@ -61,8 +64,8 @@ class ExtractionConfig:  # core/config.py:62-89 (fields used on the path; CLI de
             raise ValueError("step_size must be > 0")
         if not (0 <= self.tissue_threshold <= 1):
             raise ValueError("tissue_threshold must be between 0 and 1")
-        if not self.fast_mode:
-            raise NotImplementedError("--no-fast-mode (black/white patch filter) is not built yet (SURVEY.md section 8f rank 2)")
+        if self.white_threshold <= 0 or self.black_threshold <= 0:
+            raise ValueError("white_threshold and black_threshold must be > 0")
         return self
 
 
@@ -85,6 +88,13 @@ class B200PatchExtractionService:
         tissue, holes = self._prepare_contours(np.asarray(mask), wsi)
         geo = self._prepare_geometry(wsi)
         coords, coords_dev = extract_coords_from_contours(flatten_contours(tissue, holes), geo, return_device=True)
+        if not self.cfg.fast_mode and coords.shape[0]:  # services/extraction.py:105-119
+            if not hasattr(wsi, "device_image"):
+                raise RuntimeError("fast_mode=False needs the slide resident in device memory (wsi.device_image); "
+                                   "there is no host fallback")
+            coords, coords_dev = filter_patches(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords_dev,
+                                                patch_size=self.cfg.patch_size, black_threshold=self.cfg.black_threshold,
+                                                white_threshold=self.cfg.white_threshold)
         return ExtractionResult(slide=slide, h5_path=None, num_patches=int(coords.shape[0]), coords=coords,
                                 patch_size_level0=geo.patch_size_level0, coords_device=coords_dev)
 

@@ -89,6 +89,23 @@ int ap_extract_coords(ap_ctx* ctx, const int32_t* contour_xy, const int32_t* con
                       int32_t* out_rows_dev, int32_t* out_rows_host, int64_t capacity,
                       int64_t* out_count, void* stream);
 
+/* ---- a9b: --no-fast-mode content filter -------------------------------------------------------
+ * Replaces the per-candidate read + cv2.resize + is_black_patch / is_white_patch of
+ * PatchExtractionService._iter_patch_entries with fast_mode off (atlas_patch/services/extraction.py:105-119,
+ * atlas_patch/utils/image.py:7-41) for a slide resident in device memory.
+ *   rows_dev      int32 n x 5 candidates (x, y, read_w, read_h, level) from ap_extract_coords (device)
+ *   read_size     level-0 pixels read per candidate; must be patch_size (no resize) or 2 * patch_size (cv2.resize's
+ *                 bilinear 2:1 = rounded 2 x 2 mean); other ratios return AP_EINVAL
+ *   black_thresh  ExtractionConfig.black_threshold (gray < t), white_thresh = ExtractionConfig.white_threshold (s < t and
+ *                 v >= 200), min_fraction = 0.7 in the reference (utils/image.py defaults)
+ * Kept rows are written in input order to out_rows_dev and/or out_rows_host (capacity n rows; either may be NULL);
+ * counts_dev (optional, int32 n x 2) receives the per-candidate (black, white) pixel counts.  Pixels outside the slide
+ * read as 0, like IWSI.extract.  Synchronous on `stream`. */
+int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
+                      const int32_t* rows_dev, int64_t n, int read_size, int patch_size, int black_thresh,
+                      int white_thresh, double min_fraction, int32_t* out_rows_dev, int32_t* out_rows_host,
+                      int64_t* out_count, int32_t* counts_dev, void* stream);
+
 /* ---- a11-a13: patch read -> preprocess -> encoder forward ------------------------------------
  * Replaces PatchFeatureEmbeddingService._iter_patch_entries_coords + PatchDataset/preprocess +
  * PatchFeatureExtractor.extract_batch + the torchvision VisionTransformer forward
