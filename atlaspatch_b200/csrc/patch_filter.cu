@@ -16,123 +16,204 @@
 //                                the saturation/value test is folded into one table: white <=> min >= lo[v].
 //   filter_compact_kernel        one CTA: keep = !(black/N >= f || white/N >= f) in float64 (numpy's bool mean), stable
 //                                ballot/popc compaction of the kept rows.
+#include <algorithm>
+
 #include "ap_internal.cuh"
+#include "ptx.cuh"
 
 namespace {
+using namespace ptx;
 
 constexpr int FILTER_THREADS = 256;
-constexpr int FILTER_BAND = 32;          // output rows per CTA
-constexpr int FILTER_SMEM_BYTES = 24576; // staging buffer
+constexpr int FILTER_WARPS = FILTER_THREADS / 32;
+constexpr int FILTER_CHUNKS = 4;             // bulk-copy pipeline depth: a CTA's band arrives as 4 groups of rows
+constexpr int FILTER_MAX_BAND_ROWS = 64;     // slide rows per CTA (multiple of 8)
+constexpr int FILTER_MAX_SMEM = 100 * 1024;  // staging bytes per CTA (2 CTAs / SM at the largest reads)
 
 struct FilterParams {
     const uint8_t* slide;
     long long W, H, pitch;
     const int32_t* rows;  // n x 5 (x, y, read_w, read_h, level)
     int patch;            // output patch size P
-    int bands;            // ceil(P / FILTER_BAND)
+    int band_rows;        // slide rows staged per CTA (multiple of 4 * SCALE)
+    int bands;            // ceil(read / band_rows)
+    int stride;           // bytes between staged rows (multiple of 16, odd number of 16-byte units)
     int gray_limit;       // black <=> 9798 R + 19235 G + 3735 B + 16384 < gray_limit  (= black_thresh << 15)
     int vec_ok;           // slide base and pitch are 16-byte aligned
     int32_t* counts;      // n x 2, zeroed
     uint16_t lo[256];     // white <=> min(R,G,B) >= lo[max(R,G,B)]   (256 = never)
 };
 
-__device__ __forceinline__ void classify(uint32_t r, uint32_t g, uint32_t b, int gray_limit, const uint16_t* lo, int& nb, int& nw) {
-    const int y = (int)(r * 9798u + g * 19235u + b * 3735u + 16384u);
-    nb += (y < gray_limit);
-    const uint32_t v = max(max(r, g), b), mn = min(min(r, g), b);
-    nw += (mn >= lo[v]);
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 9798 = 38 * 256 + 70, 19235 = 75 * 256 + 35, 3735 = 14 * 256 + 151: the gray sum of a packed pixel word [R G B x] is two
+// byte dot products, no channel extraction
+constexpr uint32_t GRAY_LO = 70u | (35u << 8) | (151u << 16), GRAY_HI = 38u | (75u << 8) | (14u << 16);
+
+// Both tests are accumulated as sign bits: black <=> y - limit < 0 (the limit rides in the dot product's addend),
+// white <=> (lo[v] - 1) - min < 0.
+__device__ __forceinline__ void classify_word(uint32_t pix, uint32_t gray_bias, const int* lo_m1, uint32_t& nb, uint32_t& nw) {
+    const uint32_t y = __dp4a(pix, GRAY_HI, 0u) * 256u + __dp4a(pix, GRAY_LO, gray_bias);  // (gray sum + 2^14) - limit
+    nb += y >> 31;
+    const uint32_t r = pix & 255u, g = __byte_perm(pix, 0u, 0x4441u), b = __byte_perm(pix, 0u, 0x4442u);
+    const uint32_t v = __vimax3_u32(r, g, b), mn = __vimin3_u32(r, g, b);
+    int d;  // opaque subtraction: keeps the sign-bit accumulation (IADD + LEA.HI) instead of a compare + select + add
+    asm("sub.s32 %0, %1, %2;" : "=r"(d) : "r"(lo_m1[v]), "r"((int)mn));
+    nw += (uint32_t)d >> 31;
+}
+
+// Same test with the table addressed through a hoisted shared-window address (interior fast path).
+__device__ __forceinline__ void classify_fast(uint32_t pix, uint32_t gray_bias, uint32_t lo_addr, uint32_t& nb, uint32_t& nw) {
+    const uint32_t y = __dp4a(pix, GRAY_HI, 0u) * 256u + __dp4a(pix, GRAY_LO, gray_bias);
+    nb += y >> 31;
+    const uint32_t r = pix & 255u, g = __byte_perm(pix, 0u, 0x4441u), b = __byte_perm(pix, 0u, 0x4442u);
+    const uint32_t v = __vimax3_u32(r, g, b), mn = __vimin3_u32(r, g, b);
+    int t, d;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(lo_addr + v * 4u));
+    asm("sub.s32 %0, %1, %2;" : "=r"(d) : "r"(t), "r"((int)mn));
+    nw += (uint32_t)d >> 31;
 }
 
 template <int SCALE>
 __global__ void __launch_bounds__(FILTER_THREADS)
 filter_count_kernel(const __grid_constant__ FilterParams p) {
-    extern __shared__ __align__(16) uint8_t stage[];
-    __shared__ uint16_t lo_s[256];
+    extern __shared__ __align__(128) uint8_t stage[];
+    __shared__ __align__(8) uint64_t bars[FILTER_CHUNKS];
+    __shared__ int lo_s[256];  // lo[v] - 1
     __shared__ int tot[2];
-    const int tid = threadIdx.x;
-    lo_s[tid & 255] = p.lo[tid & 255];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    lo_s[tid & 255] = (int)p.lo[tid & 255] - 1;
+    const uint32_t gray_bias = 16384u - (uint32_t)p.gray_limit;
     if (tid < 2) tot[tid] = 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < FILTER_CHUNKS; ++c) mbar_init(&bars[c], 1);
+        fence_barrier_init();
+    }
 
     const long long cand = blockIdx.x / p.bands;
     const int band = blockIdx.x % p.bands;
     const int32_t* row = p.rows + cand * 5;
     const long long x = row[0], y = row[1];
-    const int P = p.patch, read = P * SCALE;
-    const int out_r0 = band * FILTER_BAND, out_r1 = min(P, out_r0 + FILTER_BAND);
+    const int P = p.patch, read = P * SCALE, stride = p.stride;
+    const int in_r0 = band * p.band_rows, in_r1 = min(read, in_r0 + p.band_rows);  // slide rows of this CTA, patch-relative
+    const int chunk_rows = p.band_rows / FILTER_CHUNKS;
 
     // bytes of one slide row this patch touches, clipped to the slide; staged from the 16-byte boundary below it
-    const long long sb = x * 3;
-    const long long eb = min((x + read), p.W) * 3;
-    const int mis = p.vec_ok ? (int)(sb & 15) : 0;
-    const int row_bytes = (int)(eb - sb);                 // > 0: candidates start inside the slide
-    const int stride = ((mis + read * 3 + 15) & ~15) + 16;  // +16: odd number of 16-byte units -> rows spread over the banks
     const bool inside = x >= 0 && y >= 0 && x < p.W;  // extraction never emits anything else; such a patch reads as all zero
-    const int valid_w = inside ? (int)(min((long long)read, p.W - x)) : 0;
-    const int rows_per_chunk = max(SCALE, (FILTER_SMEM_BYTES / stride) / SCALE * SCALE);
+    const long long sb = x * 3;
+    const int row_bytes = inside ? (int)((min(x + read, p.W) - x) * 3) : 0;
+    const int mis = p.vec_ok ? (int)(sb & 15) : 0;
+    const int valid_w = row_bytes / 3;
+    const uint32_t copy_bytes = (uint32_t)((mis + row_bytes + 15) & ~15);
+    const bool bulk = inside && p.vec_ok;
+    const bool interior = bulk && x + read <= p.W && y + in_r1 <= p.H && (P & 3) == 0;
+    __syncthreads();
 
-    int nb = 0, nw = 0;
-    for (int ir0 = out_r0 * SCALE; ir0 < out_r1 * SCALE; ir0 += rows_per_chunk) {
-        const int nrows = min(rows_per_chunk, out_r1 * SCALE - ir0);
-        __syncthreads();
-        if (!inside) {
-        } else if (p.vec_ok) {
-            const int units = (mis + row_bytes + 15) >> 4;
-            for (int i = tid; i < nrows * units; i += FILTER_THREADS) {
-                const int r = i / units, u = i - r * units;
-                const long long gy = y + ir0 + r;
-                uint4 val = make_uint4(0, 0, 0, 0);
-                if (gy < p.H) val = __ldg(reinterpret_cast<const uint4*>(p.slide + gy * p.pitch + (sb - mis)) + u);
-                *reinterpret_cast<uint4*>(stage + r * stride + u * 16) = val;
-            }
-        } else {
-            for (int i = tid; i < nrows * row_bytes; i += FILTER_THREADS) {
-                const int r = i / row_bytes, u = i - r * row_bytes;
-                const long long gy = y + ir0 + r;
-                stage[r * stride + u] = gy < p.H ? __ldg(p.slide + gy * p.pitch + sb + u) : (uint8_t)0;
+    // ---- producer: one bulk copy per slide row, one mbarrier per chunk of rows ------------------------------------------
+    if (bulk && warp == 0) {
+#pragma unroll
+        for (int c = 0; c < FILTER_CHUNKS; ++c) {
+            const int r0 = in_r0 + c * chunk_rows, r1 = min(in_r1, r0 + chunk_rows);
+            const int live = (int)max(0ll, min((long long)r1, p.H - y) - r0);  // rows of the chunk that exist in the slide
+            if (live > 0) {
+                if (lane == 0) mbar_arrive_expect_tx(&bars[c], (uint32_t)live * copy_bytes);
+                __syncwarp();
+                for (int r = r0 + lane; r < r0 + live; r += 32)
+                    bulk_copy_g2s(stage + (r - in_r0) * stride, p.slide + (y + r) * p.pitch + (sb - mis), copy_bytes, &bars[c]);
             }
         }
-        __syncthreads();
+    }
 
-        // 4 consecutive output pixels per thread step
-        const int groups = (P + 3) >> 2;
-        const int out_rows = nrows / SCALE;
-        for (int i = tid; i < out_rows * groups; i += FILTER_THREADS) {
-            const int r = i / groups, gq = i - r * groups;
-            const int px0 = gq * 4;
+    uint32_t nb = 0, nw = 0;
+    if (SCALE == 1 && interior && (P & 7) == 0) {
+        // ---- fast path: the band lies inside the slide; 8 pixels (24 bytes) per lane and step, no masks ---------------------
+        const uint32_t lo_addr = smem_u32(lo_s);
+        const int sh = (mis & 3) * 8, groups8 = P >> 3;
+        const uint8_t* base = stage + (mis & ~3);
+        for (int c = 0; c < FILTER_CHUNKS; ++c) {
+            const int r0 = c * chunk_rows, r1 = min(in_r1 - in_r0, r0 + chunk_rows);
+            if (r1 <= r0) break;
+            mbar_wait(&bars[c], 0, 80 + c);
+            for (int r = r0 + warp; r < r1; r += FILTER_WARPS) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(base + r * stride) + lane * 6;
+                for (int g = lane; g < groups8; g += 32, w += 32 * 6) {
+                    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4], a5 = w[5], a6 = w[6];
+                    const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh);
+                    const uint32_t w3 = __funnelshift_r(a3, a4, sh), w4 = __funnelshift_r(a4, a5, sh), w5 = __funnelshift_r(a5, a6, sh);
+                    classify_fast(w0, gray_bias, lo_addr, nb, nw);
+                    classify_fast(__funnelshift_r(w0, w1, 24), gray_bias, lo_addr, nb, nw);
+                    classify_fast(__funnelshift_r(w1, w2, 16), gray_bias, lo_addr, nb, nw);
+                    classify_fast(w2 >> 8, gray_bias, lo_addr, nb, nw);
+                    classify_fast(w3, gray_bias, lo_addr, nb, nw);
+                    classify_fast(__funnelshift_r(w3, w4, 24), gray_bias, lo_addr, nb, nw);
+                    classify_fast(__funnelshift_r(w4, w5, 16), gray_bias, lo_addr, nb, nw);
+                    classify_fast(w5 >> 8, gray_bias, lo_addr, nb, nw);
+                }
+            }
+        }
+    } else
+    for (int c = 0; c < FILTER_CHUNKS; ++c) {
+        const int r0 = in_r0 + c * chunk_rows, r1 = min(in_r1, r0 + chunk_rows);
+        if (r1 <= r0) break;
+        const int live = (int)max(0ll, min((long long)r1, p.H - y) - r0);
+        if (!interior) {
+            // rows below the slide read as zero; a slide without 16-byte alignment is staged with plain loads
+            for (int r = r0 + (bulk ? live : 0) + warp; r < r1; r += FILTER_WARPS) {
+                uint8_t* d = stage + (r - in_r0) * stride + mis;
+                const bool have = inside && y + r < p.H;
+                const uint8_t* src = p.slide + (y + r) * p.pitch + sb;
+                for (int u = lane; u < row_bytes; u += 32) d[u] = have ? __ldg(src + u) : (uint8_t)0;
+            }
+            __syncthreads();
+        }
+        if (bulk && live > 0) mbar_wait(&bars[c], 0, 70 + c);
+
+        const int groups = (P + 3) >> 2;  // 4 consecutive output pixels per thread step
+        for (int orow = r0 / SCALE + warp; orow < r1 / SCALE; orow += FILTER_WARPS) {
+            const uint8_t* srow = stage + (orow * SCALE - in_r0) * stride + mis;
             if (SCALE == 1) {
-                const uint8_t* s = stage + r * stride + mis + px0 * 3;
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
-                const int sh = (int)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
-                const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];
-                const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh);
-                const uint32_t rr[4] = {w0 & 255u, w0 >> 24, (w1 >> 16) & 255u, (w2 >> 8) & 255u};
-                const uint32_t gg[4] = {(w0 >> 8) & 255u, w1 & 255u, w1 >> 24, (w2 >> 16) & 255u};
-                const uint32_t bb[4] = {(w0 >> 16) & 255u, (w1 >> 8) & 255u, w2 & 255u, w2 >> 24};
+                const uint32_t* wrow = reinterpret_cast<const uint32_t*>(srow - (mis & 3));
+                const int sh = (mis & 3) * 8;
+                for (int gq = lane; gq < groups; gq += 32) {
+                    const uint32_t* w = wrow + gq * 3;
+                    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];
+                    const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh);
+                    uint32_t pix[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
+                    if (interior) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int px = px0 + k;
-                    if (px < P) {
-                        const bool in = px < valid_w;
-                        classify(in ? rr[k] : 0u, in ? gg[k] : 0u, in ? bb[k] : 0u, p.gray_limit, lo_s, nb, nw);
+                        for (int k = 0; k < 4; ++k) classify_word(pix[k], gray_bias, lo_s, nb, nw);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int px = gq * 4 + k;
+                            if (px < P) classify_word(px < valid_w ? pix[k] : 0u, gray_bias, lo_s, nb, nw);
+                        }
                     }
                 }
             } else {
-                // 2:1 bilinear = rounded mean of the 2 x 2 block; 4 output pixels need 8 input pixels (24 bytes) of 2 rows
-                const uint8_t* s0 = stage + (r * 2) * stride + mis + px0 * 6;
-                const uint8_t* s1 = s0 + stride;
+                // cv2.resize at 2:1 = rounded mean of each 2 x 2 block; 4 output pixels = 8 slide pixels of 2 rows
+                const uint8_t* s1 = srow + stride;
+                for (int gq = lane; gq < groups; gq += 32) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int px = px0 + k;
-                    if (px < P) {
-                        uint32_t c[3];
+                    for (int k = 0; k < 4; ++k) {
+                        const int px = gq * 4 + k;
+                        if (px < P) {
+                            const bool in0 = px * 2 < valid_w, in1 = px * 2 + 1 < valid_w;
+                            uint32_t pix = 0;
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            const int cx0 = px * 2, cx1 = px * 2 + 1;
-                            const uint32_t a = cx0 < valid_w ? s0[k * 6 + ch] : 0u, b = cx1 < valid_w ? s0[k * 6 + 3 + ch] : 0u;
-                            const uint32_t cc = cx0 < valid_w ? s1[k * 6 + ch] : 0u, d = cx1 < valid_w ? s1[k * 6 + 3 + ch] : 0u;
-                            c[ch] = (a + b + cc + d + 2u) >> 2;
+                            for (int ch = 0; ch < 3; ++ch) {
+                                const int o = px * 6 + ch;
+                                const uint32_t a = in0 ? srow[o] : 0u, b = in1 ? srow[o + 3] : 0u;
+                                const uint32_t cc = in0 ? s1[o] : 0u, d = in1 ? s1[o + 3] : 0u;
+                                pix |= ((a + b + cc + d + 2u) >> 2) << (8 * ch);
+                            }
+                            classify_word(pix, gray_bias, lo_s, nb, nw);
                         }
-                        classify(c[0], c[1], c[2], p.gray_limit, lo_s, nb, nw);
                     }
                 }
             }
@@ -140,15 +221,15 @@ filter_count_kernel(const __grid_constant__ FilterParams p) {
     }
     nb = __reduce_add_sync(0xffffffffu, nb);
     nw = __reduce_add_sync(0xffffffffu, nw);
-    if ((tid & 31) == 0) {
-        atomicAdd(&tot[0], nb);
-        atomicAdd(&tot[1], nw);
+    if (lane == 0) {
+        atomicAdd(&tot[0], (int)nb);
+        atomicAdd(&tot[1], (int)nw);
     }
     __syncthreads();
     if (tid < 2 && tot[tid] != 0) atomicAdd(p.counts + cand * 2 + tid, tot[tid]);
 }
 
-// keep flags + stable compaction, one CTA of 1024 threads
+// keep flags + stable compaction, one CTA of 1024 threads, 4 consecutive candidates per thread and iteration
 __global__ void __launch_bounds__(1024)
 filter_compact_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ counts, long long n, double n_pixels,
                       double min_fraction, int32_t* __restrict__ out_rows, unsigned long long* __restrict__ out_count) {
@@ -157,15 +238,24 @@ filter_compact_kernel(const int32_t* __restrict__ rows, const int32_t* __restric
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) base_s = 0;
     __syncthreads();
-    for (long long i0 = 0; i0 < n; i0 += 1024) {
-        const long long i = i0 + tid;
-        bool keep = false;
-        if (i < n) {
-            const double fb = (double)counts[i * 2] / n_pixels, fw = (double)counts[i * 2 + 1] / n_pixels;
-            keep = !(fb >= min_fraction || fw >= min_fraction);
+    for (long long i0 = 0; i0 < n; i0 += 4096) {
+        const long long i = i0 + tid * 4;
+        unsigned keep = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < n) {
+                const double fb = (double)counts[(i + k) * 2] / n_pixels, fw = (double)counts[(i + k) * 2 + 1] / n_pixels;
+                keep |= (unsigned)(!(fb >= min_fraction || fw >= min_fraction)) << k;
+            }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[wid] = __popc(bal);
+        const int mine = __popc(keep);
+        int incl = mine;  // inclusive warp scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
         __syncthreads();
         int before = 0, total = 0;
         for (int w = 0; w < 32; ++w) {
@@ -174,10 +264,14 @@ filter_compact_kernel(const int32_t* __restrict__ rows, const int32_t* __restric
             total += t;
         }
         const long long base = base_s;
-        if (keep) {
-            const long long o = base + before + __popc(bal & ((1u << lane) - 1u));
+        long long o = base + before + incl - mine;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) out_rows[o * 5 + k] = rows[i * 5 + k];
+        for (int k = 0; k < 4; ++k) {
+            if (keep & (1u << k)) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) out_rows[o * 5 + j] = rows[(i + k) * 5 + j];
+                ++o;
+            }
         }
         __syncthreads();
         if (tid == 0) base_s = base + total;
@@ -202,13 +296,18 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
                "filter_patches: read_size %d must be patch_size %d or exactly twice it (general cv2.resize is not implemented)",
                read_size, patch_size);
     AP_REQUIRE(ctx, pitch >= 3 * W && W > 0 && H > 0, "filter_patches: bad slide geometry");
-    AP_REQUIRE(ctx, read_size * 3 + 48 <= FILTER_SMEM_BYTES / 2, "filter_patches: read_size %d too large for the staging buffer", read_size);
-    AP_REQUIRE(ctx, n * (int64_t)((patch_size + FILTER_BAND - 1) / FILTER_BAND) < (1ll << 31), "filter_patches: too many candidates");
+    const int scale = read_size / patch_size;
+    const int stride = ((15 + read_size * 3 + 15) & ~15) + 16;  // +16 keeps the number of 16-byte units odd: rows spread over the banks
+    int band_rows = std::min(FILTER_MAX_BAND_ROWS, FILTER_MAX_SMEM / stride) & ~7;
+    AP_REQUIRE(ctx, band_rows >= 8, "filter_patches: read_size %d too large for the staging buffer", read_size);
+    while (band_rows > 8 && band_rows - 8 >= read_size) band_rows -= 8;  // small patches: do not stage rows that do not exist
+    const int bands = (read_size + band_rows - 1) / band_rows;
+    AP_REQUIRE(ctx, n * (int64_t)bands < (1ll << 31), "filter_patches: too many candidates");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     FilterParams p{};
     p.slide = slide_dev; p.W = W; p.H = H; p.pitch = pitch; p.rows = rows_dev; p.patch = patch_size;
-    p.bands = (patch_size + FILTER_BAND - 1) / FILTER_BAND;
+    p.band_rows = band_rows; p.bands = bands; p.stride = stride;
     // gray < T  <=>  9798 R + 19235 G + 3735 B + 2^14 < T << 15  (the sum is < 2^23, so clamping T to [0, 256] is exact)
     p.gray_limit = (black_thresh < 0 ? 0 : black_thresh > 256 ? 256 : black_thresh) << 15;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(slide_dev) | (uintptr_t)pitch) & 15) == 0;
@@ -243,8 +342,14 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
     {
         ProfScope prof(ctx, st, AP_K_COORDS);
         const unsigned grid = (unsigned)(n * p.bands);
-        if (read_size == patch_size) filter_count_kernel<1><<<grid, FILTER_THREADS, FILTER_SMEM_BYTES, st>>>(p);
-        else filter_count_kernel<2><<<grid, FILTER_THREADS, FILTER_SMEM_BYTES, st>>>(p);
+        const size_t smem = (size_t)band_rows * stride;
+        if (scale == 1) {
+            AP_TRY(cudaFuncSetAttribute(filter_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_MAX_SMEM));
+            filter_count_kernel<1><<<grid, FILTER_THREADS, smem, st>>>(p);
+        } else {
+            AP_TRY(cudaFuncSetAttribute(filter_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_MAX_SMEM));
+            filter_count_kernel<2><<<grid, FILTER_THREADS, smem, st>>>(p);
+        }
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         AP_TRY(cudaGetLastError());
         filter_compact_kernel<<<1, 1024, 0, st>>>(rows_dev, counts, n, (double)patch_size * (double)patch_size, min_fraction,
