@@ -236,9 +236,23 @@ def main_b200(args):
     t0 = time.perf_counter()
     coords_np, coords_dev = extract_coords(mask, level0_wh=(args.width, args.height), src_mag=20, target_mag=20, patch_size=256,
                                            step_size=256, tissue_thresh=0.0, ctx=ctx, return_device=True)
+    coords_first_ms = 1000 * (time.perf_counter() - t0)  # includes the cv2 import and the CUDA module load
+    t0 = time.perf_counter()
+    extract_coords(mask, level0_wh=(args.width, args.height), src_mag=20, target_mag=20, patch_size=256, step_size=256,
+                   tissue_thresh=0.0, ctx=ctx, return_device=True)
     coords_ms = 1000 * (time.perf_counter() - t0)
     n_coords = int(coords_np.shape[0])
     assert n_coords > 0
+    # --no-fast-mode content filter over every candidate (ap_filter_patches; both kernels timed with CUDA events on their stream)
+    from atlaspatch_b200.extraction import filter_patches
+
+    filter_patches(image, args.width, args.height, wsi.pitch, coords_dev, patch_size=256)  # warm
+    ctx.profile(True, ["coords"])
+    kept_np, _ = filter_patches(image, args.width, args.height, wsi.pitch, coords_dev, patch_size=256)
+    torch.cuda.synchronize()
+    filter_ms = ctx.profile_read()["coords"][0]
+    ctx.profile(False)
+    filter_bytes = n_coords * 256 * 256 * 3
 
     # ---- encoder weights: rank 0 builds the seeded state_dict, NCCL broadcast to the other ranks ----------
     names = vit_state_dict_names(12)
@@ -350,6 +364,11 @@ def main_b200(args):
                         "frac_of_sustained_peak": value / world * MODEL_FLOP_PER_PATCH / 1e12 / peaks["tflops_sustained"]},
         "thumbnail_hbm": {"bound": "hbm", "achieved": thumb_bytes / (thumb_ms / 1000.0) / 1e9, "peak": peaks["hbm_gbs"],
                           "unit": "GB/s", "frac": thumb_bytes / (thumb_ms / 1000.0) / 1e9 / peaks["hbm_gbs"], "ms": thumb_ms},
+        # the filter is bound by the SM's ALU pipe (ncu: 72 % ALU, 74 % issue slots; profiles/r01_ncu_full_filter_count.csv), the
+        # HBM fraction is reported because its algorithmic work is bytes (patch^2 * 3 per candidate, read exactly once)
+        "content_filter_hbm": {"bound": "hbm", "achieved": filter_bytes / (filter_ms / 1000.0) / 1e9, "peak": peaks["hbm_gbs"],
+                               "unit": "GB/s", "frac": filter_bytes / (filter_ms / 1000.0) / 1e9 / peaks["hbm_gbs"], "ms": filter_ms,
+                               "candidates": n_coords, "kept": int(kept_np.shape[0])},
     }
 
     cpu_baseline = None
@@ -377,7 +396,8 @@ def main_b200(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "aux": {"coords": n_coords, "coords_ms_incl_host_contours": coords_ms, "thumbnail_ms": thumb_ms},
+        "aux": {"coords": n_coords, "coords_ms_incl_host_contours": coords_ms, "coords_first_call_ms": coords_first_ms,
+                "thumbnail_ms": thumb_ms, "content_filter_ms": filter_ms},
     }
     print(json.dumps(line))
     if world > 1:
