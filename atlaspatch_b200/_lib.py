@@ -19,7 +19,8 @@ EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32, EPI_BIAS_F32 = 0, 1, 2, 3
 class VitDesc(C.Structure):
     _fields_ = [("image_size", C.c_int), ("patch", C.c_int), ("layers", C.c_int), ("heads", C.c_int),
                 ("hidden", C.c_int), ("mlp", C.c_int), ("input_patch", C.c_int), ("max_batch", C.c_int), ("precise_layers", C.c_int),
-                ("ln_eps", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+                ("ln_eps", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3),
+                ("preprocess", C.c_int), ("resize_to", C.c_int), ("mlp_kind", C.c_int)]
 
 
 class Sam2Desc(C.Structure):
@@ -53,6 +54,7 @@ _SIGNATURES = {
     "ap_encoder_finalize": (C.c_int, [_P]),
     "ap_encoder_embedding_dim": (C.c_int, [_P]),
     "ap_encoder_embed_coords": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int, _P, _P]),
+    "ap_encoder_preprocess": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int, _P, C.POINTER(C.c_int64), _P]),
     "ap_encoder_embed_patches_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, _P]),
     "ap_sam2_create": (C.c_int, [_P, C.POINTER(Sam2Desc), C.POINTER(_P)]),
     "ap_sam2_destroy": (C.c_int, [_P]),

@@ -140,6 +140,13 @@ int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, i
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
                       const int* centre, int dup, int read_scale, cudaStream_t stream);
+// DINOv2 preprocess (transformers BitImageProcessorFast): antialias bicubic resize + centre crop + im2col (preprocess_resize.cu)
+int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, std::vector<int32_t>& tap_min, std::vector<int32_t>& tap_cnt,
+                           std::vector<int16_t>& tap_w, int* max_taps, int* precision);
+int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords, int64_t n,
+                             int input_patch, int image, int patch, const int32_t* tap_min, const int32_t* tap_cnt, const int16_t* tap_w,
+                             int max_taps, int precision, int max_src_rows, __half* out, int64_t out_row_stride, const int* centre,
+                             cudaStream_t stream);
 int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
 int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, int64_t src_row_stride, int D, cudaStream_t stream);
 int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D,

@@ -30,6 +30,11 @@ struct ap_encoder {
     ap_vit_desc d{};
     int tokens = 0;   // patches per image (196)
     int kpe = 0;      // 3 * patch * patch
+    int kpe_pad = 0;  // kpe rounded up to the GEMM's 64-wide K block (588 -> 640 for patch 14); pad columns stay zero
+    // preprocess 1 (BitImageProcessorFast): tap tables of the input_patch -> resize_to antialias bicubic resize
+    int32_t *tap_min = nullptr, *tap_cnt = nullptr;
+    int16_t* tap_w = nullptr;
+    int max_taps = 0, tap_precision = 0, max_src_rows = 0;
     int centre[3] = {0, 0, 0};  // integer pixel centre per channel = round(255 * mean_c)
     int max_batch = 0;
     int precise_layers = 1;
@@ -118,8 +123,14 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     const int D = e->d.hidden, T = e->tokens, T1 = T + 1;
     const int rows = nb * T1;
     int rc;
-    if ((rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
-                                e->kpe, e->centre, 0, read_scale, st)))
+    if (e->d.preprocess == 1) {
+        AP_REQUIRE(ctx, read_scale == 1, "encoder: the 2x read is not implemented for the resizing (DINOv2) preprocess");
+        if ((rc = ap_preprocess_resize_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->tap_min,
+                                           e->tap_cnt, e->tap_w, e->max_taps, e->tap_precision, e->max_src_rows, e->a_pe, e->kpe_pad,
+                                           e->centre, st)))
+            return rc;
+    } else if ((rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
+                                       e->kpe_pad, e->centre, 0, read_scale, st)))
         return rc;
     if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, st))) return rc;
     {
@@ -170,13 +181,19 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
 extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc) {
     if (!ctx || !desc || !out_enc) return AP_EINVAL;
     *out_enc = nullptr;
-    AP_REQUIRE(ctx, desc->patch == 16, "encoder: conv patch %d unsupported in this build (16)", desc->patch);
+    AP_REQUIRE(ctx, desc->preprocess == 0 || desc->preprocess == 1, "encoder: unknown preprocess %d", desc->preprocess);
+    AP_REQUIRE(ctx, desc->mlp_kind == 0 || desc->mlp_kind == 1, "encoder: unknown mlp_kind %d", desc->mlp_kind);
+    AP_REQUIRE(ctx, desc->patch == 16 || (desc->preprocess == 1 && desc->patch >= 4 && desc->patch <= 16),
+               "encoder: conv patch %d unsupported (16 with the crop preprocess, 4..16 with the resizing preprocess)", desc->patch);
+    AP_REQUIRE(ctx, desc->preprocess == 0 || desc->resize_to >= desc->image_size, "encoder: resize_to %d < image_size %d", desc->resize_to,
+               desc->image_size);
+    AP_REQUIRE(ctx, desc->mlp_kind == 0 || (2 * desc->mlp) % 256 == 0, "encoder: SwiGLU needs 2 * mlp %% 256 == 0 (mlp %d)", desc->mlp);
     AP_REQUIRE(ctx, desc->image_size % desc->patch == 0, "encoder: image %d not a multiple of patch %d", desc->image_size, desc->patch);
     AP_REQUIRE(ctx, desc->hidden % desc->heads == 0 && desc->hidden / desc->heads == 64,
                "encoder: head_dim must be 64 (hidden %d, heads %d)", desc->hidden, desc->heads);
     AP_REQUIRE(ctx, desc->hidden % 128 == 0 && desc->mlp % 128 == 0, "encoder: hidden/mlp must be multiples of 128");
-    AP_REQUIRE(ctx, desc->input_patch >= desc->image_size, "encoder: input_patch %d < image_size %d (needs an up-sampling resize)",
-               desc->input_patch, desc->image_size);
+    AP_REQUIRE(ctx, desc->preprocess == 1 || desc->input_patch >= desc->image_size,
+               "encoder: input_patch %d < image_size %d (needs an up-sampling resize)", desc->input_patch, desc->image_size);
     AP_REQUIRE(ctx, desc->layers >= 1, "encoder: layers must be >= 1");
     ap_encoder* e = new ap_encoder();
     e->ctx = ctx;
@@ -184,6 +201,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     const int g = desc->image_size / desc->patch;
     e->tokens = g * g;
     e->kpe = 3 * desc->patch * desc->patch;
+    e->kpe_pad = (e->kpe + 63) / 64 * 64;
     e->max_batch = desc->max_batch > 0 ? desc->max_batch : 127;
     e->precise_layers = desc->precise_layers < 0 ? 1 : (desc->precise_layers > desc->layers ? desc->layers : desc->precise_layers);
     if ((e->tokens + 1) > 272) {
@@ -223,7 +241,8 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     if (!e) return AP_EINVAL;
     ap_ctx* ctx = e->ctx;
     if (e->finalized) return AP_OK;
-    const int D = e->d.hidden, M = e->d.mlp, P = e->d.patch, T = e->tokens, T1 = T + 1, K = e->kpe;
+    const int D = e->d.hidden, M = e->d.mlp, P = e->d.patch, T = e->tokens, T1 = T + 1, K = e->kpe, Kp = e->kpe_pad;
+    const int M1 = e->d.mlp_kind == 1 ? 2 * M : M;  // rows of mlp.0 (SwiGLU: gates and values)
     const int MB = e->max_batch;
     int rc;
 #define AP_GET(var, name, n)                                   \
@@ -241,7 +260,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     {
         AP_GET(w, "conv_proj.weight", (size_t)D * K)
         AP_GET(b, "conv_proj.bias", D)
-        std::vector<float> wcat((size_t)D * 2 * K), bf(D);
+        std::vector<float> wcat((size_t)D * 2 * Kp, 0.0f), bf(D);
         for (int c = 0; c < 3; ++c) e->centre[c] = static_cast<int>(lrint(255.0 * e->d.mean[c]));
         for (int o = 0; o < D; ++o) {
             double acc = (*b)[o];
@@ -252,8 +271,8 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
                     const float v = (*w)[(size_t)o * K + c * P * P + i];
                     const float wf = static_cast<float>(v * sc);
                     const float hi = __half2float(__float2half_rn(wf));
-                    wcat[(size_t)o * 2 * K + c * P * P + i] = hi;
-                    wcat[(size_t)o * 2 * K + K + c * P * P + i] = wf - hi;
+                    wcat[(size_t)o * 2 * Kp + c * P * P + i] = hi;
+                    wcat[(size_t)o * 2 * Kp + Kp + c * P * P + i] = wf - hi;
                     s += v;
                 }
                 acc += s * (e->centre[c] - 255.0 * e->d.mean[c]) / (255.0 * e->d.std[c]);
@@ -281,7 +300,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         AP_GET(ln2g, p + "ln_2.weight", D) AP_GET(ln2b, p + "ln_2.bias", D)
         AP_GET(wqkv, p + "self_attention.in_proj_weight", (size_t)3 * D * D) AP_GET(bqkv, p + "self_attention.in_proj_bias", 3 * D)
         AP_GET(wo, p + "self_attention.out_proj.weight", (size_t)D * D) AP_GET(bo, p + "self_attention.out_proj.bias", D)
-        AP_GET(w1, p + "mlp.0.weight", (size_t)M * D) AP_GET(b1, p + "mlp.0.bias", M)
+        AP_GET(w1, p + "mlp.0.weight", (size_t)M1 * D) AP_GET(b1, p + "mlp.0.bias", M1)
         AP_GET(w2, p + "mlp.3.weight", (size_t)D * M) AP_GET(b2, p + "mlp.3.bias", D)
         if ((rc = upload_f32(e, &L.ln1_g, *ln1g)) || (rc = upload_f32(e, &L.ln1_b, *ln1b)) ||
             (rc = upload_f32(e, &L.ln2_g, *ln2g)) || (rc = upload_f32(e, &L.ln2_b, *ln2b)) ||
@@ -291,7 +310,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         L.split = i < e->precise_layers;
         if (L.split) {
             if ((rc = upload_f16_split(e, &L.w_qkv, wqkv->data(), 3 * D, D)) || (rc = upload_f16_split(e, &L.w_o, wo->data(), D, D)) ||
-                (rc = upload_f16_split(e, &L.w_1, w1->data(), M, D)) || (rc = upload_f16_split(e, &L.w_2, w2->data(), D, M)))
+                (rc = upload_f16_split(e, &L.w_1, w1->data(), M1, D)) || (rc = upload_f16_split(e, &L.w_2, w2->data(), D, M)))
                 return rc;
         } else if ((rc = upload_f16(e, &L.w_qkv, wqkv->data(), wqkv->size())) || (rc = upload_f16(e, &L.w_o, wo->data(), wo->size())) ||
                    (rc = upload_f16(e, &L.w_1, w1->data(), w1->size())) || (rc = upload_f16(e, &L.w_2, w2->data(), w2->size())))
@@ -303,7 +322,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     // ---- workspaces (rows padded to the 128-row GEMM tile so TMA boxes never leave the allocation) ----
     const size_t rows = ((size_t)MB * T1 + 127) / 128 * 128;
     const size_t rows_pe = ((size_t)MB * T + 127) / 128 * 128;
-    if ((rc = dev_alloc(e, (void**)&e->a_pe, rows_pe * K * 2)) || (rc = dev_alloc(e, (void**)&e->x, rows * D * 4)) ||
+    if ((rc = dev_alloc(e, (void**)&e->a_pe, rows_pe * Kp * 2)) || (rc = dev_alloc(e, (void**)&e->x, rows * D * 4)) ||
         (rc = dev_alloc(e, (void**)&e->y1, rows * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2, rows * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->qkv, rows * 3 * D * 2)) || (rc = dev_alloc(e, (void**)&e->hbuf, rows * M * 2)))
         return rc;
@@ -315,7 +334,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     AP_CHECK_CUDA(ctx, cudaMemset(e->yc_ln, 0, rows_c * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->hc, 0, rows_c * M * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->xc, 0, rows_c * D * 4));
-    AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * K * 2));
+    AP_CHECK_CUDA(ctx, cudaMemset(e->a_pe, 0, rows_pe * Kp * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y1, 0, rows * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->y2, 0, rows * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->hbuf, 0, rows * M * 2));
@@ -323,17 +342,18 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     AP_CHECK_CUDA(ctx, cudaMemset(e->x, 0, rows * D * 4));
 
     // ---- GEMM plans (TMA descriptors over the fixed workspaces / weights) ------------------------------
-    if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, 2 * K, AP_EPI_BIAS_F32, K))) return rc;
+    if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, 2 * Kp, AP_EPI_BIAS_F32, Kp))) return rc;
+    const int epi1 = e->d.mlp_kind == 1 ? AP_EPI_BIAS_SWIGLU_F16 : AP_EPI_BIAS_GELU_F16;
     for (auto& L : e->layers) {
         const int s = L.split ? 2 : 1;
         if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, s * D, AP_EPI_BIAS_F16, D)) ||
             (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, s * D, AP_EPI_BIAS_RESID_F32, D)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M, s * D, AP_EPI_BIAS_GELU_F16, D)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M1, s * D, epi1, D)) ||
             (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, s * M, AP_EPI_BIAS_RESID_F32, M)))
             return rc;
         if (&L == &e->layers.back() &&
             ((rc = ap_gemm_plan(ctx, &L.pc_o, e->yc_attn, L.w_o, MB, D, s * D, AP_EPI_BIAS_RESID_F32, D)) ||
-             (rc = ap_gemm_plan(ctx, &L.pc_1, e->yc_ln, L.w_1, MB, M, s * D, AP_EPI_BIAS_GELU_F16, D)) ||
+             (rc = ap_gemm_plan(ctx, &L.pc_1, e->yc_ln, L.w_1, MB, M1, s * D, epi1, D)) ||
              (rc = ap_gemm_plan(ctx, &L.pc_2, e->hc, L.w_2, MB, D, s * M, AP_EPI_BIAS_RESID_F32, M))))
             return rc;
     }
@@ -342,6 +362,25 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         const int S_pad = (T1 + 15) / 16 * 16;
         e->attn_tc = S_pad <= 256;
         if (e->attn_tc && (rc = ap_attention_tc_plan(ctx, &e->p_attn, e->qkv, (int)rows, T1, e->d.heads))) return rc;
+    }
+
+    // ---- tap tables of the resizing preprocess ----------------------------------------------------------------
+    if (e->d.preprocess == 1) {
+        std::vector<int32_t> tmin, tcnt;
+        std::vector<int16_t> tw;
+        if ((rc = ap_build_resize_tables(ctx, e->d.input_patch, e->d.resize_to, e->d.image_size, tmin, tcnt, tw, &e->max_taps, &e->tap_precision)))
+            return rc;
+        for (int tr = 0; tr < e->d.image_size / P; ++tr) {
+            const int last = tr * P + P - 1;
+            const int nr = tmin[last] + tcnt[last] - tmin[tr * P];
+            if (nr > e->max_src_rows) e->max_src_rows = nr;
+        }
+        if ((rc = dev_alloc(e, (void**)&e->tap_min, tmin.size() * 4)) || (rc = dev_alloc(e, (void**)&e->tap_cnt, tcnt.size() * 4)) ||
+            (rc = dev_alloc(e, (void**)&e->tap_w, tw.size() * 2)))
+            return rc;
+        AP_CHECK_CUDA(ctx, cudaMemcpy(e->tap_min, tmin.data(), tmin.size() * 4, cudaMemcpyHostToDevice));
+        AP_CHECK_CUDA(ctx, cudaMemcpy(e->tap_cnt, tcnt.data(), tcnt.size() * 4, cudaMemcpyHostToDevice));
+        AP_CHECK_CUDA(ctx, cudaMemcpy(e->tap_w, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
     }
 
     // ---- host-patch path: double-buffered pinned staging + its own streams -------------------------------
@@ -390,6 +429,31 @@ extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, 
         int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, read_scale, out_features_dev + s * e->d.hidden, st);
         if (rc) return rc;
     }
+    return AP_OK;
+}
+
+// a12 alone (parity tests): the fp16 im2col rows the patch-embedding GEMM consumes, out[n * tokens, kpe_pad] (device).
+extern "C" int ap_encoder_preprocess(ap_encoder* e, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
+                                     const int32_t* coords_dev, int64_t n, int read_size, void* out_dev, int64_t* out_cols, void* stream) {
+    if (!e) return AP_EINVAL;
+    ap_ctx* ctx = e->ctx;
+    if (!e->finalized) return ap_set_error(ctx, AP_ESTATE, "encoder: ap_encoder_finalize has not been called");
+    if (out_cols) *out_cols = e->kpe_pad;
+    AP_REQUIRE(ctx, n >= 0 && n <= e->max_batch, "encoder_preprocess: n=%lld must be in [0, max_batch=%d]", (long long)n, e->max_batch);
+    if (n == 0) return AP_OK;
+    AP_REQUIRE(ctx, slide_dev && coords_dev && out_dev, "encoder_preprocess: NULL pointer");
+    AP_REQUIRE(ctx, read_size == e->d.input_patch || (e->d.preprocess == 0 && read_size == 2 * e->d.input_patch),
+               "encoder_preprocess: read size %d unsupported for patch size %d", read_size, e->d.input_patch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (e->d.preprocess == 1)
+        rc = ap_preprocess_resize_run(ctx, slide_dev, W, H, pitch, coords_dev, n, e->d.input_patch, e->d.image_size, e->d.patch, e->tap_min,
+                                      e->tap_cnt, e->tap_w, e->max_taps, e->tap_precision, e->max_src_rows, e->a_pe, e->kpe_pad, e->centre, st);
+    else
+        rc = ap_preprocess_run(ctx, slide_dev, W, H, pitch, coords_dev, n, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
+                               e->kpe_pad, e->centre, 0, read_size / e->d.input_patch, st);
+    if (rc) return rc;
+    AP_CHECK_CUDA(ctx, cudaMemcpyAsync(out_dev, e->a_pe, (size_t)n * e->tokens * e->kpe_pad * 2, cudaMemcpyDeviceToDevice, st));
     return AP_OK;
 }
 

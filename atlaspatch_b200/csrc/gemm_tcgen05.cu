@@ -196,6 +196,26 @@ __device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint
             make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
     }
 }
+// SwiGLU (Dinov2SwiGLUFFN: hidden = silu(x1) * x2): the chunk's first 16 columns are gates, the last 16 the matching values
+// (weights_in rows are interleaved on the host), so 32 accumulator columns give 16 fp16 outputs = pieces 2c, 2c+1 of the row.
+__device__ __forceinline__ void epilogue_stage_swiglu(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int col0, int lane, int c) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float4 g0 = __ldg(b4 + 2 * j), g1 = __ldg(b4 + 2 * j + 1), v0 = __ldg(b4 + 4 + 2 * j), v1 = __ldg(b4 + 5 + 2 * j);
+        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float vb[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float g = fmaf(__uint_as_float(r[8 * j + k]), ep.alpha, gb[k]);
+            const float v = fmaf(__uint_as_float(r[16 + 8 * j + k]), ep.alpha, vb[k]);
+            h[k] = g * v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * g));  // silu(g) * v
+        }
+        *reinterpret_cast<uint4*>(stg + stg_off(lane, c * 2 + j)) =
+            make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
+    }
+}
 __device__ __forceinline__ void epilogue_flush_f16(uint8_t* stg, const EpiParams& ep, int M, int N, int row_base, int col0, int lane) {
     __syncwarp();
     const int p = lane & 7;
@@ -347,7 +367,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     else ptx::mbar_arrive(&tempty_bar[as]);
                 }
             };
-            if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16) {
+            if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16 || EPI == AP_EPI_BIAS_SWIGLU_F16) {
                 ptx::mbar_wait(&tfull_bar[as], aphase, 4);
                 ptx::tc_fence_after();
                 uint32_t r[2][32];
@@ -358,6 +378,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (c + 1 < NCH) ptx::tmem_ld_32x32(taddr0 + (c + 1) * 32, r[(c + 1) & 1]);  // overlaps the math below
                     else release_tmem();
                     if (ep.debug & 1) continue;
+                    if (EPI == AP_EPI_BIAS_SWIGLU_F16) {
+                        epilogue_stage_swiglu(r[c & 1], stg, ep, col_base + c * 32, lane, c & 3);
+                        if ((c & 3) == 3) epilogue_flush_f16(stg, ep, M, N / 2, row_base, (col_base + (c - 3) * 32) / 2, lane);
+                        continue;
+                    }
                     epilogue_stage_f16<EPI>(r[c & 1], stg, ep, col_base + c * 32, lane, c & 1);
                     if (c & 1) epilogue_flush_f16(stg, ep, M, N, row_base, col_base + (c - 1) * 32, lane);
                 }
@@ -416,6 +441,9 @@ int dispatch_epi(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream
         case AP_EPI_BIAS_GELU_F16: return launch<CG, BN, AP_EPI_BIAS_GELU_F16>(ctx, p, ep, stream);
         case AP_EPI_BIAS_RESID_F32: return launch<CG, BN, AP_EPI_BIAS_RESID_F32>(ctx, p, ep, stream);
         case AP_EPI_BIAS_F32: return launch<CG, BN, AP_EPI_BIAS_F32>(ctx, p, ep, stream);
+        case AP_EPI_BIAS_SWIGLU_F16:
+            if constexpr (BN == 256) return launch<CG, BN, AP_EPI_BIAS_SWIGLU_F16>(ctx, p, ep, stream);
+            break;
     }
     return ap_set_error(ctx, AP_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
 }
@@ -427,7 +455,8 @@ int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int 
     AP_REQUIRE(ctx, M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
     AP_REQUIRE(ctx, K % BK == 0 && Ka % BK == 0 && K % Ka == 0, "gemm: K=%d (A width %d) must be multiples of %d, K %% Ka == 0", K, Ka, BK);
     AP_REQUIRE(ctx, N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
-    AP_REQUIRE(ctx, epilogue >= 0 && epilogue <= 3, "gemm: unknown epilogue %d", epilogue);
+    AP_REQUIRE(ctx, epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
+    AP_REQUIRE(ctx, epilogue != AP_EPI_BIAS_SWIGLU_F16 || N % 256 == 0, "gemm: SwiGLU epilogue needs N %% 256 == 0 (N=%d)", N);
     plan->M = M; plan->N = N; plan->K = K; plan->Ka = Ka; plan->epilogue = epilogue;
     plan->bn = (N % 256 == 0) ? 256 : 128;
     plan->cta_group = (plan->bn == 256 && ctx->gemm_cta_group == 2) ? 2 : 1;

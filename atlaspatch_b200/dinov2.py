@@ -1,0 +1,106 @@
+"""DINOv2 encoders (`dinov2_large`, `dinov2_giant`; reference: atlas_patch/models/patch/dinov2.py) on the B200 engine.
+
+Host-side weight preparation only: transformers' Dinov2Model state_dict (what `AutoModel.from_pretrained` gives the
+reference, dinov2.py:50) is renamed to the engine's tensor names, with
+* query / key / value stacked into one in_proj (one GEMM),
+* LayerScale folded into the rows of attention.output.dense and mlp.fc2 / mlp.weights_out (x + ls * (W y + b) = x + (ls W) y + ls b),
+* the 37 x 37 position grid of the 518 px checkpoints bicubically interpolated to the 16 x 16 grid of 224 px inputs, as
+  Dinov2Embeddings.interpolate_pos_encoding does at run time (torch bicubic, A = -0.75, align_corners False),
+* SwiGLU's weights_in rows interleaved in blocks of 16 (gate block, value block) so that one 32-column accumulator chunk of the
+  GEMM epilogue holds both operands of silu(x1) * x2.
+"""
+from __future__ import annotations
+
+from typing import Mapping
+
+import numpy as np
+
+# name -> (patch, layers, heads, hidden, mlp hidden features, swiglu)
+DINOV2_CONFIGS = {
+    "dinov2_large": (14, 24, 16, 1024, 4096, False),
+    "dinov2_giant": (14, 40, 24, 1536, 4096, True),
+    "dinov2_test_tiny": (14, 2, 4, 256, 1024, False),
+    "dinov2_test_tiny_swiglu": (14, 2, 6, 384, 1024, True),
+}
+SWIGLU_BLOCK = 16
+
+
+def _np(t) -> np.ndarray:
+    return t.detach().to("cpu").float().numpy() if hasattr(t, "detach") else np.asarray(t, dtype=np.float32)
+
+
+def _cubic_coeffs(t: np.ndarray, a: float = -0.75) -> np.ndarray:
+    """torch's get_cubic_upsample_coefficients."""
+    x1, x2 = t + 1.0, 1.0 - t
+    return np.stack([((a * x1 - 5 * a) * x1 + 8 * a) * x1 - 4 * a,
+                     ((a + 2) * t - (a + 3)) * t * t + 1,
+                     ((a + 2) * x2 - (a + 3)) * x2 * x2 + 1,
+                     ((a * (x2 + 1) - 5 * a) * (x2 + 1) + 8 * a) * (x2 + 1) - 4 * a], axis=-1)
+
+
+def _bicubic_matrix(n_in: int, n_out: int) -> np.ndarray:
+    """(n_out, n_in) matrix of torch.nn.functional.interpolate(mode="bicubic", align_corners=False) along one axis."""
+    src = (np.arange(n_out, dtype=np.float64) + 0.5) * (n_in / n_out) - 0.5
+    i0 = np.floor(src)
+    w = _cubic_coeffs(src - i0)
+    m = np.zeros((n_out, n_in), dtype=np.float64)
+    for k in range(4):
+        idx = np.clip(i0.astype(np.int64) - 1 + k, 0, n_in - 1)
+        np.add.at(m, (np.arange(n_out), idx), w[:, k])
+    return m
+
+
+def interpolate_pos_embedding(pos: np.ndarray, grid_out: int) -> np.ndarray:
+    """(1 + g*g, D) -> (1 + grid_out^2, D); identity when the grids match (modeling_dinov2.py interpolate_pos_encoding)."""
+    n = pos.shape[0] - 1
+    g = int(round(n ** 0.5))
+    assert g * g == n, "position embedding is not a square grid"
+    if g == grid_out:
+        return pos.astype(np.float32)
+    m = _bicubic_matrix(g, grid_out)
+    grid = pos[1:].astype(np.float64).reshape(g, g, -1)
+    out = np.einsum("yi,xj,ijd->yxd", m, m, grid)
+    return np.concatenate([pos[:1].astype(np.float32), out.reshape(grid_out * grid_out, -1).astype(np.float32)], axis=0)
+
+
+def swiglu_interleave(hidden_features: int) -> np.ndarray:
+    """Row permutation of weights_in: new row r reads old row perm[r]; blocks of 16 gate rows then their 16 value rows."""
+    assert hidden_features % SWIGLU_BLOCK == 0
+    b = np.arange(hidden_features).reshape(-1, SWIGLU_BLOCK)
+    return np.concatenate([b, b + hidden_features], axis=1).reshape(-1)
+
+
+def convert_dinov2_state_dict(sd: Mapping[str, object], *, layers: int, swiglu: bool, image_size: int = 224,
+                              patch: int = 14) -> dict[str, np.ndarray]:
+    """transformers Dinov2Model names -> engine names (the torchvision layout of encoder.py: vit_state_dict_names)."""
+    sd = {k[len("dinov2."):] if k.startswith("dinov2.") else k: v for k, v in sd.items()}
+    out: dict[str, np.ndarray] = {}
+    out["conv_proj.weight"] = _np(sd["embeddings.patch_embeddings.projection.weight"])
+    out["conv_proj.bias"] = _np(sd["embeddings.patch_embeddings.projection.bias"])
+    out["class_token"] = _np(sd["embeddings.cls_token"]).reshape(1, 1, -1)
+    pos = _np(sd["embeddings.position_embeddings"])
+    out["encoder.pos_embedding"] = interpolate_pos_embedding(pos.reshape(pos.shape[-2], pos.shape[-1]), image_size // patch)[None]
+    out["encoder.ln.weight"] = _np(sd["layernorm.weight"])
+    out["encoder.ln.bias"] = _np(sd["layernorm.bias"])
+    for i in range(layers):
+        s, d = f"encoder.layer.{i}.", f"encoder.layers.encoder_layer_{i}."
+        out[d + "ln_1.weight"], out[d + "ln_1.bias"] = _np(sd[s + "norm1.weight"]), _np(sd[s + "norm1.bias"])
+        out[d + "ln_2.weight"], out[d + "ln_2.bias"] = _np(sd[s + "norm2.weight"]), _np(sd[s + "norm2.bias"])
+        out[d + "self_attention.in_proj_weight"] = np.concatenate(
+            [_np(sd[s + f"attention.attention.{n}.weight"]) for n in ("query", "key", "value")], axis=0)
+        out[d + "self_attention.in_proj_bias"] = np.concatenate(
+            [_np(sd[s + f"attention.attention.{n}.bias"]) for n in ("query", "key", "value")], axis=0)
+        ls1, ls2 = _np(sd[s + "layer_scale1.lambda1"]), _np(sd[s + "layer_scale2.lambda1"])
+        out[d + "self_attention.out_proj.weight"] = _np(sd[s + "attention.output.dense.weight"]) * ls1[:, None]
+        out[d + "self_attention.out_proj.bias"] = _np(sd[s + "attention.output.dense.bias"]) * ls1
+        if swiglu:
+            w_in, b_in = _np(sd[s + "mlp.weights_in.weight"]), _np(sd[s + "mlp.weights_in.bias"])
+            perm = swiglu_interleave(w_in.shape[0] // 2)
+            out[d + "mlp.0.weight"], out[d + "mlp.0.bias"] = np.ascontiguousarray(w_in[perm]), np.ascontiguousarray(b_in[perm])
+            w_out, b_out = _np(sd[s + "mlp.weights_out.weight"]), _np(sd[s + "mlp.weights_out.bias"])
+        else:
+            out[d + "mlp.0.weight"], out[d + "mlp.0.bias"] = _np(sd[s + "mlp.fc1.weight"]), _np(sd[s + "mlp.fc1.bias"])
+            w_out, b_out = _np(sd[s + "mlp.fc2.weight"]), _np(sd[s + "mlp.fc2.bias"])
+        out[d + "mlp.3.weight"] = w_out * ls2[:, None]
+        out[d + "mlp.3.bias"] = b_out * ls2
+    return out

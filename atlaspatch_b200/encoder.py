@@ -13,6 +13,7 @@ from typing import Mapping, Sequence
 import numpy as np
 
 from atlaspatch_b200._lib import Context, VitDesc, current_stream_ptr
+from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, convert_dinov2_state_dict
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -36,15 +37,28 @@ def vit_state_dict_names(layers: int) -> list[str]:
 
 
 class B200FeatureExtractor:
-    """ViT encoder forward on hand-written sm_100a kernels behind the reference's FeatureExtractor interface."""
+    """ViT encoder forward on hand-written sm_100a kernels behind the reference's FeatureExtractor interface.
 
-    def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int = 256, image_size: int = 224,
+    torchvision ViTs (models/patch/vit.py) take a torchvision state_dict and the ImageClassification preset (centre crop);
+    `dinov2_*` (models/patch/dinov2.py) take a transformers Dinov2Model state_dict and the BitImageProcessorFast preprocess
+    (bicubic-antialias resize to 256, centre crop 224)."""
+
+    def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int | None = None, image_size: int = 224,
                  max_batch: int = 127, device: int = 0, config: tuple | None = None, registry_name: str | None = None,
                  precise_layers: int = -1):
-        cfg = config or VIT_CONFIGS.get(name)
-        if cfg is None:
-            raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS)}")
-        patch, layers, heads, hidden, mlp = cfg
+        preprocess, resize_to, mlp_kind = 0, 0, 0
+        if config is None and name in DINOV2_CONFIGS:
+            patch, layers, heads, hidden, mlp, swiglu = DINOV2_CONFIGS[name]
+            state_dict = convert_dinov2_state_dict(state_dict, layers=layers, swiglu=swiglu, image_size=image_size, patch=patch)
+            preprocess, resize_to, mlp_kind = 1, 256, int(swiglu)
+            input_patch = 224 if input_patch is None else input_patch
+        else:
+            cfg = config or VIT_CONFIGS.get(name)
+            if cfg is None:
+                raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS) + sorted(DINOV2_CONFIGS)}")
+            patch, layers, heads, hidden, mlp = cfg
+            input_patch = 256 if input_patch is None else input_patch
+        self._patch, self._grid = int(patch), int(image_size) // int(patch)
         self.name = registry_name or name   # H5 dataset name: features/<name> (services/storage.py:250-337)
         self.embedding_dim = int(hidden)
         self.input_patch = int(input_patch)
@@ -53,7 +67,8 @@ class B200FeatureExtractor:
         lib = self.ctx.lib
         desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
                        input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=1e-6,
-                       mean=(C.c_float * 3)(*IMAGENET_MEAN), std=(C.c_float * 3)(*IMAGENET_STD))
+                       mean=(C.c_float * 3)(*IMAGENET_MEAN), std=(C.c_float * 3)(*IMAGENET_STD), preprocess=preprocess,
+                       resize_to=resize_to, mlp_kind=mlp_kind)
         h = C.c_void_p()
         self.ctx.check(lib.ap_encoder_create(self.ctx.handle, C.byref(desc), C.byref(h)))
         self._h = h
@@ -96,6 +111,25 @@ class B200FeatureExtractor:
             self._h = None
 
     __del__ = cleanup
+
+    def preprocess_pixels(self, image, W: int, H: int, pitch: int, coords_dev, read_size: int | None = None) -> np.ndarray:
+        """a12 alone: the uint8 pixels (n, image, image, 3) the encoder sees after crop / resize, decoded from the im2col rows
+        (parity tests; n <= max_batch)."""
+        import torch
+
+        n = int(coords_dev.shape[0])
+        g, p = self._grid, self._patch
+        kp = (3 * p * p + 63) // 64 * 64
+        buf = torch.empty((max(n, 1) * g * g, kp), dtype=torch.float16, device="cuda")
+        cols = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.ap_encoder_preprocess(
+            self._h, C.c_void_p(image.data_ptr()), W, H, pitch, C.c_void_p(coords_dev.contiguous().data_ptr()), n,
+            int(read_size or self.input_patch), C.c_void_p(buf.data_ptr()), C.byref(cols), C.c_void_p(current_stream_ptr())))
+        assert cols.value == kp
+        a = buf[:n * g * g, :3 * p * p].float().cpu().numpy() * 256.0           # (n g g, 3 p p) = pixel - centre
+        a = a.reshape(n, g, g, 3, p, p).transpose(0, 1, 4, 2, 5, 3).reshape(n, g * p, g * p, 3)
+        centre = np.rint(255.0 * np.asarray(IMAGENET_MEAN)).astype(np.float32)
+        return np.rint(a + centre).astype(np.uint8)
 
     # ---- device-resident fast path -----------------------------------------------------------------
     def embed_coords(self, image, W: int, H: int, pitch: int, coords_dev, out=None, read_size: int | None = None):

@@ -125,6 +125,14 @@ typedef struct ap_vit_desc {
     float ln_eps;     /* 1e-6 */
     float mean[3];    /* ImageNet mean / std of the torchvision preset */
     float std[3];
+    int preprocess;   /* 0: centre crop of the input patch to image_size (torchvision preset whose resize == input_patch);
+                         1: transformers BitImageProcessorFast as configured by the DINOv2 checkpoints
+                            (atlas_patch/models/patch/dinov2.py:20-25,49): uint8 bicubic-antialias resize of the
+                            input_patch^2 patch to resize_to^2, centre crop to image_size, rescale + normalise */
+    int resize_to;    /* 256 (preprocess 1) */
+    int mlp_kind;     /* 0: Linear - GELU - Linear, mlp = hidden features;
+                         1: SwiGLU (Dinov2SwiGLUFFN): "mlp.0" = weights_in with 2 * mlp rows interleaved as AP_EPI_BIAS_SWIGLU_F16
+                            expects, "mlp.3" = weights_out [hidden, mlp] */
 } ap_vit_desc;
 
 int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc);
@@ -143,6 +151,11 @@ int ap_encoder_embedding_dim(const ap_encoder* enc);
  * is the 2x2 box mean (a+b+c+d+2)>>2); other ratios -> AP_EINVAL (not implemented). */
 int ap_encoder_embed_coords(ap_encoder* enc, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
                             const int32_t* coords_dev, int64_t n, int read_size, float* out_features_dev, void* stream);
+/* a12 alone (used by the parity tests): run only the patch read + preprocess of n <= max_batch coordinates and copy the fp16
+ * im2col rows the patch-embedding GEMM consumes to out_dev [n * tokens, *out_cols]: value = (pixel - round(255 mean_c)) / 256 at
+ * column c * patch^2 + ky * patch + kx (exact in fp16), columns >= 3 * patch^2 are zero padding. */
+int ap_encoder_preprocess(ap_encoder* enc, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
+                          const int32_t* coords_dev, int64_t n, int read_size, void* out_dev, int64_t* out_cols, void* stream);
 /* extract_batch-compatible path: n HOST patches (each input_patch x input_patch x 3 uint8,
  * contiguous) given by pointer; features (n x D fp32) to HOST.  Includes H2D / D2H; synchronous. */
 int ap_encoder_embed_patches_host(ap_encoder* enc, const uint8_t* const* patches_host, int64_t n,
@@ -180,6 +193,9 @@ int ap_sam2_debug_copy(ap_sam2* s, const char* buffer_name, float* host_out, int
 #define AP_EPI_BIAS_GELU_F16 1   /* out fp16 = gelu_erf(acc + bias)                */
 #define AP_EPI_BIAS_RESID_F32 2  /* out fp32 = resid + acc + bias (resid may == out) */
 #define AP_EPI_BIAS_F32 3        /* out fp32 = acc + bias                          */
+#define AP_EPI_BIAS_SWIGLU_F16 4 /* out fp16 [M, N/2] = silu(g) * v, (g, v) = acc + bias in 16-column blocks: columns
+                                    32b..32b+15 hold the gates and 32b+16..32b+31 the values of outputs 16b..16b+15
+                                    (Dinov2SwiGLUFFN with weights_in rows interleaved); N % 256 == 0 */
 /* out[M,N] = epilogue(A[M,K] (fp16, row-major) x W[N,K]^T (fp16, row-major)); tcgen05/TMEM/TMA.
  * K % 64 == 0, N % 128 == 0. */
 int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,

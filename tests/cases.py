@@ -60,6 +60,29 @@ FILTER_CASES = [
 FEATURE_CASE = dict(weight_seed=1234, slide=dict(width=4096, height=4096, seed=11, mpp=0.5), n=16)
 
 
+# DINOv2 encoders (BASELINE.json configs[3..4]): patches cut from a synthetic slide at the patch size the config names
+DINOV2_CASES = {
+    "dinov2_large": dict(weight_seed=4321, slide=dict(width=4096, height=4096, seed=12, mpp=0.5), n=8, patch=224),
+    "dinov2_giant": dict(weight_seed=777, slide=dict(width=4096, height=4096, seed=13, mpp=0.5), n=4, patch=512),
+}
+
+
+def dinov2_coords(name: str) -> np.ndarray:
+    """Seeded (n, 5) int32 rows (x, y, patch, patch, 0): tissue, edge and background, one hanging over the slide border."""
+    c = DINOV2_CASES[name]
+    rng = np.random.default_rng(99)
+    P, s = c["patch"], c["slide"]
+    xy = np.stack([rng.integers(0, s["width"] - P, c["n"]), rng.integers(0, s["height"] - P, c["n"])], 1)
+    xy[-1] = (s["width"] - P // 2, s["height"] - P // 3)          # overhang: zeros outside, like IWSI.extract
+    return np.concatenate([xy, np.full((c["n"], 2), P), np.zeros((c["n"], 1))], 1).astype(np.int32)
+
+
+def dinov2_patches(name: str) -> list[np.ndarray]:
+    c = DINOV2_CASES[name]
+    spec = make_spec(c["slide"]["width"], c["slide"]["height"], c["slide"]["seed"], mpp=c["slide"]["mpp"])
+    return [render_region_host(spec, int(x), int(y), c["patch"], c["patch"]) for x, y in dinov2_coords(name)[:, :2]]
+
+
 def _noisy_mask(h: int, w: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(1000 + seed)
     yy, xx = np.mgrid[0:h, 0:w]

@@ -136,7 +136,7 @@ def main() -> None:
     (OUT / "versions.json").write_text(json.dumps(versions, indent=1) + "\n")
 
 
-if __name__ == "__main__" and "--sam2" not in sys.argv and "--filter" not in sys.argv:
+if __name__ == "__main__" and not ({"--sam2", "--filter", "--dinov2"} & set(sys.argv)):
     os.environ.setdefault("OMP_NUM_THREADS", "8")
     main()
 
@@ -185,3 +185,25 @@ def make_filter_golden() -> None:
 
 if __name__ == "__main__" and "--filter" in sys.argv:
     make_filter_golden()
+
+
+def make_dinov2_golden() -> None:
+    """dinov2_<name>.npz: features of transformers' Dinov2Model + BitImageProcessorFast (what the reference's DinoV2Encoder calls,
+    models/patch/dinov2.py:49-62) with the seeded weights of oracle/dinov2_hf.py, plus the uint8 pixels the processor normalises."""
+    from oracle import dinov2_hf
+    from tests.cases import DINOV2_CASES, dinov2_patches
+
+    for name, case in DINOV2_CASES.items():
+        patches = dinov2_patches(name)
+        sd = dinov2_hf.dinov2_state_dict(name, seed=case["weight_seed"])
+        feats = dinov2_hf.extract_features(patches, sd, name, batch_size=4)
+        x = dinov2_hf.preprocess(patches[-2:])
+        mean, std = torch.tensor(dinov2_hf.MEAN).view(1, 3, 1, 1), torch.tensor(dinov2_hf.STD).view(1, 3, 1, 1)
+        pix = torch.round((x * std + mean) * 255.0).to(torch.uint8).permute(0, 2, 3, 1).numpy()
+        np.savez_compressed(OUT / f"{name}.npz", feats=feats.astype(np.float32), pixels=pix)
+        print(name, feats.shape, float(np.abs(feats).mean()), pix.shape)
+
+
+if __name__ == "__main__" and "--dinov2" in sys.argv:
+    os.environ.setdefault("OMP_NUM_THREADS", "8")
+    make_dinov2_golden()
