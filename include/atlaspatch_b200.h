@@ -121,7 +121,7 @@ typedef struct ap_vit_desc {
     int input_patch;  /* edge of the RGB patches fed in (256): centre crop to image_size */
     int max_batch;    /* patches per forward chunk (workspace size); 0 = default 127 */
     int precise_layers; /* leading encoder layers whose GEMM weights are kept as fp16 hi/lo pairs (2 MMAs per weight):
-                           keeps worst-case feature error under 1e-3 (DESIGN.md "precision"); -1 = default (1) */
+                           keeps worst-case feature error under 1e-3 (DESIGN.md "precision"); -1 = default (1; 8 when layers > 32) */
     float ln_eps;     /* 1e-6 */
     float mean[3];    /* ImageNet mean / std of the torchvision preset */
     float std[3];
