@@ -5,7 +5,8 @@
 
 The hook signature is the reference's CustomRegistryHook (atlas_patch/models/patch/custom.py:92-146).  Weights come
 from torchvision exactly as the reference's own `vit_b_16` builder resolves them (models/patch/base.py:126-180); the
-forward runs on the sm_100a kernels.  A CUDA device is mandatory: there is no CPU fallback.
+forward runs on the sm_100a kernels.  `b200_dinov2_large` / `b200_dinov2_giant` load transformers' Dinov2Model like the
+reference's DinoV2Encoder (models/patch/dinov2.py).  A CUDA device is mandatory: there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -28,6 +29,28 @@ def _build(name: str, device) -> B200FeatureExtractor:
     return B200FeatureExtractor(name, model.state_dict(), device=idx, registry_name=f"b200_{name}")
 
 
+_DINOV2 = {"dinov2_large": "facebook/dinov2-large", "dinov2_giant": "facebook/dinov2-giant"}  # models/patch/dinov2.py:12-17
+
+
+def _build_dinov2(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
+    """Weights exactly as the reference's DinoV2Encoder loads them (models/patch/dinov2.py:50); the processor's resize / crop /
+    normalise (dinov2.py:49) runs in the CUDA preprocess kernel.  The engine is built for one input patch size: pass
+    ATLASPATCH_B200_PATCH_SIZE (the --patch-size of the run; default 224)."""
+    import os
+
+    import torch
+    from transformers import AutoModel
+
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("atlaspatch_b200 encoders need a CUDA device (B200); no CPU fallback exists")
+    model = AutoModel.from_pretrained(_DINOV2[name])
+    idx = torch.device(device).index or 0
+    patch = int(patch_size or os.environ.get("ATLASPATCH_B200_PATCH_SIZE", 224))
+    return B200FeatureExtractor(name, model.state_dict(), input_patch=patch, device=idx, registry_name=f"b200_{name}")
+
+
 def register_feature_extractors(registry, device, dtype, num_workers) -> None:
     for name in _TORCHVISION:
         registry.register(f"b200_{name}", lambda n=name: _build(n, device))
+    for name in _DINOV2:
+        registry.register(f"b200_{name}", lambda n=name: _build_dinov2(n, device, None))
