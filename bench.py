@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=96, help="patches timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=int (ap_set_option), for A/B measurements")
     ap.add_argument("--ref-sample", type=int, default=32, help="patches per step of the reference arm")
     return ap.parse_args()
 
@@ -218,6 +219,9 @@ def main_b200(args):
     from atlaspatch_b200.slide import SyntheticWSI
 
     ctx = Context.get(local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     peaks = measured_peaks()
 
     # ---- slide resident in HBM, thumbnail, coords (one slide per rank, seed = rank) ----------------------
