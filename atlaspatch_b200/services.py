@@ -105,13 +105,25 @@ class B200FeatureEmbeddingService:
     def __init__(self, extractor):
         self.extractor = extractor
 
-    def embed_features(self, result: ExtractionResult, *, wsi) -> ExtractionResult:
+    def embed_features(self, result: ExtractionResult, *, wsi, shard_group=None, sharded: bool = False) -> ExtractionResult:
+        """sharded=True (intra-slide mode, BASELINE.json configs[4]): every rank of `shard_group` holds the same slide and
+        coordinate rows, embeds its contiguous row range and all-gathers the (N, D) matrix (sharding.gather_rows)."""
         name = self.extractor.name
         if result.num_patches == 0:
             result.features[name] = np.empty((0, self.extractor.embedding_dim), dtype=np.float32)
         elif hasattr(wsi, "device_image") and result.coords_device is not None:
-            feats = self.extractor.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, result.coords_device.contiguous(),
-                                                read_size=int(result.coords[0, 2]))
+            rows = result.coords_device.contiguous()
+            if sharded:
+                import torch.distributed as dist
+
+                from atlaspatch_b200.sharding import gather_rows, row_range
+
+                b, e = row_range(result.num_patches, dist.get_rank(shard_group), dist.get_world_size(shard_group))
+                local = self.extractor.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows[b:e].contiguous(),
+                                                    read_size=int(result.coords[0, 2]))
+                feats = gather_rows(local, result.num_patches, group=shard_group)
+            else:
+                feats = self.extractor.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows, read_size=int(result.coords[0, 2]))
             result.features[name] = feats.cpu().numpy()
         else:  # reference-style host reads (feature_embedding.py:81-96)
             patches = [wsi.extract((int(x), int(y)), int(lv), (int(rw), int(rh))) for x, y, rw, rh, lv in result.coords.tolist()]

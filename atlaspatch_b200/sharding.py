@@ -37,3 +37,27 @@ def row_range(n_rows: int, rank: int, world_size: int) -> tuple[int, int]:
     base, rem = divmod(int(n_rows), world_size)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def gather_rows(local, n_rows: int, *, group=None):
+    """Intra-slide mode (BASELINE.json configs[4]): every rank holds the feature rows of its `row_range`; one all_gather
+    (NCCL over NVLink for CUDA tensors, gloo for CPU tensors) returns the full (n_rows, D) matrix on every rank, in the reference's
+    row order.  This is the path's only data-path collective: (N, D) fp32 once per slide (100 k x 1536 x 4 B = 614 MB)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    b, e = row_range(n_rows, rank, world)
+    if local.shape[0] != e - b:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} rows, its range [{b}, {e}) has {e - b}")
+    pad = row_range(n_rows, 0, world)[1]                          # rank 0 owns the longest range
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: e - b] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    out = []
+    for r, p in enumerate(parts):
+        rb, re_ = row_range(n_rows, r, world)
+        out.append(p[: re_ - rb])
+    return torch.cat(out)

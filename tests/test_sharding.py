@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from atlaspatch_b200.sharding import assign_slides, row_range
+from atlaspatch_b200.sharding import assign_slides, gather_rows, row_range
 
 
 def test_assign_slides_lpt_covers_everything_once():
@@ -65,6 +65,12 @@ def _worker(rank, world, port, n_rows, out_dir):
     dist.all_gather(parts, buf)
     full = torch.cat([p[: int(c.item())] for p, c in zip(parts, counts)])
     assert torch.equal(full, coords[:, :1].to(torch.float32) * 2.0 + 1.0)
+    # the product function for the same exchange, (N, D) features
+    f2 = torch.stack([coords[b:e, 0].float(), coords[b:e, 1].float() * 0.5, torch.full((e - b,), float(rank))], 1)
+    g2 = gather_rows(f2, n_rows)
+    assert g2.shape == (n_rows, 3) and torch.equal(g2[:, 0], coords[:, 0].float()) and torch.equal(g2[:, 1], coords[:, 1].float() * 0.5)
+    owners = torch.cat([torch.full((row_range(n_rows, r, world)[1] - row_range(n_rows, r, world)[0],), float(r)) for r in range(world)])
+    assert torch.equal(g2[:, 2], owners)
     # timing reduction used by bench.py: max over ranks
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
