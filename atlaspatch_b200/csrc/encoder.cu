@@ -124,7 +124,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     const int rows = nb * T1;
     int rc;
     if (e->d.preprocess == 1) {
-        AP_REQUIRE(ctx, read_scale == 1, "encoder: the 2x read is not implemented for the resizing (DINOv2) preprocess");
+        AP_REQUIRE(ctx, read_scale == 1, "encoder: reads larger than the patch are not implemented for the resizing (DINOv2) preprocess");
         if ((rc = ap_preprocess_resize_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->tap_min,
                                            e->tap_cnt, e->tap_w, e->max_taps, e->tap_precision, e->max_src_rows, e->a_pe, e->kpe_pad,
                                            e->centre, st)))
@@ -422,8 +422,8 @@ extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, 
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, slide_dev && coords_dev && out_features_dev, "embed_coords: NULL pointer");
     AP_REQUIRE(ctx, pitch >= W * 3, "embed_coords: pitch %lld < 3*W", (long long)pitch);
-    AP_REQUIRE(ctx, read_size == e->d.input_patch || read_size == 2 * e->d.input_patch,
-               "embed_coords: read size %d with patch size %d needs a resize that is not implemented (1x and exact 2x only)", read_size,
+    AP_REQUIRE(ctx, read_size >= e->d.input_patch && read_size % e->d.input_patch == 0,
+               "embed_coords: read size %d with patch size %d needs a non-integer resize, which is not implemented", read_size,
                e->d.input_patch);
     const int read_scale = read_size / e->d.input_patch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -445,7 +445,7 @@ extern "C" int ap_encoder_preprocess(ap_encoder* e, const uint8_t* slide_dev, in
     AP_REQUIRE(ctx, n >= 0 && n <= e->max_batch, "encoder_preprocess: n=%lld must be in [0, max_batch=%d]", (long long)n, e->max_batch);
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, slide_dev && coords_dev && out_dev, "encoder_preprocess: NULL pointer");
-    AP_REQUIRE(ctx, read_size == e->d.input_patch || (e->d.preprocess == 0 && read_size == 2 * e->d.input_patch),
+    AP_REQUIRE(ctx, read_size == e->d.input_patch || (e->d.preprocess == 0 && read_size > 0 && read_size % e->d.input_patch == 0),
                "encoder_preprocess: read size %d unsupported for patch size %d", read_size, e->d.input_patch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;

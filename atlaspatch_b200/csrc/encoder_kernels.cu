@@ -43,24 +43,25 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
             s_rows[i] = v;
         }
     } else {
-        // read size = 2 x patch size (e.g. a 40x slide read for 20x patches): the reference resizes the 2P x 2P read with
-        // cv2.resize(patch, (P, P)) (feature_embedding.py:93-95), whose exact-2x uint8 path is the 2x2 box mean
-        // (a + b + c + d + 2) >> 2; pixels outside the slide count as 0 (the read is zero-padded before the resize).
-        const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + 2 * off;
-        const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + 2 * (off + ty * P);
+        // read size = r x patch size, r an integer (e.g. a 40x slide read for 20x patches, r = 2): the reference resizes the
+        // rP x rP read with cv2.resize(patch, (P, P)) (feature_embedding.py:93-95).  INTER_LINEAR samples at r d + (r - 1) / 2:
+        // for even r that is the midpoint of pixels r d + r/2 - 1 and r d + r/2 on both axes, whose fixed-point weights (1024/2048
+        // each) collapse to the rounded 2 x 2 mean (a + b + c + d + 2) >> 2; for odd r it is exactly the centre pixel.
+        // Pixels outside the slide count as 0 (the read is zero-padded before the resize).  Verified against cv2 for r = 2..8.
+        const int rs = read_scale, k0 = (rs - 1) / 2, taps = (rs & 1) ? 1 : 2;
+        const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + static_cast<int64_t>(rs) * off;
+        const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + static_cast<int64_t>(rs) * (off + ty * P);
         for (int i = threadIdx.x; i < P * row_bytes; i += blockDim.x) {
             const int r = i / row_bytes;
             const int bx = i - r * row_bytes;
             const int px = bx / 3, c = bx - px * 3;
-            unsigned s = 2;
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const int64_t y = y0 + 2 * r + dy, x = x0 + 2 * px + dx;
+            unsigned s = 0;
+            for (int dy = 0; dy < taps; ++dy)
+                for (int dx = 0; dx < taps; ++dx) {
+                    const int64_t y = y0 + static_cast<int64_t>(rs) * r + k0 + dy, x = x0 + static_cast<int64_t>(rs) * px + k0 + dx;
                     if (y >= 0 && y < H && x >= 0 && x < W) s += __ldg(slide + y * pitch + x * 3 + c);
                 }
-            s_rows[i] = static_cast<uint8_t>(s >> 2);
+            s_rows[i] = static_cast<uint8_t>(taps == 2 ? (s + 2) >> 2 : s);
         }
     }
     __syncthreads();
@@ -419,7 +420,7 @@ int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, in
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
                       const int* centre, int dup, int read_scale, cudaStream_t stream) {
-    AP_REQUIRE(ctx, read_scale == 1 || read_scale == 2, "preprocess: read size must be 1x or 2x the patch size (got %dx)", read_scale);
+    AP_REQUIRE(ctx, read_scale >= 1 && read_scale <= 64, "preprocess: read size must be an integer multiple (1..64) of the patch size (got %dx)", read_scale);
     AP_REQUIRE(ctx, patch == 16, "preprocess: conv patch %d unsupported (16 only)", patch);
     AP_REQUIRE(ctx, image % patch == 0 && input_patch >= image, "preprocess: bad geometry input %d image %d patch %d",
                input_patch, image, patch);

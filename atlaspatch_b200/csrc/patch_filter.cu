@@ -229,6 +229,50 @@ filter_count_kernel(const __grid_constant__ FilterParams p) {
     if (tid < 2 && tot[tid] != 0) atomicAdd(p.counts + cand * 2 + tid, tot[tid]);
 }
 
+// Any integer read ratio r >= 3 (e.g. an 80x slide filtered at 20x): cv2.resize's bilinear sample of an r x r block is the rounded
+// mean of its central 2 x 2 pixels (even r) or its centre pixel (odd r), so only 4 (1) of the r^2 source pixels are touched and
+// staging whole rows would mostly move unused bytes: direct loads, one CTA per (candidate, 32 output rows).
+__global__ void __launch_bounds__(FILTER_THREADS)
+filter_count_direct_kernel(const __grid_constant__ FilterParams p, int ratio) {
+    __shared__ uint16_t lo_s[256];
+    __shared__ int tot[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    lo_s[tid & 255] = p.lo[tid & 255];
+    if (tid < 2) tot[tid] = 0;
+    __syncthreads();
+    const long long cand = blockIdx.x / p.bands;
+    const int band = blockIdx.x % p.bands;
+    const long long x0 = p.rows[cand * 5 + 0], y0 = p.rows[cand * 5 + 1];
+    const int P = p.patch, r0 = band * 32, r1 = min(P, r0 + 32);
+    const int k0 = (ratio - 1) / 2, taps = (ratio & 1) ? 1 : 2;
+    int nb = 0, nw = 0;
+    for (int i = tid; i < (r1 - r0) * P; i += FILTER_THREADS) {
+        const int oy = r0 + i / P, ox = i % P;
+        uint32_t ch[3] = {0u, 0u, 0u};
+        for (int dy = 0; dy < taps; ++dy)
+            for (int dx = 0; dx < taps; ++dx) {
+                const long long y = y0 + (long long)ratio * oy + k0 + dy, x = x0 + (long long)ratio * ox + k0 + dx;
+                if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                    const uint8_t* s = p.slide + y * p.pitch + x * 3;
+                    ch[0] += __ldg(s); ch[1] += __ldg(s + 1); ch[2] += __ldg(s + 2);
+                }
+            }
+        if (taps == 2) { ch[0] = (ch[0] + 2u) >> 2; ch[1] = (ch[1] + 2u) >> 2; ch[2] = (ch[2] + 2u) >> 2; }
+        const int y = (int)(ch[0] * 9798u + ch[1] * 19235u + ch[2] * 3735u + 16384u);
+        nb += (y < p.gray_limit);
+        const uint32_t v = max(max(ch[0], ch[1]), ch[2]), mn = min(min(ch[0], ch[1]), ch[2]);
+        nw += (mn >= lo_s[v]);
+    }
+    nb = __reduce_add_sync(0xffffffffu, nb);
+    nw = __reduce_add_sync(0xffffffffu, nw);
+    if (lane == 0) {
+        atomicAdd(&tot[0], nb);
+        atomicAdd(&tot[1], nw);
+    }
+    __syncthreads();
+    if (tid < 2 && tot[tid] != 0) atomicAdd(p.counts + cand * 2 + tid, tot[tid]);
+}
+
 // keep flags + stable compaction, one CTA of 1024 threads, 4 consecutive candidates per thread and iteration
 __global__ void __launch_bounds__(1024)
 filter_compact_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ counts, long long n, double n_pixels,
@@ -292,16 +336,17 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, slide_dev && rows_dev && n > 0, "filter_patches: NULL pointer / negative n");
     AP_REQUIRE(ctx, out_rows_dev || out_rows_host, "filter_patches: no output buffer");
-    AP_REQUIRE(ctx, patch_size > 0 && (read_size == patch_size || read_size == 2 * patch_size),
-               "filter_patches: read_size %d must be patch_size %d or exactly twice it (general cv2.resize is not implemented)",
+    AP_REQUIRE(ctx, patch_size > 0 && read_size >= patch_size && read_size % patch_size == 0,
+               "filter_patches: read_size %d must be an integer multiple of patch_size %d (non-integer cv2.resize is not implemented)",
                read_size, patch_size);
     AP_REQUIRE(ctx, pitch >= 3 * W && W > 0 && H > 0, "filter_patches: bad slide geometry");
     const int scale = read_size / patch_size;
-    const int stride = ((15 + read_size * 3 + 15) & ~15) + 16;  // +16 keeps the number of 16-byte units odd: rows spread over the banks
+    const int staged_read = scale <= 2 ? read_size : patch_size;  // ratios >= 3 use the direct kernel: nothing is staged
+    const int stride = ((15 + staged_read * 3 + 15) & ~15) + 16;  // +16 keeps the number of 16-byte units odd: rows spread over the banks
     int band_rows = std::min(FILTER_MAX_BAND_ROWS, FILTER_MAX_SMEM / stride) & ~7;
     AP_REQUIRE(ctx, band_rows >= 8, "filter_patches: read_size %d too large for the staging buffer", read_size);
-    while (band_rows > 8 && band_rows - 8 >= read_size) band_rows -= 8;  // small patches: do not stage rows that do not exist
-    const int bands = (read_size + band_rows - 1) / band_rows;
+    while (band_rows > 8 && band_rows - 8 >= staged_read) band_rows -= 8;  // small patches: do not stage rows that do not exist
+    const int bands = scale <= 2 ? (read_size + band_rows - 1) / band_rows : (patch_size + 31) / 32;
     AP_REQUIRE(ctx, n * (int64_t)bands < (1ll << 31), "filter_patches: too many candidates");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -346,9 +391,11 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
         if (scale == 1) {
             AP_TRY(cudaFuncSetAttribute(filter_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_MAX_SMEM));
             filter_count_kernel<1><<<grid, FILTER_THREADS, smem, st>>>(p);
-        } else {
+        } else if (scale == 2) {
             AP_TRY(cudaFuncSetAttribute(filter_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_MAX_SMEM));
             filter_count_kernel<2><<<grid, FILTER_THREADS, smem, st>>>(p);
+        } else {
+            filter_count_direct_kernel<<<grid, FILTER_THREADS, 0, st>>>(p, scale);
         }
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         AP_TRY(cudaGetLastError());

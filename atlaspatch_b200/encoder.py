@@ -134,7 +134,7 @@ class B200FeatureExtractor:
     # ---- device-resident fast path -----------------------------------------------------------------
     def embed_coords(self, image, W: int, H: int, pitch: int, coords_dev, out=None, read_size: int | None = None):
         """image: uint8 CUDA tensor (level-0 RGB rows, `pitch` bytes/row); coords_dev: int32 CUDA (n,5) -> (n,D) fp32 CUDA.
-        read_size: the rows' read_w (= read_h); defaults to the patch size (no resize), 2x the patch size is supported."""
+        read_size: the rows' read_w (= read_h); defaults to the patch size (no resize); any integer multiple of it is supported."""
         import torch
 
         n = int(coords_dev.shape[0])

@@ -43,8 +43,18 @@ def rgb_to_sv(rgb: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
 
 
 def halve_bilinear(rgb: np.ndarray) -> np.ndarray:
+    return shrink_bilinear(rgb, 2)
+
+
+def shrink_bilinear(rgb: np.ndarray, r: int) -> np.ndarray:
+    """cv2.resize(rgb, (w / r, h / r)) (INTER_LINEAR, uint8) for an integer ratio r: the sample point r d + (r - 1) / 2 is the
+    midpoint of the block's central 2 x 2 pixels (even r: both taps weigh 1024/2048 -> (a + b + c + d + 2) >> 2) or exactly its
+    centre pixel (odd r).  Pinned against cv2 for r = 2..8 in tests/test_oracle_filter.py."""
     a = rgb.astype(np.int64)
-    return ((a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    k = (r - 1) // 2
+    if r % 2:
+        return a[k::r, k::r].astype(np.uint8)
+    return ((a[k::r, k::r] + a[k::r, k + 1::r] + a[k + 1::r, k::r] + a[k + 1::r, k + 1::r] + 2) >> 2).astype(np.uint8)
 
 
 def patch_counts(patch: np.ndarray, black_thresh: int, white_thresh: int, value_thresh: int = 200) -> tuple[int, int]:
@@ -70,9 +80,9 @@ def filter_rows(read_region, rows: np.ndarray, patch_size: int, black_thresh: in
     for i, (x, y, rw, rh, _lv) in enumerate(rows.tolist()):
         patch = read_region(x, y, rw, rh)
         if rw != patch_size:
-            if rw != 2 * patch_size:
-                raise ValueError("oracle restates cv2.resize only for the exact 2:1 read")
-            patch = halve_bilinear(patch)
+            if rw % patch_size:
+                raise ValueError("oracle restates cv2.resize only for integer read ratios")
+            patch = shrink_bilinear(patch, rw // patch_size)
         counts[i] = patch_counts(patch, black_thresh, white_thresh)
         n = patch_size * patch_size
         keep[i] = not (counts[i, 0] / n >= float(min_fraction) or counts[i, 1] / n >= float(min_fraction))

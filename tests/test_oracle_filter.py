@@ -31,6 +31,15 @@ def test_halving_matches_cv2_resize():
         assert np.array_equal(pf.halve_bilinear(a), cv2.resize(a, (hw[1] // 2, hw[0] // 2)))
 
 
+def test_integer_ratio_shrink_matches_cv2_resize():
+    import cv2
+
+    rng = np.random.default_rng(4)
+    for r in (2, 3, 4, 5, 6, 8):
+        a = rng.integers(0, 256, (48 * r, 40 * r, 3), dtype=np.uint8)
+        assert np.array_equal(pf.shrink_bilinear(a, r), cv2.resize(a, (40, 48))), r
+
+
 def test_predicates_match_reference_functions():
     """utils/image.py restated: same decisions as cv2-based code on random and near-threshold patches."""
     import cv2
