@@ -40,6 +40,8 @@ _SIGNATURES = {
     "ap_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ap_profile_enable": (C.c_int, [_P, C.c_int]),
     "ap_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "ap_profile_read_tagged": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int,
+                                         C.POINTER(C.c_int)]),
     "ap_synth_render": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, _P, C.c_int, _P, C.c_int,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "ap_thumbnail_area": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P]),
@@ -148,6 +150,14 @@ class Context:
         cnt = (C.c_int64 * n)()
         self.check(self.lib.ap_profile_read(self.handle, ms, cnt, n))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+
+    def profile_read_gemm_shapes(self) -> dict[tuple[int, int, int], tuple[float, int]]:
+        """{(N, K, epilogue): (total ms, launches)} of the GEMM launches timed since the last read (clears all records)."""
+        cap = 64
+        keys, ms, cnt, n = (C.c_int64 * cap)(), (C.c_double * cap)(), (C.c_int64 * cap)(), C.c_int(0)
+        self.check(self.lib.ap_profile_read_tagged(self.handle, 0, keys, ms, cnt, cap, C.byref(n)))
+        return {(int(keys[i]) >> 32, (int(keys[i]) & 0xFFFFFFFF) >> 4, int(keys[i]) & 15): (float(ms[i]), int(cnt[i])) for i in range(n.value)}
 
 
 def current_stream_ptr() -> int:

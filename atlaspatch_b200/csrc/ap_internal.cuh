@@ -32,7 +32,7 @@ struct ap_ctx {
     // optional per-launch CUDA-event timing (ap_profile_*): bench.py's live roofline measurement
     unsigned profiling = 0;  // bit mask of ApKernelClass values to time (0 = off)
     std::mutex prof_mu;
-    struct ProfRec { cudaEvent_t start, stop; int cls; };
+    struct ProfRec { cudaEvent_t start, stop; int cls; int64_t tag; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
 };
@@ -43,7 +43,7 @@ enum ApKernelClass { AP_K_GEMM = 0, AP_K_ATTENTION = 1, AP_K_LAYERNORM = 2, AP_K
 // Records a CUDA-event pair around the launches issued in its scope when profiling is on (same stream as the kernel).
 struct ProfScope {
     ap_ctx* ctx; cudaStream_t st; cudaEvent_t stop = nullptr;
-    ProfScope(ap_ctx* c, cudaStream_t s, int cls);
+    ProfScope(ap_ctx* c, cudaStream_t s, int cls, int64_t tag = 0);  // tag: e.g. the GEMM shape, see ap_profile_read_tagged
     ~ProfScope();
 };
 

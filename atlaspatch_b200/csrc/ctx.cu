@@ -108,13 +108,13 @@ static cudaEvent_t prof_get_event(ap_ctx* ctx) {
     return e;
 }
 
-ProfScope::ProfScope(ap_ctx* c, cudaStream_t s, int cls) : ctx(c), st(s) {
+ProfScope::ProfScope(ap_ctx* c, cudaStream_t s, int cls, int64_t tag) : ctx(c), st(s) {
     if (!ctx || !((ctx->profiling >> cls) & 1u)) return;
     std::lock_guard<std::mutex> lk(ctx->prof_mu);
     cudaEvent_t start = prof_get_event(ctx);
     stop = prof_get_event(ctx);
     cudaEventRecord(start, st);
-    ctx->prof_recs.push_back({start, stop, cls});
+    ctx->prof_recs.push_back({start, stop, cls, tag});
 }
 ProfScope::~ProfScope() {
     if (stop) cudaEventRecord(stop, st);
@@ -139,6 +139,29 @@ extern "C" int ap_profile_read(ap_ctx* ctx, double* total_ms, int64_t* counts, i
         ctx->prof_pool.push_back(r.stop);
     }
     ctx->prof_recs.clear();
+    return AP_OK;
+}
+
+// Like ap_profile_read for ONE kernel class, but split by the launches' tags (GEMM: (N << 32) | (K << 4) | epilogue).
+// Clears all records.  keys / total_ms / counts have room for `cap` distinct tags; *n_out receives how many were seen.
+extern "C" int ap_profile_read_tagged(ap_ctx* ctx, int cls, int64_t* keys, double* total_ms, int64_t* counts, int cap, int* n_out) {
+    if (!ctx || !keys || !total_ms || !counts || !n_out || cap <= 0) return AP_EINVAL;
+    AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(ctx->prof_mu);
+    int n = 0;
+    for (auto& r : ctx->prof_recs) {
+        float ms = 0.f;
+        if (r.cls == cls && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            int i = 0;
+            while (i < n && keys[i] != r.tag) ++i;
+            if (i == n && n < cap) { keys[n] = r.tag; total_ms[n] = 0.0; counts[n] = 0; ++n; }
+            if (i < n) { total_ms[i] += ms; counts[i] += 1; }
+        }
+        ctx->prof_pool.push_back(r.start);
+        ctx->prof_pool.push_back(r.stop);
+    }
+    ctx->prof_recs.clear();
+    *n_out = n;
     return AP_OK;
 }
 

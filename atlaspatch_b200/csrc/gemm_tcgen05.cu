@@ -426,7 +426,7 @@ int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t str
     const int tiles = ((p->M + tile_m - 1) / tile_m) * (p->N / BN);
     const int max_workers = ctx->sm_count / CG;
     const int workers = tiles < max_workers ? tiles : max_workers;
-    ProfScope prof(ctx, stream, AP_K_GEMM);
+    ProfScope prof(ctx, stream, AP_K_GEMM, (static_cast<int64_t>(p->N) << 32) | (static_cast<int64_t>(p->K) << 4) | EPI);
     const CUtensorMap& mw = CG == 2 ? p->map_w_half : p->map_w;
     AP_CHECK_CUDA(ctx, ap_launch_pdl(kern, dim3(workers * CG), dim3(NUM_THREADS), L::DYN_BYTES, stream, CG, ctx->pdl != 0, p->map_a, mw,
                                      p->M, p->N, p->K, ep));

@@ -49,6 +49,8 @@ int ap_set_option(ap_ctx* ctx, const char* key, int value);
  * ap_profile_read sums and clears the records into total_ms[n_classes] / counts[n_classes] (n_classes >= 7). */
 int ap_profile_enable(ap_ctx* ctx, int on);
 int ap_profile_read(ap_ctx* ctx, double* total_ms, int64_t* counts, int n_classes);
+/* The same for one class, split by launch tag (GEMM launches: (N << 32) | (K << 4) | epilogue); clears all records. */
+int ap_profile_read_tagged(ap_ctx* ctx, int cls, int64_t* keys, double* total_ms, int64_t* counts, int cap, int* n_out);
 
 /* ---- synthetic slide (benchmark input) ---------------------------------
  * Renders the region [x0,x0+w) x [y0,y0+h) of the synthetic slide (W x H, seed, blobs, holes)
