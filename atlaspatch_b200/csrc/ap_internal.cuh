@@ -139,7 +139,8 @@ int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int row
 int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream);
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
-                      const int* centre, int dup, int read_scale, cudaStream_t stream);
+                      const int* centre, int dup, const int32_t* lin_s, const int16_t* lin_w, cudaStream_t stream);
+int ap_build_linear_tables(ap_ctx* ctx, int n_src, int n_dst, std::vector<int32_t>& taps, std::vector<int16_t>& weights);
 // DINOv2 preprocess (transformers BitImageProcessorFast): antialias bicubic resize + centre crop + im2col (preprocess_resize.cu)
 int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, std::vector<int32_t>& tap_min, std::vector<int32_t>& tap_cnt,
                            std::vector<int16_t>& tap_w, int* max_taps, int* precision);

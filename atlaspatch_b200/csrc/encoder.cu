@@ -5,6 +5,7 @@
 //   conv_proj (k = s = patch) -> [class_token ; tokens] + pos_embedding
 //   -> layers x [ x += out_proj(MHA(ln_1(x))) ; x += mlp.3(GELU(mlp.0(ln_2(x)))) ] -> ln -> x[:, 0]
 // Residual stream, LayerNorm and softmax are fp32; GEMM operands are fp16 with fp32 accumulation.
+#include <map>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -58,6 +59,9 @@ struct ap_encoder {
     uint8_t *pin_in[2] = {nullptr, nullptr}, *dev_patches[2] = {nullptr, nullptr};
     float *pin_out[2] = {nullptr, nullptr}, *dev_feats[2] = {nullptr, nullptr};
     int32_t* dev_tall_coords = nullptr;
+    // cv2.resize (INTER_LINEAR) tap tables per read size > input_patch, built on first use (device pointers)
+    std::map<int, std::pair<int32_t*, int16_t*>> lin_tables;
+    std::mutex lin_mu;
     cudaStream_t s_copy = nullptr, s_compute = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
@@ -116,21 +120,48 @@ const std::vector<float>* find(ap_encoder* e, const std::string& name, size_t nu
     return &it->second;
 }
 
+// Tables of the read_size -> input_patch resize (nullptrs for read_size == input_patch).
+int get_linear_tables(ap_encoder* e, int read_size, const int32_t** taps, const int16_t** weights) {
+    *taps = nullptr;
+    *weights = nullptr;
+    if (read_size == e->d.input_patch) return AP_OK;
+    std::lock_guard<std::mutex> lk(e->lin_mu);
+    auto it = e->lin_tables.find(read_size);
+    if (it == e->lin_tables.end()) {
+        std::vector<int32_t> t;
+        std::vector<int16_t> w;
+        int rc = ap_build_linear_tables(e->ctx, read_size, e->d.input_patch, t, w);
+        if (rc) return rc;
+        int32_t* dt = nullptr;
+        int16_t* dw = nullptr;
+        if ((rc = dev_alloc(e, (void**)&dt, t.size() * 4)) || (rc = dev_alloc(e, (void**)&dw, w.size() * 2))) return rc;
+        AP_CHECK_CUDA(e->ctx, cudaMemcpy(dt, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+        AP_CHECK_CUDA(e->ctx, cudaMemcpy(dw, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+        it = e->lin_tables.emplace(read_size, std::make_pair(dt, dw)).first;
+    }
+    *taps = it->second.first;
+    *weights = it->second.second;
+    return AP_OK;
+}
+
 // One forward chunk: nb images whose patches are at `coords` (device) inside `slide`.
 int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords, int nb,
-                  int read_scale, float* out_feats, cudaStream_t st) {
+                  int read_size, float* out_feats, cudaStream_t st) {
     ap_ctx* ctx = e->ctx;
     const int D = e->d.hidden, T = e->tokens, T1 = T + 1;
     const int rows = nb * T1;
     int rc;
+    const int32_t* lin_s = nullptr;
+    const int16_t* lin_w = nullptr;
     if (e->d.preprocess == 1) {
-        AP_REQUIRE(ctx, read_scale == 1, "encoder: reads larger than the patch are not implemented for the resizing (DINOv2) preprocess");
+        AP_REQUIRE(ctx, read_size == e->d.input_patch, "encoder: reads larger than the patch are not implemented for the resizing (DINOv2) preprocess");
         if ((rc = ap_preprocess_resize_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->tap_min,
                                            e->tap_cnt, e->tap_w, e->max_taps, e->tap_precision, e->max_src_rows, e->a_pe, e->kpe_pad,
                                            e->centre, st)))
             return rc;
-    } else if ((rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
-                                       e->kpe_pad, e->centre, 0, read_scale, st)))
+    } else if ((rc = get_linear_tables(e, read_size, &lin_s, &lin_w)) ||
+               (rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
+                                       e->kpe_pad, e->centre, 0, lin_s, lin_w, st)))
         return rc;
     if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, st))) return rc;
     {
@@ -422,14 +453,12 @@ extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, 
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, slide_dev && coords_dev && out_features_dev, "embed_coords: NULL pointer");
     AP_REQUIRE(ctx, pitch >= W * 3, "embed_coords: pitch %lld < 3*W", (long long)pitch);
-    AP_REQUIRE(ctx, read_size >= e->d.input_patch && read_size % e->d.input_patch == 0,
-               "embed_coords: read size %d with patch size %d needs a non-integer resize, which is not implemented", read_size,
-               e->d.input_patch);
-    const int read_scale = read_size / e->d.input_patch;
+    AP_REQUIRE(ctx, read_size >= e->d.input_patch, "embed_coords: read size %d is smaller than the patch size %d (up-sampling reads do not occur: "
+               "the reference rejects target magnifications above the slide's)", read_size, e->d.input_patch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int64_t s = 0; s < n; s += e->max_batch) {
         const int nb = static_cast<int>(n - s < e->max_batch ? n - s : e->max_batch);
-        int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, read_scale, out_features_dev + s * e->d.hidden, st);
+        int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, read_size, out_features_dev + s * e->d.hidden, st);
         if (rc) return rc;
     }
     return AP_OK;
@@ -445,16 +474,20 @@ extern "C" int ap_encoder_preprocess(ap_encoder* e, const uint8_t* slide_dev, in
     AP_REQUIRE(ctx, n >= 0 && n <= e->max_batch, "encoder_preprocess: n=%lld must be in [0, max_batch=%d]", (long long)n, e->max_batch);
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, slide_dev && coords_dev && out_dev, "encoder_preprocess: NULL pointer");
-    AP_REQUIRE(ctx, read_size == e->d.input_patch || (e->d.preprocess == 0 && read_size > 0 && read_size % e->d.input_patch == 0),
+    AP_REQUIRE(ctx, read_size == e->d.input_patch || (e->d.preprocess == 0 && read_size > e->d.input_patch),
                "encoder_preprocess: read size %d unsupported for patch size %d", read_size, e->d.input_patch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
     if (e->d.preprocess == 1)
         rc = ap_preprocess_resize_run(ctx, slide_dev, W, H, pitch, coords_dev, n, e->d.input_patch, e->d.image_size, e->d.patch, e->tap_min,
                                       e->tap_cnt, e->tap_w, e->max_taps, e->tap_precision, e->max_src_rows, e->a_pe, e->kpe_pad, e->centre, st);
-    else
+    else {
+        const int32_t* lin_s = nullptr;
+        const int16_t* lin_w = nullptr;
+        if ((rc = get_linear_tables(e, read_size, &lin_s, &lin_w))) return rc;
         rc = ap_preprocess_run(ctx, slide_dev, W, H, pitch, coords_dev, n, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
-                               e->kpe_pad, e->centre, 0, read_size / e->d.input_patch, st);
+                               e->kpe_pad, e->centre, 0, lin_s, lin_w, st);
+    }
     if (rc) return rc;
     AP_CHECK_CUDA(ctx, cudaMemcpyAsync(out_dev, e->a_pe, (size_t)n * e->tokens * e->kpe_pad * 2, cudaMemcpyDeviceToDevice, st));
     return AP_OK;
@@ -499,7 +532,7 @@ extern "C" int ap_encoder_embed_patches_host(ap_encoder* e, const uint8_t* const
             AP_CHECK_CUDA(ctx, cudaMemcpyAsync(e->dev_patches[buf], e->pin_in[buf], (size_t)nb * patch_bytes, cudaMemcpyHostToDevice, e->s_copy));
             AP_CHECK_CUDA(ctx, cudaEventRecord(e->ev_h2d[buf], e->s_copy));
             AP_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->s_compute, e->ev_h2d[buf], 0));
-            int rc = forward_chunk(e, e->dev_patches[buf], (int64_t)IP, (int64_t)IP * nb, (int64_t)IP * 3, e->dev_tall_coords, nb, 1,
+            int rc = forward_chunk(e, e->dev_patches[buf], (int64_t)IP, (int64_t)IP * nb, (int64_t)IP * 3, e->dev_tall_coords, nb, (int)IP,
                                    e->dev_feats[buf], e->s_compute);
             if (rc) return rc;
             AP_CHECK_CUDA(ctx, cudaMemcpyAsync(e->pin_out[buf], e->dev_feats[buf], (size_t)nb * D * 4, cudaMemcpyDeviceToHost, e->s_compute));

@@ -1,5 +1,8 @@
 // Non-GEMM kernels of the encoder forward: patch crop -> fp16 im2col (preprocess), class-token rows,
 // LayerNorm, multi-head attention.  All fp32 statistics / softmax; fp16 only as tensor-core operands.
+#include <cmath>
+#include <vector>
+
 #include "ap_internal.cuh"
 #include "ptx.cuh"
 
@@ -21,7 +24,7 @@ template <int P>  // conv patch edge (16)
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64_t pitch,
                   const int32_t* __restrict__ coords, int input_patch, int image, __half* __restrict__ out,
-                  int64_t out_row_stride, int3 centre, int dup, int read_scale) {
+                  int64_t out_row_stride, int3 centre, int dup, const int32_t* __restrict__ lin_s, const int16_t* __restrict__ lin_w) {
     extern __shared__ uint8_t s_rows[];  // [P][image*3]
     ptx::pdl_wait();
     ptx::pdl_launch_dependents();
@@ -30,7 +33,7 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
     const int ty = blockIdx.x % g;
     const int off = (input_patch - image) / 2;  // centre crop: int(round((256-224)/2)) = 16
     const int row_bytes = image * 3;
-    if (read_scale == 1) {
+    if (lin_s == nullptr) {
         const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + off;
         const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + off + ty * P;
         for (int i = threadIdx.x; i < P * row_bytes; i += blockDim.x) {
@@ -43,25 +46,24 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
             s_rows[i] = v;
         }
     } else {
-        // read size = r x patch size, r an integer (e.g. a 40x slide read for 20x patches, r = 2): the reference resizes the
-        // rP x rP read with cv2.resize(patch, (P, P)) (feature_embedding.py:93-95).  INTER_LINEAR samples at r d + (r - 1) / 2:
-        // for even r that is the midpoint of pixels r d + r/2 - 1 and r d + r/2 on both axes, whose fixed-point weights (1024/2048
-        // each) collapse to the rounded 2 x 2 mean (a + b + c + d + 2) >> 2; for odd r it is exactly the centre pixel.
-        // Pixels outside the slide count as 0 (the read is zero-padded before the resize).  Verified against cv2 for r = 2..8.
-        const int rs = read_scale, k0 = (rs - 1) / 2, taps = (rs & 1) ? 1 : 2;
-        const int64_t x0 = static_cast<int64_t>(coords[b * 5 + 0]) + static_cast<int64_t>(rs) * off;
-        const int64_t y0 = static_cast<int64_t>(coords[b * 5 + 1]) + static_cast<int64_t>(rs) * (off + ty * P);
+        // read size > patch size (e.g. a 40x slide read for 20x patches): the reference resizes the R x R read with
+        // cv2.resize(patch, (P, P)) (feature_embedding.py:93-95) = OpenCV's 8-bit INTER_LINEAR: two taps per axis with 11-bit
+        // coefficients from the tables built by ap_build_linear_tables (same float arithmetic as cv2), horizontal pass in int32,
+        // vertical pass ((b0 (h0 >> 4)) >> 16) + ((b1 (h1 >> 4)) >> 16) + 2) >> 2.  Pixels outside the slide count as 0 (the read is
+        // zero-padded before the resize).  oracle/patch_filter.py: resize_linear_u8 restates it and is pinned against cv2.
+        const int64_t x0 = coords[b * 5 + 0], y0 = coords[b * 5 + 1];
         for (int i = threadIdx.x; i < P * row_bytes; i += blockDim.x) {
             const int r = i / row_bytes;
             const int bx = i - r * row_bytes;
             const int px = bx / 3, c = bx - px * 3;
-            unsigned s = 0;
-            for (int dy = 0; dy < taps; ++dy)
-                for (int dx = 0; dx < taps; ++dx) {
-                    const int64_t y = y0 + static_cast<int64_t>(rs) * r + k0 + dy, x = x0 + static_cast<int64_t>(rs) * px + k0 + dx;
-                    if (y >= 0 && y < H && x >= 0 && x < W) s += __ldg(slide + y * pitch + x * 3 + c);
-                }
-            s_rows[i] = static_cast<uint8_t>(taps == 2 ? (s + 2) >> 2 : s);
+            const int ox = off + px, oy = off + ty * P + r;
+            const int a0 = lin_w[2 * ox], a1 = lin_w[2 * ox + 1], b0 = lin_w[2 * oy], b1 = lin_w[2 * oy + 1];
+            const int64_t xa = x0 + lin_s[2 * ox], xb = x0 + lin_s[2 * ox + 1], ya = y0 + lin_s[2 * oy], yb = y0 + lin_s[2 * oy + 1];
+            auto px_at = [&](int64_t y, int64_t x) -> int {
+                return (y >= 0 && y < H && x >= 0 && x < W) ? static_cast<int>(__ldg(slide + y * pitch + x * 3 + c)) : 0;
+            };
+            const int h0 = px_at(ya, xa) * a0 + px_at(ya, xb) * a1, h1 = px_at(yb, xa) * a0 + px_at(yb, xb) * a1;
+            s_rows[i] = static_cast<uint8_t>((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
         }
     }
     __syncthreads();
@@ -419,8 +421,8 @@ int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, in
 
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
-                      const int* centre, int dup, int read_scale, cudaStream_t stream) {
-    AP_REQUIRE(ctx, read_scale >= 1 && read_scale <= 64, "preprocess: read size must be an integer multiple (1..64) of the patch size (got %dx)", read_scale);
+                      const int* centre, int dup, const int32_t* lin_s, const int16_t* lin_w, cudaStream_t stream) {
+    AP_REQUIRE(ctx, (lin_s == nullptr) == (lin_w == nullptr), "preprocess: resize tables must be given together");
     AP_REQUIRE(ctx, patch == 16, "preprocess: conv patch %d unsupported (16 only)", patch);
     AP_REQUIRE(ctx, image % patch == 0 && input_patch >= image, "preprocess: bad geometry input %d image %d patch %d",
                input_patch, image, patch);
@@ -430,8 +432,31 @@ int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, i
     ProfScope prof(ctx, stream, AP_K_PREPROCESS);
     AP_CHECK_CUDA(ctx, ap_launch_pdl(preprocess_kernel<16>, dim3(static_cast<unsigned>(n * g)), dim3(256), smem, stream, 1, ctx->pdl != 0, slide, W,
                                      H, pitch, coords, input_patch, image, out, out_row_stride, make_int3(centre[0], centre[1], centre[2]), dup,
-                                     read_scale));
+                                     lin_s, lin_w));
     AP_CHECK_LAUNCH(ctx, "preprocess_kernel");
+    return AP_OK;
+}
+
+// OpenCV's INTER_LINEAR tap tables for an n_src -> n_dst downscale (resize.cpp: resizeGeneric_ / HResizeLinear, 8-bit path):
+//   fx = (float)((d + 0.5) * scale - 0.5), scale = 1 / ((double)n_dst / n_src);  s = floor(fx);  fx -= s;
+//   coefficients saturate_cast<short>((1 - fx) * 2048), saturate_cast<short>(fx * 2048)   (cvRound = round half to even)
+// taps[2 d] = s, taps[2 d + 1] = s + 1; weights[2 d], weights[2 d + 1].  For n_src > n_dst no tap leaves [0, n_src), so the x rule
+// (fx zeroed at the border) and the y rule (row index clamped) coincide and one table serves both axes.
+int ap_build_linear_tables(ap_ctx* ctx, int n_src, int n_dst, std::vector<int32_t>& taps, std::vector<int16_t>& weights) {
+    AP_REQUIRE(ctx, n_dst > 0 && n_src > n_dst, "linear resize tables: only down-scaling is built (%d -> %d)", n_src, n_dst);
+    const double scale = 1.0 / (static_cast<double>(n_dst) / n_src);
+    taps.resize(2 * static_cast<size_t>(n_dst));
+    weights.resize(2 * static_cast<size_t>(n_dst));
+    for (int d = 0; d < n_dst; ++d) {
+        float fx = static_cast<float>((d + 0.5) * scale - 0.5);
+        int sx = static_cast<int>(floorf(fx));
+        fx -= sx;
+        AP_REQUIRE(ctx, sx >= 0 && sx + 1 <= n_src - 1, "linear resize tables: tap %d of %d -> %d leaves the source", d, n_src, n_dst);
+        taps[2 * d] = sx;
+        taps[2 * d + 1] = sx + 1;
+        weights[2 * d] = static_cast<int16_t>(lrintf((1.f - fx) * 2048.f));
+        weights[2 * d + 1] = static_cast<int16_t>(lrintf(fx * 2048.f));
+    }
     return AP_OK;
 }
 

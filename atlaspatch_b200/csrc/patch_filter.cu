@@ -17,6 +17,7 @@
 //   filter_compact_kernel        one CTA: keep = !(black/N >= f || white/N >= f) in float64 (numpy's bool mean), stable
 //                                ballot/popc compaction of the kept rows.
 #include <algorithm>
+#include <vector>
 
 #include "ap_internal.cuh"
 #include "ptx.cuh"
@@ -229,11 +230,12 @@ filter_count_kernel(const __grid_constant__ FilterParams p) {
     if (tid < 2 && tot[tid] != 0) atomicAdd(p.counts + cand * 2 + tid, tot[tid]);
 }
 
-// Any integer read ratio r >= 3 (e.g. an 80x slide filtered at 20x): cv2.resize's bilinear sample of an r x r block is the rounded
-// mean of its central 2 x 2 pixels (even r) or its centre pixel (odd r), so only 4 (1) of the r^2 source pixels are touched and
-// staging whole rows would mostly move unused bytes: direct loads, one CTA per (candidate, 32 output rows).
+// Any other read size (e.g. an 80x slide filtered at 20x, or 40x at 15x): the patch is cv2.resize()d to patch_size first, i.e.
+// OpenCV's 8-bit INTER_LINEAR with two taps per axis (tables from ap_build_linear_tables; same arithmetic as preprocess_kernel).
+// Only 4 source pixels per output pixel are touched, so staging whole rows would mostly move unused bytes: direct loads, one
+// CTA per (candidate, 32 output rows).
 __global__ void __launch_bounds__(FILTER_THREADS)
-filter_count_direct_kernel(const __grid_constant__ FilterParams p, int ratio) {
+filter_count_direct_kernel(const __grid_constant__ FilterParams p, const int32_t* __restrict__ lin_s, const int16_t* __restrict__ lin_w) {
     __shared__ uint16_t lo_s[256];
     __shared__ int tot[2];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -244,20 +246,22 @@ filter_count_direct_kernel(const __grid_constant__ FilterParams p, int ratio) {
     const int band = blockIdx.x % p.bands;
     const long long x0 = p.rows[cand * 5 + 0], y0 = p.rows[cand * 5 + 1];
     const int P = p.patch, r0 = band * 32, r1 = min(P, r0 + 32);
-    const int k0 = (ratio - 1) / 2, taps = (ratio & 1) ? 1 : 2;
     int nb = 0, nw = 0;
     for (int i = tid; i < (r1 - r0) * P; i += FILTER_THREADS) {
         const int oy = r0 + i / P, ox = i % P;
-        uint32_t ch[3] = {0u, 0u, 0u};
-        for (int dy = 0; dy < taps; ++dy)
-            for (int dx = 0; dx < taps; ++dx) {
-                const long long y = y0 + (long long)ratio * oy + k0 + dy, x = x0 + (long long)ratio * ox + k0 + dx;
-                if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-                    const uint8_t* s = p.slide + y * p.pitch + x * 3;
-                    ch[0] += __ldg(s); ch[1] += __ldg(s + 1); ch[2] += __ldg(s + 2);
-                }
+        const int a0 = lin_w[2 * ox], a1 = lin_w[2 * ox + 1], b0 = lin_w[2 * oy], b1 = lin_w[2 * oy + 1];
+        const long long xa = x0 + lin_s[2 * ox], xb = x0 + lin_s[2 * ox + 1], ya = y0 + lin_s[2 * oy], yb = y0 + lin_s[2 * oy + 1];
+        int h0[3] = {0, 0, 0}, h1[3] = {0, 0, 0};
+        auto add = [&](long long y, long long x, int w, int (&h)[3]) {
+            if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                const uint8_t* s = p.slide + y * p.pitch + x * 3;
+                h[0] += w * __ldg(s); h[1] += w * __ldg(s + 1); h[2] += w * __ldg(s + 2);
             }
-        if (taps == 2) { ch[0] = (ch[0] + 2u) >> 2; ch[1] = (ch[1] + 2u) >> 2; ch[2] = (ch[2] + 2u) >> 2; }
+        };
+        add(ya, xa, a0, h0); add(ya, xb, a1, h0); add(yb, xa, a0, h1); add(yb, xb, a1, h1);
+        uint32_t ch[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ch[c] = static_cast<uint32_t>((((b0 * (h0[c] >> 4)) >> 16) + ((b1 * (h1[c] >> 4)) >> 16) + 2) >> 2);
         const int y = (int)(ch[0] * 9798u + ch[1] * 19235u + ch[2] * 3735u + 16384u);
         nb += (y < p.gray_limit);
         const uint32_t v = max(max(ch[0], ch[1]), ch[2]), mn = min(min(ch[0], ch[1]), ch[2]);
@@ -336,17 +340,17 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, slide_dev && rows_dev && n > 0, "filter_patches: NULL pointer / negative n");
     AP_REQUIRE(ctx, out_rows_dev || out_rows_host, "filter_patches: no output buffer");
-    AP_REQUIRE(ctx, patch_size > 0 && read_size >= patch_size && read_size % patch_size == 0,
-               "filter_patches: read_size %d must be an integer multiple of patch_size %d (non-integer cv2.resize is not implemented)",
-               read_size, patch_size);
+    AP_REQUIRE(ctx, patch_size > 0 && read_size >= patch_size,
+               "filter_patches: read_size %d is smaller than patch_size %d (up-sampling reads do not occur in the reference)", read_size,
+               patch_size);
     AP_REQUIRE(ctx, pitch >= 3 * W && W > 0 && H > 0, "filter_patches: bad slide geometry");
-    const int scale = read_size / patch_size;
-    const int staged_read = scale <= 2 ? read_size : patch_size;  // ratios >= 3 use the direct kernel: nothing is staged
+    const int scale = read_size == patch_size ? 1 : (read_size == 2 * patch_size ? 2 : 0);  // 0: general cv2.resize, direct kernel
+    const int staged_read = scale != 0 ? read_size : patch_size;   // the direct kernel stages nothing
     const int stride = ((15 + staged_read * 3 + 15) & ~15) + 16;  // +16 keeps the number of 16-byte units odd: rows spread over the banks
     int band_rows = std::min(FILTER_MAX_BAND_ROWS, FILTER_MAX_SMEM / stride) & ~7;
     AP_REQUIRE(ctx, band_rows >= 8, "filter_patches: read_size %d too large for the staging buffer", read_size);
     while (band_rows > 8 && band_rows - 8 >= staged_read) band_rows -= 8;  // small patches: do not stage rows that do not exist
-    const int bands = scale <= 2 ? (read_size + band_rows - 1) / band_rows : (patch_size + 31) / 32;
+    const int bands = scale != 0 ? (read_size + band_rows - 1) / band_rows : (patch_size + 31) / 32;
     AP_REQUIRE(ctx, n * (int64_t)bands < (1ll << 31), "filter_patches: too many candidates");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -370,7 +374,15 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
 
     const bool own_counts = counts_dev == nullptr, own_rows = out_rows_dev == nullptr;
     const size_t o_rows = ((size_t)n * 8 + 255) & ~(size_t)255;
-    const size_t total = o_rows + (own_rows ? (size_t)n * 20 : 0) + 256;
+    std::vector<int32_t> lin_s;
+    std::vector<int16_t> lin_w;
+    if (scale == 0) {
+        int rc = ap_build_linear_tables(ctx, read_size, patch_size, lin_s, lin_w);
+        if (rc) return rc;
+    }
+    const size_t o_tab = o_rows + (own_rows ? (((size_t)n * 20 + 255) & ~(size_t)255) : 0);
+    const size_t tab_bytes = scale == 0 ? (size_t)patch_size * 16 : 0;   // 2 int32 taps + 2 int16 weights per index, padded
+    const size_t total = o_tab + tab_bytes + 256;
     uint8_t* scratch = nullptr;
     AP_CHECK_CUDA(ctx, cudaMallocAsync((void**)&scratch, total, st));
     auto fail = [&](int rc) { cudaFreeAsync(scratch, st); return rc; };
@@ -395,7 +407,11 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
             AP_TRY(cudaFuncSetAttribute(filter_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_MAX_SMEM));
             filter_count_kernel<2><<<grid, FILTER_THREADS, smem, st>>>(p);
         } else {
-            filter_count_direct_kernel<<<grid, FILTER_THREADS, 0, st>>>(p, scale);
+            int32_t* d_s = reinterpret_cast<int32_t*>(scratch + o_tab);
+            int16_t* d_w = reinterpret_cast<int16_t*>(scratch + o_tab + (size_t)patch_size * 8);
+            AP_TRY(cudaMemcpyAsync(d_s, lin_s.data(), lin_s.size() * 4, cudaMemcpyHostToDevice, st));
+            AP_TRY(cudaMemcpyAsync(d_w, lin_w.data(), lin_w.size() * 2, cudaMemcpyHostToDevice, st));
+            filter_count_direct_kernel<<<grid, FILTER_THREADS, 0, st>>>(p, d_s, d_w);
         }
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         AP_TRY(cudaGetLastError());

@@ -96,9 +96,8 @@ int ap_extract_coords(ap_ctx* ctx, const int32_t* contour_xy, const int32_t* con
  * PatchExtractionService._iter_patch_entries with fast_mode off (atlas_patch/services/extraction.py:105-119,
  * atlas_patch/utils/image.py:7-41) for a slide resident in device memory.
  *   rows_dev      int32 n x 5 candidates (x, y, read_w, read_h, level) from ap_extract_coords (device)
- *   read_size     level-0 pixels read per candidate: an integer multiple r of patch_size.  r > 1 is cv2.resize to the patch
- *                 size, which for an integer ratio on uint8 is the rounded mean (a+b+c+d+2)>>2 of the central 2 x 2 pixels of
- *                 each r x r block (even r) or its centre pixel (odd r); non-integer ratios return AP_EINVAL
+ *   read_size     level-0 pixels read per candidate (>= patch_size); a larger read is cv2.resize()d to patch_size first
+ *                 (OpenCV's 8-bit INTER_LINEAR restated bit for bit, any ratio)
  *   black_thresh  ExtractionConfig.black_threshold (gray < t), white_thresh = ExtractionConfig.white_threshold (s < t and
  *                 v >= 200), min_fraction = 0.7 in the reference (utils/image.py defaults)
  * Kept rows are written in input order to out_rows_dev and/or out_rows_host (capacity n rows; either may be NULL);
@@ -149,10 +148,10 @@ int ap_encoder_finalize(ap_encoder* enc);
 int ap_encoder_embedding_dim(const ap_encoder* enc);
 /* Device-resident fast path: patches are cut straight out of the level-0 slide in HBM at
  * coords_dev rows (x, y, read_w, read_h, level) [int32, n x 5]; features (n x D fp32) to
- * out_features_dev.  Asynchronous on `stream`.  read_size = the rows' read_w = read_h: an integer multiple r of input_patch.
- * r > 1 is the reference's cv2.resize to the patch size (feature_embedding.py:93-95), which for an integer ratio on uint8 is
- * the rounded mean (a+b+c+d+2)>>2 of the central 2x2 pixels of each r x r block (even r) or its centre pixel (odd r);
- * non-integer ratios -> AP_EINVAL (not implemented). */
+ * out_features_dev.  Asynchronous on `stream`.  read_size = the rows' read_w = read_h >= input_patch.  A larger read is
+ * resized like the reference's cv2.resize to the patch size (feature_embedding.py:93-95): OpenCV's 8-bit INTER_LINEAR
+ * (two taps per axis, 11-bit coefficients, fixed-point passes), bit for bit, for any ratio; the DINOv2 preprocess
+ * (ap_vit_desc.preprocess = 1) only takes read_size == input_patch. */
 int ap_encoder_embed_coords(ap_encoder* enc, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
                             const int32_t* coords_dev, int64_t n, int read_size, float* out_features_dev, void* stream);
 /* a12 alone (used by the parity tests): run only the patch read + preprocess of n <= max_batch coordinates and copy the fp16

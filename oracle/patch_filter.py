@@ -13,8 +13,8 @@ against the cv2 build recorded in tests/golden/versions.json by tests/test_oracl
 
 * COLOR_RGB2GRAY (8u):  gray = (9798 R + 19235 G + 3735 B + 2^14) >> 15
 * COLOR_RGB2HSV  (8u):  v = max(R,G,B);  s = ((v - min) * sdiv[v] + 2^11) >> 12,  sdiv[v] = round((255 << 12) / v), sdiv[0] = 0
-* cv2.resize INTER_LINEAR at exactly 2:1 (8u): out = (a + b + c + d + 2) >> 2 over each 2 x 2 block (both taps weigh 1024/2048;
-  the vertical pass's ((b*(S>>4))>>16 ... +2)>>2 collapses to this)
+* cv2.resize INTER_LINEAR (8u), any ratio: two taps per axis with 11-bit coefficients (resize_linear_u8 below); at an integer
+  ratio r it collapses to the rounded mean of each block's central 2 x 2 pixels (even r) or its centre pixel (odd r)
 
 Pinned against the reference itself by tests/golden/filter_*.npz (make_golden.py --filter runs the reference's
 _iter_patch_entries with fast_mode=False on the synthetic slides).
@@ -57,6 +57,38 @@ def shrink_bilinear(rgb: np.ndarray, r: int) -> np.ndarray:
     return ((a[k::r, k::r] + a[k::r, k + 1::r] + a[k + 1::r, k::r] + a[k + 1::r, k + 1::r] + 2) >> 2).astype(np.uint8)
 
 
+def resize_linear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """cv2.resize(img, (out_w, out_h)) with the default INTER_LINEAR on uint8, any ratio (OpenCV resize.cpp, 8-bit path):
+    per axis fx = float32((d + 0.5) * scale - 0.5), scale = 1 / (n_dst / n_src) in float64; s = floor(fx); fx -= s; on x the
+    border zeroes fx and pins s, on y the two row indices are clamped; coefficients round-half-even((1 - fx) * 2048) and
+    (fx * 2048); horizontal pass in int32; vertical pass (((b0 (h0 >> 4)) >> 16) + ((b1 (h1 >> 4)) >> 16) + 2) >> 2.
+    Pinned bit-exactly against cv2 on ten size pairs in tests/test_oracle_filter.py."""
+    h, w, _ = img.shape
+
+    def axis(n_src, n_dst):
+        scale = 1.0 / (n_dst / n_src)
+        f = ((np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        return s, (f - s.astype(np.float32)).astype(np.float32)
+
+    def coef(f):
+        return np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int64), np.rint(f * np.float32(2048)).astype(np.int64)
+
+    sx, fx = axis(w, out_w)
+    lo = sx < 0
+    fx, sx = np.where(lo, np.float32(0), fx), np.where(lo, 0, sx)
+    hi = sx >= w - 1
+    fx, sx = np.where(hi, np.float32(0), fx), np.where(hi, w - 1, sx)
+    a0, a1 = coef(fx)
+    src = img.astype(np.int64)
+    hp = src[:, sx, :] * a0[None, :, None] + src[:, np.minimum(sx + 1, w - 1), :] * a1[None, :, None]
+    sy, fy = axis(h, out_h)
+    b0, b1 = coef(fy)
+    y0, y1 = np.clip(sy, 0, h - 1), np.clip(sy + 1, 0, h - 1)
+    out = (((b0[:, None, None] * (hp[y0] >> 4)) >> 16) + ((b1[:, None, None] * (hp[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def patch_counts(patch: np.ndarray, black_thresh: int, white_thresh: int, value_thresh: int = 200) -> tuple[int, int]:
     """(# pixels with gray < black_thresh, # pixels with s < white_thresh and v >= value_thresh)."""
     gray = rgb_to_gray(patch)
@@ -80,9 +112,7 @@ def filter_rows(read_region, rows: np.ndarray, patch_size: int, black_thresh: in
     for i, (x, y, rw, rh, _lv) in enumerate(rows.tolist()):
         patch = read_region(x, y, rw, rh)
         if rw != patch_size:
-            if rw % patch_size:
-                raise ValueError("oracle restates cv2.resize only for integer read ratios")
-            patch = shrink_bilinear(patch, rw // patch_size)
+            patch = resize_linear_u8(patch, patch_size, patch_size)
         counts[i] = patch_counts(patch, black_thresh, white_thresh)
         n = patch_size * patch_size
         keep[i] = not (counts[i, 0] / n >= float(min_fraction) or counts[i, 1] / n >= float(min_fraction))

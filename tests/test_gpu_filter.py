@@ -54,8 +54,8 @@ def test_filter_edges_overhang_unaligned_pitch_and_empty():
     wsi = SyntheticWSI(spec)
     img = wsi.device_image
     rng = np.random.default_rng(9)
-    for P, scale in ((256, 1), (61, 1), (128, 2), (33, 2), (64, 3), (48, 4), (20, 8)):
-        read = P * scale
+    for P, read in ((256, 256), (61, 61), (128, 256), (33, 66), (64, 192), (48, 192), (20, 160), (100, 267), (64, 171), (256, 683)):
+        scale = read // P
         xs = np.concatenate([rng.integers(0, spec.width - 1, 40), [spec.width - 1, spec.width - read // 2, 0, 7]])
         ys = np.concatenate([rng.integers(0, spec.height + 40, 40), [spec.height - 1, 0, spec.height - read // 3, spec.height + 500]])
         rows = np.stack([xs, ys, np.full_like(xs, read), np.full_like(xs, read), np.zeros_like(xs)], 1).astype(np.int32)
@@ -77,8 +77,8 @@ def test_filter_edges_overhang_unaligned_pitch_and_empty():
     assert kept.shape == (0, 5) and kept_dev.shape[0] == 0
     from atlaspatch_b200._lib import AtlasB200Error
 
-    with pytest.raises(AtlasB200Error):  # a non-integer read ratio is not implemented and must say so
-        bad = np.array([[0, 0, 384, 384, 0]], dtype=np.int32)
+    with pytest.raises(AtlasB200Error):  # a read smaller than the patch (up-sampling) does not occur in the reference and is refused
+        bad = np.array([[0, 0, 128, 128, 0]], dtype=np.int32)
         filter_patches(img, wsi.w, wsi.h, wsi.pitch, torch.from_numpy(bad).cuda(), patch_size=256)
 
 

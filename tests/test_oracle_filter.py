@@ -40,6 +40,18 @@ def test_integer_ratio_shrink_matches_cv2_resize():
         assert np.array_equal(pf.shrink_bilinear(a, r), cv2.resize(a, (40, 48))), r
 
 
+@pytest.mark.parametrize("sizes", [(683, 256), (384, 256), (320, 256), (512, 256), (768, 256), (300, 224), (1000, 256), (257, 256),
+                                   (640, 512), (341, 128)])
+def test_general_linear_resize_matches_cv2(sizes):
+    import cv2
+
+    n, m = sizes
+    img = np.random.default_rng(n).integers(0, 256, (n, n, 3), dtype=np.uint8)
+    assert np.array_equal(pf.resize_linear_u8(img, m, m), cv2.resize(img, (m, m)))
+    if n % m == 0:
+        assert np.array_equal(pf.shrink_bilinear(img, n // m), cv2.resize(img, (m, m)))
+
+
 def test_predicates_match_reference_functions():
     """utils/image.py restated: same decisions as cv2-based code on random and near-threshold patches."""
     import cv2
