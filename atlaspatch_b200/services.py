@@ -4,8 +4,8 @@
 (services/extraction.py:131-197) for the coordinate path (fast mode, and the black/white content filter of --no-fast-mode on an HBM-resident slide):
 same contours / geometry / order, coordinates computed by the CUDA kernels.  `B200FeatureEmbeddingService.embed_features(result, *, wsi)` replaces
 PatchFeatureEmbeddingService._embed_with_extractor (services/feature_embedding.py:179-249) with the zero-copy path
-when the slide is resident in HBM.  The H5 container (services/storage.py) is not written by this round's build
-(no h5py / libhdf5 in the image): results are returned in memory and can be saved as .npz.
+when the slide is resident in HBM.  Results are returned in memory; `storage.write_result` writes them into the reference's H5
+container through h5py (services/storage.py layout) where that library is installed.
 """
 from __future__ import annotations
 
@@ -32,7 +32,7 @@ class Slide:  # core/models.py:10-18
 
 
 @dataclass
-class ExtractionResult:  # core/models.py:27-36 (h5_path is None until the H5 writer lands)
+class ExtractionResult:  # core/models.py:27-36 (h5_path is set by storage.write_result)
     slide: Slide
     h5_path: Path | None
     num_patches: int
