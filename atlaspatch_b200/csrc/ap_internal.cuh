@@ -23,6 +23,7 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split weights: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
     int pdl = 1;                  // programmatic dependent launch for the encoder kernel chain (ap_set_option "pdl")
     int cls_only_last_layer = 1;  // last layer: attention / out_proj / MLP only for the class-token row (ap_set_option)
     int attn_mode = 2;       // 2: tcgen05 attention when 16 <= S_pad <= 256, 1: warp-MMA (mma.sync) kernel

@@ -76,6 +76,11 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         ctx->cls_only_last_layer = value != 0;
         return AP_OK;
     }
+    if (!strcmp(key, "precise_mask")) {   // read at ap_encoder_finalize
+        AP_REQUIRE(ctx, value >= 0 && value <= 15, "precise_mask must be in [0, 15]");
+        ctx->precise_mask = value;
+        return AP_OK;
+    }
     if (!strcmp(key, "attn_variant")) {
         ctx->attn_variant = value;
         return AP_OK;

@@ -21,7 +21,7 @@ struct LayerWeights {
     float *b_qkv, *b_o, *b_1, *b_2;
     GemmPlan p_qkv, p_o, p_1, p_2;
     GemmPlan pc_o, pc_1, pc_2;  // last layer only: class-token rows (M = images)
-    bool split = false;  // weights stored as [hi | lo] fp16 pairs (K doubled)
+    int split = 0;  // bit mask of GEMMs whose weights are stored as [hi | lo] fp16 pairs (K doubled): 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
 };
 
 }  // namespace
@@ -341,13 +341,12 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
             (rc = upload_f32(e, &L.b_qkv, *bqkv)) || (rc = upload_f32(e, &L.b_o, *bo)) ||
             (rc = upload_f32(e, &L.b_1, *b1)) || (rc = upload_f32(e, &L.b_2, *b2)))
             return rc;
-        L.split = i < e->precise_layers;
-        if (L.split) {
-            if ((rc = upload_f16_split(e, &L.w_qkv, wqkv->data(), 3 * D, D)) || (rc = upload_f16_split(e, &L.w_o, wo->data(), D, D)) ||
-                (rc = upload_f16_split(e, &L.w_1, w1->data(), M1, D)) || (rc = upload_f16_split(e, &L.w_2, w2->data(), D, M)))
-                return rc;
-        } else if ((rc = upload_f16(e, &L.w_qkv, wqkv->data(), wqkv->size())) || (rc = upload_f16(e, &L.w_o, wo->data(), wo->size())) ||
-                   (rc = upload_f16(e, &L.w_1, w1->data(), w1->size())) || (rc = upload_f16(e, &L.w_2, w2->data(), w2->size())))
+        L.split = i < e->precise_layers ? (ctx->precise_mask & 15) : 0;
+        auto up = [&](__half** dst, const std::vector<float>* w, size_t rows_w, size_t k, int bit) {
+            return (L.split & bit) ? upload_f16_split(e, dst, w->data(), rows_w, k) : upload_f16(e, dst, w->data(), w->size());
+        };
+        if ((rc = up(&L.w_qkv, wqkv, 3 * D, D, 1)) || (rc = up(&L.w_o, wo, D, D, 2)) || (rc = up(&L.w_1, w1, M1, D, 4)) ||
+            (rc = up(&L.w_2, w2, D, M, 8)))
             return rc;
     }
 #undef AP_GET
@@ -379,16 +378,16 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, 2 * Kp, AP_EPI_BIAS_F32, Kp))) return rc;
     const int epi1 = e->d.mlp_kind == 1 ? AP_EPI_BIAS_SWIGLU_F16 : AP_EPI_BIAS_GELU_F16;
     for (auto& L : e->layers) {
-        const int s = L.split ? 2 : 1;
-        if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, s * D, AP_EPI_BIAS_F16, D)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, s * D, AP_EPI_BIAS_RESID_F32, D)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M1, s * D, epi1, D)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, s * M, AP_EPI_BIAS_RESID_F32, M)))
+        const int sq = (L.split & 1) ? 2 : 1, so = (L.split & 2) ? 2 : 1, s1 = (L.split & 4) ? 2 : 1, s2 = (L.split & 8) ? 2 : 1;
+        if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, sq * D, AP_EPI_BIAS_F16, D)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, so * D, AP_EPI_BIAS_RESID_F32, D)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M1, s1 * D, epi1, D)) ||
+            (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, s2 * M, AP_EPI_BIAS_RESID_F32, M)))
             return rc;
         if (&L == &e->layers.back() &&
-            ((rc = ap_gemm_plan(ctx, &L.pc_o, e->yc_attn, L.w_o, MB, D, s * D, AP_EPI_BIAS_RESID_F32, D)) ||
-             (rc = ap_gemm_plan(ctx, &L.pc_1, e->yc_ln, L.w_1, MB, M1, s * D, epi1, D)) ||
-             (rc = ap_gemm_plan(ctx, &L.pc_2, e->hc, L.w_2, MB, D, s * M, AP_EPI_BIAS_RESID_F32, M))))
+            ((rc = ap_gemm_plan(ctx, &L.pc_o, e->yc_attn, L.w_o, MB, D, so * D, AP_EPI_BIAS_RESID_F32, D)) ||
+             (rc = ap_gemm_plan(ctx, &L.pc_1, e->yc_ln, L.w_1, MB, M1, s1 * D, epi1, D)) ||
+             (rc = ap_gemm_plan(ctx, &L.pc_2, e->hc, L.w_2, MB, D, s2 * M, AP_EPI_BIAS_RESID_F32, M))))
             return rc;
     }
 
