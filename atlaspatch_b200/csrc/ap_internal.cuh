@@ -23,6 +23,7 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    int sam_tensor_cores = 1;     // SAM2 linears on mma.sync: 1 split-fp16 operands (3 MMAs, fp32-like), 2 plain fp16 (1 MMA), 0 fp32 SIMT
     int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split weights: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
     int pdl = 1;                  // programmatic dependent launch for the encoder kernel chain (ap_set_option "pdl")
     int cls_only_last_layer = 1;  // last layer: attention / out_proj / MLP only for the class-token row (ap_set_option)

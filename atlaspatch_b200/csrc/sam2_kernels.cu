@@ -1,8 +1,11 @@
-// fp32 building blocks of the SAM2 image path (a4): correctness-first SIMT kernels.  The SAM2 forward runs once per slide on a
-// 1024 x 1024 thumbnail (~210 GFLOP for Hiera-T, against ~900 TFLOP for embedding a slide), so round 1 keeps it in exact fp32
-// -- which also makes parity with the fp32 oracle tight -- and leaves the tcgen05 port of its GEMMs / attention to a later round.
+// Building blocks of the SAM2 image path (a4).  The SAM2 forward runs once per slide on a 1024 x 1024 thumbnail (~210 GFLOP for
+// Hiera-T, 1.6 TFLOP for Hiera-L, against ~900 TFLOP for embedding a slide).  Activations stay fp32 end to end; the linear layers
+// (78 % of the time) run on the tensor cores with split-fp16 operands (fp32-like accuracy, see sam_linear_tc_kernel), attention,
+// LayerNorm, pooling and resampling are fp32 SIMT kernels.  Porting the whole path to the tcgen05 GEMM / attention of the ViT
+// encoder (fp16 activation buffers, padded 144/288/432-wide layers) is left for a later round.
 // Layout everywhere: tokens x channels, row-major ("NHWC").
 #include "ap_internal.cuh"
+#include "ptx.cuh"
 #include "sam2_internal.cuh"
 
 namespace {
@@ -56,6 +59,118 @@ sam_linear_kernel(const float* __restrict__ A, int lda, const float* __restrict_
             *dst = accumulate ? *dst + v : v;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same contract on the tensor cores: fp32 operands are rounded to fp16 while they are staged in shared memory, products are
+// accumulated in fp32 (mma.sync m16n8k16).  128 x 128 x 32 tiles, 8 warps (2 x 4, 64 x 32 each), register prefetch of the next
+// k-tile, two smem buffers (one __syncthreads per k-tile).  The Hiera linears are 78 % of the fp32 forward (ncu launch list in
+// profiles/); this kernel takes every linear with M >= 64 and 4-element-aligned operands, the SIMT kernel above the rest.
+// (The ViT encoder's tcgen05 GEMM needs fp16 activations, K % 64 == 0 and N % 128 == 0; Hiera's 144/288/432-wide layers and fp32
+// activation buffers do not fit it without re-laying out the whole SAM2 path, which is left for a later round.)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TCM = 128, TCN = 128, TCK = 32, TCP = 40;  // TCP: padded smem row (halfs): 80 B stride keeps ldmatrix conflict-free
+constexpr float TC_WSCALE = 256.0f;  // weights are staged as 256 w so that the low half of the split stays a normal fp16 number
+constexpr int TC_TILE_HALFS = TCM * TCP;
+constexpr int TC_SMEM_BYTES = 2 * 4 * TC_TILE_HALFS * 2;  // 2 buffers x (A_hi, A_lo, W_hi, W_lo)
+
+// SPLIT: every operand is staged as an fp16 pair x = hi + lo (hi = fp16(x), lo = fp16(x - hi), ~22 significant bits) and the
+// product is three MMAs, A_hi W_hi + A_lo W_hi + A_hi W_lo (the dropped A_lo W_lo term is ~2^-22 relative): fp32-like accuracy on
+// the tensor cores.  The randomly initialised Hiera of the parity oracle amplifies a per-layer error ~1000x over its 48 blocks,
+// so plain fp16 operands (2.3e-4 per layer) come out at 4 % / 22 % logit error (Hiera-T / -L) and cannot be pinned; the split can.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+sam_linear_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ C,
+                     int ldc, int M, int N, int K, int act, int accumulate) {
+    extern __shared__ __align__(16) __half tc_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int m0 = blockIdx.y * TCM, n0 = blockIdx.x * TCN;
+    float acc[4][4][4] = {};
+    float4 ra[4], rw[4];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 256 * i, r = idx >> 3, k = k0 + (idx & 7) * 4;
+            ra[i] = (m0 + r < M && k < K) ? __ldg(reinterpret_cast<const float4*>(A + static_cast<int64_t>(m0 + r) * lda + k))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            rw[i] = (n0 + r < N && k < K) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n0 + r) * K + k))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto put = [&](__half* hi_tile, __half* lo_tile, int off, float4 v, float scale) {
+        const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2half_rn(x[j]);
+            l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+        }
+        *reinterpret_cast<uint2*>(hi_tile + off) = *reinterpret_cast<uint2*>(h);
+        if (SPLIT) *reinterpret_cast<uint2*>(lo_tile + off) = *reinterpret_cast<uint2*>(l);
+    };
+    auto store_tile = [&](int buf) {
+        __half* base = tc_smem + buf * 4 * TC_TILE_HALFS;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 256 * i, off = (idx >> 3) * TCP + (idx & 7) * 4;
+            put(base, base + TC_TILE_HALFS, off, ra[i], 1.0f);
+            put(base + 2 * TC_TILE_HALFS, base + 3 * TC_TILE_HALFS, off, rw[i], TC_WSCALE);
+        }
+    };
+    const int k_tiles = (K + TCK - 1) / TCK;
+    load_tile(0);
+    for (int kt = 0; kt < k_tiles; ++kt) {
+        const int buf = kt & 1;
+        store_tile(buf);
+        __syncthreads();
+        if (kt + 1 < k_tiles) load_tile((kt + 1) * TCK);
+        const uint32_t a_hi = ptx::smem_u32(tc_smem + buf * 4 * TC_TILE_HALFS), a_lo = a_hi + TC_TILE_HALFS * 2;
+        const uint32_t w_hi = a_hi + 2 * TC_TILE_HALFS * 2, w_lo = a_hi + 3 * TC_TILE_HALFS * 2;
+#pragma unroll
+        for (int ks = 0; ks < TCK; ks += 16) {
+            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {   // two 8-wide n tiles per ldmatrix.x4
+                const int n = wn * 32 + np * 16 + (lane & 7) + ((lane >> 4) << 3), k = ks + ((lane >> 3) & 1) * 8;
+                ptx::ldmatrix_x4(w_hi + (n * TCP + k) * 2, bh[2 * np][0], bh[2 * np][1], bh[2 * np + 1][0], bh[2 * np + 1][1]);
+                if (SPLIT) ptx::ldmatrix_x4(w_lo + (n * TCP + k) * 2, bl[2 * np][0], bl[2 * np][1], bl[2 * np + 1][0], bl[2 * np + 1][1]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                uint32_t a0, a1, a2, a3;
+                const int r = wm * 64 + mi * 16 + (lane & 15), k = ks + (lane >> 4) * 8;
+                ptx::ldmatrix_x4(a_hi + (r * TCP + k) * 2, a0, a1, a2, a3);
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    if (SPLIT) ptx::mma_m16n8k16_f16(acc[mi][ni], a0, a1, a2, a3, bl[ni][0], bl[ni][1]);   // small terms first
+                }
+                if (SPLIT) {
+                    uint32_t l0, l1, l2, l3;
+                    ptx::ldmatrix_x4(a_lo + (r * TCP + k) * 2, l0, l1, l2, l3);
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) ptx::mma_m16n8k16_f16(acc[mi][ni], l0, l1, l2, l3, bh[ni][0], bh[ni][1]);
+                }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) ptx::mma_m16n8k16_f16(acc[mi][ni], a0, a1, a2, a3, bh[ni][0], bh[ni][1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = m0 + wm * 64 + mi * 16 + (lane >> 2) + (e >> 1) * 8;
+                const int n = n0 + wn * 32 + ni * 8 + (lane & 3) * 2 + (e & 1);
+                if (m >= M || n >= N) continue;
+                float v = acc[mi][ni][e] * (1.0f / TC_WSCALE) + (bias ? bias[n] : 0.f);
+                if (act == SAM_ACT_GELU) v = gelu_exact(v);
+                else if (act == SAM_ACT_RELU) v = fmaxf(v, 0.f);
+                float* dst = C + static_cast<int64_t>(m) * ldc + n;
+                *dst = accumulate ? *dst + v : v;
+            }
 }
 
 // LayerNorm over the last dim (any D), one warp per row, optional GELU afterwards.
@@ -328,6 +443,20 @@ inline unsigned blocks_for(int64_t n, int t = 256) { return static_cast<unsigned
 int sam_linear(ap_ctx* ctx, const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, int act,
                int accumulate, cudaStream_t st) {
     if (M == 0) return AP_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0 && lda % 4 == 0 && K % 4 == 0;
+    if (ctx->sam_tensor_cores && aligned && M >= 64) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            attr_set = true;
+        }
+        dim3 grid((N + TCN - 1) / TCN, (M + TCM - 1) / TCM);
+        if (ctx->sam_tensor_cores == 2) sam_linear_tc_kernel<false><<<grid, 256, TC_SMEM_BYTES, st>>>(A, lda, W, bias, C, ldc, M, N, K, act, accumulate);
+        else sam_linear_tc_kernel<true><<<grid, 256, TC_SMEM_BYTES, st>>>(A, lda, W, bias, C, ldc, M, N, K, act, accumulate);
+        SAM_LAUNCH_CHECK(ctx, "sam_linear_tc_kernel");
+        return AP_OK;
+    }
     dim3 grid((N + LT - 1) / LT, (M + LT - 1) / LT);
     sam_linear_kernel<<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K, act, accumulate);
     SAM_LAUNCH_CHECK(ctx, "sam_linear_kernel");
