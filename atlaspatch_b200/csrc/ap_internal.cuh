@@ -23,6 +23,8 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    int fold_ln = 0;              // LayerNorm folded into the GEMMs around it (read at ap_encoder_finalize; "fold_ln"): measured equal
+                                  // to the separate LayerNorm kernels end to end (the GEMM epilogues pay what the LayerNorms save), so off
     int sam_tensor_cores = 1;     // SAM2 linears on mma.sync: 1 split-fp16 operands (3 MMAs, fp32-like), 2 plain fp16 (1 MMA), 0 fp32 SIMT
     int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split weights: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
     int pdl = 1;                  // programmatic dependent launch for the encoder kernel chain (ap_set_option "pdl")
@@ -124,6 +126,18 @@ struct GemmExtra {
     const float* pos = nullptr;  // [(T+1), N] fp32 or null
     int tokens_per_image = 0;    // T (0 = no remap)
     float alpha = 1.0f;          // scale applied to the accumulator before bias
+    // ---- LayerNorm folded into the GEMMs around it (encoder.cu "LN folding") -----------------------------------------------
+    // producer side (fp32-output epilogues): also write the output as fp16 (the next GEMM's A operand) and, per output row,
+    // the partial (sum, sum of squares) of each block of bn/2 columns: stats_out[out_row * (N / (bn/2)) + column block]
+    __half* out_h = nullptr;
+    float2* stats_out = nullptr;
+    // consumer side (fp16-output epilogues): A holds raw x, W has gamma folded in; the epilogue finishes the normalisation,
+    //   out = rstd[m] * acc - rstd[m] * mean[m] * colsum[n] + bias[n],  mean / rstd from the ln_parts partials of row m
+    const float2* stats_in = nullptr;
+    const float* colsum = nullptr;   // [N]: sum_k W'[n, k] of the weights as stored (fp16-rounded, hi + lo)
+    int ln_parts = 0;
+    int ln_dim = 0;                  // length of the normalised rows (hidden size)
+    float ln_eps = 0.f;
 };
 int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const float* resid, void* out,
                 const GemmExtra* extra, cudaStream_t stream);
@@ -152,5 +166,5 @@ int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64
                              cudaStream_t stream);
 int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
 int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, int64_t src_row_stride, int D, cudaStream_t stream);
-int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D,
-                    cudaStream_t stream);
+int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D, __half* xh,
+                    float2* stats, int parts, cudaStream_t stream);

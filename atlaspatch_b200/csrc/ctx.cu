@@ -76,6 +76,10 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         ctx->cls_only_last_layer = value != 0;
         return AP_OK;
     }
+    if (!strcmp(key, "fold_ln")) {   // read at ap_encoder_finalize
+        ctx->fold_ln = value != 0;
+        return AP_OK;
+    }
     if (!strcmp(key, "sam_tensor_cores")) {
         ctx->sam_tensor_cores = value;   // 0: fp32 SIMT, 1: split-fp16 (3 MMAs, fp32-like), 2: plain fp16 operands (1 MMA)
         return AP_OK;

@@ -17,6 +17,7 @@ namespace {
 
 struct LayerWeights {
     float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    float *cs_qkv = nullptr, *cs_1 = nullptr;  // LayerNorm folding: column sums of the gamma-folded in_proj / mlp.0 weights as stored
     __half *w_qkv, *w_o, *w_1, *w_2;
     float *b_qkv, *b_o, *b_1, *b_2;
     GemmPlan p_qkv, p_o, p_1, p_2;
@@ -59,6 +60,12 @@ struct ap_encoder {
     uint8_t *pin_in[2] = {nullptr, nullptr}, *dev_patches[2] = {nullptr, nullptr};
     float *pin_out[2] = {nullptr, nullptr}, *dev_feats[2] = {nullptr, nullptr};
     int32_t* dev_tall_coords = nullptr;
+    // LayerNorm folding (see forward_chunk): per-row statistics partials written by the producers of x, unit gamma / zero beta for
+    // the class-token tail; the fp16 copy of x lives in y1
+    bool fold_ln = false;
+    int ln_parts = 0;
+    float2 *stats1 = nullptr, *stats2 = nullptr;
+    float *ones = nullptr, *zeros = nullptr;
     // cv2.resize (INTER_LINEAR) tap tables per read size > input_patch, built on first use (device pointers)
     std::map<int, std::pair<int32_t*, int16_t*>> lin_tables;
     std::mutex lin_mu;
@@ -105,6 +112,35 @@ int upload_f16(ap_encoder* e, __half** dst, const float* src, size_t n) {
     if (rc) return rc;
     AP_CHECK_CUDA(e->ctx, cudaMemcpy(*dst, h.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
     return AP_OK;
+}
+
+// Column sums s[n] = sum_k W[n, k] of a weight matrix AS STORED (fp16-rounded; hi + lo for split weights), fp32 on the device.
+int upload_colsum(ap_encoder* e, float** dst, const float* src, size_t rows, size_t K, bool split) {
+    std::vector<float> cs(rows);
+    for (size_t r = 0; r < rows; ++r) {
+        double acc = 0.0;
+        for (size_t k = 0; k < K; ++k) {
+            const float w = src[r * K + k];
+            const float hi = __half2float(__float2half_rn(w));
+            acc += hi;
+            if (split) acc += __half2float(__float2half_rn(w - hi));
+        }
+        cs[r] = static_cast<float>(acc);
+    }
+    return upload_f32(e, dst, cs);
+}
+
+// LayerNorm(x) W^T + b = xhat (gamma o W)^T + (b + W beta): fold the affine part of the LayerNorm into the weights it feeds.
+void fold_ln_affine(std::vector<float>& w, std::vector<float>& b, const std::vector<float>& gamma, const std::vector<float>& beta,
+                    size_t rows, size_t K) {
+    for (size_t r = 0; r < rows; ++r) {
+        double acc = b[r];
+        for (size_t k = 0; k < K; ++k) {
+            acc += static_cast<double>(w[r * K + k]) * beta[k];
+            w[r * K + k] *= gamma[k];
+        }
+        b[r] = static_cast<float>(acc);
+    }
 }
 
 const std::vector<float>* find(ap_encoder* e, const std::string& name, size_t numel) {
@@ -163,11 +199,26 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
                (rc = ap_preprocess_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->a_pe,
                                        e->kpe_pad, e->centre, 0, lin_s, lin_w, st)))
         return rc;
-    if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, st))) return rc;
+    // LayerNorm folding: x is normalised right before in_proj and mlp.0, and
+    //     LN(x) W^T + b = rstd (x (gamma o W)^T) - rstd mean colsum(gamma o W) + (b + W beta),
+    // so those two GEMMs read the RAW residual stream (its fp16 copy, written by whichever epilogue produced x) and finish the
+    // normalisation in their epilogue from per-row (sum, sum of squares) partials that the same producer epilogues emit.  24 of
+    // the 25 LayerNorm launches per chunk disappear together with their 115 MB of traffic each.  Same operand roundings as
+    // before minus one (gamma is applied in fp32 before the weight is rounded): the CPU simulation gives 5.3e-4 vs 5.5e-4.
+    const bool fold = e->fold_ln;
+    GemmExtra prod1, prod2, cons;
+    prod1.out_h = prod2.out_h = e->y1;
+    prod1.stats_out = e->stats1;
+    prod2.stats_out = e->stats2;
+    prod1.ln_parts = prod2.ln_parts = cons.ln_parts = e->ln_parts;
+    cons.ln_dim = D;
+    cons.ln_eps = e->d.ln_eps;
+    if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, fold ? e->y1 : nullptr, fold ? e->stats1 : nullptr, e->ln_parts, st)))
+        return rc;
     {
         GemmPlan p = e->p_pe;
         p.M = nb * T;
-        GemmExtra ex;
+        GemmExtra ex = fold ? prod1 : GemmExtra();
         ex.pos = e->pos;
         ex.tokens_per_image = T;
         if ((rc = ap_gemm_run(ctx, &p, e->b_pe, nullptr, e->x, &ex, st))) return rc;
@@ -175,9 +226,11 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     for (size_t li = 0; li < e->layers.size(); ++li) {
         auto& L = e->layers[li];
         GemmPlan p;
-        if ((rc = ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
+        if (!fold && (rc = ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
         p = L.p_qkv; p.M = rows;
-        if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, nullptr, st))) return rc;
+        cons.stats_in = e->stats1;
+        cons.colsum = L.cs_qkv;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, fold ? &cons : nullptr, st))) return rc;
         if (li + 1 == e->layers.size() && ctx->cls_only_last_layer) {
             // Only x[:, 0] survives the final LayerNorm (models/patch/base.py:100 -> torchvision forward `x[:, 0]`): the last
             // layer's attention needs every token's K/V but only the class-token query, and out_proj / MLP only that row.
@@ -185,7 +238,10 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
             if ((rc = ap_gather_rows_run(ctx, e->x, e->xc, nb, static_cast<int64_t>(T1) * D, D, st))) return rc;
             p = L.pc_o; p.M = nb;
             if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->xc, e->xc, nullptr, st))) return rc;
-            if ((rc = ap_layernorm_run(ctx, e->xc, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->yc_ln, nullptr, nb, D, st))) return rc;
+            // with folding mlp.0 already carries gamma / beta: the tail's explicit LayerNorm only normalises
+            if ((rc = ap_layernorm_run(ctx, e->xc, D, fold ? e->ones : L.ln2_g, fold ? e->zeros : L.ln2_b, e->d.ln_eps, e->yc_ln, nullptr, nb,
+                                       D, st)))
+                return rc;
             p = L.pc_1; p.M = nb;
             if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hc, nullptr, st))) return rc;
             p = L.pc_2; p.M = nb;
@@ -196,12 +252,14 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
             if ((rc = ap_attention_tc_run(ctx, &e->p_attn, e->y2, nb, T1, e->d.heads, st))) return rc;
         } else if ((rc = ap_attention_run(ctx, e->qkv, e->y2, nb, T1, e->d.heads, st))) return rc;
         p = L.p_o; p.M = rows;
-        if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->x, e->x, nullptr, st))) return rc;
-        if ((rc = ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->x, e->x, fold ? &prod2 : nullptr, st))) return rc;
+        if (!fold && (rc = ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
         p = L.p_1; p.M = rows;
-        if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hbuf, nullptr, st))) return rc;
+        cons.stats_in = e->stats2;
+        cons.colsum = L.cs_1;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hbuf, fold ? &cons : nullptr, st))) return rc;
         p = L.p_2; p.M = rows;
-        if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->x, e->x, nullptr, st))) return rc;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->x, e->x, fold ? &prod1 : nullptr, st))) return rc;
     }
     // final LayerNorm on the class-token rows only -> fp32 features
     return ap_layernorm_run(ctx, e->x, static_cast<int64_t>(T1) * D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
@@ -326,6 +384,8 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         if ((rc = upload_f32(e, &e->lnf_g, *g))) return rc;
         if ((rc = upload_f32(e, &e->lnf_b, *b))) return rc;
     }
+    e->fold_ln = ctx->fold_ln != 0;
+    e->ln_parts = D / ((D % 256 == 0 ? 256 : 128) / 2);   // one partial per bn/2-column block of the N = D producer GEMMs
     e->layers.resize(e->d.layers);
     for (int i = 0; i < e->d.layers; ++i) {
         const std::string p = "encoder.layers.encoder_layer_" + std::to_string(i) + ".";
@@ -336,17 +396,25 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         AP_GET(wo, p + "self_attention.out_proj.weight", (size_t)D * D) AP_GET(bo, p + "self_attention.out_proj.bias", D)
         AP_GET(w1, p + "mlp.0.weight", (size_t)M1 * D) AP_GET(b1, p + "mlp.0.bias", M1)
         AP_GET(w2, p + "mlp.3.weight", (size_t)D * M) AP_GET(b2, p + "mlp.3.bias", D)
+        L.split = i < e->precise_layers ? (ctx->precise_mask & 15) : 0;
+        std::vector<float> wq(*wqkv), bq(*bqkv), wf(*w1), bf1(*b1);
+        if (e->fold_ln) {
+            fold_ln_affine(wq, bq, *ln1g, *ln1b, (size_t)3 * D, D);
+            fold_ln_affine(wf, bf1, *ln2g, *ln2b, (size_t)M1, D);
+            if ((rc = upload_colsum(e, &L.cs_qkv, wq.data(), (size_t)3 * D, D, (L.split & 1) != 0)) ||
+                (rc = upload_colsum(e, &L.cs_1, wf.data(), (size_t)M1, D, (L.split & 4) != 0)))
+                return rc;
+        }
         if ((rc = upload_f32(e, &L.ln1_g, *ln1g)) || (rc = upload_f32(e, &L.ln1_b, *ln1b)) ||
             (rc = upload_f32(e, &L.ln2_g, *ln2g)) || (rc = upload_f32(e, &L.ln2_b, *ln2b)) ||
-            (rc = upload_f32(e, &L.b_qkv, *bqkv)) || (rc = upload_f32(e, &L.b_o, *bo)) ||
-            (rc = upload_f32(e, &L.b_1, *b1)) || (rc = upload_f32(e, &L.b_2, *b2)))
+            (rc = upload_f32(e, &L.b_qkv, bq)) || (rc = upload_f32(e, &L.b_o, *bo)) ||
+            (rc = upload_f32(e, &L.b_1, bf1)) || (rc = upload_f32(e, &L.b_2, *b2)))
             return rc;
-        L.split = i < e->precise_layers ? (ctx->precise_mask & 15) : 0;
-        auto up = [&](__half** dst, const std::vector<float>* w, size_t rows_w, size_t k, int bit) {
-            return (L.split & bit) ? upload_f16_split(e, dst, w->data(), rows_w, k) : upload_f16(e, dst, w->data(), w->size());
+        auto up = [&](__half** dst, const float* w, size_t n_elems, size_t rows_w, size_t k, int bit) {
+            return (L.split & bit) ? upload_f16_split(e, dst, w, rows_w, k) : upload_f16(e, dst, w, n_elems);
         };
-        if ((rc = up(&L.w_qkv, wqkv, 3 * D, D, 1)) || (rc = up(&L.w_o, wo, D, D, 2)) || (rc = up(&L.w_1, w1, M1, D, 4)) ||
-            (rc = up(&L.w_2, w2, D, M, 8)))
+        if ((rc = up(&L.w_qkv, wq.data(), wq.size(), 3 * D, D, 1)) || (rc = up(&L.w_o, wo->data(), wo->size(), D, D, 2)) ||
+            (rc = up(&L.w_1, wf.data(), wf.size(), M1, D, 4)) || (rc = up(&L.w_2, w2->data(), w2->size(), D, M, 8)))
             return rc;
     }
 #undef AP_GET
@@ -359,6 +427,15 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         (rc = dev_alloc(e, (void**)&e->y1, rows * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2, rows * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->qkv, rows * 3 * D * 2)) || (rc = dev_alloc(e, (void**)&e->hbuf, rows * M * 2)))
         return rc;
+    {
+        std::vector<float> ones(D, 1.0f), zeros(D, 0.0f);
+        if ((rc = upload_f32(e, &e->ones, ones)) || (rc = upload_f32(e, &e->zeros, zeros)) ||
+            (rc = dev_alloc(e, (void**)&e->stats1, rows * e->ln_parts * sizeof(float2))) ||
+            (rc = dev_alloc(e, (void**)&e->stats2, rows * e->ln_parts * sizeof(float2))))
+            return rc;
+        AP_CHECK_CUDA(ctx, cudaMemset(e->stats1, 0, rows * e->ln_parts * sizeof(float2)));
+        AP_CHECK_CUDA(ctx, cudaMemset(e->stats2, 0, rows * e->ln_parts * sizeof(float2)));
+    }
     const size_t rows_c = ((size_t)MB + 127) / 128 * 128;
     if ((rc = dev_alloc(e, (void**)&e->yc_attn, rows_c * D * 2)) || (rc = dev_alloc(e, (void**)&e->yc_ln, rows_c * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->hc, rows_c * M * 2)) || (rc = dev_alloc(e, (void**)&e->xc, rows_c * D * 4)))

@@ -93,15 +93,32 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
     }
 }
 
-// x[b*tokens + 0, :] = class_token + pos[0, :]
+// x[b*tokens + 0, :] = class_token + pos[0, :]; with LayerNorm folding also the fp16 copy of the row and its statistics partials
+// (one warp per block of D / parts columns, fixed shuffle tree: same layout and reproducibility as the GEMM producers').
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
-                                int n_images, int tokens, int D) {
+                                int n_images, int tokens, int D, __half* __restrict__ xh, float2* __restrict__ stats, int parts) {
     ptx::pdl_wait();
     ptx::pdl_launch_dependents();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_images * D) return;
-    const int b = i / D, d = i - b * D;
-    x[static_cast<int64_t>(b) * tokens * D + d] = cls[d] + pos[d];
+    const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (b >= n_images || w >= parts) return;
+    const int slot = D / parts;
+    const int64_t row = static_cast<int64_t>(b) * tokens;
+    float s = 0.f, q = 0.f;
+    for (int d = w * slot + lane; d < (w + 1) * slot; d += 32) {
+        const float v = cls[d] + pos[d];
+        x[row * D + d] = v;
+        if (xh != nullptr) xh[row * D + d] = __float2half_rn(v);
+        s += v;
+        q += v * v;
+    }
+    if (stats != nullptr) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) stats[row * parts + w] = make_float2(s, q);
+    }
 }
 
 // =====================================================================================================
@@ -460,13 +477,14 @@ int ap_build_linear_tables(ap_ctx* ctx, int n_src, int n_dst, std::vector<int32_
     return AP_OK;
 }
 
-int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D,
-                    cudaStream_t stream) {
+int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D, __half* xh,
+                    float2* stats, int parts, cudaStream_t stream) {
     if (n_images == 0) return AP_OK;
-    const int total = n_images * D;
+    if (parts <= 0) parts = D % 128 == 0 ? D / 128 : 1;
+    AP_REQUIRE(ctx, D % parts == 0 && parts <= 32, "cls rows: D=%d parts=%d unsupported", D, parts);
     ProfScope prof(ctx, stream, AP_K_OTHER);
-    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_rows_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, 1, ctx->pdl != 0, x, cls, pos, n_images,
-                                     tokens, D));
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_rows_kernel, dim3(n_images), dim3(parts * 32), 0, stream, 1, ctx->pdl != 0, x, cls, pos, n_images,
+                                     tokens, D, xh, stats, parts));
     AP_CHECK_LAUNCH(ctx, "cls_rows_kernel");
     return AP_OK;
 }

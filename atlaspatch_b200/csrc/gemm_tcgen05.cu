@@ -56,7 +56,35 @@ struct EpiParams {
     int a_k_blocks;  // A has this many 64-wide K blocks; block kb of the contraction reads A block kb % a_k_blocks
                      // (hi/lo split weights: W = [W_hi | W_lo] over 2K while A is stored once)
     int debug;  // diagnostics only (ap_set_option "gemm_debug"): 1 = no epilogue math/stores, 2 = no MMA issue, 4 = no TMA loads
+    // LayerNorm folding (GemmExtra in ap_internal.cuh)
+    __half* out_h;
+    float2* stats_out;
+    const float2* stats_in;
+    const float* colsum;
+    int ln_parts;
+    float ln_inv_dim, ln_eps;
 };
+
+// Per-row LayerNorm coefficients of the consumer epilogues: v = acc * rstd + (bias + nrm * colsum), nrm = -rstd * mean.
+struct LnRow {
+    float rstd, nrm;
+};
+__device__ __forceinline__ LnRow ln_row_coeffs(const EpiParams& ep, int row, int M) {
+    LnRow c{1.0f, 0.0f};
+    if (ep.stats_in == nullptr || row >= M) return c;
+    float s = 0.f, q = 0.f;
+    const float2* p = ep.stats_in + static_cast<int64_t>(row) * ep.ln_parts;
+    for (int j = 0; j < ep.ln_parts; ++j) {   // fixed order: bitwise reproducible
+        const float2 t = __ldg(p + j);
+        s += t.x;
+        q += t.y;
+    }
+    const float mean = s * ep.ln_inv_dim;
+    const float var = fmaxf(q * ep.ln_inv_dim - mean * mean, 0.f);
+    c.rstd = rsqrtf(var + ep.ln_eps);
+    c.nrm = -c.rstd * mean;
+    return c;
+}
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): halves the issue slots of the epilogue math ----------------
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
@@ -142,7 +170,7 @@ __device__ __forceinline__ void resid_prefetch(float4 (&rr)[8], const EpiParams&
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], const float4 (&rr)[8], uint8_t* stg, const EpiParams& ep,
-                                                   int M, int N, int row_base, int col0, int lane) {
+                                                   int M, int N, int row_base, int col0, int lane, float (&rs)[8], float (&rq)[8]) {
     const int p = lane & 7;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
@@ -169,26 +197,75 @@ __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], cons
                 }
             }
             *(reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * N + col0) + p) = v;
+            if (ep.out_h != nullptr) {   // the next GEMM's A operand: raw x in fp16 (its LayerNorm is finished in that GEMM's epilogue)
+                *reinterpret_cast<uint2*>(ep.out_h + out_row * N + col0 + p * 4) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+                rs[it] += (v.x + v.y) + (v.z + v.w);
+                rq[it] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
         }
     }
     __syncwarp();
 }
 
+// After the last chunk of a tile: the 8 lanes that share a row combine their partial sums (fixed shuffle tree: reproducible) and
+// one of them writes the (sum, sum of squares) of this warp's COLS_PER_WARP columns of that row.
+__device__ __forceinline__ void epilogue_write_stats(const EpiParams& ep, int M, int row_base, int col_block, int lane, float (&rs)[8],
+                                                     float (&rq)[8]) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        float s = rs[it], q = rq[it];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        const int row = row_base + it * 4 + (lane >> 3);
+        if ((lane & 7) == 0 && row < M) {
+            int64_t out_row = row;
+            if (ep.tokens_per_image > 0) {
+                const int b = row / ep.tokens_per_image;
+                out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + 1) + 1 + (row - b * ep.tokens_per_image);
+            }
+            ep.stats_out[out_row * ep.ln_parts + col_block] = make_float2(s, q);
+        }
+        rs[it] = 0.f;
+        rq[it] = 0.f;
+    }
+}
+
+// The bias / column-sum values of a warp's COLS_PER_WARP columns are the same for all of its 32 rows.  Loading them with one
+// LDG per lane and chunk put a global-load latency (long scoreboard) in front of every chunk's math (ncu: ~1/3 of the epilogue
+// warps' stall samples); instead each lane fetches 4 of the 128 values once per tile -- before the accumulator is ready -- and the
+// chunks pick them up with warp shuffles.
+__device__ __forceinline__ float4 bcast4(const float4& v, int src_lane) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src_lane), __shfl_sync(0xffffffffu, v.y, src_lane),
+                       __shfl_sync(0xffffffffu, v.z, src_lane), __shfl_sync(0xffffffffu, v.w, src_lane));
+}
+
 // fp16 output: bias (+GELU) in the row-per-lane layout, packed halves staged; `half_sel` = which 64 B half of the
 // 128 B row this 32-column chunk fills.  Call flush after both halves.
 template <int EPI>
-__device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int col0, int lane,
-                                                   int half_sel) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-    const uint64_t alpha2 = pk2(ep.alpha, ep.alpha);
+__device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int c, int lane,
+                                                   int half_sel, const LnRow& ln, const float4& bias_reg, const float4& cs_reg) {
+    const bool fold = ep.stats_in != nullptr;
+    const uint64_t alpha2 = fold ? pk2(ln.rstd, ln.rstd) : pk2(ep.alpha, ep.alpha);
+    const uint64_t nrm2 = pk2(ln.nrm, ln.nrm);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
+        const float4 b0 = bcast4(bias_reg, c * 8 + 2 * j), b1 = bcast4(bias_reg, c * 8 + 2 * j + 1);
+        uint64_t t0 = pk2(b0.x, b0.y), t1 = pk2(b0.z, b0.w), t2 = pk2(b1.x, b1.y), t3 = pk2(b1.z, b1.w);
+        if (fold) {   // bias + nrm * colsum: the mean term of the folded LayerNorm
+            const float4 c0 = bcast4(cs_reg, c * 8 + 2 * j), c1 = bcast4(cs_reg, c * 8 + 2 * j + 1);
+            t0 = fma2(pk2(c0.x, c0.y), nrm2, t0);
+            t1 = fma2(pk2(c0.z, c0.w), nrm2, t1);
+            t2 = fma2(pk2(c1.x, c1.y), nrm2, t2);
+            t3 = fma2(pk2(c1.z, c1.w), nrm2, t3);
+        }
         float v[8];
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), alpha2, pk2(b0.x, b0.y)), v[0], v[1]);
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), alpha2, pk2(b0.z, b0.w)), v[2], v[3]);
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), alpha2, pk2(b1.x, b1.y)), v[4], v[5]);
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), alpha2, pk2(b1.z, b1.w)), v[6], v[7]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), alpha2, t0), v[0], v[1]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), alpha2, t1), v[2], v[3]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), alpha2, t2), v[4], v[5]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), alpha2, t3), v[6], v[7]);
         if (EPI == AP_EPI_BIAS_GELU_F16) {
             gelu_erf2(v[0], v[1]); gelu_erf2(v[2], v[3]); gelu_erf2(v[4], v[5]); gelu_erf2(v[6], v[7]);
         }
@@ -198,18 +275,32 @@ __device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint
 }
 // SwiGLU (Dinov2SwiGLUFFN: hidden = silu(x1) * x2): the chunk's first 16 columns are gates, the last 16 the matching values
 // (weights_in rows are interleaved on the host), so 32 accumulator columns give 16 fp16 outputs = pieces 2c, 2c+1 of the row.
-__device__ __forceinline__ void epilogue_stage_swiglu(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int col0, int lane, int c) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+__device__ __forceinline__ void epilogue_stage_swiglu(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int cc, int lane, int c,
+                                                      const LnRow& ln, const float4& bias_reg, const float4& cs_reg) {
+    const bool fold = ep.stats_in != nullptr;
+    const float scale = fold ? ln.rstd : ep.alpha;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const float4 g0 = __ldg(b4 + 2 * j), g1 = __ldg(b4 + 2 * j + 1), v0 = __ldg(b4 + 4 + 2 * j), v1 = __ldg(b4 + 5 + 2 * j);
-        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float vb[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    for (int j = 0; j < 2; ++j) {   // cc = chunk index inside the warp's 128 columns: gates at cc*32 + 0..15, values at cc*32 + 16..31
+        const float4 g0 = bcast4(bias_reg, cc * 8 + 2 * j), g1 = bcast4(bias_reg, cc * 8 + 2 * j + 1);
+        const float4 v0 = bcast4(bias_reg, cc * 8 + 4 + 2 * j), v1 = bcast4(bias_reg, cc * 8 + 5 + 2 * j);
+        float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float vb[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (fold) {
+            const float4 a0 = bcast4(cs_reg, cc * 8 + 2 * j), a1 = bcast4(cs_reg, cc * 8 + 2 * j + 1);
+            const float4 c0 = bcast4(cs_reg, cc * 8 + 4 + 2 * j), c1 = bcast4(cs_reg, cc * 8 + 5 + 2 * j);
+            const float gs[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float vs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                gb[k] = fmaf(ln.nrm, gs[k], gb[k]);
+                vb[k] = fmaf(ln.nrm, vs[k], vb[k]);
+            }
+        }
         float h[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float g = fmaf(__uint_as_float(r[8 * j + k]), ep.alpha, gb[k]);
-            const float v = fmaf(__uint_as_float(r[16 + 8 * j + k]), ep.alpha, vb[k]);
+            const float g = fmaf(__uint_as_float(r[8 * j + k]), scale, gb[k]);
+            const float v = fmaf(__uint_as_float(r[16 + 8 * j + k]), scale, vb[k]);
             h[k] = g * v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * g));  // silu(g) * v
         }
         *reinterpret_cast<uint4*>(stg + stg_off(lane, c * 2 + j)) =
@@ -363,11 +454,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_remote(tempty_remote[as]);
-                    else ptx::mbar_arrive(&tempty_bar[as]);
+                    if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_remote_relaxed(tempty_remote[as]);
+                    else ptx::mbar_arrive_relaxed(&tempty_bar[as]);
                 }
             };
             if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16 || EPI == AP_EPI_BIAS_SWIGLU_F16) {
+                // lane = accumulator row; its LayerNorm statistics are fetched (L2) while this tile's MMAs are still running
+                const LnRow ln = ln_row_coeffs(ep, row_base + lane, M);
+                const bool owns = lane * 4 < COLS_PER_WARP;   // BN = 128: 64 columns per warp, lanes 16..31 hold nothing
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 bias_reg = owns ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + lane) : zero4;
+                const float4 cs_reg = owns && ep.stats_in != nullptr ? __ldg(reinterpret_cast<const float4*>(ep.colsum + col_base) + lane) : zero4;
                 ptx::mbar_wait(&tfull_bar[as], aphase, 4);
                 ptx::tc_fence_after();
                 uint32_t r[2][32];
@@ -379,15 +476,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     else release_tmem();
                     if (ep.debug & 1) continue;
                     if (EPI == AP_EPI_BIAS_SWIGLU_F16) {
-                        epilogue_stage_swiglu(r[c & 1], stg, ep, col_base + c * 32, lane, c & 3);
+                        epilogue_stage_swiglu(r[c & 1], stg, ep, c, lane, c & 3, ln, bias_reg, cs_reg);
                         if ((c & 3) == 3) epilogue_flush_f16(stg, ep, M, N / 2, row_base, (col_base + (c - 3) * 32) / 2, lane);
                         continue;
                     }
-                    epilogue_stage_f16<EPI>(r[c & 1], stg, ep, col_base + c * 32, lane, c & 1);
+                    epilogue_stage_f16<EPI>(r[c & 1], stg, ep, c, lane, c & 1, ln, bias_reg, cs_reg);
                     if (c & 1) epilogue_flush_f16(stg, ep, M, N, row_base, col_base + (c - 1) * 32, lane);
                 }
             } else {
                 float4 rr[2][8];
+                float rs[8] = {}, rq[8] = {};   // LayerNorm statistics of this warp's rows (when the output feeds a folded LayerNorm)
                 resid_prefetch<EPI>(rr[0], ep, M, N, row_base, col_base, lane);  // in flight while the MMAs of this tile run
                 ptx::mbar_wait(&tfull_bar[as], aphase, 4);
                 ptx::tc_fence_after();
@@ -399,8 +497,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     ptx::tc_wait_ld();
                     if (c + 1 == NCH) release_tmem();
                     if (ep.debug & 1) continue;
-                    epilogue_group_f32<EPI>(r, rr[c & 1], stg, ep, M, N, row_base, col_base + c * 32, lane);
+                    epilogue_group_f32<EPI>(r, rr[c & 1], stg, ep, M, N, row_base, col_base + c * 32, lane, rs, rq);
                 }
+                if (ep.stats_out != nullptr && !(ep.debug & 1)) epilogue_write_stats(ep, M, row_base, col_base / COLS_PER_WARP, lane, rs, rq);
             }
         }
     }
@@ -478,6 +577,20 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
     ep.alpha = extra ? extra->alpha : 1.0f;
     ep.debug = ctx->gemm_debug;
     ep.a_k_blocks = plan->Ka / BK;
+    ep.out_h = extra ? extra->out_h : nullptr;
+    ep.stats_out = extra ? extra->stats_out : nullptr;
+    ep.stats_in = extra ? extra->stats_in : nullptr;
+    ep.colsum = extra && extra->colsum ? extra->colsum : bias;   // never dereferenced without stats_in; keeps the pointer valid
+    ep.ln_parts = extra ? extra->ln_parts : 0;
+    ep.ln_inv_dim = extra && extra->ln_dim > 0 ? 1.0f / static_cast<float>(extra->ln_dim) : 0.f;
+    ep.ln_eps = extra ? extra->ln_eps : 0.f;
+    const bool f32_out = plan->epilogue == AP_EPI_BIAS_RESID_F32 || plan->epilogue == AP_EPI_BIAS_F32;
+    AP_REQUIRE(ctx, (ep.out_h == nullptr) == (ep.stats_out == nullptr) && (ep.out_h == nullptr || f32_out),
+               "gemm: out_h / stats_out belong together and to the fp32-output epilogues");
+    AP_REQUIRE(ctx, ep.stats_out == nullptr || ep.ln_parts == plan->N / (plan->bn / 2),
+               "gemm: producer ln_parts %d must be N / (bn / 2) = %d", ep.ln_parts, plan->N / (plan->bn / 2));
+    AP_REQUIRE(ctx, ep.stats_in == nullptr || (!f32_out && extra->colsum != nullptr && ep.ln_parts > 0 && extra->ln_dim > 0),
+               "gemm: folded LayerNorm needs an fp16-output epilogue, colsum, ln_parts and ln_dim");
     if (plan->cta_group == 2) return dispatch_epi<2, 256>(ctx, plan, ep, stream);
     if (plan->bn == 256) return dispatch_epi<1, 256>(ctx, plan, ep, stream);
     return dispatch_epi<1, 128>(ctx, plan, ep, stream);

@@ -97,6 +97,16 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed arrivals for "I am done READING tensor memory" signals.  The default (.release) arrive makes the warp drain all of its
+// outstanding global stores first (MEMBAR + ERRBAR in SASS: ~8 % of the epilogue warps' stall samples in the GEMM), but nothing the
+// waiting MMA warp does depends on those stores: the only dependency is on the tcgen05.ld results, which are in registers (after
+// tcgen05.wait::ld) before this instruction is even issued.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a cta_group::2 pair; completion bytes are signalled on the LEADER CTA's mbarrier
 // (same smem offset, CTA-rank bit cleared -- the convention of CUTLASS' SM100_TMA_2SM_LOAD).
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;

@@ -176,3 +176,44 @@ def test_preprocess_pixels_bit_exact_vs_cv2_for_any_read_size(R):
         want = (cv2.resize(src, (256, 256)) if R != 256 else src)[16:240, 16:240]
         assert np.array_equal(pix[i], want), (R, i)
     ext.cleanup()
+
+
+@pytest.mark.parametrize("name", ["vit_test_tiny", "dinov2_test_tiny_swiglu"])
+def test_folded_layernorm_option_matches_oracle(name):
+    """`fold_ln` (LayerNorm finished in the epilogues of in_proj / mlp.0 from statistics emitted by the epilogues that produce the
+    residual stream) must give the same features as the LayerNorm kernels -- same tolerance against the fp32 oracle -- and stay
+    bitwise reproducible from run to run (no atomics in the statistics)."""
+    from atlaspatch_b200._lib import Context
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec, render_region_host
+
+    spec = make_spec(4096, 3072, seed=17)
+    wsi = SyntheticWSI(spec)
+    P = 256 if name.startswith("vit") else 224
+    rng = np.random.default_rng(2)
+    xy = [(int(rng.integers(-60, spec.width - 100)), int(rng.integers(-60, spec.height - 100))) for _ in range(40)]
+    coords = torch.tensor([[x, y, P, P, 0] for x, y in xy], dtype=torch.int32, device="cuda")
+    patches = [render_region_host(spec, x, y, P, P) for x, y in xy]
+    if name.startswith("vit"):
+        sd = vit_state_dict(name, seed=3)
+        want = ov.extract_features(patches, sd, name)
+    else:
+        from oracle import dinov2_hf
+
+        sd = dinov2_hf.dinov2_state_dict(name, seed=3)
+        want = dinov2_hf.extract_features(patches, sd, name)
+    ctx = Context.get(0)
+    feats = {}
+    try:
+        for fold in (0, 1):
+            ctx.set_option("fold_ln", fold)
+            ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=16)
+            feats[fold] = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords).cpu().numpy()
+            again = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords).cpu().numpy()
+            assert np.array_equal(again, feats[fold])
+            assert _rel(feats[fold], want).max() < REL_TOL, (fold, _rel(feats[fold], want))
+            ext.cleanup()
+    finally:
+        ctx.set_option("fold_ln", 0)
+    assert _rel(feats[1], feats[0]).max() < REL_TOL   # two independent sets of fp16 roundings, each within REL_TOL of the oracle

@@ -15,6 +15,8 @@ from oracle.weights import vit_state_dict  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "vit_b_16"
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 127
 n = chunk * 16
+for kv in sys.argv[3:]:                      # library options key=int (ap_set_option), e.g. fold_ln=0
+    Context.get(0).set_option(kv.split("=")[0], int(kv.split("=")[1]))
 ext = B200FeatureExtractor(name, vit_state_dict(name, seed=1), max_batch=chunk)
 wsi = SyntheticWSI(make_spec(30000, 30000, 3))
 rng = np.random.default_rng(0)
