@@ -40,7 +40,8 @@ struct SmemLayout {
     static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE;
     static constexpr int NUM_BARS = 2 * STAGES + 4;
     static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
-    static constexpr int STAGING_OFF = (TMEM_PTR_OFF + 16 + 255) / 256 * 256;  // 8 epilogue warps x (32 rows x 128 B)
+    static constexpr int STAGING_OFF = (TMEM_PTR_OFF + 16 + 1023) / 1024 * 1024;  // 8 epilogue warps x (32 rows x 128 B); 1 KB-aligned
+                                                                                   // tiles: the TMA store's 128B swizzle is address-based
     static constexpr int STAGING_BYTES = 8 * 32 * 128;
     static constexpr int TOTAL = STAGING_OFF + STAGING_BYTES;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
@@ -307,23 +308,26 @@ __device__ __forceinline__ void epilogue_stage_swiglu(const uint32_t (&r)[32], u
             make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
     }
 }
-__device__ __forceinline__ void epilogue_flush_f16(uint8_t* stg, const EpiParams& ep, int M, int N, int row_base, int col0, int lane) {
+// The staged 32 rows x 128 B tile has exactly the layout of a 128B-swizzled TMA box (16-byte chunk index XOR row & 7), so the
+// tile goes to global memory with ONE bulk tensor store issued by one lane instead of 8 x (LDS.128 + guarded STG.128) per thread;
+// rows >= M are clipped by the tensor map.  The staging tile may be rewritten once the bulk group has been READ (wait_group.read).
+__device__ __forceinline__ void epilogue_flush_tma(uint8_t* stg, const CUtensorMap* map_out, int row_base, int col0, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's st.shared -> visible to the async proxy
     __syncwarp();
-    const int p = lane & 7;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int rl = it * 4 + (lane >> 3);
-        const int row = row_base + rl;
-        const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(rl, p));
-        if (row < M) *(reinterpret_cast<uint4*>(static_cast<__half*>(ep.out) + static_cast<int64_t>(row) * N + col0) + p) = u;
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_out), "r"(ptx::smem_u32(stg)),
+                     "r"(col0), "r"(row_base)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     __syncwarp();
 }
 
 template <int CG, int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
-                    int K, EpiParams ep) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_out, int M, int N, int K, EpiParams ep) {
     using L = SmemLayout<CG, BN>;
     constexpr int STAGES = L::STAGES;
     constexpr int TILE_M = 128 * CG;
@@ -349,6 +353,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&map_a);
         ptx::prefetch_tmap(&map_w);
+        ptx::prefetch_tmap(&map_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -477,11 +482,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (ep.debug & 1) continue;
                     if (EPI == AP_EPI_BIAS_SWIGLU_F16) {
                         epilogue_stage_swiglu(r[c & 1], stg, ep, c, lane, c & 3, ln, bias_reg, cs_reg);
-                        if ((c & 3) == 3) epilogue_flush_f16(stg, ep, M, N / 2, row_base, (col_base + (c - 3) * 32) / 2, lane);
+                        if ((c & 3) == 3) epilogue_flush_tma(stg, &map_out, row_base, (col_base + (c - 3) * 32) / 2, lane);
                         continue;
                     }
                     epilogue_stage_f16<EPI>(r[c & 1], stg, ep, c, lane, c & 1, ln, bias_reg, cs_reg);
-                    if (c & 1) epilogue_flush_f16(stg, ep, M, N, row_base, col_base + (c - 1) * 32, lane);
+                    if (c & 1) epilogue_flush_tma(stg, &map_out, row_base, col_base + (c - 1) * 32, lane);
                 }
             } else {
                 float4 rr[2][8];
@@ -514,6 +519,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
 template <int CG, int BN, int EPI>
 int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t stream) {
+    // fp16 outputs leave through TMA stores: box = 32 rows x 64 halfs (one staged tile), 128B swizzle, rows clipped at M
+    CUtensorMap map_out{};
+    if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16 || EPI == AP_EPI_BIAS_SWIGLU_F16) {
+        const int n_out = EPI == AP_EPI_BIAS_SWIGLU_F16 ? p->N / 2 : p->N;
+        int rc = ap_make_tmap_f16_2d(ctx, &map_out, ep.out, (uint64_t)p->M, (uint64_t)n_out, (uint64_t)n_out, 32, 64);
+        if (rc) return rc;
+    }
     using L = SmemLayout<CG, BN>;
     auto kern = gemm_tcgen05_kernel<CG, BN, EPI>;
     static bool attr_set = false;  // per instantiation
@@ -528,7 +540,7 @@ int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t str
     ProfScope prof(ctx, stream, AP_K_GEMM, (static_cast<int64_t>(p->N) << 32) | (static_cast<int64_t>(p->K) << 4) | EPI);
     const CUtensorMap& mw = CG == 2 ? p->map_w_half : p->map_w;
     AP_CHECK_CUDA(ctx, ap_launch_pdl(kern, dim3(workers * CG), dim3(NUM_THREADS), L::DYN_BYTES, stream, CG, ctx->pdl != 0, p->map_a, mw,
-                                     p->M, p->N, p->K, ep));
+                                     map_out, p->M, p->N, p->K, ep));
     AP_CHECK_LAUNCH(ctx, "gemm_tcgen05_kernel");
     return AP_OK;
 }
