@@ -4,8 +4,8 @@ The reference's SAM2SegmentationService (atlas_patch/services/segmentation.py:19
   a1  wsi.get_thumbnail_at_power(1.25)                       -> device kernel here (slide.py / ap_thumbnail_area)
   a2  thumb.thumbnail((1024, 1024))                          -> Pillow, same call (host; <= 3 MB)
   a3  PIL resize to 1024 x 1024, BILINEAR                     -> Pillow, same call (host)
-  a4  SAM2ImagePredictor.set_image + predict(box=full image)  -> `predict_logits` callable (NOT built in round 1: the sm_100a
-      Hiera / mask-decoder kernels and their parity oracle are round-2 work)
+  a4  SAM2ImagePredictor.set_image + predict(box=full image)  -> `predict_logits` callable = sam2.py: B200Sam2Predictor
+      (ap_sam2_* : Hiera trunk + FPN + prompt encoder + mask decoder in CUDA)
   a5  mask > threshold, *255, PIL NEAREST back to thumbnail   -> Pillow, same call (host)
 Pillow's fixed-point resamplers define the exact result of a2/a3/a5 and the images are tiny, so these steps deliberately stay
 on the host with the very same library calls (SURVEY.md section 2.3 "Placement guidance").

@@ -261,12 +261,10 @@ def main_b200(args):
     # ---- encoder weights: rank 0 builds the seeded state_dict, NCCL broadcast to the other ranks ----------
     names = vit_state_dict_names(12)
     if rank == 0:
-        from oracle.weights import vit_state_dict  # seeded random weights shared with the CPU arm
+        from atlaspatch_b200.weights import vit_state_dict  # seeded random-init weights (input data), shared with the CPU arm
 
         sd = vit_state_dict("vit_b_16", seed=WEIGHT_SEED)
     else:
-        from oracle.weights import VIT_SPECS  # noqa: F401  (shapes only)
-
         sd = None
     if world > 1:
         shapes = [None]
