@@ -23,8 +23,8 @@ struct ap_ctx {
     std::atomic<int64_t> launches{0};
     // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
     void* encode_tiled = nullptr;
-    int fold_ln = 0;              // LayerNorm folded into the GEMMs around it (read at ap_encoder_finalize; "fold_ln"): measured equal
-                                  // to the separate LayerNorm kernels end to end (the GEMM epilogues pay what the LayerNorms save), so off
+    int fold_ln = 1;              // LayerNorm folded into the GEMMs around it: 0 off, 1 automatic (<= 32 layers), 2 on (read at
+                                  // ap_encoder_finalize; "fold_ln"; encoder.cu)
     int sam_tensor_cores = 1;     // SAM2 linears on mma.sync: 1 split-fp16 operands (3 MMAs, fp32-like), 2 plain fp16 (1 MMA), 0 fp32 SIMT
     int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split weights: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
     int pdl = 1;                  // programmatic dependent launch for the encoder kernel chain (ap_set_option "pdl")
@@ -131,10 +131,10 @@ struct GemmExtra {
     // the partial (sum, sum of squares) of each block of bn/2 columns: stats_out[out_row * (N / (bn/2)) + column block]
     __half* out_h = nullptr;
     float2* stats_out = nullptr;
-    // consumer side (fp16-output epilogues): A holds raw x, W has gamma folded in; the epilogue finishes the normalisation,
-    //   out = rstd[m] * acc - rstd[m] * mean[m] * colsum[n] + bias[n],  mean / rstd from the ln_parts partials of row m
+    // consumer side (fp16-output epilogues): A holds raw x, W has gamma folded in and its rows centred (zero row sums absorb the
+    // mean: x W''^T = (x - mean) W'^T); the epilogue only scales by this row's 1 / sigma from the ln_parts partials of the row:
+    //   out = rstd[m] * acc + bias'[n]
     const float2* stats_in = nullptr;
-    const float* colsum = nullptr;   // [N]: sum_k W'[n, k] of the weights as stored (fp16-rounded, hi + lo)
     int ln_parts = 0;
     int ln_dim = 0;                  // length of the normalised rows (hidden size)
     float ln_eps = 0.f;

@@ -77,7 +77,8 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         return AP_OK;
     }
     if (!strcmp(key, "fold_ln")) {   // read at ap_encoder_finalize
-        ctx->fold_ln = value != 0;
+        AP_REQUIRE(ctx, value >= 0 && value <= 2, "fold_ln must be 0 (off), 1 (automatic) or 2 (on)");
+        ctx->fold_ln = value;
         return AP_OK;
     }
     if (!strcmp(key, "sam_tensor_cores")) {

@@ -61,17 +61,17 @@ struct EpiParams {
     __half* out_h;
     float2* stats_out;
     const float2* stats_in;
-    const float* colsum;
     int ln_parts;
     float ln_inv_dim, ln_eps;
 };
 
-// Per-row LayerNorm coefficients of the consumer epilogues: v = acc * rstd + (bias + nrm * colsum), nrm = -rstd * mean.
+// Per-row scale of the consumer epilogues: with gamma folded into the weights AND their rows centred (sum_k W''[n, k] = 0, which
+// absorbs the mean: x W''^T = (x - mean) W'^T), the folded LayerNorm is v = acc * rstd + bias'.
 struct LnRow {
-    float rstd, nrm;
+    float rstd;
 };
 __device__ __forceinline__ LnRow ln_row_coeffs(const EpiParams& ep, int row, int M) {
-    LnRow c{1.0f, 0.0f};
+    LnRow c{ep.alpha};
     if (ep.stats_in == nullptr || row >= M) return c;
     float s = 0.f, q = 0.f;
     const float2* p = ep.stats_in + static_cast<int64_t>(row) * ep.ln_parts;
@@ -83,7 +83,6 @@ __device__ __forceinline__ LnRow ln_row_coeffs(const EpiParams& ep, int row, int
     const float mean = s * ep.ln_inv_dim;
     const float var = fmaxf(q * ep.ln_inv_dim - mean * mean, 0.f);
     c.rstd = rsqrtf(var + ep.ln_eps);
-    c.nrm = -c.rstd * mean;
     return c;
 }
 
@@ -246,27 +245,17 @@ __device__ __forceinline__ float4 bcast4(const float4& v, int src_lane) {
 // fp16 output: bias (+GELU) in the row-per-lane layout, packed halves staged; `half_sel` = which 64 B half of the
 // 128 B row this 32-column chunk fills.  Call flush after both halves.
 template <int EPI>
-__device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int c, int lane,
-                                                   int half_sel, const LnRow& ln, const float4& bias_reg, const float4& cs_reg) {
-    const bool fold = ep.stats_in != nullptr;
-    const uint64_t alpha2 = fold ? pk2(ln.rstd, ln.rstd) : pk2(ep.alpha, ep.alpha);
-    const uint64_t nrm2 = pk2(ln.nrm, ln.nrm);
+__device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint8_t* stg, int c, int lane, int half_sel, const LnRow& ln,
+                                                   const float4& bias_reg) {
+    const uint64_t alpha2 = pk2(ln.rstd, ln.rstd);   // the constant alpha, or this row's 1 / sigma (folded LayerNorm)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float4 b0 = bcast4(bias_reg, c * 8 + 2 * j), b1 = bcast4(bias_reg, c * 8 + 2 * j + 1);
-        uint64_t t0 = pk2(b0.x, b0.y), t1 = pk2(b0.z, b0.w), t2 = pk2(b1.x, b1.y), t3 = pk2(b1.z, b1.w);
-        if (fold) {   // bias + nrm * colsum: the mean term of the folded LayerNorm
-            const float4 c0 = bcast4(cs_reg, c * 8 + 2 * j), c1 = bcast4(cs_reg, c * 8 + 2 * j + 1);
-            t0 = fma2(pk2(c0.x, c0.y), nrm2, t0);
-            t1 = fma2(pk2(c0.z, c0.w), nrm2, t1);
-            t2 = fma2(pk2(c1.x, c1.y), nrm2, t2);
-            t3 = fma2(pk2(c1.z, c1.w), nrm2, t3);
-        }
         float v[8];
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), alpha2, t0), v[0], v[1]);
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), alpha2, t1), v[2], v[3]);
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), alpha2, t2), v[4], v[5]);
-        upk2(fma2(pk2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), alpha2, t3), v[6], v[7]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), alpha2, pk2(b0.x, b0.y)), v[0], v[1]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), alpha2, pk2(b0.z, b0.w)), v[2], v[3]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), alpha2, pk2(b1.x, b1.y)), v[4], v[5]);
+        upk2(fma2(pk2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), alpha2, pk2(b1.z, b1.w)), v[6], v[7]);
         if (EPI == AP_EPI_BIAS_GELU_F16) {
             gelu_erf2(v[0], v[1]); gelu_erf2(v[2], v[3]); gelu_erf2(v[4], v[5]); gelu_erf2(v[6], v[7]);
         }
@@ -276,27 +265,15 @@ __device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint
 }
 // SwiGLU (Dinov2SwiGLUFFN: hidden = silu(x1) * x2): the chunk's first 16 columns are gates, the last 16 the matching values
 // (weights_in rows are interleaved on the host), so 32 accumulator columns give 16 fp16 outputs = pieces 2c, 2c+1 of the row.
-__device__ __forceinline__ void epilogue_stage_swiglu(const uint32_t (&r)[32], uint8_t* stg, const EpiParams& ep, int cc, int lane, int c,
-                                                      const LnRow& ln, const float4& bias_reg, const float4& cs_reg) {
-    const bool fold = ep.stats_in != nullptr;
-    const float scale = fold ? ln.rstd : ep.alpha;
+__device__ __forceinline__ void epilogue_stage_swiglu(const uint32_t (&r)[32], uint8_t* stg, int cc, int lane, int c, const LnRow& ln,
+                                                      const float4& bias_reg) {
+    const float scale = ln.rstd;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {   // cc = chunk index inside the warp's 128 columns: gates at cc*32 + 0..15, values at cc*32 + 16..31
         const float4 g0 = bcast4(bias_reg, cc * 8 + 2 * j), g1 = bcast4(bias_reg, cc * 8 + 2 * j + 1);
         const float4 v0 = bcast4(bias_reg, cc * 8 + 4 + 2 * j), v1 = bcast4(bias_reg, cc * 8 + 5 + 2 * j);
-        float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        float vb[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (fold) {
-            const float4 a0 = bcast4(cs_reg, cc * 8 + 2 * j), a1 = bcast4(cs_reg, cc * 8 + 2 * j + 1);
-            const float4 c0 = bcast4(cs_reg, cc * 8 + 4 + 2 * j), c1 = bcast4(cs_reg, cc * 8 + 5 + 2 * j);
-            const float gs[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float vs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                gb[k] = fmaf(ln.nrm, gs[k], gb[k]);
-                vb[k] = fmaf(ln.nrm, vs[k], vb[k]);
-            }
-        }
+        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float vb[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         float h[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -308,6 +285,7 @@ __device__ __forceinline__ void epilogue_stage_swiglu(const uint32_t (&r)[32], u
             make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
     }
 }
+
 // The staged 32 rows x 128 B tile has exactly the layout of a 128B-swizzled TMA box (16-byte chunk index XOR row & 7), so the
 // tile goes to global memory with ONE bulk tensor store issued by one lane instead of 8 x (LDS.128 + guarded STG.128) per thread;
 // rows >= M are clipped by the tensor map.  The staging tile may be rewritten once the bulk group has been READ (wait_group.read).
@@ -467,9 +445,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 // lane = accumulator row; its LayerNorm statistics are fetched (L2) while this tile's MMAs are still running
                 const LnRow ln = ln_row_coeffs(ep, row_base + lane, M);
                 const bool owns = lane * 4 < COLS_PER_WARP;   // BN = 128: 64 columns per warp, lanes 16..31 hold nothing
-                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 bias_reg = owns ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + lane) : zero4;
-                const float4 cs_reg = owns && ep.stats_in != nullptr ? __ldg(reinterpret_cast<const float4*>(ep.colsum + col_base) + lane) : zero4;
+                const float4 bias_reg = owns ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
                 ptx::mbar_wait(&tfull_bar[as], aphase, 4);
                 ptx::tc_fence_after();
                 uint32_t r[2][32];
@@ -481,11 +457,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     else release_tmem();
                     if (ep.debug & 1) continue;
                     if (EPI == AP_EPI_BIAS_SWIGLU_F16) {
-                        epilogue_stage_swiglu(r[c & 1], stg, ep, c, lane, c & 3, ln, bias_reg, cs_reg);
+                        epilogue_stage_swiglu(r[c & 1], stg, c, lane, c & 3, ln, bias_reg);
                         if ((c & 3) == 3) epilogue_flush_tma(stg, &map_out, row_base, (col_base + (c - 3) * 32) / 2, lane);
                         continue;
                     }
-                    epilogue_stage_f16<EPI>(r[c & 1], stg, ep, c, lane, c & 1, ln, bias_reg, cs_reg);
+                    epilogue_stage_f16<EPI>(r[c & 1], stg, c, lane, c & 1, ln, bias_reg);
                     if (c & 1) epilogue_flush_tma(stg, &map_out, row_base, col_base + (c - 1) * 32, lane);
                 }
             } else {
@@ -592,7 +568,6 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
     ep.out_h = extra ? extra->out_h : nullptr;
     ep.stats_out = extra ? extra->stats_out : nullptr;
     ep.stats_in = extra ? extra->stats_in : nullptr;
-    ep.colsum = extra && extra->colsum ? extra->colsum : bias;   // never dereferenced without stats_in; keeps the pointer valid
     ep.ln_parts = extra ? extra->ln_parts : 0;
     ep.ln_inv_dim = extra && extra->ln_dim > 0 ? 1.0f / static_cast<float>(extra->ln_dim) : 0.f;
     ep.ln_eps = extra ? extra->ln_eps : 0.f;
@@ -601,8 +576,8 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
                "gemm: out_h / stats_out belong together and to the fp32-output epilogues");
     AP_REQUIRE(ctx, ep.stats_out == nullptr || ep.ln_parts == plan->N / (plan->bn / 2),
                "gemm: producer ln_parts %d must be N / (bn / 2) = %d", ep.ln_parts, plan->N / (plan->bn / 2));
-    AP_REQUIRE(ctx, ep.stats_in == nullptr || (!f32_out && extra->colsum != nullptr && ep.ln_parts > 0 && extra->ln_dim > 0),
-               "gemm: folded LayerNorm needs an fp16-output epilogue, colsum, ln_parts and ln_dim");
+    AP_REQUIRE(ctx, ep.stats_in == nullptr || (!f32_out && ep.ln_parts > 0 && extra->ln_dim > 0),
+               "gemm: folded LayerNorm needs an fp16-output epilogue, ln_parts and ln_dim");
     if (plan->cta_group == 2) return dispatch_epi<2, 256>(ctx, plan, ep, stream);
     if (plan->bn == 256) return dispatch_epi<1, 256>(ctx, plan, ep, stream);
     return dispatch_epi<1, 128>(ctx, plan, ep, stream);

@@ -105,8 +105,9 @@ def test_cls_only_last_layer_and_attention_flavours_agree():
     finally:
         ctx.set_option("cls_only_last_layer", 1)
         ctx.set_option("attn_mode", 2)
-    # same attention flavour, class-token-only last layer vs full last layer: only accumulation order differs
-    assert _rel(full, base).max() < 1e-4
+    # same attention flavour, class-token-only last layer vs full last layer: accumulation order differs, and with the folded
+    # LayerNorm the tail normalises the fp32 row explicitly while the full path scales the GEMM of the fp16 row (1e-4 level)
+    assert _rel(full, base).max() < 2e-4
     # the two attention kernels round P against different row maxima: independent fp16-level noise, both within tolerance
     for f in (base, full, full_mma):
         assert _rel(f, want).max() < REL_TOL
@@ -206,7 +207,7 @@ def test_folded_layernorm_option_matches_oracle(name):
     ctx = Context.get(0)
     feats = {}
     try:
-        for fold in (0, 1):
+        for fold in (0, 2):
             ctx.set_option("fold_ln", fold)
             ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=16)
             feats[fold] = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords).cpu().numpy()
@@ -215,5 +216,5 @@ def test_folded_layernorm_option_matches_oracle(name):
             assert _rel(feats[fold], want).max() < REL_TOL, (fold, _rel(feats[fold], want))
             ext.cleanup()
     finally:
-        ctx.set_option("fold_ln", 0)
-    assert _rel(feats[1], feats[0]).max() < REL_TOL   # two independent sets of fp16 roundings, each within REL_TOL of the oracle
+        ctx.set_option("fold_ln", 1)   # the library default
+    assert _rel(feats[2], feats[0]).max() < REL_TOL   # two independent sets of fp16 roundings, each within REL_TOL of the oracle
