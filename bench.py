@@ -354,9 +354,10 @@ def main_b200(args):
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all 49 launches per 127-patch chunk: conv_proj, in_proj, out_proj, mlp.0, mlp.3)",
         "achieved": achieved_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": (achieved_tflops / peaks["tflops_sustained"]) if achieved_tflops else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 49 GEMM launches of one 127-patch chunk, from
-        # the ncu --set full capture profiles/r01_ncu_full_gemm_attention.csv (algorithmic bytes A + W + out (+ resid): 219 MB)
-        "traffic": 170.0e6, "traffic_unit": "B/launch (ncu, profiles/r01_ncu_full_gemm_attention.csv)",
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 49 GEMM launches of one 127-patch chunk (ncu,
+        # profiles/r01_ncu_gemm_dram_traffic.csv: 103.7 MB read + 64.7 MB written); algorithmic bytes A + W + out (+ resid + the fp16
+        # copy of the residual stream the folded LayerNorm needs) average 233 MB per launch, the difference is served by L2
+        "traffic": 168.4e6, "traffic_unit": "B/launch (ncu, profiles/r01_ncu_gemm_dram_traffic.csv)",
         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
         "algorithmic_flop_per_launch": GEMM_FLOP_PER_PATCH * patches_timed / max(gemm_n, 1),
         "avg_launch_ms": gemm_ms / max(gemm_n, 1), "launches_timed": gemm_n,
