@@ -35,6 +35,8 @@ struct ap_ctx {
     int gemm_cta_group = 2;  // default GEMM flavour (ap_set_option "gemm_cta_group"; env AP_GEMM_CTA_GROUP)
     // optional per-launch CUDA-event timing (ap_profile_*): bench.py's live roofline measurement
     unsigned profiling = 0;  // bit mask of ApKernelClass values to time (0 = off)
+    int prof_stride = 1;     // time every prof_stride-th launch of a class ("profile_stride"): sampling keeps the event records from
+    unsigned prof_seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // serialising the programmatic-dependent-launch chain around every kernel
     std::mutex prof_mu;
     struct ProfRec { cudaEvent_t start, stop; int cls; int64_t tag; };
     std::vector<ProfRec> prof_recs;

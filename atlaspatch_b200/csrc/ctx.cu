@@ -76,6 +76,12 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         ctx->cls_only_last_layer = value != 0;
         return AP_OK;
     }
+    if (!strcmp(key, "profile_stride")) {
+        AP_REQUIRE(ctx, value >= 1, "profile_stride must be >= 1");
+        ctx->prof_stride = value;
+        for (auto& v : ctx->prof_seen) v = 0;
+        return AP_OK;
+    }
     if (!strcmp(key, "fold_ln")) {   // read at ap_encoder_finalize
         AP_REQUIRE(ctx, value >= 0 && value <= 2, "fold_ln must be 0 (off), 1 (automatic) or 2 (on)");
         ctx->fold_ln = value;
@@ -125,6 +131,7 @@ static cudaEvent_t prof_get_event(ap_ctx* ctx) {
 ProfScope::ProfScope(ap_ctx* c, cudaStream_t s, int cls, int64_t tag) : ctx(c), st(s) {
     if (!ctx || !((ctx->profiling >> cls) & 1u)) return;
     std::lock_guard<std::mutex> lk(ctx->prof_mu);
+    if (ctx->prof_stride > 1 && (ctx->prof_seen[cls & 7]++ % static_cast<unsigned>(ctx->prof_stride)) != 0) return;
     cudaEvent_t start = prof_get_event(ctx);
     stop = prof_get_event(ctx);
     cudaEventRecord(start, st);

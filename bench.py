@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=96, help="patches timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-stride", type=int, default=4,
+                    help="time every Nth GEMM launch of the timed region with CUDA events (0 = none: roofline from the extra step only)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=int (ap_set_option), for A/B measurements")
     ap.add_argument("--ref-sample", type=int, default=32, help="patches per step of the reference arm")
     return ap.parse_args()
@@ -298,7 +300,13 @@ def main_b200(args):
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count
-    ctx.profile(True, classes=("gemm",))   # live per-launch CUDA events for the dominant kernel only (49 of 88 launches)
+    # live CUDA events for the dominant kernel inside the timed region: every --profile-stride-th GEMM launch (the stride, 4, is
+    # coprime with the 49 GEMM launches of a chunk, so over a step every shape is sampled evenly); timing EVERY launch costs the
+    # step ~2 % because an event record between two kernels breaks their programmatic-dependent-launch overlap
+    stride = max(args.profile_stride, 0)
+    if stride:
+        ctx.set_option("profile_stride", stride)
+        ctx.profile(True, classes=("gemm",))
     ctx.profile_read()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -311,6 +319,7 @@ def main_b200(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     prof = ctx.profile_read()
+    ctx.set_option("profile_stride", 1)
     ctx.profile(True)                        # one extra, untimed step with every kernel class timed: per-class breakdown
     step(args.warmup + args.steps)
     prof_all = ctx.profile_read()
@@ -348,7 +357,12 @@ def main_b200(args):
         return 0
 
     gemm_ms, gemm_n = prof["gemm"]
-    patches_timed = args.steps * B
+    if stride == 0:                          # nothing timed inside the region: fall back to the extra profiled step
+        gemm_ms, gemm_n = prof_all["gemm"]
+        patches_timed = B
+    else:
+        gemm_ms, gemm_n = gemm_ms * stride, gemm_n * stride   # sampled mean x all launches
+        patches_timed = args.steps * B
     achieved_tflops = (patches_timed * GEMM_FLOP_PER_PATCH) / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
     roofline = {
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all 49 launches per 127-patch chunk: conv_proj, in_proj, out_proj, mlp.0, mlp.3)",
@@ -360,8 +374,9 @@ def main_b200(args):
         "traffic": 168.4e6, "traffic_unit": "B/launch (ncu, profiles/r01_ncu_gemm_dram_traffic.csv)",
         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
         "algorithmic_flop_per_launch": GEMM_FLOP_PER_PATCH * patches_timed / max(gemm_n, 1),
-        "avg_launch_ms": gemm_ms / max(gemm_n, 1), "launches_timed": gemm_n,
-        "kernel_share_of_step": gemm_ms / ms if ms > 0 else None,
+        "avg_launch_ms": gemm_ms / max(gemm_n, 1), "launches_timed": gemm_n // max(stride, 1) if stride else gemm_n,
+        "launch_sampling": (f"every {stride}th GEMM launch of the timed region" if stride else "the extra profiled step only"),
+        "kernel_share_of_step": gemm_ms / (ms * patches_timed / (args.steps * B)) if ms > 0 else None,
         "per_class_ms_one_step": {k: round(v[0], 3) for k, v in prof_all.items() if v[1]},
         "whole_model": {"tflops": value / world * MODEL_FLOP_PER_PATCH / 1e12,
                         "frac_of_sustained_peak": value / world * MODEL_FLOP_PER_PATCH / 1e12 / peaks["tflops_sustained"]},
