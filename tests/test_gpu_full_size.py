@@ -94,3 +94,39 @@ def test_coords_filter_and_encoder_inputs_at_full_size(big):
     rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
     assert rel.max() < 1e-3, rel
     ext.cleanup()
+
+
+def test_config3_dinov2_large_on_a_40000_square_slide():
+    """BASELINE.json configs[3] (one rank's share): 40000 x 40000 slide, 224 px patches, dinov2_large.  The coordinate list must be
+    the CPU oracle's (the reference's algorithm), the encoder inputs bit-exact and the features within 1e-3 of transformers' for the
+    candidates farthest into the 4.8 GB image."""
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.services import B200PatchExtractionService, ExtractionConfig, Slide
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec, render_region_host, truth_mask
+    from oracle import coords as oc
+    from oracle import dinov2_hf, resize_aa
+    from PIL import Image
+
+    spec = make_spec(40000, 40000, 3)
+    wsi = SyntheticWSI(spec)
+    m = (truth_mask(spec) * 255).astype(np.uint8)
+    mask = np.asarray(Image.fromarray(m).resize((1000, 1000), Image.Resampling.NEAREST), dtype=np.float32) / 255.0
+    svc = B200PatchExtractionService(ExtractionConfig(patch_size=224, target_magnification=20, step_size=224))
+    res = svc.extract(wsi, mask, slide=Slide(Path(wsi.path), mpp=0.5))
+    want = oc.coords_from_mask(mask, level0_wh=(40000, 40000), src_mag=20, target_mag=20, patch_size=224, step_size=224, tissue_thresh=0.0)
+    assert res.num_patches > 8000 and np.array_equal(res.coords, want)
+
+    sd = dinov2_hf.dinov2_state_dict("dinov2_large", seed=4321)
+    ext = B200FeatureExtractor("dinov2_large", sd, input_patch=224, max_batch=16)
+    far = np.argsort(res.coords[:, 1].astype(np.int64) * 40000 + res.coords[:, 0])[-3:]
+    rows = torch.from_numpy(res.coords[far]).cuda()
+    patches = [render_region_host(spec, int(x), int(y), 224, 224) for x, y in res.coords[far, :2]]
+    pix = ext.preprocess_pixels(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows)
+    for i, p in enumerate(patches):
+        assert np.array_equal(pix[i], resize_aa.dinov2_pixels(p)), i
+    got = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows).cpu().numpy()
+    ref = dinov2_hf.extract_features(patches, sd, "dinov2_large")
+    rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 1e-3, rel
+    ext.cleanup()
