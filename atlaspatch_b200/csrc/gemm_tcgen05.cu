@@ -152,6 +152,15 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // fully coalesced accesses: 8 lanes cover one 128 B row segment, one warp instruction covers 4 rows.
 __device__ __forceinline__ uint32_t stg_off(int row, int piece) { return static_cast<uint32_t>(row * 128 + ((piece ^ (row & 7)) << 4)); }
 
+// The bias / column-sum values of a warp's COLS_PER_WARP columns are the same for all of its 32 rows.  Loading them with one
+// LDG per lane and chunk put a global-load latency (long scoreboard) in front of every chunk's math (ncu: ~1/3 of the epilogue
+// warps' stall samples); instead each lane fetches 4 of the 128 values once per tile -- before the accumulator is ready -- and the
+// chunks pick them up with warp shuffles.
+__device__ __forceinline__ float4 bcast4(const float4& v, int src_lane) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src_lane), __shfl_sync(0xffffffffu, v.y, src_lane),
+                       __shfl_sync(0xffffffffu, v.z, src_lane), __shfl_sync(0xffffffffu, v.w, src_lane));
+}
+
 // fp32 output (residual add / positional embedding): one 32-column chunk = 128 B per row.
 // The residual rows are fetched (coalesced) one chunk AHEAD -- the first chunk even before the accumulator is ready, i.e.
 // under the tile's MMAs -- because the epilogue of out_proj / mlp.3 is bound by the latency of these loads, not by
@@ -170,13 +179,14 @@ __device__ __forceinline__ void resid_prefetch(float4 (&rr)[8], const EpiParams&
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], const float4 (&rr)[8], uint8_t* stg, const EpiParams& ep,
-                                                   int M, int N, int row_base, int col0, int lane, float (&rs)[8], float (&rq)[8]) {
+                                                   int M, int N, int row_base, int col0, int lane, float (&rs)[8], float (&rq)[8],
+                                                   const float4& bias_reg, int c) {
     const int p = lane & 7;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
         *reinterpret_cast<uint4*>(stg + stg_off(lane, q)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     __syncwarp();
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + p);
+    const float4 bb = bcast4(bias_reg, c * 8 + p);   // this lane's 4 columns of chunk c (a global load here stalled every chunk: ncu)
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int rl = it * 4 + (lane >> 3);
@@ -231,15 +241,6 @@ __device__ __forceinline__ void epilogue_write_stats(const EpiParams& ep, int M,
         rs[it] = 0.f;
         rq[it] = 0.f;
     }
-}
-
-// The bias / column-sum values of a warp's COLS_PER_WARP columns are the same for all of its 32 rows.  Loading them with one
-// LDG per lane and chunk put a global-load latency (long scoreboard) in front of every chunk's math (ncu: ~1/3 of the epilogue
-// warps' stall samples); instead each lane fetches 4 of the 128 values once per tile -- before the accumulator is ready -- and the
-// chunks pick them up with warp shuffles.
-__device__ __forceinline__ float4 bcast4(const float4& v, int src_lane) {
-    return make_float4(__shfl_sync(0xffffffffu, v.x, src_lane), __shfl_sync(0xffffffffu, v.y, src_lane),
-                       __shfl_sync(0xffffffffu, v.z, src_lane), __shfl_sync(0xffffffffu, v.w, src_lane));
 }
 
 // fp16 output: bias (+GELU) in the row-per-lane layout, packed halves staged; `half_sel` = which 64 B half of the
@@ -468,6 +469,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 float4 rr[2][8];
                 float rs[8] = {}, rq[8] = {};   // LayerNorm statistics of this warp's rows (when the output feeds a folded LayerNorm)
                 resid_prefetch<EPI>(rr[0], ep, M, N, row_base, col_base, lane);  // in flight while the MMAs of this tile run
+                const float4 bias_reg = lane * 4 < COLS_PER_WARP ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + lane)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                 ptx::mbar_wait(&tfull_bar[as], aphase, 4);
                 ptx::tc_fence_after();
 #pragma unroll
@@ -478,7 +481,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     ptx::tc_wait_ld();
                     if (c + 1 == NCH) release_tmem();
                     if (ep.debug & 1) continue;
-                    epilogue_group_f32<EPI>(r, rr[c & 1], stg, ep, M, N, row_base, col_base + c * 32, lane, rs, rq);
+                    epilogue_group_f32<EPI>(r, rr[c & 1], stg, ep, M, N, row_base, col_base + c * 32, lane, rs, rq, bias_reg, c);
                 }
                 if (ep.stats_out != nullptr && !(ep.debug & 1)) epilogue_write_stats(ep, M, row_base, col_base / COLS_PER_WARP, lane, rs, rq);
             }
