@@ -177,6 +177,15 @@ __device__ __forceinline__ void resid_prefetch(float4 (&rr)[8], const EpiParams&
     }
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {   // explicit shared-space load: the generic LD the compiler emitted for the
+    float4 v;                                               // staging reads is a long-scoreboard access
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// ncu (source view) showed this epilogue bound by single-warp instruction latency: ~43 instructions per 4-row step in eight
+// separate basic blocks (row < M and "fold" branches), each starting with a staging load whose latency nothing overlapped.  Now all
+// eight staged rows are fetched first, the arithmetic is branch-free and only the stores are predicated.
 template <int EPI>
 __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], const float4 (&rr)[8], uint8_t* stg, const EpiParams& ep,
                                                    int M, int N, int row_base, int col0, int lane, float (&rs)[8], float (&rq)[8],
@@ -186,32 +195,36 @@ __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], cons
     for (int q = 0; q < 8; ++q)
         *reinterpret_cast<uint4*>(stg + stg_off(lane, q)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     __syncwarp();
-    const float4 bb = bcast4(bias_reg, c * 8 + p);   // this lane's 4 columns of chunk c (a global load here stalled every chunk: ncu)
+    const float4 bb = bcast4(bias_reg, c * 8 + p);   // this lane's 4 columns of chunk c
+    const uint32_t stg_u = ptx::smem_u32(stg);
+    float4 v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) v[it] = lds128(stg_u + stg_off(it * 4 + (lane >> 3), p));
+    const bool fold = ep.out_h != nullptr;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-        const int rl = it * 4 + (lane >> 3);
-        const int row = row_base + rl;
-        const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(rl, p));
-        float4 v = make_float4(a.x * ep.alpha + bb.x, a.y * ep.alpha + bb.y, a.z * ep.alpha + bb.z, a.w * ep.alpha + bb.w);
-        if (row < M) {
-            int64_t out_row = row;
-            if (EPI == AP_EPI_BIAS_RESID_F32) {
-                v.x += rr[it].x; v.y += rr[it].y; v.z += rr[it].z; v.w += rr[it].w;
-            } else if (ep.tokens_per_image > 0) {   // conv_proj: token row -> sequence row (+1 class token per image), + pos
-                const int b = row / ep.tokens_per_image;
-                const int tk = row - b * ep.tokens_per_image;
-                out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + 1) + 1 + tk;
-                if (ep.pos != nullptr) {
-                    const float4 pp = __ldg(reinterpret_cast<const float4*>(ep.pos + static_cast<int64_t>(1 + tk) * N + col0) + p);
-                    v.x += pp.x; v.y += pp.y; v.z += pp.z; v.w += pp.w;
-                }
+        const int row = row_base + it * 4 + (lane >> 3);
+        v[it] = make_float4(fmaf(v[it].x, ep.alpha, bb.x), fmaf(v[it].y, ep.alpha, bb.y), fmaf(v[it].z, ep.alpha, bb.z),
+                            fmaf(v[it].w, ep.alpha, bb.w));
+        int64_t out_row = row;
+        if (EPI == AP_EPI_BIAS_RESID_F32) {
+            v[it].x += rr[it].x; v[it].y += rr[it].y; v[it].z += rr[it].z; v[it].w += rr[it].w;
+        } else if (ep.tokens_per_image > 0) {   // conv_proj: token row -> sequence row (+1 class token per image), + pos
+            const int b = row / ep.tokens_per_image;
+            const int tk = row - b * ep.tokens_per_image;
+            out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + 1) + 1 + tk;
+            if (ep.pos != nullptr && row < M) {
+                const float4 pp = __ldg(reinterpret_cast<const float4*>(ep.pos + static_cast<int64_t>(1 + tk) * N + col0) + p);
+                v[it].x += pp.x; v[it].y += pp.y; v[it].z += pp.z; v[it].w += pp.w;
             }
-            *(reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * N + col0) + p) = v;
-            if (ep.out_h != nullptr) {   // the next GEMM's A operand: raw x in fp16 (its LayerNorm is finished in that GEMM's epilogue)
-                *reinterpret_cast<uint2*>(ep.out_h + out_row * N + col0 + p * 4) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
-                rs[it] += (v.x + v.y) + (v.z + v.w);
-                rq[it] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-            }
+        }
+        if (row < M) *(reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * N + col0) + p) = v[it];
+        if (fold) {   // the next GEMM's A operand: raw x in fp16 (its LayerNorm is finished in that GEMM's epilogue) + row statistics
+            if (row < M)
+                *reinterpret_cast<uint2*>(ep.out_h + out_row * N + col0 + p * 4) =
+                    make_uint2(pack_half2(v[it].x, v[it].y), pack_half2(v[it].z, v[it].w));
+            rs[it] += (v[it].x + v[it].y) + (v[it].z + v[it].w);   // rows >= M accumulate values that are never written out
+            rq[it] += (v[it].x * v[it].x + v[it].y * v[it].y) + (v[it].z * v[it].z + v[it].w * v[it].w);
         }
     }
     __syncwarp();
