@@ -147,11 +147,15 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
 int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const float* gamma, const float* beta,
                      float eps, __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream);
 int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
-// tcgen05 attention (16 <= S_pad <= 256): TMA descriptors over the packed QKV buffer [rows, 3 * heads * 64]
+// tcgen05 attention (S <= 257): TMA descriptors over the packed QKV buffer [rows, 3 * heads * 64]
 struct AttnPlan {
     CUtensorMap map_q;   // box 128 rows x 64
     CUtensorMap map_kv;  // box S_pad rows x 64
-    int S_pad;
+    const __half* qkv;   // the packed QKV buffer the maps describe
+    int S_pad;           // MMA keys rounded up to 16
+    int q0, nq;          // query token window per image
+    int k0, nk;          // MMA key token window per image
+    int xkey;            // extra key token folded in as a rank-1 update (257-token sequences: the class token), else -1
 };
 int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int rows, int S, int heads);
 int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream);
@@ -166,7 +170,8 @@ int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64
                              int input_patch, int image, int patch, const int32_t* tap_min, const int32_t* tap_cnt, const int16_t* tap_w,
                              int max_taps, int precision, int max_src_rows, __half* out, int64_t out_row_stride, const int* centre,
                              cudaStream_t stream);
-int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
+// class-token query only; image b's output row is out[b * out_row_stride] (1: compact rows, S: row 0 of every image's block)
+int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, int out_row_stride, cudaStream_t stream);
 int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, int64_t src_row_stride, int D, cudaStream_t stream);
 int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D, __half* xh,
                     float2* stats, int parts, cudaStream_t stream);

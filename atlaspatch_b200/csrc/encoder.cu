@@ -219,7 +219,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         if (li + 1 == e->layers.size() && ctx->cls_only_last_layer) {
             // Only x[:, 0] survives the final LayerNorm (models/patch/base.py:100 -> torchvision forward `x[:, 0]`): the last
             // layer's attention needs every token's K/V but only the class-token query, and out_proj / MLP only that row.
-            if ((rc = ap_cls_attention_run(ctx, e->qkv, e->yc_attn, nb, T1, e->d.heads, st))) return rc;
+            if ((rc = ap_cls_attention_run(ctx, e->qkv, e->yc_attn, nb, T1, e->d.heads, 1, st))) return rc;
             if ((rc = ap_gather_rows_run(ctx, e->x, e->xc, nb, static_cast<int64_t>(T1) * D, D, st))) return rc;
             p = L.pc_o; p.M = nb;
             if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->xc, e->xc, nullptr, st))) return rc;
@@ -453,8 +453,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     }
 
     {
-        const int S_pad = (T1 + 15) / 16 * 16;
-        e->attn_tc = S_pad <= 256;
+        e->attn_tc = T1 <= 257;   // 257 (DINOv2 @ 224): 256 patch keys through the MMA + the class token as a rank-1 extra key
         if (e->attn_tc && (rc = ap_attention_tc_plan(ctx, &e->p_attn, e->qkv, (int)rows, T1, e->d.heads))) return rc;
     }
 

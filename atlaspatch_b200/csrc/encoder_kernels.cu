@@ -331,7 +331,7 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S
 // One warp per (image, head): lane j scores keys j, j+32, ...; softmax over the warp; lane pair d accumulates P.V.
 // =====================================================================================================
 __global__ void __launch_bounds__(384)
-cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int heads) {
+cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int heads, int out_row_stride) {
     ptx::pdl_wait();
     ptx::pdl_launch_dependents();
     const int b = blockIdx.x;
@@ -400,7 +400,7 @@ cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
             o1 = fmaf(p, v.y, o1);
         }
         const float inv = 1.0f / l;
-        *reinterpret_cast<__half2*>(out + static_cast<int64_t>(b) * D + h * HD + 2 * lane) = __floats2half2_rn(o0 * inv, o1 * inv);
+        *reinterpret_cast<__half2*>(out + static_cast<int64_t>(b) * out_row_stride * D + h * HD + 2 * lane) = __floats2half2_rn(o0 * inv, o1 * inv);
         __syncwarp();
     }
 }
@@ -417,11 +417,11 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restr
 
 }  // namespace
 
-int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream) {
+int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, int out_row_stride, cudaStream_t stream) {
     AP_REQUIRE(ctx, S >= 1 && S <= 288 && heads <= 24, "cls attention: S=%d heads=%d unsupported", S, heads);
     if (B == 0) return AP_OK;
     ProfScope prof(ctx, stream, AP_K_ATTENTION);
-    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_attention_kernel, dim3(B), dim3(384), 0, stream, 1, ctx->pdl != 0, qkv, out, S, heads));
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_attention_kernel, dim3(B), dim3(384), 0, stream, 1, ctx->pdl != 0, qkv, out, S, heads, out_row_stride));
     AP_CHECK_LAUNCH(ctx, "cls_attention_kernel");
     return AP_OK;
 }
@@ -537,8 +537,7 @@ extern "C" int ap_layernorm_f16(ap_ctx* ctx, const float* x_dev, int64_t x_row_s
 
 extern "C" int ap_attention_f16(ap_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int S, int heads, void* stream) {
     if (!ctx) return AP_EINVAL;
-    const int S_pad = (S + 15) / 16 * 16;
-    if (ctx->attn_mode == 2 && S_pad >= 16 && S_pad <= 256 && B > 0) {
+    if (ctx->attn_mode == 2 && S >= 1 && S <= 257 && B > 0) {
         AttnPlan plan;
         int rc = ap_attention_tc_plan(ctx, &plan, static_cast<const __half*>(qkv_dev), B * S, S, heads);
         if (rc) return rc;

@@ -10,7 +10,16 @@ reference's DinoV2Encoder (models/patch/dinov2.py).  A CUDA device is mandatory:
 """
 from __future__ import annotations
 
-from atlaspatch_b200.encoder import B200FeatureExtractor
+import sys
+from pathlib import Path
+
+# The reference loads a plug-in BY FILE PATH (models/patch/custom.py:104-111: spec_from_file_location + exec_module), so
+# nothing has put this package's parent directory on sys.path: do it here, before the first package import.
+_ROOT = str(Path(__file__).resolve().parent.parent)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from atlaspatch_b200.encoder import B200FeatureExtractor  # noqa: E402
 
 _TORCHVISION = {"vit_b_16": ("vit_b_16", "ViT_B_16_Weights"), "vit_l_16": ("vit_l_16", "ViT_L_16_Weights")}
 
@@ -49,7 +58,22 @@ def _build_dinov2(name: str, device, patch_size: int | None) -> B200FeatureExtra
     return B200FeatureExtractor(name, model.state_dict(), input_patch=patch, device=idx, registry_name=f"b200_{name}")
 
 
+def resolve_feature_dtype(device, precision: str):
+    """services/feature_embedding.py:28-39: the reference's dtype policy (float16 is downgraded to float32 on CPU devices)."""
+    import torch
+
+    dtype = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}.get(precision, torch.float32)
+    if torch.device(device).type == "cpu" and dtype == torch.float16:
+        dtype = torch.float32
+    return dtype
+
+
 def register_feature_extractors(registry, device, dtype, num_workers) -> None:
+    """The reference's CustomRegistryHook (models/patch/custom.py:92-103).  `dtype` (cli.py --feature-precision through
+    resolve_feature_dtype) selects the precision the REFERENCE runs its torch model in; the features it returns are float32 numpy
+    either way (models/patch/base.py:105-106).  The B200 engine has one arithmetic (fp16 operands, fp32 accumulate / residual /
+    LayerNorm / softmax) that meets the fp32 tolerance, so every dtype maps onto it and the returned array is float32 as well;
+    `num_workers` configures the reference's DataLoader, which this path does not have."""
     for name in _TORCHVISION:
         registry.register(f"b200_{name}", lambda n=name: _build(n, device))
     for name in _DINOV2:

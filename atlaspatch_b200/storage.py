@@ -12,12 +12,15 @@ Layout produced (identical names, dtypes, shapes, chunking and attributes):
     file attrs            patch_size, patch_size_level0, level0_magnification, target_magnification, overlap, level0_width,
                           level0_height, wsi_path, passport_format, passport_version, creation_date, filename, num_patches
 
-The HDF5 library is the reference's own dependency (h5py); it is imported lazily, and this build image has neither h5py nor
-libhdf5, so here the writer is only exercised against an API double (tests/test_storage.py) -- PARITY UNPINNED until it runs
-where h5py exists.  There is no alternative container: without h5py `write_*` raises.
+The HDF5 library is the reference's own dependency (h5py) and is used when it is installed.  This build image and the GPU
+boxes have neither h5py nor libhdf5: there the same calls go to `atlaspatch_b200.h5lite`, a self-contained writer / reader of
+the HDF5 subset this container needs (see its header for what is and is not pinned: the reader is checked against a file
+written by the real library, the writer by round trips; acceptance of h5lite's bytes by libhdf5 is UNPINNED until
+tests/test_h5lite.py::test_h5py_reads_h5lite_file_and_back runs where h5py exists).
 """
 from __future__ import annotations
 
+import json
 import os
 import uuid
 from datetime import datetime, timezone
@@ -31,12 +34,17 @@ PASSPORT_DTYPE = np.dtype("S160")
 
 
 def _h5py():
+    """h5py where it exists, else the in-tree HDF5 subset implementation with the same calls."""
     try:
         import h5py
-    except ImportError as e:  # pragma: no cover - depends on the deployment image
-        raise ImportError("writing the AtlasPatch H5 container needs h5py (the reference's own dependency); "
-                          "results stay available in memory on ExtractionResult") from e
-    return h5py
+
+        if getattr(h5py, "File", None) is not None:   # tests may have a stub module installed under this name
+            return h5py
+    except ImportError:
+        pass
+    from atlaspatch_b200 import h5lite
+
+    return h5lite
 
 
 def passports(stem: str, coords: np.ndarray, level0_mag: int, target_mag: int) -> np.ndarray:
@@ -66,6 +74,7 @@ def write_coords(path: str | os.PathLike, coords: np.ndarray, *, slide_stem: str
         "creation_date": datetime.now(timezone.utc).isoformat(), "filename": Path(wsi_path).name,
     }
     attrs.update(dict(extra_file_attrs or {}))
+    attrs = {k: (json.dumps(v) if isinstance(v, dict) else v) for k, v in attrs.items()}   # utils/h5.py:69-73
     f = h5.File(tmp, "w")
     try:
         dc = f.create_dataset("coords", shape=(0, 5), maxshape=(None, 5), chunks=(rows, 5), dtype=np.int32)
@@ -125,10 +134,15 @@ def append_features(path: str | os.PathLike, name: str, feats: np.ndarray, *, fe
 
 
 def write_result(path: str | os.PathLike, result, *, wsi, cfg, write_batch: int = 8192, feature_batch: int = 32, h5=None) -> Path:
-    """ExtractionResult (services.py) -> the reference's H5: coords first, then one dataset per embedded feature set."""
+    """ExtractionResult (services.py) -> the reference's H5: coords first, then one dataset per embedded feature set.
+    File attributes as services/extraction.py:146-164 passes them: filename = the slide's file name, then wsi.metadata_attrs()
+    (mpp, magnification, vendor ...)."""
+    extra = {"filename": Path(result.slide.path).name}
+    extra.update(wsi.metadata_attrs() if hasattr(wsi, "metadata_attrs") else {})
     write_coords(path, result.coords, slide_stem=result.slide.stem, wsi_path=str(wsi.path), patch_size=cfg.patch_size,
                  patch_size_level0=int(result.patch_size_level0), level0_mag=int(wsi.mag or 0), target_mag=cfg.target_magnification,
-                 level0_wh=tuple(int(v) for v in wsi.get_size(lv=0)), step_size=cfg.step_size, write_batch=write_batch, h5=h5)
+                 level0_wh=tuple(int(v) for v in wsi.get_size(lv=0)), step_size=cfg.step_size, write_batch=write_batch,
+                 extra_file_attrs=extra, h5=h5)
     for name, feats in result.features.items():
         append_features(path, name, feats, feature_batch=feature_batch, expected_total=result.num_patches, h5=h5)
     result.h5_path = Path(path)

@@ -7,8 +7,10 @@ container so that its own functions can (a) pin the oracle restatements in
 The reference needs packages this image lacks (openslide, h5py, hydra,
 omegaconf, sam2, matplotlib, timm); none of them is touched by the functions we
 call on the hot path (coordinate extraction, thumbnailing, the torchvision ViT
-extractor), so they are satisfied with empty stub modules.  Nothing here runs
-on the GPU box: `/root/reference` does not exist there.
+extractor), so they are satisfied with empty stub modules.  On the GPU box
+`/root/reference` does not exist; there the same unmodified package is found under
+`baseline/_ref` when oracle/make_ref.sh has installed it (bench.py --impl reference and the
+reference-in-the-loop GPU tests use it; they skip / fall back to the port when it is absent).
 """
 from __future__ import annotations
 
@@ -18,7 +20,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ATLAS_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# baseline/_ref: the unmodified reference installed by oracle/make_ref.sh (pip install --target; git-ignored, travels to the GPU box)
+INSTALLED_REF = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("ATLAS_REF")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/atlas_patch"):
+        return "/root/reference"
+    return INSTALLED_REF
+
+
+REFERENCE_ROOT = _pick_root()
 
 _STUBS = {
     "openslide": {"OpenSlide": type("OpenSlide", (), {}), "OpenSlideError": Exception,
@@ -46,6 +62,15 @@ def reference_available() -> bool:
 
 
 def install_stubs() -> None:
+    if "h5py" not in sys.modules:
+        try:
+            importlib.import_module("h5py")
+        except Exception:
+            # no libhdf5 in this image: the reference's h5py calls (utils/h5.py, services/storage.py, utils/features.py,
+            # orchestration/runner.py) run on the in-tree HDF5 subset implementation, which exposes the same API
+            from atlaspatch_b200 import h5lite
+
+            sys.modules["h5py"] = h5lite
     for name, attrs in _STUBS.items():
         if name in sys.modules:
             continue

@@ -217,4 +217,4 @@ def test_folded_layernorm_option_matches_oracle(name):
             ext.cleanup()
     finally:
         ctx.set_option("fold_ln", 1)   # the library default
-    assert _rel(feats[2], feats[0]).max() < REL_TOL   # two independent sets of fp16 roundings, each within REL_TOL of the oracle
+    assert _rel(feats[2], feats[0]).max() < 2 * REL_TOL   # two independent sets of fp16 roundings, each within REL_TOL of the oracle (triangle inequality)

@@ -82,11 +82,15 @@ def test_layernorm(ctx, rows, D):
     assert (out.float() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("B,S,heads", [(1, 197, 12), (3, 197, 4), (2, 257, 16), (2, 16, 2), (1, 1, 1), (2, 64, 3), (1, 272, 2)])
-def test_attention(ctx, B, S, heads):
+# (64, 197, 12), (30, 257, 16): several jobs per CTA (the two-buffer tile pipeline wraps its stages / phases many times);
+# (200, 50, 12), (300, 130, 2): one / two query tiles with fewer than 128 keys; 257 = 256 MMA keys + the class token as the extra key
+@pytest.mark.parametrize("amp", [1.5, 6.0])
+@pytest.mark.parametrize("B,S,heads", [(1, 197, 12), (3, 197, 4), (2, 257, 16), (2, 16, 2), (1, 1, 1), (2, 64, 3), (1, 272, 2),
+                                       (64, 197, 12), (30, 257, 16), (200, 50, 12), (300, 130, 2), (5, 256, 3), (3, 129, 1)])
+def test_attention(ctx, B, S, heads, amp):
     D = heads * 64
     g = torch.Generator(device="cuda").manual_seed(B * 100 + S + heads)
-    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 1.5).half()
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * amp).half()   # amp 6: logits of +-100, one-hot-like rows
     out = torch.full((B * S, D), float("nan"), device="cuda", dtype=torch.float16)
     ctx.check(ctx.lib.ap_attention_f16(ctx.handle, _p(qkv), _p(out), B, S, heads, _stream()))
     torch.cuda.synchronize()

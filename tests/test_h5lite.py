@@ -1,0 +1,157 @@
+"""CPU: the self-contained HDF5 subset writer / reader (atlaspatch_b200/h5lite.py) behind the reference's h5py calls.
+
+* the READER is pinned against a file written by the real HDF5 library (the only libhdf5 artefact in this image: scipy's
+  MATLAB v7.3 test file, 512-byte user block + superblock v0 + B-tree / heap / SNOD + v1 object headers + attribute);
+* the WRITER is checked by round trips through that reader, over everything the AtlasPatch container uses (resizable chunked
+  int32 / S160 / float32 datasets, multi-level chunk B-trees, > 8 links per group, every attribute type the reference writes);
+* where h5py is installed, h5py must read the files h5lite writes and vice versa (skipped here: no libhdf5 in the image).
+"""
+import os
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from atlaspatch_b200 import h5lite as h5
+
+MAT73 = Path(np.__file__).resolve().parents[1] / "scipy" / "io" / "matlab" / "tests" / "data" / "testhdf5_7.4_GLNX86.mat"
+
+
+@pytest.mark.skipif(not MAT73.exists(), reason="scipy's MATLAB v7.3 (HDF5) test file is not installed")
+def test_reader_on_a_file_written_by_libhdf5():
+    with h5.File(MAT73, "r") as f:
+        assert list(f.keys()) == ["testdouble"]
+        ds = f["testdouble"]
+        assert ds.shape == (9, 1) and ds.dtype == np.float64
+        np.testing.assert_allclose(ds[...].ravel(), np.linspace(0, 2 * np.pi, 9), rtol=0, atol=1e-15)   # scipy's own expectation
+        assert ds.attrs["MATLAB_class"] == b"double"
+
+
+def _container(path, n=20000, d=96, with_features=True):
+    rng = np.random.default_rng(0)
+    coords = rng.integers(0, 80000, (n, 5)).astype(np.int32)
+    passports = np.asarray([f"slide__x{x}_y{y}_total{n}" for x, y in coords[:, :2].tolist()], dtype="S160")
+    feats = rng.standard_normal((n, d)).astype(np.float32)
+    with h5.File(path, "w") as f:
+        dc = f.create_dataset("coords", shape=(0, 5), maxshape=(None, 5), chunks=(8192, 5), dtype=np.int32)
+        dp = f.create_dataset("passports", shape=(0,), maxshape=(None,), chunks=(8192,), dtype=np.dtype("S160"))
+        for s in range(0, n, 8192):
+            e = min(n, s + 8192)
+            dc.resize(e, axis=0)
+            dc[s:e] = coords[s:e]
+            dp.resize(e, axis=0)
+            dp[s:e] = passports[s:e]
+        f.attrs["patch_size"] = 256
+        f.attrs["mpp"] = 0.5
+        f.attrs["wsi_path"] = "/data/slides/süd/slide.svs"
+        f.attrs["passport_format"] = "{stem}__x{X}_y{Y}"
+        f.attrs["magnification"] = np.int32(20)
+        f.attrs["num_patches"] = n
+        f.attrs["empty"] = ""
+        f.attrs["vec"] = np.arange(5, dtype=np.float32)
+    if with_features:
+        with h5.File(path, "a") as f:
+            grp = f.require_group("features")
+            ds = grp.create_dataset("__tmp_enc", shape=(0, d), maxshape=(None, d), chunks=(32, d), dtype=np.float32)
+            for s in range(0, n, 32):
+                e = min(n, s + 32)
+                ds.resize((e, d))
+                ds[s:e, :] = feats[s:e]
+            grp.move("__tmp_enc", "enc")
+    return coords, passports, feats
+
+
+def test_container_round_trip(tmp_path):
+    p = tmp_path / "slide.h5"
+    coords, passports, feats = _container(p)            # 625 feature chunks: a two-level chunk B-tree (64 entries per node)
+    with h5.File(p, "r") as f:
+        assert set(f.keys()) == {"coords", "passports", "features"}
+        assert f["coords"].shape == (20000, 5) and f["coords"].dtype == np.int32 and f["coords"].chunks == (8192, 5)
+        assert f["coords"].maxshape == (None, 5)
+        assert np.array_equal(f["coords"][...], coords)
+        assert np.array_equal(f["coords"][17], coords[17])
+        assert f["passports"].dtype == np.dtype("S160") and np.array_equal(f["passports"][...], passports)
+        assert list(f["features"].keys()) == ["enc"] and "__tmp_enc" not in f["features"]
+        assert np.array_equal(f["features/enc"][...], feats) and f["features"]["enc"].chunks == (32, 96)
+        a = f.attrs
+        assert a["patch_size"] == 256 and isinstance(a["patch_size"], np.int64)
+        assert a["mpp"] == 0.5 and isinstance(a["mpp"], np.float64)
+        assert a["wsi_path"] == "/data/slides/süd/slide.svs" and isinstance(a["wsi_path"], str)
+        assert a["magnification"] == 20 and a["magnification"].dtype == np.int32
+        assert a.get("num_patches") == 20000 and a.get("nope") is None and a["empty"] == ""
+        assert np.array_equal(a["vec"], np.arange(5, dtype=np.float32))
+        with pytest.raises(OSError):
+            f.attrs["x"] = 1                                  # read-only
+
+
+def test_three_level_chunk_btree_and_many_links(tmp_path):
+    p = tmp_path / "big.h5"
+    x = np.arange(5000 * 3, dtype=np.float32).reshape(5000, 3)
+    with h5.File(p, "w") as f:
+        f.create_dataset("x", data=x, maxshape=(None, 3), chunks=(1, 3))      # 5000 chunks > 64 * 64: three B-tree levels
+        g = f.create_group("many")
+        for i in range(40):                                                   # 40 links: five symbol-table nodes
+            g.create_dataset(f"d{i:02d}", data=np.full((3,), i, dtype=np.int64))
+        g.attrs["note"] = "forty"
+    with h5.File(p, "r") as f:
+        assert np.array_equal(f["x"][...], x)
+        assert list(f["many"].keys()) == [f"d{i:02d}" for i in range(40)]
+        assert all(int(f["many"][f"d{i:02d}"][0]) == i for i in range(40))
+        assert f["many"].attrs["note"] == "forty"
+    raw = p.read_bytes()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0
+    assert struct.unpack_from("<Q", raw, 40)[0] == len(raw)                   # end-of-file address of the superblock
+    assert raw.count(b"SNOD") >= 6 and raw.count(b"TREE") >= 5000 // 64 + 3
+
+
+def test_append_mode_delete_and_atomicity(tmp_path):
+    p = tmp_path / "a.h5"
+    _container(p, n=100, d=8)
+    with h5.File(p, "a") as f:
+        grp = f.require_group("features")
+        assert "enc" in grp
+        with pytest.raises(ValueError):
+            grp.create_dataset("enc", shape=(0, 8), maxshape=(None, 8), chunks=(32, 8), dtype=np.float32)
+        grp.create_dataset("__tmp_other", shape=(3, 8), maxshape=(None, 8), chunks=(32, 8), dtype=np.float32)
+        del grp["__tmp_other"]
+        f["coords"].attrs["unit"] = "level-0 pixels"
+    with h5.File(p, "r") as f:
+        assert list(f["features"].keys()) == ["enc"] and f["coords"].attrs["unit"] == "level-0 pixels"
+        assert f["features/enc"].shape == (100, 8)
+    assert [q.name for q in tmp_path.iterdir()] == ["a.h5"]                   # no temporary file left behind
+    with pytest.raises(FileNotFoundError):
+        h5.File(tmp_path / "missing.h5", "r")
+    (tmp_path / "junk.h5").write_bytes(b"not hdf5" * 100)
+    with pytest.raises(OSError):
+        h5.File(tmp_path / "junk.h5", "r")
+
+
+def test_shrink_then_grow_reads_fill_value(tmp_path):
+    p = tmp_path / "s.h5"
+    with h5.File(p, "w") as f:
+        d = f.create_dataset("v", shape=(10, 2), maxshape=(None, 2), chunks=(4, 2), dtype=np.int32)
+        d[...] = 7
+        d.resize(3, axis=0)
+        d.resize(6, axis=0)
+        with pytest.raises(ValueError):
+            f.create_dataset("w", shape=(2, 2), maxshape=(4, 2), chunks=(2, 2), dtype=np.int32).resize(5, axis=0)
+    with h5.File(p, "r") as f:
+        assert np.array_equal(f["v"][...], np.array([[7, 7]] * 3 + [[0, 0]] * 3, dtype=np.int32))
+
+
+def test_h5py_reads_h5lite_file_and_back(tmp_path):
+    h5py = pytest.importorskip("h5py")   # absent from this image: byte-level acceptance by libhdf5 is pinned wherever this runs
+    p = tmp_path / "x.h5"
+    coords, passports, feats = _container(p, n=3000, d=16)
+    with h5py.File(p, "r") as f:
+        assert np.array_equal(f["coords"][...], coords) and np.array_equal(f["passports"][...], passports)
+        assert np.array_equal(f["features/enc"][...], feats)
+        assert f.attrs["wsi_path"] == "/data/slides/süd/slide.svs" and int(f.attrs["num_patches"]) == 3000
+    q = tmp_path / "y.h5"
+    with h5py.File(q, "w") as f:
+        f.create_dataset("coords", data=coords, maxshape=(None, 5), chunks=(8192, 5))
+        f.attrs["wsi_path"] = "abc"
+        f.attrs["n"] = 3
+    with h5.File(q, "r") as f:
+        assert np.array_equal(f["coords"][...], coords) and f.attrs["wsi_path"] == "abc" and f.attrs["n"] == 3

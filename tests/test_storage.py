@@ -1,6 +1,8 @@
-"""CPU: the H5 writer (a10 / a14) against an in-memory double of the h5py calls it makes.  Neither h5py nor libhdf5 exists in the
-build image, so what is checked here is the layout logic (names, dtypes, shapes, chunking, attributes, tmp-then-move, atomic
-replace) -- not the bytes on disk; with h5py installed the same test runs against the real library."""
+"""CPU: the H5 writer (a10 / a14).  The layout logic (names, dtypes, shapes, chunking, attributes, tmp-then-move, atomic
+replace) is checked on real files: through h5py where it is installed, else through atlaspatch_b200.h5lite (the in-tree HDF5
+subset writer / reader; neither h5py nor libhdf5 exists in the build image) -- and against the file the reference's OWN,
+unmodified H5PatchWriter produces for the same rows through the same HDF5 layer.  An in-memory double is kept only to inject
+failures."""
 import os
 from pathlib import Path
 
@@ -81,13 +83,7 @@ class _FakeH5:
 
 
 def _real_or_fake():
-    try:
-        import h5py
-    except ImportError:
-        return _FakeH5, False
-    if not (hasattr(h5py, "h5f") and callable(getattr(h5py, "File", None))):   # oracle/refimport.py's stub module, not the library
-        return _FakeH5, False
-    return h5py, True
+    return storage._h5py(), True
 
 
 def test_passports_follow_the_reference_format():
@@ -125,8 +121,8 @@ def test_layout_names_dtypes_chunks_attrs_and_feature_move(tmp_path):
     data = (lambda d: d[...]) if real else (lambda d: d.data)
     assert np.array_equal(data(dc), coords) and np.array_equal(data(df), feats)
     assert data(dp)[-1] == f"slideA__x{(n - 1) * 256}_y{(n - 1) * 3}_rw256_rh256_lv0_mag40_tmag20_total{n}".encode()
-    a = dict(f.attrs)
-    assert {k: a[k] for k in ("patch_size", "patch_size_level0", "level0_magnification", "target_magnification", "overlap",
+    a = dict(f.attrs.items())
+    assert {k: int(a[k]) for k in ("patch_size", "patch_size_level0", "level0_magnification", "target_magnification", "overlap",
                               "level0_width", "level0_height", "num_patches", "passport_version")} == \
         dict(patch_size=256, patch_size_level0=512, level0_magnification=40, target_magnification=20, overlap=128,
              level0_width=80000, level0_height=60000, num_patches=n, passport_version=2)
@@ -144,3 +140,47 @@ def test_failed_write_leaves_no_partial_file(tmp_path):
         storage.write_coords(tmp_path / "x.h5", np.zeros((3, 5), np.int32), slide_stem="x", wsi_path="x.svs", patch_size=256,
                              patch_size_level0=256, level0_mag=20, target_mag=20, level0_wh=(10, 10), h5=Boom)
     assert list(tmp_path.iterdir()) == []
+
+
+def test_same_file_as_the_reference_writer(tmp_path):
+    """The reference's unmodified H5PatchWriter.write_coords + append_features (services/storage.py:106-161,250-337) and
+    storage.write_coords + append_features, both through the same HDF5 layer: identical datasets, dtypes, chunking and attributes."""
+    from oracle import refimport
+
+    if not refimport.reference_available():
+        pytest.skip("reference not available")
+    refimport.import_reference()
+    from atlas_patch.services.storage import H5PatchWriter
+
+    h5 = storage._h5py()
+    n, d = 700, 24
+    rng = np.random.default_rng(1)
+    coords = np.concatenate([rng.integers(0, 50000, (n, 2)), np.full((n, 2), 512), np.zeros((n, 1))], 1).astype(np.int32)
+    feats = rng.standard_normal((n, d)).astype(np.float32)
+    extra = {"filename": "slideB.svs", "mpp": 0.25, "magnification": 40, "vendor": "aperio", "props": {"a": 1}}
+    ref_path, our_path = tmp_path / "ref.h5", tmp_path / "our.h5"
+    w = H5PatchWriter(chunk_rows=256, patch_size=256, patch_size_level0=512, level0_mag=40, target_mag=20, level0_wh=(50000, 40000),
+                      overlap=64, slide_stem="slideB", wsi_path="/d/slideB.svs", extra_file_attrs=extra)
+    total, _ = w.write_coords(ref_path, ((int(x), int(y), int(rw), int(rh), int(lv), None) for x, y, rw, rh, lv in coords), batch=256)
+    assert total == n
+    patches = [np.zeros((1, 1, 3), np.uint8)] * n
+    it = iter(range(0, n, 32))
+    w.append_features(output_path=ref_path, entries=((0, 0, 0, 0, 0, p) for p in patches), feature_name="enc",
+                      feature_fn=lambda buf: feats[(s := next(it)):s + len(buf)], feature_attrs={"name": "enc", "embedding_dim": d},
+                      feature_batch=32, expected_total=n)
+    storage.write_coords(our_path, coords, slide_stem="slideB", wsi_path="/d/slideB.svs", patch_size=256, patch_size_level0=512,
+                         level0_mag=40, target_mag=20, level0_wh=(50000, 40000), step_size=192, write_batch=256, extra_file_attrs=extra,
+                         h5=h5)
+    storage.append_features(our_path, "enc", feats, feature_batch=32, expected_total=n, h5=h5)
+    with h5.File(str(ref_path), "r") as fr, h5.File(str(our_path), "r") as fo:
+        assert sorted(fr.keys()) == sorted(fo.keys()) == ["coords", "features", "passports"]
+        for key in ("coords", "passports", "features/enc"):
+            a, b = fr[key], fo[key]
+            assert a.shape == b.shape and a.dtype == b.dtype and a.chunks == b.chunks and a.maxshape == b.maxshape, key
+            assert np.array_equal(a[...], b[...]), key
+        ar, ao = dict(fr.attrs.items()), dict(fo.attrs.items())
+        assert sorted(ar) == sorted(ao)
+        for k in ar:
+            if k != "creation_date":
+                assert type(ar[k]) is type(ao[k]) and ar[k] == ao[k], k
+        assert ao["props"] == '{"a": 1}' and ao["overlap"] == 64
