@@ -32,6 +32,7 @@ _P = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
 _SIGNATURES = {
     "ap_version": (C.c_int, []),
+    "ap_sizeof": (C.c_int, [C.c_char_p]),
     "ap_init": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "ap_destroy": (C.c_int, [_P]),
     "ap_last_error": (C.c_char_p, [_P]),
@@ -45,6 +46,7 @@ _SIGNATURES = {
     "ap_synth_render": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, _P, C.c_int, _P, C.c_int,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "ap_thumbnail_area": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P]),
+    "ap_thumbnail_resize": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, _P, _P]),
     "ap_coords_capacity": (C.c_int64, [_P, _P, C.c_int, C.c_int]),
     "ap_extract_coords": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     _P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
@@ -95,6 +97,10 @@ def load_library() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        for name, struct in (("ap_vit_desc", VitDesc), ("ap_sam2_desc", Sam2Desc)):
+            if lib.ap_sizeof(name.encode()) != C.sizeof(struct):
+                raise ImportError(f"{LIB_PATH}: sizeof({name}) = {lib.ap_sizeof(name.encode())} but the ctypes declaration has "
+                                  f"{C.sizeof(struct)} bytes (stale library? rebuild with __graft_entry__.build())")
         _lib = lib
         return lib
 

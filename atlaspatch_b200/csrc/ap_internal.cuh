@@ -55,6 +55,23 @@ struct ProfScope {
 
 int ap_set_error(ap_ctx* ctx, int code, const char* fmt, ...);
 
+// Every C-ABI entry runs on ITS context's device whatever the calling thread's current device is (another thread, or torch having
+// switched devices since ap_init), and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(const ap_ctx* ctx) {
+        if (!ctx) return;
+        want = ctx->device;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 #define AP_CHECK_CUDA(ctx, call)                                                                   \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \
@@ -106,6 +123,13 @@ inline cudaError_t ap_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
     cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// cudaFuncSetAttribute is per device: remember per device (bit = device index) that an instantiation has been configured
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool need(int dev) const { return ((mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0; }
+    void done(int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
 
 // ---- TMA descriptor helper (host) --------------------------------------------------------------
 // 2-D row-major fp16 matrix [rows, cols] (cols contiguous), box = box_cols x box_rows, 128B swizzle.

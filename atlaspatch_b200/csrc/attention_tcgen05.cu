@@ -18,11 +18,19 @@
 // softmax warpgroup i & 1 has published P_i -- whichever comes first -- so one warpgroup's tcgen05.ld traffic overlaps the
 // other's MMAs and waits.
 //
+// Variants measured and dropped this round (B200, B = 127, 12 heads, S = 197; profiles/r02_attention_notes.md has the ncu stall
+// tables): this kernel 56.9 us; the same with one blocking MMA-issuer thread per warpgroup instead of the polling thread 63.9 us;
+// every tile cut into two key-half units (S_a | S_b in separate 128-column buffers, four units in flight, O_a read out while
+// P_b V_b runs) 62.3-68.5 us with blocking issuers, 78.5 us with one event-loop issuer (a failed mbarrier test costs ~150 cycles, so
+// a loop over four pending events reacts ~450 cycles late); a two-pass streaming softmax (no half row in registers) +1-2 us.  In all
+// of them the softmax warps compute for ~35 % of their time, wait for P.V / the next S for ~35 % (mostly for the slowest sibling
+// warp: two warps share each scheduler's MUFU) and spend ~17 % in the O read-out; MUFU is 31-34 % busy, the tensor pipe 17-18 %.
+//
 // Key / query windows: queries are tokens [q0, q0 + nq) of every image, MMA keys tokens [k0, k0 + nk) (nk <= 256, padded to
 // S_pad = a multiple of 16; padded keys get probability 0).  XK: one EXTRA key token `xkey` outside that window is folded in
 // as a rank-1 update (its score is a 64-term dot product per row on the CUDA cores, its value row is added to O in the
 // epilogue).  That is how the 257-token DINOv2 sequence fits: 256 patch keys through the MMA (2 x 256 fp32 columns = all of
-// TMEM) + the class token as the extra key; the class-token QUERY row is computed by cls_attention_kernel.
+// TMEM) + the class token as the extra key; the 257th query row rides in a third, almost empty tile.
 // Warps: 0 = TMA producer (Q, K), 3 = TMA producer (V), 1 = MMA issuer, 2 = TMEM allocator, 4-7 / 8-11 = softmax + epilogue
 // warpgroups 0 / 1 (warp % 4 selects the TMEM lane quarter).  TMEM columns of buffer b: S at [256 b, 256 b + S_pad), P at
 // [256 b, 256 b + S_pad / 2), O_a at [256 b + 128, +192), O_b at [256 b + 192, +256).
@@ -84,7 +92,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const int heads = a.heads, S = a.S;
     const int D = heads * 64;
     const int kv_bytes = S_pad * 128;
-    const int stage_bytes = 2 * Q_TILE_BYTES + 2 * kv_bytes;   // per job stage: [Q0 | Q1 | K | V]
+    const int n_qt = (a.nq + 127) / 128;                        // query tiles per job: 1, 2 or 3 (257 queries = 128 + 128 + 1)
+    const int q_bytes = n_qt * Q_TILE_BYTES;
+    const int stage_bytes = q_bytes + 2 * kv_bytes;             // per job stage: [Q tiles | K | V]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
     uint64_t* qk_full = bars;        // [2 stages] TMA -> MMA   (Q tiles + K)
     uint64_t* qk_empty = bars + 2;   // [2 stages] MMA -> TMA   (released as soon as the job's S MMAs retire)
@@ -98,7 +108,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_jobs = a.B * heads;
-    const int n_qt = a.nq > 128 ? 2 : 1;
     const int my_jobs = blockIdx.x < n_jobs ? (n_jobs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int n_tiles = my_jobs * n_qt;
 
@@ -144,11 +153,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     ptx::mbar_arrive_expect_tx(&qk_full[st], n_qt * Q_TILE_BYTES + kv_bytes);
                     for (int g = 0; g < n_qt; ++g)
                         ptx::tma_load_2d(sb + g * Q_TILE_BYTES, &map_q, &qk_full[st], h * 64, b * S + a.q0 + g * 128);
-                    ptx::tma_load_2d(sb + 2 * Q_TILE_BYTES, &map_kv, &qk_full[st], D + h * 64, b * S + a.k0);
+                    ptx::tma_load_2d(sb + q_bytes, &map_kv, &qk_full[st], D + h * 64, b * S + a.k0);
                 } else {
                     ptx::mbar_wait(&v_empty[st], sph ^ 1, 17);
                     ptx::mbar_arrive_expect_tx(&v_full[st], kv_bytes);
-                    ptx::tma_load_2d(sb + 2 * Q_TILE_BYTES + kv_bytes, &map_kv, &v_full[st], 2 * D + h * 64, b * S + a.k0);
+                    ptx::tma_load_2d(sb + q_bytes + kv_bytes, &map_kv, &v_full[st], 2 * D + h * 64, b * S + a.k0);
                 }
             }
         }
@@ -168,7 +177,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
                 uint8_t* sb = smem + st * stage_bytes;
                 ptx::tc_fence_after();
-                const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + 2 * Q_TILE_BYTES));
+                const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes));
                 const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + g * Q_TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -186,7 +195,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
                 uint8_t* sb = smem + st * stage_bytes;
                 ptx::tc_fence_after();
-                const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + 2 * Q_TILE_BYTES + kv_bytes), 64);
+                const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes + kv_bytes), 64);
                 constexpr int NA = (NC + 1) / 2;
                 for (int ks = 0; ks < k_steps_pv; ++ks) {   // 16 keys per step: 8 TMEM columns of P, two 8-key groups (2 KB) of V
                     const bool half_b = NC > 0 && ks >= NA;   // second half of the keys accumulates into O_b
@@ -460,11 +469,11 @@ template <int NC, bool XK>
 int launch_attn(ap_ctx* ctx, const AttnPlan* plan, const __half* qkv, __half* out, const AttnArgs& a, int grid, size_t smem,
                 cudaStream_t stream) {
     auto kern = attention_tc_kernel<NC, XK>;
-    static int attr_dev_mask = 0;   // per instantiation, per device
-    if (!(attr_dev_mask & (1 << (ctx->device & 31)))) {
-        const int max_smem = 2 * (2 * Q_TILE_BYTES + 2 * 256 * 128) + 17 * 8 + 16 + 1024;
+    static PerDeviceOnce attr;   // per instantiation
+    if (attr.need(ctx->device)) {
+        const int max_smem = 2 * (3 * Q_TILE_BYTES + 2 * 256 * 128) + 17 * 8 + 16 + 1024;
         AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_dev_mask |= 1 << (ctx->device & 31);
+        attr.done(ctx->device);
     }
     AP_CHECK_CUDA(ctx, ap_launch_pdl(kern, dim3(grid), dim3(ATC_THREADS), smem, stream, 1, ctx->pdl != 0, plan->map_q, plan->map_kv, qkv, out, a));
     return AP_OK;
@@ -473,14 +482,17 @@ int launch_attn(ap_ctx* ctx, const AttnPlan* plan, const __half* qkv, __half* ou
 }  // namespace
 
 // S tokens per image; the key window is the whole sequence when it fits 256 MMA keys, else tokens [1, S) with token 0 (the class
-// token) as the extra key -- then the class-token QUERY is not covered here (ap_attention_tc_run launches cls_attention for it).
+// token) as the extra key.  All S query rows are covered: 257 = two full 128-row tiles + a third tile with one valid row (a
+// separate class-token kernel re-read every K and V from L2 and cost half as much again as this kernel).
 int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int rows, int S, int heads) {
     const int D = heads * 64;
     AP_REQUIRE(ctx, S >= 1 && S <= 257, "attention(tcgen05): S=%d unsupported (1..257)", S);
     plan->qkv = qkv;
     plan->xkey = S > 256 ? 0 : -1;
-    plan->k0 = plan->q0 = S > 256 ? 1 : 0;
-    plan->nk = plan->nq = S > 256 ? S - 1 : S;
+    plan->k0 = S > 256 ? 1 : 0;
+    plan->nk = S > 256 ? S - 1 : S;
+    plan->q0 = 0;
+    plan->nq = S;       // 257 queries: two full tiles + a third tile that holds the last token only (its other warps idle)
     plan->S_pad = (plan->nk + 15) / 16 * 16;
     int rc = ap_make_tmap_f16_2d(ctx, &plan->map_q, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D, 128, 64);
     if (rc) return rc;
@@ -490,7 +502,8 @@ int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int row
 int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream) {
     if (B == 0) return AP_OK;
     const int S_pad = plan->S_pad;
-    const size_t smem = 2 * (2 * (size_t)Q_TILE_BYTES + 2 * (size_t)S_pad * 128) + 17 * 8 + 16 + 1024;
+    const size_t n_qt = (plan->nq + 127) / 128;
+    const size_t smem = 2 * (n_qt * (size_t)Q_TILE_BYTES + 2 * (size_t)S_pad * 128) + 17 * 8 + 16 + 1024;
     const int jobs = B * heads;
     const int grid = jobs < ctx->sm_count ? jobs : ctx->sm_count;
     AttnArgs a;
@@ -511,7 +524,5 @@ int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, i
         if (rc) return rc;
         AP_CHECK_LAUNCH(ctx, "attention_tc_kernel");
     }
-    if (plan->xkey >= 0)   // the class-token query row of every image: out[b * S + 0]
-        return ap_cls_attention_run(ctx, plan->qkv, out, B, S, heads, S, stream);
     return AP_OK;
 }

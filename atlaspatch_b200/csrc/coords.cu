@@ -227,6 +227,7 @@ extern "C" int ap_extract_coords(ap_ctx* ctx, const int32_t* contour_xy, const i
                                  int patch_src, int step_src, int read_w, int read_h, int level, int32_t* out_rows_dev,
                                  int32_t* out_rows_host, int64_t capacity, int64_t* out_count, void* stream) {
     if (!ctx) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     AP_REQUIRE(ctx, out_count != nullptr, "extract_coords: out_count is NULL");
     *out_count = 0;
     AP_REQUIRE(ctx, n_contours >= 0 && patch_src > 0 && step_src > 0, "extract_coords: bad arguments (n_contours %d patch %d step %d)",

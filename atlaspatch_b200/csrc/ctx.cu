@@ -14,7 +14,15 @@ int ap_set_error(ap_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-extern "C" int ap_version(void) { return 1; }
+extern "C" int ap_version(void) { return 2; }
+
+// sizeof of the structs that cross the ABI, so that a binding can check its own declaration against the library it loaded
+extern "C" int ap_sizeof(const char* struct_name) {
+    if (!struct_name) return -1;
+    if (!strcmp(struct_name, "ap_vit_desc")) return static_cast<int>(sizeof(ap_vit_desc));
+    if (!strcmp(struct_name, "ap_sam2_desc")) return static_cast<int>(sizeof(ap_sam2_desc));
+    return -1;
+}
 
 extern "C" const char* ap_last_error(const ap_ctx* ctx) {
     if (!ctx) return g_init_error;
@@ -39,6 +47,8 @@ extern "C" int ap_init(int device, ap_ctx** out_ctx) {
     if (prop.major != 10)
         return ap_set_error(nullptr, AP_ECUDA, "ap_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                             device, prop.major, prop.minor);
+    int prev_device = -1;
+    if (cudaGetDevice(&prev_device) != cudaSuccess) prev_device = -1;
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return ap_set_error(nullptr, AP_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     ap_ctx* ctx = new ap_ctx();
@@ -52,7 +62,8 @@ extern "C" int ap_init(int device, ap_ctx** out_ctx) {
         return ap_set_error(nullptr, AP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
     }
     if (const char* env = getenv("AP_GEMM_CTA_GROUP")) ctx->gemm_cta_group = atoi(env) == 1 ? 1 : 2;
-    *out_ctx = ctx;
+    if (prev_device >= 0 && prev_device != device) cudaSetDevice(prev_device);   // the caller's current device is left as it was;
+    *out_ctx = ctx;                                                               // every later entry selects ctx->device itself
     return AP_OK;
 }
 
@@ -150,6 +161,7 @@ extern "C" int ap_profile_enable(ap_ctx* ctx, int on) {
 // Sums (and clears) the recorded event pairs: total_ms[AP_K_NUM], counts[AP_K_NUM].  Synchronises the device.
 extern "C" int ap_profile_read(ap_ctx* ctx, double* total_ms, int64_t* counts, int n_classes) {
     if (!ctx || !total_ms || !counts || n_classes < AP_K_NUM) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
     std::lock_guard<std::mutex> lk(ctx->prof_mu);
     for (int i = 0; i < n_classes; ++i) { total_ms[i] = 0.0; counts[i] = 0; }
@@ -167,6 +179,7 @@ extern "C" int ap_profile_read(ap_ctx* ctx, double* total_ms, int64_t* counts, i
 // Clears all records.  keys / total_ms / counts have room for `cap` distinct tags; *n_out receives how many were seen.
 extern "C" int ap_profile_read_tagged(ap_ctx* ctx, int cls, int64_t* keys, double* total_ms, int64_t* counts, int cap, int* n_out) {
     if (!ctx || !keys || !total_ms || !counts || !n_out || cap <= 0) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
     std::lock_guard<std::mutex> lk(ctx->prof_mu);
     int n = 0;

@@ -253,11 +253,12 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
 
 extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc) {
     if (!ctx || !desc || !out_enc) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     *out_enc = nullptr;
     AP_REQUIRE(ctx, desc->preprocess == 0 || desc->preprocess == 1, "encoder: unknown preprocess %d", desc->preprocess);
     AP_REQUIRE(ctx, desc->mlp_kind == 0 || desc->mlp_kind == 1, "encoder: unknown mlp_kind %d", desc->mlp_kind);
-    AP_REQUIRE(ctx, desc->patch == 16 || (desc->preprocess == 1 && desc->patch >= 4 && desc->patch <= 16),
-               "encoder: conv patch %d unsupported (16 with the crop preprocess, 4..16 with the resizing preprocess)", desc->patch);
+    AP_REQUIRE(ctx, desc->patch == 16 || desc->patch == 32 || (desc->preprocess == 1 && desc->patch >= 4 && desc->patch <= 16),
+               "encoder: conv patch %d unsupported (16 / 32 with the crop preprocess, 4..16 with the resizing preprocess)", desc->patch);
     AP_REQUIRE(ctx, desc->preprocess == 0 || desc->resize_to >= desc->image_size, "encoder: resize_to %d < image_size %d", desc->resize_to,
                desc->image_size);
     AP_REQUIRE(ctx, desc->mlp_kind == 0 || (2 * desc->mlp) % 256 == 0, "encoder: SwiGLU needs 2 * mlp %% 256 == 0 (mlp %d)", desc->mlp);
@@ -276,9 +277,10 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     e->kpe = 3 * desc->patch * desc->patch;
     e->kpe_pad = (e->kpe + 63) / 64 * 64;
     e->max_batch = desc->max_batch > 0 ? desc->max_batch : 127;
-    // default: 1 layer (DESIGN.md "precision"); 8 for models deeper than 32 layers (DINOv2 giant: 40 layers of fp16 roundings put an
-    // ordinary patch at 9e-4 with 1 split layer, 7.5e-4 with 8, measured by tools/dinov2_precision.py)
-    const int default_precise = desc->layers > 32 ? 8 : 1;
+    // default: 1 layer (DESIGN.md "precision"); 20 for models deeper than 32 layers (DINOv2 giant: 40 layers of fp16 roundings put
+    // its worst golden row -- an 83 % black overhang patch -- at 1.31e-3 with 1 split layer, 1.09e-3 with 8, 0.97e-3 with 20; every
+    // golden row has to be inside 1e-3 at the default, tools/dinov2_precision.py)
+    const int default_precise = desc->layers > 32 ? 20 : 1;
     e->precise_layers = desc->precise_layers < 0 ? default_precise : (desc->precise_layers > desc->layers ? desc->layers : desc->precise_layers);
     if ((e->tokens + 1) > 272) {
         delete e;
@@ -290,6 +292,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
 
 extern "C" int ap_encoder_destroy(ap_encoder* e) {
     if (!e) return AP_OK;
+    DeviceGuard guard(e->ctx);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -315,6 +318,7 @@ extern "C" int ap_encoder_set_tensor(ap_encoder* e, const char* name, const floa
 
 extern "C" int ap_encoder_finalize(ap_encoder* e) {
     if (!e) return AP_EINVAL;
+    DeviceGuard guard(e->ctx);
     ap_ctx* ctx = e->ctx;
     if (e->finalized) return AP_OK;
     const int D = e->d.hidden, M = e->d.mlp, P = e->d.patch, T = e->tokens, T1 = T + 1, K = e->kpe, Kp = e->kpe_pad;
@@ -506,6 +510,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
 extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
                                        const int32_t* coords_dev, int64_t n, int read_size, float* out_features_dev, void* stream) {
     if (!e) return AP_EINVAL;
+    DeviceGuard guard(e->ctx);
     ap_ctx* ctx = e->ctx;
     if (!e->finalized) return ap_set_error(ctx, AP_ESTATE, "encoder: ap_encoder_finalize has not been called");
     AP_REQUIRE(ctx, n >= 0, "embed_coords: n < 0");
@@ -527,6 +532,7 @@ extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, 
 extern "C" int ap_encoder_preprocess(ap_encoder* e, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
                                      const int32_t* coords_dev, int64_t n, int read_size, void* out_dev, int64_t* out_cols, void* stream) {
     if (!e) return AP_EINVAL;
+    DeviceGuard guard(e->ctx);
     ap_ctx* ctx = e->ctx;
     if (!e->finalized) return ap_set_error(ctx, AP_ESTATE, "encoder: ap_encoder_finalize has not been called");
     if (out_cols) *out_cols = e->kpe_pad;
@@ -555,6 +561,7 @@ extern "C" int ap_encoder_preprocess(ap_encoder* e, const uint8_t* slide_dev, in
 extern "C" int ap_encoder_embed_patches_host(ap_encoder* e, const uint8_t* const* patches_host, int64_t n,
                                              float* out_features_host) {
     if (!e) return AP_EINVAL;
+    DeviceGuard guard(e->ctx);
     ap_ctx* ctx = e->ctx;
     if (!e->finalized) return ap_set_error(ctx, AP_ESTATE, "encoder: ap_encoder_finalize has not been called");
     AP_REQUIRE(ctx, n >= 0, "embed_patches_host: n < 0");

@@ -330,15 +330,19 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S
 // evaluated for that single query per (image, head) and out_proj / MLP run on B rows instead of B * S.
 // One warp per (image, head): lane j scores keys j, j+32, ...; softmax over the warp; lane pair d accumulates P.V.
 // =====================================================================================================
-__global__ void __launch_bounds__(384)
-cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int heads, int out_row_stride) {
+// Parallelism: one warp per (image, head), 4 warps per CTA, so B * heads / 4 CTAs spread over all SMs (the first version ran one
+// 12-warp CTA per image: 127 CTAs, 2 heads in sequence on a third of the warps -- fine once per forward, but DINOv2's 257-token
+// attention calls it in every layer, where it cost as much as the tensor-core kernel beside it).
+__global__ void __launch_bounds__(128)
+cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int heads, int out_row_stride, int n_jobs) {
     ptx::pdl_wait();
     ptx::pdl_launch_dependents();
-    const int b = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const int D = heads * HD;
-    __shared__ float s_p[12][288];
-    for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
+    __shared__ float s_p[4][288];
+    const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (job < n_jobs) {
+        const int b = job / heads, h = job - b * heads;
         float* sp = s_p[threadIdx.x >> 5];
         const __half* base = qkv + static_cast<int64_t>(b) * S * 3 * D + h * HD;
         // q (class-token row) -> every lane holds all 64 values as 32 half2
@@ -393,7 +397,20 @@ cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
         // O[d] = sum_j p_j V[j][d]; lane owns d = 2 lane, 2 lane + 1
         float o0 = 0.f, o1 = 0.f;
         const __half* vbase = base + 2 * D + 2 * lane;
-        for (int key = 0; key < S; ++key) {
+        int key = 0;
+        for (; key + 8 <= S; key += 8) {   // 8 independent 128 B row loads in flight per warp; the sum stays in key order
+            __half2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const __half2*>(vbase + static_cast<int64_t>(key + u) * 3 * D));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float2 f = __half22float2(v[u]);
+                const float p = sp[key + u];
+                o0 = fmaf(p, f.x, o0);
+                o1 = fmaf(p, f.y, o1);
+            }
+        }
+        for (; key < S; ++key) {
             const float2 v = __half22float2(*reinterpret_cast<const __half2*>(vbase + static_cast<int64_t>(key) * 3 * D));
             const float p = sp[key];
             o0 = fmaf(p, v.x, o0);
@@ -418,10 +435,12 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restr
 }  // namespace
 
 int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, int out_row_stride, cudaStream_t stream) {
-    AP_REQUIRE(ctx, S >= 1 && S <= 288 && heads <= 24, "cls attention: S=%d heads=%d unsupported", S, heads);
+    AP_REQUIRE(ctx, S >= 1 && S <= 288, "cls attention: S=%d unsupported (<= 288)", S);
     if (B == 0) return AP_OK;
     ProfScope prof(ctx, stream, AP_K_ATTENTION);
-    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_attention_kernel, dim3(B), dim3(384), 0, stream, 1, ctx->pdl != 0, qkv, out, S, heads, out_row_stride));
+    const int n_jobs = B * heads;
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_attention_kernel, dim3((n_jobs + 3) / 4), dim3(128), 0, stream, 1, ctx->pdl != 0, qkv, out, S, heads,
+                                     out_row_stride, n_jobs));
     AP_CHECK_LAUNCH(ctx, "cls_attention_kernel");
     return AP_OK;
 }
@@ -440,16 +459,21 @@ int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, i
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
                       const int* centre, int dup, const int32_t* lin_s, const int16_t* lin_w, cudaStream_t stream) {
     AP_REQUIRE(ctx, (lin_s == nullptr) == (lin_w == nullptr), "preprocess: resize tables must be given together");
-    AP_REQUIRE(ctx, patch == 16, "preprocess: conv patch %d unsupported (16 only)", patch);
+    AP_REQUIRE(ctx, patch == 16 || patch == 32, "preprocess: conv patch %d unsupported (16 or 32)", patch);
     AP_REQUIRE(ctx, image % patch == 0 && input_patch >= image, "preprocess: bad geometry input %d image %d patch %d",
                input_patch, image, patch);
     if (n == 0) return AP_OK;
     const int g = image / patch;
     const size_t smem = static_cast<size_t>(patch) * image * 3;
     ProfScope prof(ctx, stream, AP_K_PREPROCESS);
-    AP_CHECK_CUDA(ctx, ap_launch_pdl(preprocess_kernel<16>, dim3(static_cast<unsigned>(n * g)), dim3(256), smem, stream, 1, ctx->pdl != 0, slide, W,
-                                     H, pitch, coords, input_patch, image, out, out_row_stride, make_int3(centre[0], centre[1], centre[2]), dup,
-                                     lin_s, lin_w));
+    if (patch == 16)
+        AP_CHECK_CUDA(ctx, ap_launch_pdl(preprocess_kernel<16>, dim3(static_cast<unsigned>(n * g)), dim3(256), smem, stream, 1, ctx->pdl != 0, slide,
+                                         W, H, pitch, coords, input_patch, image, out, out_row_stride,
+                                         make_int3(centre[0], centre[1], centre[2]), dup, lin_s, lin_w));
+    else   // vit_b_32 / vit_l_32: 7 x 7 tokens of 32 x 32 pixels
+        AP_CHECK_CUDA(ctx, ap_launch_pdl(preprocess_kernel<32>, dim3(static_cast<unsigned>(n * g)), dim3(256), smem, stream, 1, ctx->pdl != 0, slide,
+                                         W, H, pitch, coords, input_patch, image, out, out_row_stride,
+                                         make_int3(centre[0], centre[1], centre[2]), dup, lin_s, lin_w));
     AP_CHECK_LAUNCH(ctx, "preprocess_kernel");
     return AP_OK;
 }
@@ -516,10 +540,10 @@ int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, 
     if (B == 0) return AP_OK;
     const int S_pad = (S + 15) / 16 * 16;
     const size_t smem = static_cast<size_t>(S_pad) * 128 * 3;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 272 * 128 * 3));
-        attr_set = true;
+        attr.done(ctx->device);
     }
     ProfScope prof(ctx, stream, AP_K_ATTENTION);
     AP_CHECK_CUDA(ctx, ap_launch_pdl(attention_kernel, dim3(heads, B), dim3(ATT_THREADS), smem, stream, 1, ctx->pdl != 0, qkv, out, S, S_pad,
@@ -531,12 +555,14 @@ int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, 
 extern "C" int ap_layernorm_f16(ap_ctx* ctx, const float* x_dev, int64_t x_row_stride, const float* gamma_dev,
                                 const float* beta_dev, float eps, void* y_dev, int rows, int D, void* stream) {
     if (!ctx) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     return ap_layernorm_run(ctx, x_dev, x_row_stride, gamma_dev, beta_dev, eps, static_cast<__half*>(y_dev), nullptr, rows, D,
                             static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ap_attention_f16(ap_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int S, int heads, void* stream) {
     if (!ctx) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     if (ctx->attn_mode == 2 && S >= 1 && S <= 257 && B > 0) {
         AttnPlan plan;
         int rc = ap_attention_tc_plan(ctx, &plan, static_cast<const __half*>(qkv_dev), B * S, S, heads);

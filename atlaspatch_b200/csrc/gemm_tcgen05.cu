@@ -520,10 +520,10 @@ int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t str
     }
     using L = SmemLayout<CG, BN>;
     auto kern = gemm_tcgen05_kernel<CG, BN, EPI>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
+    static PerDeviceOnce attr;  // per instantiation
+    if (attr.need(ctx->device)) {
         AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-        attr_set = true;
+        attr.done(ctx->device);
     }
     const int tile_m = 128 * CG;
     const int tiles = ((p->M + tile_m - 1) / tile_m) * (p->N / BN);
@@ -602,6 +602,7 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
 extern "C" int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,
                            const float* resid_dev, void* out_dev, int M, int N, int K, int epilogue, void* stream) {
     if (!ctx) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     GemmPlan plan;
     int rc = ap_gemm_plan(ctx, &plan, A_dev, W_dev, M, N, K, epilogue, K);
     if (rc) return rc;

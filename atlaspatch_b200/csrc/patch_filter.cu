@@ -335,6 +335,7 @@ extern "C" int ap_filter_patches(ap_ctx* ctx, const uint8_t* slide_dev, int64_t 
                                  int white_thresh, double min_fraction, int32_t* out_rows_dev, int32_t* out_rows_host,
                                  int64_t* out_count, int32_t* counts_dev, void* stream) {
     if (!ctx) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     AP_REQUIRE(ctx, out_count, "filter_patches: out_count is NULL");
     *out_count = 0;
     if (n == 0) return AP_OK;

@@ -158,10 +158,10 @@ int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64
     const size_t smem = ((static_cast<size_t>(max_src_rows) * input_patch * 3 + 15) & ~static_cast<size_t>(15)) +
                         static_cast<size_t>(max_src_rows) * image * 3;
     AP_REQUIRE(ctx, smem <= 200 * 1024, "preprocess(resize): input patch %d needs %zu bytes of shared memory (<= 200 KB)", input_patch, smem);
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) {
-        AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(preprocess_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_bytes = smem;
+    static PerDeviceOnce attr;   // the attribute is per device: set it to the 200 KB ceiling checked above, once per device
+    if (attr.need(ctx->device)) {
+        AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(preprocess_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr.done(ctx->device);
     }
     ProfScope prof(ctx, stream, AP_K_PREPROCESS);
     AP_CHECK_CUDA(ctx, ap_launch_pdl(preprocess_resize_kernel, dim3(static_cast<unsigned>(n * g)), dim3(256), smem, stream, 1, ctx->pdl != 0,

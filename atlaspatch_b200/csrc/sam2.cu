@@ -117,6 +117,7 @@ int sam_ln_named(ap_sam2* s, const std::string& p, const float* x, float* y, int
 
 extern "C" int ap_sam2_create(ap_ctx* ctx, const ap_sam2_desc* desc, ap_sam2** out) {
     if (!ctx || !desc || !out) return AP_EINVAL;
+    DeviceGuard guard(ctx);
     *out = nullptr;
     AP_REQUIRE(ctx, desc->embed_dim > 0 && desc->embed_dim % desc->heads_per_stage[0] == 0, "sam2: bad embed_dim / heads");
     for (int i = 0; i < 4; ++i) {
@@ -135,6 +136,7 @@ extern "C" int ap_sam2_create(ap_ctx* ctx, const ap_sam2_desc* desc, ap_sam2** o
 
 extern "C" int ap_sam2_destroy(ap_sam2* s) {
     if (!s) return AP_OK;
+    DeviceGuard guard(s->ctx);
     cudaDeviceSynchronize();
     for (void* p : s->allocs) cudaFree(p);
     if (s->img_dev) cudaFree(s->img_dev);
@@ -151,6 +153,7 @@ extern "C" int ap_sam2_set_tensor(ap_sam2* s, const char* name, const float* dat
 
 extern "C" int ap_sam2_finalize(ap_sam2* s) {
     if (!s) return AP_EINVAL;
+    DeviceGuard guard(s->ctx);
     if (s->finalized) return AP_OK;
     ap_ctx* ctx = s->ctx;
     const int C0 = s->d.embed_dim;
@@ -256,6 +259,7 @@ extern "C" int ap_sam2_finalize(ap_sam2* s) {
 // image_dev: uint8 [1024, 1024, 3] on the device.  logits_dev: float [1024, 1024]; lowres_dev (optional): float [256, 256].
 extern "C" int ap_sam2_forward(ap_sam2* s, const uint8_t* image_dev, float* logits_dev, float* lowres_dev, void* stream) {
     if (!s) return AP_EINVAL;
+    DeviceGuard guard(s->ctx);
     ap_ctx* ctx = s->ctx;
     if (!s->finalized) return ap_set_error(ctx, AP_ESTATE, "sam2: ap_sam2_finalize has not been called");
     AP_REQUIRE(ctx, image_dev && logits_dev, "sam2_forward: NULL pointer");
@@ -467,6 +471,7 @@ extern "C" int ap_sam2_forward(ap_sam2* s, const uint8_t* image_dev, float* logi
 // Host-side convenience for the segmentation adapter / tests: uint8 image on the host in, logits on the host out.
 extern "C" int ap_sam2_predict_host(ap_sam2* s, const uint8_t* image_host, float* logits_host, float* lowres_host) {
     if (!s || !image_host || !logits_host) return AP_EINVAL;
+    DeviceGuard guard(s->ctx);
     ap_ctx* ctx = s->ctx;
     if (!s->finalized) return ap_set_error(ctx, AP_ESTATE, "sam2: ap_sam2_finalize has not been called");
     float* lg = buf(s, "logits", static_cast<size_t>(IMG) * IMG);
@@ -482,6 +487,7 @@ extern "C" int ap_sam2_predict_host(ap_sam2* s, const uint8_t* image_host, float
 
 extern "C" int ap_sam2_debug_copy(ap_sam2* s, const char* buffer_name, float* host_out, int64_t numel) {
     if (!s || !buffer_name || !host_out) return AP_EINVAL;
+    DeviceGuard guard(s->ctx);
     auto it = s->bufs.find(buffer_name);
     if (it == s->bufs.end()) return ap_set_error(s->ctx, AP_EINVAL, "sam2: no buffer named '%s'", buffer_name);
     if (static_cast<size_t>(numel) > it->second.second) return ap_set_error(s->ctx, AP_EINVAL, "sam2: buffer '%s' has %zu floats", buffer_name, it->second.second);

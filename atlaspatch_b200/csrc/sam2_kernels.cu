@@ -445,11 +445,11 @@ int sam_linear(ap_ctx* ctx, const float* A, int lda, const float* W, const float
     if (M == 0) return AP_OK;
     const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0 && lda % 4 == 0 && K % 4 == 0;
     if (ctx->sam_tensor_cores && aligned && M >= 64) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr;
+        if (attr.need(ctx->device)) {
             AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
             AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-            attr_set = true;
+            attr.done(ctx->device);
         }
         dim3 grid((N + TCN - 1) / TCN, (M + TCM - 1) / TCM);
         if (ctx->sam_tensor_cores == 2) sam_linear_tc_kernel<false><<<grid, 256, TC_SMEM_BYTES, st>>>(A, lda, W, bias, C, ldc, M, N, K, act, accumulate);
@@ -493,11 +493,11 @@ int sam_attention(ap_ctx* ctx, const float* q, int q_stride, const float* k, con
                   int Lq, int Lk, int heads, int hd, float scale, cudaStream_t st) {
     AP_REQUIRE(ctx, hd >= 1 && hd <= 128, "sam attention: head_dim %d unsupported", hd);
     const size_t smem = sizeof(float) * (static_cast<size_t>(AQ + 2 * AK) * (hd + 1) + AQ * (AK + 1) + 3 * AQ);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(sizeof(float) * ((AQ + 2 * AK) * 129 + AQ * (AK + 1) + 3 * AQ))));
-        attr_set = true;
+        attr.done(ctx->device);
     }
     dim3 grid((Lq + AQ - 1) / AQ, heads, nB);
     sam_attention_kernel<<<grid, 256, smem, st>>>(q, q_stride, k, v, kv_stride, out, out_stride, Lq, Lk, heads, hd, scale);

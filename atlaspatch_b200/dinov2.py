@@ -17,6 +17,8 @@ import numpy as np
 
 # name -> (patch, layers, heads, hidden, mlp hidden features, swiglu)
 DINOV2_CONFIGS = {
+    "dinov2_small": (14, 12, 6, 384, 1536, False),     # models/patch/dinov2.py:12-17
+    "dinov2_base": (14, 12, 12, 768, 3072, False),
     "dinov2_large": (14, 24, 16, 1024, 4096, False),
     "dinov2_giant": (14, 40, 24, 1536, 4096, True),
     "dinov2_test_tiny": (14, 2, 4, 256, 1024, False),

@@ -21,7 +21,10 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 # name -> (patch, layers, heads, hidden, mlp); the torchvision ViTs the reference registers (models/patch/vit.py:9-15)
 VIT_CONFIGS = {
     "vit_b_16": (16, 12, 12, 768, 3072),
+    "vit_b_32": (32, 12, 12, 768, 3072),
     "vit_l_16": (16, 24, 16, 1024, 4096),
+    "vit_l_32": (32, 24, 16, 1024, 4096),
+    # vit_h_14 (models/patch/vit.py:14) has head_dim 80: not built -- the attention kernels are head_dim 64
     "vit_test_tiny": (16, 2, 4, 256, 512),
 }
 

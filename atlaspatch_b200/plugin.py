@@ -21,7 +21,8 @@ if _ROOT not in sys.path:
 
 from atlaspatch_b200.encoder import B200FeatureExtractor  # noqa: E402
 
-_TORCHVISION = {"vit_b_16": ("vit_b_16", "ViT_B_16_Weights"), "vit_l_16": ("vit_l_16", "ViT_L_16_Weights")}
+_TORCHVISION = {"vit_b_16": ("vit_b_16", "ViT_B_16_Weights"), "vit_l_16": ("vit_l_16", "ViT_L_16_Weights"),
+                "vit_b_32": ("vit_b_32", "ViT_B_32_Weights"), "vit_l_32": ("vit_l_32", "ViT_L_32_Weights")}   # models/patch/vit.py:9-15
 
 
 def _build(name: str, device) -> B200FeatureExtractor:
@@ -38,7 +39,8 @@ def _build(name: str, device) -> B200FeatureExtractor:
     return B200FeatureExtractor(name, model.state_dict(), device=idx, registry_name=f"b200_{name}")
 
 
-_DINOV2 = {"dinov2_large": "facebook/dinov2-large", "dinov2_giant": "facebook/dinov2-giant"}  # models/patch/dinov2.py:12-17
+_DINOV2 = {"dinov2_small": "facebook/dinov2-small", "dinov2_base": "facebook/dinov2-base",
+           "dinov2_large": "facebook/dinov2-large", "dinov2_giant": "facebook/dinov2-giant"}  # models/patch/dinov2.py:12-17
 
 
 def _build_dinov2(name: str, device, patch_size: int | None) -> B200FeatureExtractor:

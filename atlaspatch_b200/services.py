@@ -92,6 +92,7 @@ class B200PatchExtractionService:
             if not hasattr(wsi, "device_image"):
                 raise RuntimeError("fast_mode=False needs the slide resident in device memory (wsi.device_image); "
                                    "there is no host fallback")
+            _require_level0(coords, "extract(fast_mode=False)")
             coords, coords_dev = filter_patches(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords_dev,
                                                 patch_size=self.cfg.patch_size, black_threshold=self.cfg.black_threshold,
                                                 white_threshold=self.cfg.white_threshold)
@@ -99,11 +100,25 @@ class B200PatchExtractionService:
                                 patch_size_level0=geo.patch_size_level0, coords_device=coords_dev)
 
 
-class B200FeatureEmbeddingService:
-    """One extractor at a time, like embed_all (services/feature_embedding.py:251-316)."""
+def _require_level0(coords: np.ndarray, what: str) -> None:
+    """The device paths read level-0 pixels of `wsi.device_image`; rows that name another pyramid level would silently get the
+    wrong field of view (services/extraction.py:44-64 picks level > 0 for multi-level slides)."""
+    if coords.shape[0] and not (np.asarray(coords)[:, 4] == 0).all():
+        raise NotImplementedError(f"{what}: coordinate rows on pyramid level > 0 need that level resident in device memory; "
+                                  "only single-level (level 0) device slides are supported")
 
-    def __init__(self, extractor):
+
+class B200FeatureEmbeddingService:
+    """One extractor at a time, like embed_all (services/feature_embedding.py:251-316).  `extraction_cfg` carries the patch size
+    the reference resizes every read to (feature_embedding.py:93-95); without it the extractor's own input size is used."""
+
+    def __init__(self, extractor, extraction_cfg: ExtractionConfig | None = None):
         self.extractor = extractor
+        self.cfg = extraction_cfg.validated() if extraction_cfg is not None else None
+
+    @property
+    def patch_size(self) -> int:
+        return int(self.cfg.patch_size) if self.cfg is not None else int(getattr(self.extractor, "input_patch", 0) or 0)
 
     def embed_features(self, result: ExtractionResult, *, wsi, shard_group=None, sharded: bool = False) -> ExtractionResult:
         """sharded=True (intra-slide mode, BASELINE.json configs[4]): every rank of `shard_group` holds the same slide and
@@ -112,6 +127,7 @@ class B200FeatureEmbeddingService:
         if result.num_patches == 0:
             result.features[name] = np.empty((0, self.extractor.embedding_dim), dtype=np.float32)
         elif hasattr(wsi, "device_image") and result.coords_device is not None:
+            _require_level0(result.coords, "embed_features")
             rows = result.coords_device.contiguous()
             if sharded:
                 import torch.distributed as dist
@@ -125,8 +141,16 @@ class B200FeatureEmbeddingService:
             else:
                 feats = self.extractor.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows, read_size=int(result.coords[0, 2]))
             result.features[name] = feats.cpu().numpy()
-        else:  # reference-style host reads (feature_embedding.py:81-96)
-            patches = [wsi.extract((int(x), int(y)), int(lv), (int(rw), int(rh))) for x, y, rw, rh, lv in result.coords.tolist()]
+        else:  # reference-style host reads (feature_embedding.py:81-96): read, cv2.resize to the patch size if the read differs
+            P = self.patch_size
+            patches = []
+            for x, y, rw, rh, lv in result.coords.tolist():
+                patch = wsi.extract((int(x), int(y)), int(lv), (int(rw), int(rh)))
+                if P and (patch.shape[0] != P or patch.shape[1] != P):
+                    import cv2
+
+                    patch = cv2.resize(patch, (P, P))
+                patches.append(patch)
             result.features[name] = self.extractor.extract_batch(patches, batch_size=32)
         result.metadata.setdefault("feature_sets", []).append(name)
         return result

@@ -45,6 +45,18 @@ def thumbnail_area(image, W: int, H: int, pitch: int, factor: int, *, ctx: Conte
     return out
 
 
+def thumbnail_resize(image, W: int, H: int, pitch: int, out_w: int, out_h: int, *, ctx: Context | None = None):
+    """a1, any size: (out_h, out_w, 3) uint8 CUDA tensor = cv2.resize(level, (out_w, out_h), INTER_AREA), bit for bit, for a
+    down-scale (integer-factor kernels when both scale factors are integral, OpenCV's fractional cell weights otherwise)."""
+    import torch
+
+    ctx = ctx or Context.get(torch.cuda.current_device())
+    out = torch.empty((out_h, out_w, 3), dtype=torch.uint8, device="cuda")
+    ctx.check(ctx.lib.ap_thumbnail_resize(ctx.handle, C.c_void_p(image.data_ptr()), W, H, pitch, int(out_w), int(out_h),
+                                          C.c_void_p(out.data_ptr()), C.c_void_p(current_stream_ptr())))
+    return out
+
+
 class SyntheticWSI:
     """Single-level synthetic slide living in HBM (generated on the device, never on the host)."""
 
@@ -99,11 +111,15 @@ class SyntheticWSI:
         return arr
 
     def thumbnail_at_power_device(self, power: float = 1.25):
-        """iwsi.py:246-323 for the single-level, integer-factor case, on the device."""
-        f = thumbnail_factor(self.mag, power)
-        if f != int(f) or self.w % int(f) or self.h % int(f):
-            raise NotImplementedError(f"non-integer thumbnail factor {f} for {self.w}x{self.h} is not implemented")
-        return thumbnail_area(self.device_image, self.w, self.h, self.pitch, int(f), ctx=self._ctx)
+        """iwsi.py:246-323 on the device (single level): ds = mag / power, output round(W / ds) x round(H / ds) (Python round),
+        cv2.resize(INTER_AREA) semantics for any level size."""
+        ds = thumbnail_factor(self.mag, power)
+        out_w, out_h = max(1, int(round(self.w / ds))), max(1, int(round(self.h / ds)))
+        if (out_w, out_h) == (self.w, self.h):
+            return self.device_image[:, :self.w * 3].reshape(self.h, self.w, 3).clone()
+        if out_w > self.w or out_h > self.h:
+            raise NotImplementedError(f"thumbnail power {power} above the slide's magnification {self.mag} (cubic up-scaling) is not built")
+        return thumbnail_resize(self.device_image, self.w, self.h, self.pitch, out_w, out_h, ctx=self._ctx)
 
     def get_thumbnail_at_power(self, *, power: float = 1.25, interpolation: str = "optimise"):
         from PIL import Image

@@ -151,3 +151,15 @@ def render_region_host(spec: SyntheticSlideSpec, x: int, y: int, w: int, h: int)
     reg[..., 1] = np.where(t, g_t, g_b).astype(np.uint8)
     reg[..., 2] = np.where(t, b_t, b_b).astype(np.uint8)
     return out
+
+
+def sam2_benchmark_image(width: int = 8192, height: int = 8192, seed: int = 0) -> np.ndarray:
+    """The 1024 x 1024 uint8 image the segmentation service hands to SAM2 for a synthetic slide: 1.25x thumbnail (exact area mean of
+    16 x 16 blocks) -> PIL BILINEAR to 1024^2 (reference: services/segmentation.py:104-110).  Input data of BASELINE.json configs[2]."""
+    from PIL import Image
+
+    spec = make_spec(width, height, seed)
+    lvl0 = render_region_host(spec, 0, 0, width, height)
+    s = lvl0.reshape(height // 16, 16, width // 16, 16, 3).astype(np.uint32).sum(axis=(1, 3))
+    thumb = np.clip(np.rint(s.astype(np.float32) * np.float32(1 / 256.0)), 0, 255).astype(np.uint8)
+    return np.array(Image.fromarray(thumb).resize((1024, 1024), Image.Resampling.BILINEAR))

@@ -64,3 +64,120 @@ def vit_state_dict(name: str, seed: int = 0, image_size: int = 224) -> dict[str,
     sd["encoder.ln.weight"] = 1.0 + normal((d,), 0.1)
     sd["encoder.ln.bias"] = normal((d,), 0.05)
     return sd
+
+
+# ---- DINOv2 (transformers Dinov2Model key layout; reference: atlas_patch/models/patch/dinov2.py:12-17 + the hub config.json files) ----
+DINOV2_SPECS = {
+    # name: (layers, heads, hidden, swiglu)
+    "dinov2_small": (12, 6, 384, False),
+    "dinov2_base": (12, 12, 768, False),
+    "dinov2_large": (24, 16, 1024, False),
+    "dinov2_giant": (40, 24, 1536, True),
+    # tiny configs used only by fast unit tests
+    "dinov2_test_tiny": (2, 4, 256, False),
+    "dinov2_test_tiny_swiglu": (2, 6, 384, True),
+}
+PATCH = 14
+
+
+def swiglu_hidden(d: int) -> int:
+    """modeling_dinov2.py Dinov2SwiGLUFFN: hidden = (int(4 d * 2 / 3) + 7) // 8 * 8."""
+    return (int(int(d * 4) * 2 / 3) + 7) // 8 * 8
+
+
+def dinov2_state_dict(name: str, seed: int = 0, image_size: int = 518) -> dict[str, torch.Tensor]:
+    """Seeded weights in transformers' Dinov2Model key layout (numpy PCG64, independent of the torch build).  Biases, LayerNorm
+    affine parameters, LayerScale and the class token are perturbed away from their init so that dropping one fails parity."""
+    layers, heads, d, swiglu = DINOV2_SPECS[name]
+    rng = np.random.default_rng(seed)
+    g = image_size // PATCH
+
+    def normal(shape, std):
+        return torch.from_numpy((rng.standard_normal(shape, dtype=np.float32) * np.float32(std)))
+
+    def uniform(shape, bound):
+        return torch.from_numpy(rng.uniform(-bound, bound, shape).astype(np.float32))
+
+    sd: dict[str, torch.Tensor] = {}
+    sd["embeddings.cls_token"] = normal((1, 1, d), 0.02)
+    sd["embeddings.mask_token"] = normal((1, d), 0.02)
+    sd["embeddings.position_embeddings"] = normal((1, g * g + 1, d), 0.02)
+    sd["embeddings.patch_embeddings.projection.weight"] = normal((d, 3, PATCH, PATCH), math.sqrt(1.0 / (3 * PATCH * PATCH)))
+    sd["embeddings.patch_embeddings.projection.bias"] = normal((d,), 0.02)
+    hs = swiglu_hidden(d) if swiglu else 4 * d
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        sd[p + "norm1.weight"] = 1.0 + normal((d,), 0.1)
+        sd[p + "norm1.bias"] = normal((d,), 0.05)
+        for nm in ("query", "key", "value"):
+            sd[p + f"attention.attention.{nm}.weight"] = uniform((d, d), math.sqrt(6.0 / (d + 3 * d)))
+            sd[p + f"attention.attention.{nm}.bias"] = normal((d,), 0.02)
+        sd[p + "attention.output.dense.weight"] = uniform((d, d), math.sqrt(1.0 / d))
+        sd[p + "attention.output.dense.bias"] = normal((d,), 0.02)
+        sd[p + "layer_scale1.lambda1"] = uniform((d,), 0.4) + 0.6        # 0.2 .. 1.0
+        sd[p + "norm2.weight"] = 1.0 + normal((d,), 0.1)
+        sd[p + "norm2.bias"] = normal((d,), 0.05)
+        if swiglu:
+            sd[p + "mlp.weights_in.weight"] = uniform((2 * hs, d), math.sqrt(6.0 / (d + hs)))
+            sd[p + "mlp.weights_in.bias"] = normal((2 * hs,), 0.02)
+            sd[p + "mlp.weights_out.weight"] = uniform((d, hs), math.sqrt(6.0 / (d + hs)))
+            sd[p + "mlp.weights_out.bias"] = normal((d,), 0.02)
+        else:
+            sd[p + "mlp.fc1.weight"] = uniform((hs, d), math.sqrt(6.0 / (d + hs)))
+            sd[p + "mlp.fc1.bias"] = normal((hs,), 0.02)
+            sd[p + "mlp.fc2.weight"] = uniform((d, hs), math.sqrt(6.0 / (d + hs)))
+            sd[p + "mlp.fc2.bias"] = normal((d,), 0.02)
+        sd[p + "layer_scale2.lambda1"] = uniform((d,), 0.4) + 0.6
+    sd["layernorm.weight"] = 1.0 + normal((d,), 0.1)
+    sd["layernorm.bias"] = normal((d,), 0.05)
+    return sd
+
+
+
+# ---- SAM2 (transformers Sam2Model key layout; 'tiny' = the model the reference ships, 'large' = BASELINE.json configs[2]) ----
+def sam2_config(variant: str = "tiny"):
+    """'tiny' = the model the reference ships (configs/sam2.1_hiera_t.yaml); 'large' = BASELINE.json configs[2] (Hiera-L)."""
+    from transformers import Sam2Config, Sam2HieraDetConfig, Sam2VisionConfig
+
+    if variant == "tiny":
+        cfg = Sam2Config()
+    elif variant == "large":
+        bb = Sam2HieraDetConfig(hidden_size=144, num_attention_heads=2, blocks_per_stage=[2, 6, 36, 4],
+                                embed_dim_per_stage=[144, 288, 576, 1152], num_attention_heads_per_stage=[2, 4, 8, 16],
+                                window_size_per_stage=[8, 4, 16, 8], global_attention_blocks=[23, 33, 43])
+        cfg = Sam2Config(vision_config=Sam2VisionConfig(backbone_config=bb, backbone_channel_list=[1152, 576, 288, 144]))
+    else:
+        raise ValueError(variant)
+    cfg.mask_decoder_config.dynamic_multimask_via_stability = False
+    return cfg
+
+
+def sam2_state_dict(seed: int = 0, variant: str = "tiny") -> dict[str, torch.Tensor]:
+    """Seeded random parameters in transformers' Sam2Model naming."""
+    from transformers import Sam2Model
+
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in Sam2Model(sam2_config(variant)).state_dict().items()}
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        if k.endswith("positional_embedding"):                     # gaussian Fourier matrices (scale 1)
+            a = rng.standard_normal(shp)
+        elif "layer_norm" in k or ".norm" in k:
+            a = 1.0 + 0.1 * rng.standard_normal(shp) if k.endswith("weight") else 0.05 * rng.standard_normal(shp)
+        elif k.endswith("bias"):
+            a = 0.02 * rng.standard_normal(shp)
+        elif len(shp) >= 2 and k.endswith("weight") and not any(s in k for s in ("token", "embed")):
+            if "upscale_conv" in k:                                # ConvTranspose2d weight is (in, out, kh, kw)
+                fan_in = shp[0]
+            else:
+                fan_in = int(np.prod(shp[1:]))
+            a = rng.standard_normal(shp) / math.sqrt(fan_in)
+        elif "patch_embed.projection.weight" in k:
+            a = rng.standard_normal(shp) / math.sqrt(int(np.prod(shp[1:])))
+        else:                                                      # tokens, embeddings, pos_embed, no_memory_embedding
+            a = 0.5 * rng.standard_normal(shp)
+        sd[k] = torch.from_numpy(np.asarray(a, dtype=np.float32))
+    return sd
+
+

@@ -49,7 +49,12 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=CHUNK, help="patches per forward chunk (workspace size)")
     ap.add_argument("--width", type=int, default=80000)
     ap.add_argument("--height", type=int, default=60000)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10, help="steps of the host-buffer (e2e) measurement; each step embeds DIFFERENT patches")
+    ap.add_argument("--aux", default="c2,c3,c4", help="comma list of the other BASELINE.json configs measured beside the headline "
+                    "(c2 SAM2 Hiera-L, c3 one 40000^2 slide per rank with dinov2_large, c4 the 100k-patch slide with dinov2_giant split "
+                    "by row range + all-gather); 'none' to skip")
+    ap.add_argument("--c4-cap", type=int, default=12500, help="rows of the C4 slide each rank embeds at most (12 500 = one rank's share "
+                    "of 100 k at 8 GPUs; with fewer ranks the run is a bounded sample of the same slide)")
     ap.add_argument("--cpu-sample", type=int, default=96, help="patches timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-stride", type=int, default=4,
@@ -129,67 +134,364 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own CPU pipeline (oracle port; /root/reference is absent on the GPU box)
+# CPU arm: the reference's own CPU pipeline.  Preferred: the UNMODIFIED reference installed under baseline/_ref by
+# oracle/make_ref.sh (kind "reference": its PatchFeatureEmbeddingService / PatchFeatureExtractor / H5PatchWriter run as they are);
+# fallback when that install is absent: the port in oracle/reference_loop.py (kind "port").
 # ---------------------------------------------------------------------------------------------------------
-def cpu_pipeline_setup(width, height, seed):
+def use_all_host_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms must use the host cores the process may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["MKL_NUM_THREADS"] = str(n)
     import torch
 
-    from atlaspatch_b200.synthetic import render_region_host
-    from oracle import reference_loop as rl
-    from oracle.weights import vit_state_dict
-
-    spec, mask = slide_mask_coords_cpu(width, height, seed)
-    gold = ROOT / "tests" / "golden" / "coords_c1_80000x60000_p256.npz"
-    if (width, height, seed) == (80000, 60000, 0) and gold.exists():
-        coords = np.load(gold)["coords"]     # produced by the reference itself on this exact slide / mask
-    else:
-        from oracle import coords as oc
-
-        coords = oc.coords_from_mask(mask, level0_wh=(width, height), src_mag=20, target_mag=20, patch_size=256,
-                                     step_size=256, tissue_thresh=0.0)
-    model, preprocess = rl.build_vit_b_16(vit_state_dict("vit_b_16", seed=WEIGHT_SEED))
-    read = lambda x, y, w, h: render_region_host(spec, x, y, w, h)  # noqa: E731
-    return spec, coords, model, preprocess, read, torch.get_num_threads()
+    torch.set_num_threads(n)
+    return n
 
 
-def run_cpu_sample(coords, model, preprocess, read, start, n):
-    from oracle import reference_loop as rl
+class ReferenceArm:
+    """One slide's embedding through the reference's own services, `n` coordinate rows at a time."""
 
-    rows = coords[start:start + n]
-    t0 = time.perf_counter()
-    feats = rl.embed_slide_rows(model, preprocess, read, rows, patch_size=256, feature_batch=32, num_workers=4)
-    dt = time.perf_counter() - t0
-    assert feats.shape == (rows.shape[0], 768)
-    return dt
+    def __init__(self, width, height, seed):
+        import tempfile as _tf
+
+        from atlaspatch_b200.weights import vit_state_dict
+
+        self.cores = use_all_host_cores()
+        self.spec, mask = slide_mask_coords_cpu(width, height, seed)
+        gold = ROOT / "tests" / "golden" / "coords_c1_80000x60000_p256.npz"
+        if (width, height, seed) == (80000, 60000, 0) and gold.exists():
+            self.coords = np.load(gold)["coords"]     # produced by the reference itself on this exact slide / mask
+        else:
+            from oracle import coords as oc
+
+            self.coords = oc.coords_from_mask(mask, level0_wh=(width, height), src_mag=20, target_mag=20, patch_size=256,
+                                              step_size=256, tissue_thresh=0.0)
+        sd = vit_state_dict("vit_b_16", seed=WEIGHT_SEED)
+        self.kind = "port"
+        self.tmp = _tf.TemporaryDirectory(prefix="ap_ref_")
+        try:
+            from oracle import ref_pipeline as rp
+
+            if not rp.reference_available():
+                raise RuntimeError("reference not installed (baseline/_ref)")
+            rp.import_reference()
+            self.rp = rp
+            self.wsi = rp.host_synthetic_wsi_class()(self.spec)
+            _, self.embedding = rp.reference_services(self.tmp.name, patch_size=256, target_mag=20,
+                                                      extractors={"vit_b_16": rp.reference_vit_builder(sd, num_workers=4)},
+                                                      feature_batch=32, num_workers=4)
+            self.extractor = self.embedding.registry.create("vit_b_16")
+            self.kind = "reference"
+            self.what = ("the unmodified reference (baseline/_ref): PatchFeatureEmbeddingService._embed_with_extractor -> per-row H5 "
+                         "coordinate read, IWSI.extract, H5PatchWriter.append_features, PatchFeatureExtractor.extract_batch (new "
+                         "DataLoader(num_workers=4) per 32 patches), torchvision vit_b_16 fp32")
+        except Exception as e:  # noqa: BLE001
+            from atlaspatch_b200.synthetic import render_region_host
+            from oracle import reference_loop as rl
+
+            self.model, self.preprocess = rl.build_vit_b_16(sd)
+            self.read = lambda x, y, w, h: render_region_host(self.spec, x, y, w, h)  # noqa: E731
+            self.what = f"oracle/reference_loop.py (port; the reference install was unavailable: {e})"
+        self._n = 0
+
+    def run(self, start, n) -> float:
+        rows = self.coords[start:start + n]
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self._n += 1
+            slide = self.rp.reference_slide(Path(self.tmp.name) / f"step{self._n}.synth", mpp=self.spec.mpp)
+            res = self.rp.write_reference_coords(self.embedding, self.wsi, slide, rows, patch_size_level0=256)
+            t0 = time.perf_counter()                      # the coordinate file exists before embedding starts, as in the reference
+            self.embedding._embed_with_extractor(result=res, wsi=self.wsi, extractor=self.extractor)
+            dt = time.perf_counter() - t0
+            feats = self.rp.read_h5(res.h5_path)["features"]["vit_b_16"]
+            os.remove(res.h5_path)
+        else:
+            from oracle import reference_loop as rl
+
+            feats = rl.embed_slide_rows(self.model, self.preprocess, self.read, rows, patch_size=256, feature_batch=32, num_workers=4)
+            dt = time.perf_counter() - t0
+        assert feats.shape == (rows.shape[0], 768)
+        return dt
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    spec, coords, model, preprocess, read, threads = cpu_pipeline_setup(args.width, args.height, 0)
+    arm = ReferenceArm(args.width, args.height, 0)
     n = args.ref_sample
+    last = max(1, len(arm.coords) - n)
     for i in range(args.warmup):
-        run_cpu_sample(coords, model, preprocess, read, (i * n) % max(1, len(coords) - n), n)
+        arm.run((i * n) % last, n)
     t = 0.0
     for i in range(args.steps):
-        t += run_cpu_sample(coords, model, preprocess, read, ((args.warmup + i) * n) % max(1, len(coords) - n), n)
+        t += arm.run(((args.warmup + i) * n) % last, n)
     value = args.steps * n / t
-    sample = (f"{args.steps} steps x {n} consecutive coordinate rows of the {args.width}x{args.height} slide "
-              f"({len(coords)} patches total), batch 32, DataLoader num_workers=4, fp32")
+    sample = (f"{args.steps} steps x {n} consecutive coordinate rows of the {args.width}x{args.height} slide ({len(arm.coords)} patches "
+              f"total) through {arm.what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"single synthetic {args.width}x{args.height} RGB slide, 256px patches stride 256, ViT-B/16 "
-                               "random-init (seeded), reference CPU pipeline port (oracle/reference_loop.py)",
+                               "random-init (seeded), the reference's CPU pipeline on the host cores",
                    "patches_per_step": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def host_patches_from_slide(wsi, rows_np, P):
+    """The (P, P, 3) uint8 host patches a caller of extract_batch would hold for `rows_np`: gathered on the device in blocks, one
+    D2H copy per block (zeros outside the slide, like IWSI.extract)."""
+    import torch
+
+    img, W, H = wsi.device_image, wsi.w, wsi.h
+    n = int(rows_np.shape[0])
+    out = np.empty((n, P, P, 3), dtype=np.uint8)
+    blk = 512
+    for s0 in range(0, n, blk):
+        m = min(blk, n - s0)
+        buf = torch.zeros((m, P, P, 3), dtype=torch.uint8, device="cuda")
+        for i, (x, y) in enumerate(rows_np[s0:s0 + m, :2].tolist()):
+            x0, y0, x1, y1 = max(x, 0), max(y, 0), min(x + P, W), min(y + P, H)
+            if x1 > x0 and y1 > y0:
+                buf[i, y0 - y:y1 - y, x0 - x:x1 - x] = img[y0:y1, x0 * 3:x1 * 3].reshape(y1 - y0, x1 - x0, 3)
+        out[s0:s0 + m] = buf.cpu().numpy()
+    return [out[i] for i in range(n)]
+
+
+def _cuda_time(fn):
+    import torch
+
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return r, e0.elapsed_time(e1)
+
+
+def _max_over_ranks(ms, world):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(v, world):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def _rel_rows(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+def _capped_mask(spec):
+    from PIL import Image
+
+    from atlaspatch_b200.synthetic import truth_mask
+
+    m = (truth_mask(spec) * 255).astype(np.uint8)
+    f = 1024 / max(m.shape)
+    if f < 1:
+        m = np.asarray(Image.fromarray(m).resize((round(m.shape[1] * f), round(m.shape[0] * f)), Image.Resampling.NEAREST))
+    return m.astype(np.float32) / 255.0
+
+
+def _golden_check(ext, name):
+    """max relative row error of the extractor on the committed golden rows of `name` (tests/golden/<name>.npz, produced by
+    transformers' Dinov2Model; slide / coordinates of tests/cases.py: DINOV2_CASES)."""
+    import torch
+
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec
+
+    case = GOLDEN_CASES[name]
+    g = np.load(ROOT / "tests" / "golden" / f"{name}.npz")
+    sl = case["slide"]
+    w = SyntheticWSI(make_spec(sl["width"], sl["height"], sl["seed"], mpp=sl["mpp"]))
+    rng = np.random.default_rng(99)
+    P = case["patch"]
+    xy = np.stack([rng.integers(0, sl["width"] - P, case["n"]), rng.integers(0, sl["height"] - P, case["n"])], 1)
+    xy[-1] = (sl["width"] - P // 2, sl["height"] - P // 3)
+    rows = np.concatenate([xy, np.full((case["n"], 2), P), np.zeros((case["n"], 1))], 1).astype(np.int32)
+    got = ext.embed_coords(w.device_image, w.w, w.h, w.pitch, torch.from_numpy(rows).cuda()).cpu().numpy()
+    w.cleanup()
+    return float(_rel_rows(got, g["feats"]).max())
+
+
+# the golden cases of tests/cases.py: DINOV2_CASES (kept in step by tests/test_bench_config.py)
+GOLDEN_CASES = {
+    "dinov2_large": dict(weight_seed=4321, slide=dict(width=4096, height=4096, seed=12, mpp=0.5), n=8, patch=224),
+    "dinov2_giant": dict(weight_seed=777, slide=dict(width=4096, height=4096, seed=13, mpp=0.5), n=4, patch=512),
+}
+GFLOP_PER_PATCH = {"dinov2_large": 162.02, "dinov2_giant": 598.78}   # SURVEY.md section 8d
+
+
+def aux_c2_sam2(ctx, rank, world):
+    """BASELINE.json configs[2]: SAM2 Hiera-L forward on the 1024 x 1024 thumbnail; mask IoU against the golden mask of the fp32
+    restatement (tests/golden/sam2_hiera_l_mask.npz, transformers' Sam2Model -- the reference's sam2 package is not installable
+    offline)."""
+    import torch
+
+    from atlaspatch_b200.sam2 import HIERA_L, B200Sam2Predictor
+    from atlaspatch_b200.synthetic import sam2_benchmark_image
+    from atlaspatch_b200.weights import sam2_state_dict
+
+    pred = B200Sam2Predictor(sam2_state_dict(1, "large"), config=HIERA_L, device=torch.cuda.current_device())
+    img = sam2_benchmark_image()
+    pred.predict_logits(img)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        up = pred.predict_logits(img)
+    ms = (time.perf_counter() - t0) * 1000 / reps
+    pred.close()
+    out = {"model": "sam2 hiera-large, 1024x1024, box prompt = whole image", "ms_per_thumbnail_incl_h2d_d2h": ms,
+           "gflop_per_forward": 1625.4, "tflops": 1625.4 / ms}
+    gpath = ROOT / "tests" / "golden" / "sam2_hiera_l_mask.npz"
+    if gpath.exists():
+        g = np.load(gpath)
+        ref = np.unpackbits(g["mask_bits"])[:1024 * 1024].reshape(1024, 1024).astype(bool)
+        a = up > 0
+        out["mask_iou_vs_golden"] = float((a & ref).sum() / max((a | ref).sum(), 1))
+        out["positives"] = [int(a.sum()), int(g["positives"])]
+    out["ms_max_over_ranks"] = _max_over_ranks(ms, world)
+    return out
+
+
+def _encoder_for(name, patch, seed, chunk=127):
+    import torch
+
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.weights import dinov2_state_dict
+
+    sd = dinov2_state_dict(name, seed=seed)     # seeded input data: every rank draws the same values (no collective needed)
+    ext = B200FeatureExtractor(name, sd, input_patch=patch, max_batch=chunk, device=torch.cuda.current_device())
+    del sd
+    return ext
+
+
+def aux_c3_slides(ctx, rank, world, local_rank, peaks):
+    """BASELINE.json configs[3]: a batch of `world` synthetic 40000 x 40000 slides, "ViT-L/14" = dinov2_large, 224 px patches, one
+    slide per rank (sharding.assign_slides; with 8 ranks this is the named 8-slide batch).  Per rank: slide in HBM -> coords of the
+    whole slide -> features of every coordinate; no collective on the data path."""
+    import torch
+
+    from atlaspatch_b200.services import B200PatchExtractionService, ExtractionConfig, Slide
+    from atlaspatch_b200.sharding import assign_slides
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec
+
+    name = "dinov2_large"
+    slides = [dict(width=40000, height=40000, seed=100 + i) for i in range(world)]
+    mine = assign_slides([sl["width"] * sl["height"] for sl in slides], world)[rank]
+    ext = _encoder_for(name, 224, GOLDEN_CASES[name]["weight_seed"])
+    golden_err = _golden_check(ext, name)
+    svc = B200PatchExtractionService(ExtractionConfig(patch_size=224, target_magnification=20, step_size=224))
+    n_patches, ms_total = 0, 0.0
+    for i in mine:
+        sl = slides[i]
+        wsi = SyntheticWSI(make_spec(sl["width"], sl["height"], sl["seed"]))
+        wsi.device_image
+        res = svc.extract(wsi, _capped_mask(wsi.spec), slide=Slide(Path(wsi.path), mpp=0.5))
+        rows = res.coords_device.contiguous()
+        ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows[:254].contiguous(), read_size=224)   # warm
+        _, ms = _cuda_time(lambda: ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows, read_size=224))
+        n_patches += int(rows.shape[0])
+        ms_total += ms
+        wsi.cleanup()
+        del wsi, rows, res
+        torch.cuda.empty_cache()
+    ext.cleanup()
+    total = _sum_over_ranks(n_patches, world)
+    ms_max = _max_over_ranks(ms_total, world)
+    pps = total / (ms_max / 1000.0)
+    return {"workload": f"{world} synthetic 40000x40000 slides (seeds 100..), dinov2_large (ViT-L/14), 224px patches stride 224, one slide "
+                        "per rank, whole slide embedded", "slides": world, "patches_total": int(total), "patches_rank0": n_patches,
+            "embed_ms_max_over_ranks": ms_max, "patches_per_s": pps, "model_tflops_per_gpu": pps / world * GFLOP_PER_PATCH[name] / 1000,
+            "frac_of_sustained_peak": pps / world * GFLOP_PER_PATCH[name] / 1000 / peaks["tflops_sustained"],
+            "max_rel_err_vs_golden": golden_err, "tolerance": 1e-3}
+
+
+def aux_c4_intra_slide(ctx, rank, world, local_rank, peaks, cap):
+    """BASELINE.json configs[4]: ONE synthetic slide, 512 px patches at stride 256 (overlap) -> ~100 k patches, dinov2_giant.  Every
+    rank holds the slide and the coordinate list, embeds its contiguous row range (sharding.row_range) and the (N, 1536) fp32
+    matrix is all-gathered over NCCL (sharding.gather_rows) -- the path's only data-path collective, timed here.  With fewer than 8
+    ranks each rank embeds at most `cap` rows of its range (a bounded sample of the same slide; at 8 ranks the whole slide)."""
+    import torch
+    import torch.distributed as dist
+
+    from atlaspatch_b200.services import B200PatchExtractionService, ExtractionConfig, Slide
+    from atlaspatch_b200.sharding import gather_rows, row_range
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec
+
+    name = "dinov2_giant"
+    ext = _encoder_for(name, 512, GOLDEN_CASES[name]["weight_seed"])
+    golden_err = _golden_check(ext, name)
+    wsi = SyntheticWSI(make_spec(90000, 80000, 5))
+    wsi.device_image
+    svc = B200PatchExtractionService(ExtractionConfig(patch_size=512, target_magnification=20, step_size=256))
+    res = svc.extract(wsi, _capped_mask(wsi.spec), slide=Slide(Path(wsi.path), mpp=0.5))
+    n_all = res.num_patches
+    b, e = row_range(n_all, rank, world)
+    e = min(e, b + cap)
+    rows = res.coords_device[b:e].contiguous()
+    ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows[:127].contiguous(), read_size=512)   # warm
+    local, ms = _cuda_time(lambda: ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows, read_size=512))
+    n_local = int(rows.shape[0])
+    out = {"workload": "one synthetic 90000x80000 slide, 512px patches stride 256, dinov2_giant (ViT-g/14, SwiGLU, 40 layers), rows split "
+                       "by contiguous range over the ranks", "coords_total": int(n_all), "rows_per_rank_cap": int(cap)}
+    gather_ms, identical = None, None
+    if world > 1:
+        sizes = [min(row_range(n_all, r, world)[1], row_range(n_all, r, world)[0] + cap) - row_range(n_all, r, world)[0] for r in range(world)]
+        full = all(sz == row_range(n_all, r, world)[1] - row_range(n_all, r, world)[0] for r, sz in enumerate(sizes))
+        if full:
+            dist.barrier()
+            gathered, gather_ms = _cuda_time(lambda: gather_rows(local, n_all))
+        else:   # bounded sample: gather the equal-sized blocks that were embedded
+            n_eq = min(sizes)
+            dist.barrier()
+            gathered, gather_ms = _cuda_time(lambda: gather_rows(local[:n_eq].contiguous(), n_eq * world))
+        gather_ms = _max_over_ranks(gather_ms, world)
+        # bit-identity of the sharded result with a single-rank run: rank 0 recomputes the first rows of rank 1's block itself
+        if rank == 0:
+            b1 = row_range(n_all, 1, world)[0]
+            k = min(16, sizes[1])
+            mine = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, res.coords_device[b1:b1 + k].contiguous(), read_size=512)
+            off = (b1 if full else min(sizes))
+            identical = bool(torch.equal(mine, gathered[off:off + k]))
+        out["gather"] = {"collective": "all_gather (NCCL) of the fp32 feature blocks", "ms_max_over_ranks": gather_ms,
+                         "bytes_total": int((n_all if full else min(sizes) * world) * 1536 * 4), "whole_slide": bool(full),
+                         "rows_identical_to_single_rank_run": identical}
+    ext.cleanup()
+    wsi.cleanup()
+    total = _sum_over_ranks(n_local, world)
+    ms_max = _max_over_ranks(ms, world)
+    pps = total / (ms_max / 1000.0)
+    out.update({"patches_embedded": int(total), "embed_ms_max_over_ranks": ms_max, "patches_per_s": pps,
+                "patches_per_s_incl_gather": total / ((ms_max + (gather_ms or 0.0)) / 1000.0),
+                "model_tflops_per_gpu": pps / world * GFLOP_PER_PATCH[name] / 1000,
+                "frac_of_sustained_peak": pps / world * GFLOP_PER_PATCH[name] / 1000 / peaks["tflops_sustained"],
+                "precise_layers": "library default for > 32 layers", "max_rel_err_vs_golden": golden_err, "tolerance": 1e-3})
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -333,26 +635,47 @@ def main_b200(args):
     value = world * args.steps * B / (ms_max / 1000.0)
 
     # ---- e2e: the reference-facing plug-in call with HOST patches (H2D + D2H inside the timed region) -----
+    # every step embeds DIFFERENT patches: a pool of e2e_steps x B patches read from the slide beforehand (not timed), as a
+    # caller of extract_batch would hold them
     n_e2e = B
-    host_rows = coords_np[:n_e2e] if n_coords >= n_e2e else np.concatenate([coords_np] * (n_e2e // n_coords + 1))[:n_e2e]
-    host_patches = []
-    img3 = image  # (H, pitch) uint8
-    for (x, y, _rw, _rh, _lv) in host_rows.tolist():     # patches a caller would have read from the slide (not timed)
-        host_patches.append(wsi.extract((x, y), 0, (256, 256)))
-    ext.extract_batch(host_patches[:256], batch_size=32)  # warm
+    e2e_steps = max(1, args.e2e_steps)
+    pool_n = min(n_coords, e2e_steps * B) if n_coords >= B else B
+    pool_rows = coords_np[:pool_n] if n_coords >= B else np.concatenate([coords_np] * (B // n_coords + 1))[:B]
+    pool = host_patches_from_slide(wsi, pool_rows, 256)
+    ext.extract_batch(pool[:256], batch_size=32)  # warm
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        f_host = ext.extract_batch(host_patches, batch_size=32)
+    for i in range(e2e_steps):
+        s0 = (i * B) % (pool_n - B + 1)
+        f_host = ext.extract_batch(pool[s0:s0 + B], batch_size=32)
     e2e_s = time.perf_counter() - t0
     assert f_host.shape == (n_e2e, 768)
+    del pool
     t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.barrier()
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.e2e_steps * n_e2e / float(t_e2e.item())
+    e2e_value = world * e2e_steps * n_e2e / float(t_e2e.item())
+
+    # ---- the other BASELINE.json configs, measured beside the headline (every rank takes part) ------------
+    ext.cleanup()
+    del ext, feats, coords_ring
+    aux_cfg = {} if args.aux.strip().lower() in ("", "none") else {k.strip(): True for k in args.aux.split(",")}
+    aux_out = {}
+    if "c2" in aux_cfg:
+        aux_out["c2"] = aux_c2_sam2(ctx, rank, world)
+    wsi.cleanup()
+    del wsi, image
+    torch.cuda.empty_cache()
+    if "c3" in aux_cfg:
+        aux_out["c3"] = aux_c3_slides(ctx, rank, world, local_rank, peaks)
+    if "c4" in aux_cfg:
+        aux_out["c4"] = aux_c4_intra_slide(ctx, rank, world, local_rank, peaks, args.c4_cap)
 
     if rank != 0:
         if world > 1:
+            dist.barrier()           # rank 0 is still timing the CPU baseline and printing the line
             dist.destroy_process_group()
         return 0
 
@@ -390,14 +713,13 @@ def main_b200(args):
     }
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        _spec, c_coords, model, preprocess, read, threads = cpu_pipeline_setup(args.width, args.height, 0)
-        run_cpu_sample(c_coords, model, preprocess, read, 0, 32)  # warm
-        dt = run_cpu_sample(c_coords, model, preprocess, read, 32, args.cpu_sample)
-        cpu_baseline = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    if not args.no_cpu_baseline:     # rank 0, at every N (the other ranks are idle at the final barrier meanwhile)
+        arm = ReferenceArm(args.width, args.height, 0)
+        arm.run(0, 32)  # warm
+        dt = arm.run(32, args.cpu_sample)
+        cpu_baseline = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                         "sample": f"{args.cpu_sample} consecutive coordinate rows (after a 32-patch warm-up) of the same slide through "
-                                  "oracle/reference_loop.py: per-row read, new DataLoader(num_workers=4) per 32 patches, "
-                                  "torchvision vit_b_16 fp32 on the host cores"}
+                                  f"{arm.what}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -410,15 +732,16 @@ def main_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * PATCH_BYTES, "d2h_bytes_per_step": n_e2e * 768 * 4,
                 "api": "B200FeatureExtractor.extract_batch(list of host uint8 patches) -> host float32 features",
-                "patches_per_step": n_e2e, "steps": args.e2e_steps},
+                "patches_per_step": n_e2e, "steps": e2e_steps, "distinct_patches": int(pool_n)},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "aux": {"coords": n_coords, "coords_ms_incl_host_contours": coords_ms, "coords_first_call_ms": coords_first_ms,
-                "thumbnail_ms": thumb_ms, "content_filter_ms": filter_ms},
+                "thumbnail_ms": thumb_ms, "content_filter_ms": filter_ms, **aux_out},
     }
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -32,6 +32,9 @@ typedef struct ap_encoder ap_encoder;
 
 /* ---- context ------------------------------------------------------------------------- */
 int ap_version(void);
+/* sizeof("ap_vit_desc" | "ap_sam2_desc") as compiled into the library (-1: unknown name): lets a binding (ctypes, cgo ...)
+ * assert that its own struct declaration matches before it passes one in. */
+int ap_sizeof(const char* struct_name);
 /* One ctx per GPU/process (SURVEY.md section 8b "Threading").  Fails (AP_ECUDA) when no sm_100 device. */
 int ap_init(int device, ap_ctx** out_ctx);
 int ap_destroy(ap_ctx* ctx);
@@ -68,6 +71,14 @@ int ap_synth_render(ap_ctx* ctx, uint8_t* out_dev, int64_t pitch, int64_t W, int
  * packed RGB.  One pass over W*H*3 bytes: the HBM-roofline kernel of the path. */
 int ap_thumbnail_area(ap_ctx* ctx, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
                       int factor, uint8_t* out_dev, void* stream);
+/* The general case of the same reference step: the reference's output size is round(W/ds) x round(H/ds)
+ * (core/wsi/iwsi.py:302-303); when the level size is not a multiple of ds, cv2.resize(INTER_AREA) leaves its
+ * integer-factor path and weights partial source cells in float32 (computeResizeAreaTab / ResizeArea_).  This entry
+ * reproduces cv2.resize(level, (out_w, out_h), INTER_AREA) bit for bit for any down-scale and dispatches to the
+ * integer-factor kernels when both scale factors are integral. */
+int ap_thumbnail_resize(ap_ctx* ctx, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
+                        int out_w, int out_h, uint8_t* out_dev, void* stream);
+
 
 /* ---- a9: patch-coordinate extraction -------------------------------------------------------
  * Replaces PatchExtractionService._iter_patch_entries (fast mode) + _in_tissue +
@@ -123,7 +134,7 @@ typedef struct ap_vit_desc {
     int input_patch;  /* edge of the RGB patches fed in (256): centre crop to image_size */
     int max_batch;    /* patches per forward chunk (workspace size); 0 = default 127 */
     int precise_layers; /* leading encoder layers whose GEMM weights are kept as fp16 hi/lo pairs (2 MMAs per weight):
-                           keeps worst-case feature error under 1e-3 (DESIGN.md "precision"); -1 = default (1; 8 when layers > 32) */
+                           keeps worst-case feature error under 1e-3 (DESIGN.md "precision"); -1 = default (1; 20 when layers > 32) */
     float ln_eps;     /* 1e-6 */
     float mean[3];    /* ImageNet mean / std of the torchvision preset */
     float std[3];

@@ -28,22 +28,10 @@ from typing import Sequence
 import numpy as np
 import torch
 
-DINOV2_SPECS = {
-    # name: (layers, heads, hidden, swiglu)       atlas_patch/models/patch/dinov2.py:12-17 + the hub config.json files
-    "dinov2_large": (24, 16, 1024, False),
-    "dinov2_giant": (40, 24, 1536, True),
-    # tiny configs used only by fast unit tests
-    "dinov2_test_tiny": (2, 4, 256, False),
-    "dinov2_test_tiny_swiglu": (2, 6, 384, True),
-}
-PATCH = 14
+from atlaspatch_b200.weights import DINOV2_SPECS, PATCH, dinov2_state_dict, swiglu_hidden  # noqa: E402,F401  (seeded input data)
+
 MEAN = (0.485, 0.456, 0.406)
 STD = (0.229, 0.224, 0.225)
-
-
-def swiglu_hidden(d: int) -> int:
-    """modeling_dinov2.py Dinov2SwiGLUFFN: hidden = (int(4 d * 2 / 3) + 7) // 8 * 8."""
-    return (int(int(d * 4) * 2 / 3) + 7) // 8 * 8
 
 
 def make_config(name: str, image_size: int = 518):
@@ -52,54 +40,6 @@ def make_config(name: str, image_size: int = 518):
     layers, heads, d, swiglu = DINOV2_SPECS[name]
     return Dinov2Config(hidden_size=d, num_hidden_layers=layers, num_attention_heads=heads, mlp_ratio=4, patch_size=PATCH,
                         image_size=image_size, use_swiglu_ffn=swiglu, layer_norm_eps=1e-6, qkv_bias=True, layerscale_value=1.0)
-
-
-def dinov2_state_dict(name: str, seed: int = 0, image_size: int = 518) -> dict[str, torch.Tensor]:
-    """Seeded weights in transformers' Dinov2Model key layout (numpy PCG64, independent of the torch build).  Biases, LayerNorm
-    affine parameters, LayerScale and the class token are perturbed away from their init so that dropping one fails parity."""
-    layers, heads, d, swiglu = DINOV2_SPECS[name]
-    rng = np.random.default_rng(seed)
-    g = image_size // PATCH
-
-    def normal(shape, std):
-        return torch.from_numpy((rng.standard_normal(shape, dtype=np.float32) * np.float32(std)))
-
-    def uniform(shape, bound):
-        return torch.from_numpy(rng.uniform(-bound, bound, shape).astype(np.float32))
-
-    sd: dict[str, torch.Tensor] = {}
-    sd["embeddings.cls_token"] = normal((1, 1, d), 0.02)
-    sd["embeddings.mask_token"] = normal((1, d), 0.02)
-    sd["embeddings.position_embeddings"] = normal((1, g * g + 1, d), 0.02)
-    sd["embeddings.patch_embeddings.projection.weight"] = normal((d, 3, PATCH, PATCH), math.sqrt(1.0 / (3 * PATCH * PATCH)))
-    sd["embeddings.patch_embeddings.projection.bias"] = normal((d,), 0.02)
-    hs = swiglu_hidden(d) if swiglu else 4 * d
-    for i in range(layers):
-        p = f"encoder.layer.{i}."
-        sd[p + "norm1.weight"] = 1.0 + normal((d,), 0.1)
-        sd[p + "norm1.bias"] = normal((d,), 0.05)
-        for nm in ("query", "key", "value"):
-            sd[p + f"attention.attention.{nm}.weight"] = uniform((d, d), math.sqrt(6.0 / (d + 3 * d)))
-            sd[p + f"attention.attention.{nm}.bias"] = normal((d,), 0.02)
-        sd[p + "attention.output.dense.weight"] = uniform((d, d), math.sqrt(1.0 / d))
-        sd[p + "attention.output.dense.bias"] = normal((d,), 0.02)
-        sd[p + "layer_scale1.lambda1"] = uniform((d,), 0.4) + 0.6        # 0.2 .. 1.0
-        sd[p + "norm2.weight"] = 1.0 + normal((d,), 0.1)
-        sd[p + "norm2.bias"] = normal((d,), 0.05)
-        if swiglu:
-            sd[p + "mlp.weights_in.weight"] = uniform((2 * hs, d), math.sqrt(6.0 / (d + hs)))
-            sd[p + "mlp.weights_in.bias"] = normal((2 * hs,), 0.02)
-            sd[p + "mlp.weights_out.weight"] = uniform((d, hs), math.sqrt(6.0 / (d + hs)))
-            sd[p + "mlp.weights_out.bias"] = normal((d,), 0.02)
-        else:
-            sd[p + "mlp.fc1.weight"] = uniform((hs, d), math.sqrt(6.0 / (d + hs)))
-            sd[p + "mlp.fc1.bias"] = normal((hs,), 0.02)
-            sd[p + "mlp.fc2.weight"] = uniform((d, hs), math.sqrt(6.0 / (d + hs)))
-            sd[p + "mlp.fc2.bias"] = normal((d,), 0.02)
-        sd[p + "layer_scale2.lambda1"] = uniform((d,), 0.4) + 0.6
-    sd["layernorm.weight"] = 1.0 + normal((d,), 0.1)
-    sd["layernorm.bias"] = normal((d,), 0.05)
-    return sd
 
 
 def build_model(name: str, sd: dict[str, torch.Tensor], image_size: int = 518):

@@ -21,50 +21,7 @@ MEAN = (0.485, 0.456, 0.406)
 STD = (0.229, 0.224, 0.225)
 
 
-def make_config(variant: str = "tiny"):
-    """'tiny' = the model the reference ships (configs/sam2.1_hiera_t.yaml); 'large' = BASELINE.json configs[2] (Hiera-L)."""
-    from transformers import Sam2Config, Sam2HieraDetConfig, Sam2VisionConfig
-
-    if variant == "tiny":
-        cfg = Sam2Config()
-    elif variant == "large":
-        bb = Sam2HieraDetConfig(hidden_size=144, num_attention_heads=2, blocks_per_stage=[2, 6, 36, 4],
-                                embed_dim_per_stage=[144, 288, 576, 1152], num_attention_heads_per_stage=[2, 4, 8, 16],
-                                window_size_per_stage=[8, 4, 16, 8], global_attention_blocks=[23, 33, 43])
-        cfg = Sam2Config(vision_config=Sam2VisionConfig(backbone_config=bb, backbone_channel_list=[1152, 576, 288, 144]))
-    else:
-        raise ValueError(variant)
-    cfg.mask_decoder_config.dynamic_multimask_via_stability = False
-    return cfg
-
-
-def sam2_state_dict(seed: int = 0, variant: str = "tiny") -> dict[str, torch.Tensor]:
-    """Seeded random parameters in transformers' Sam2Model naming."""
-    from transformers import Sam2Model
-
-    with torch.device("meta"):
-        shapes = {k: tuple(v.shape) for k, v in Sam2Model(make_config(variant)).state_dict().items()}
-    rng = np.random.default_rng(seed)
-    sd = {}
-    for k, shp in shapes.items():
-        if k.endswith("positional_embedding"):                     # gaussian Fourier matrices (scale 1)
-            a = rng.standard_normal(shp)
-        elif "layer_norm" in k or ".norm" in k:
-            a = 1.0 + 0.1 * rng.standard_normal(shp) if k.endswith("weight") else 0.05 * rng.standard_normal(shp)
-        elif k.endswith("bias"):
-            a = 0.02 * rng.standard_normal(shp)
-        elif len(shp) >= 2 and k.endswith("weight") and not any(s in k for s in ("token", "embed")):
-            if "upscale_conv" in k:                                # ConvTranspose2d weight is (in, out, kh, kw)
-                fan_in = shp[0]
-            else:
-                fan_in = int(np.prod(shp[1:]))
-            a = rng.standard_normal(shp) / math.sqrt(fan_in)
-        elif "patch_embed.projection.weight" in k:
-            a = rng.standard_normal(shp) / math.sqrt(int(np.prod(shp[1:])))
-        else:                                                      # tokens, embeddings, pos_embed, no_memory_embedding
-            a = 0.5 * rng.standard_normal(shp)
-        sd[k] = torch.from_numpy(np.asarray(a, dtype=np.float32))
-    return sd
+from atlaspatch_b200.weights import sam2_config as make_config, sam2_state_dict  # noqa: E402,F401  (seeded input data)
 
 
 def build_model(sd, variant: str = "tiny"):

@@ -47,6 +47,15 @@ THUMB_CASES = [
     dict(name="2000x3008_mag10", width=2000, height=3008, seed=2, mpp=1.0),   # f = 8
 ]
 
+# a1 beyond power-of-two factors and dividing sizes: ds = 48 (60x slides: 1/48^2 is not exact in fp32, the ADVICE rounding case) and
+# level sizes the factor does not divide (cv2's fractional INTER_AREA tables; output round(W/ds) x round(H/ds))
+THUMB_GENERAL_CASES = [
+    dict(name="4800x2400_mag60", width=4800, height=2400, seed=3, mpp=0.18),     # f = 48, dividing
+    dict(name="4100x3001_mag20", width=4100, height=3001, seed=4, mpp=0.5),      # 256 x 188, scales 16.016 / 15.963
+    dict(name="5000x3000_mag60", width=5000, height=3000, seed=5, mpp=0.18),     # 104 x 62 (round half even), scales 48.08 / 48.39
+    dict(name="4097x4096_mag40", width=4097, height=4096, seed=6, mpp=0.25),     # x fractional, y integral -> general tables on both axes
+]
+
 # --no-fast-mode content filter (services/extraction.py:105-119): geometry from COORD_CASES + thresholds.  The synthetic
 # tissue's gray level straddles 142 (about 70 % of a tissue patch below it) and the background's saturation straddles 6, so
 # the non-default thresholds put hundreds of patches right at the 0.7 decision fraction.
@@ -134,12 +143,7 @@ def feature_patches() -> list[np.ndarray]:
 
 
 def sam2_input_image() -> np.ndarray:
-    """The 1024 x 1024 uint8 image the segmentation service would hand to SAM2 for the 8192^2 synthetic slide (seed 0):
-    1.25x thumbnail (512^2, exact area mean) -> PIL BILINEAR to 1024^2 (services/segmentation.py:104-110)."""
-    from PIL import Image
+    """The 1024 x 1024 uint8 image the segmentation service would hand to SAM2 for the 8192^2 synthetic slide (seed 0)."""
+    from atlaspatch_b200.synthetic import sam2_benchmark_image
 
-    spec = make_spec(8192, 8192, 0)
-    lvl0 = render_region_host(spec, 0, 0, 8192, 8192)
-    s = lvl0.reshape(512, 16, 512, 16, 3).astype(np.uint32).sum(axis=(1, 3))
-    thumb = np.clip(np.rint(s.astype(np.float32) * np.float32(1 / 256.0)), 0, 255).astype(np.uint8)
-    return np.array(Image.fromarray(thumb).resize((1024, 1024), Image.Resampling.BILINEAR))
+    return sam2_benchmark_image(8192, 8192, 0)

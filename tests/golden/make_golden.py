@@ -136,7 +136,7 @@ def main() -> None:
     (OUT / "versions.json").write_text(json.dumps(versions, indent=1) + "\n")
 
 
-if __name__ == "__main__" and not ({"--sam2", "--filter", "--dinov2"} & set(sys.argv)):
+if __name__ == "__main__" and not ({"--sam2", "--sam2-large", "--filter", "--dinov2", "--thumb-general"} & set(sys.argv)):
     os.environ.setdefault("OMP_NUM_THREADS", "8")
     main()
 
@@ -153,8 +153,23 @@ def make_sam2_golden() -> None:
     print("sam2 golden:", low.shape, float(low.std()), int((up > 0).sum()))
 
 
+def make_sam2_large_golden() -> None:
+    """BASELINE.json configs[2] (Hiera-L): low-res logits (fp16) and the packed 1024 x 1024 mask of the same restatement, weights
+    seed 1 as in tests/test_gpu_sam2.py::test_hiera_large_matches_live_hf_model (bench.py's aux.c2 IoU check reads this file)."""
+    from oracle import sam2_hf
+    from tests.cases import sam2_input_image
+
+    model = sam2_hf.build_model(sam2_hf.sam2_state_dict(1, "large"), "large")
+    up, low = sam2_hf.predict_logits(model, sam2_input_image())
+    np.savez_compressed(OUT / "sam2_hiera_l_mask.npz", low=low.astype(np.float16), mask_bits=np.packbits(up > 0),
+                        positives=np.int64((up > 0).sum()))
+    print("sam2 large golden:", low.shape, float(low.std()), int((up > 0).sum()))
+
+
 if __name__ == "__main__" and "--sam2" in sys.argv:
     make_sam2_golden()
+if __name__ == "__main__" and "--sam2-large" in sys.argv:
+    make_sam2_large_golden()
 
 
 def make_filter_golden() -> None:
@@ -207,3 +222,19 @@ def make_dinov2_golden() -> None:
 if __name__ == "__main__" and "--dinov2" in sys.argv:
     os.environ.setdefault("OMP_NUM_THREADS", "8")
     make_dinov2_golden()
+
+
+def make_thumb_general_golden() -> None:
+    """IWSI.get_thumbnail_at_power (core/wsi/iwsi.py:246-323), unmodified, on slides whose level size the factor does not divide
+    and on a 60x slide (factor 48)."""
+    from tests.cases import THUMB_GENERAL_CASES
+
+    for case in THUMB_GENERAL_CASES:
+        spec = make_spec(case["width"], case["height"], case["seed"], mpp=case["mpp"])
+        thumb = np.asarray(RefSyntheticWSI(spec).get_thumbnail_at_power(power=1.25))
+        np.savez_compressed(OUT / f"thumb_{case['name']}.npz", thumb=thumb)
+        print(f"thumb_{case['name']}: {thumb.shape}")
+
+
+if __name__ == "__main__" and "--thumb-general" in sys.argv:
+    make_thumb_general_golden()

@@ -130,6 +130,22 @@ def test_vit_l_16_matches_oracle():
     ext.cleanup()
 
 
+@pytest.mark.parametrize("name", ["vit_b_32", "vit_l_32"])
+def test_patch32_vits_match_oracle(name):
+    """models/patch/vit.py:9-15: the 32-pixel-patch torchvision ViTs (7 x 7 + 1 = 50 tokens) on the same kernels."""
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+
+    sd = vit_state_dict(name, seed=11)
+    patches = feature_patches()[:5]
+    want = ov.extract_features(patches, sd, name)
+    ext = B200FeatureExtractor(name, sd, max_batch=3)          # 5 patches -> two forward chunks
+    got = ext.extract_batch(patches)
+    rel = _rel(got, want)
+    print(name, "rel err per row:", rel)
+    assert got.shape == want.shape and rel.max() < REL_TOL, rel
+    ext.cleanup()
+
+
 def test_mag40_read_2x_box_resize_matches_oracle():
     """a11 with read size = 2 x patch size (40x slide, 20x patches): coords rows carry read_w = 512; the reference reads
     512 x 512 and cv2.resize()s to 256 (feature_embedding.py:88-95).  Oracle: cv2 itself + the fp32 ViT."""

@@ -100,3 +100,22 @@ def test_attention(ctx, B, S, heads, amp):
     got = out.float()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("variant", [16])   # 16: the generic run-time (two-pass) kernel instead of the register-resident instantiations
+@pytest.mark.parametrize("B,S,heads", [(64, 197, 12), (30, 257, 16), (3, 197, 4)])
+def test_attention_kernel_variants(ctx, B, S, heads, variant):
+    D = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(B + S + heads)
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 2.0).half()
+    out = torch.full((B * S, D), float("nan"), device="cuda", dtype=torch.float16)
+    ctx.set_option("attn_variant", variant)
+    try:
+        ctx.check(ctx.lib.ap_attention_f16(ctx.handle, _p(qkv), _p(out), B, S, heads, _stream()))
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option("attn_variant", 0)
+    q, k, v = qkv.float().view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())

@@ -5,7 +5,7 @@ import torch
 
 from oracle import coords as oc
 from oracle import thumbnail as ot
-from tests.cases import COORD_CASES, THUMB_CASES, build_mask, case_spec
+from tests.cases import THUMB_GENERAL_CASES, COORD_CASES, THUMB_CASES, build_mask, case_spec
 
 pytestmark = pytest.mark.gpu
 
@@ -59,6 +59,32 @@ def test_thumbnail_rejects_non_dividing_factor():
     dev = torch.zeros((100, 304), dtype=torch.uint8, device="cuda")
     with pytest.raises(ValueError):
         thumbnail_area(dev, 100, 100, 304, 16)
+
+
+@pytest.mark.parametrize("case", THUMB_GENERAL_CASES, ids=[c["name"] for c in THUMB_GENERAL_CASES])
+def test_thumbnail_general_matches_reference_golden(case, golden_dir):
+    """Level sizes the factor does not divide (cv2's fractional INTER_AREA weights) and the 60x factor 48, against thumbnails the
+    unmodified reference produced (IWSI.get_thumbnail_at_power)."""
+    from atlaspatch_b200.slide import SyntheticWSI
+
+    gold = np.load(golden_dir / f"thumb_{case['name']}.npz")["thumb"]
+    got = SyntheticWSI(case_spec(case)).thumbnail_at_power_device(1.25).cpu().numpy()
+    assert got.shape == gold.shape and np.array_equal(got, gold)
+
+
+@pytest.mark.parametrize("W,H,ow,oh", [(1000, 777, 63, 49), (515, 300, 32, 19), (999, 1001, 125, 63), (640, 480, 40, 60), (20000, 9000, 1237, 561)])
+def test_thumbnail_resize_matches_cv2(W, H, ow, oh):
+    """ap_thumbnail_resize against cv2.resize(INTER_AREA) itself: fractional scales, unequal integer scales (16 x 8), a large level."""
+    import cv2
+
+    from atlaspatch_b200.slide import thumbnail_resize
+
+    src = np.random.default_rng(W + H).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    pitch = (W * 3 + 15) // 16 * 16
+    dev = torch.zeros((H, pitch), dtype=torch.uint8, device="cuda")
+    dev[:, :W * 3] = torch.from_numpy(src.reshape(H, W * 3)).cuda()
+    got = thumbnail_resize(dev, W, H, pitch, ow, oh).cpu().numpy()
+    assert np.array_equal(got, cv2.resize(src, (ow, oh), interpolation=cv2.INTER_AREA))
 
 
 @pytest.mark.parametrize("case", COORD_CASES, ids=[c["name"] for c in COORD_CASES])

@@ -27,7 +27,18 @@ def test_every_header_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(EXPORTED_SYMBOLS)
-    assert lib.ap_version() == 1
+    assert lib.ap_version() == 2
+    # the ctypes struct declarations (and INTEGRATION.md's copy of them) match the structs compiled into the library
+    import ctypes as C
+
+    from atlaspatch_b200._lib import Sam2Desc, VitDesc
+
+    assert lib.ap_sizeof(b"ap_vit_desc") == C.sizeof(VitDesc) == 76
+    assert lib.ap_sizeof(b"ap_sam2_desc") == C.sizeof(Sam2Desc)
+    assert lib.ap_sizeof(b"nope") == -1
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    fields = re.search(r"class VitDesc\(C.Structure\):.*?_fields_ = \[(.*?)\]\s", doc, re.S).group(1)
+    assert re.findall(r'\("(\w+)"', fields) == [f[0] for f in VitDesc._fields_]
 
 
 def test_init_fails_loudly_without_gpu(lib):
