@@ -57,27 +57,30 @@ def thumbnail_resize(image, W: int, H: int, pitch: int, out_w: int, out_h: int, 
     return out
 
 
-class SyntheticWSI:
-    """Single-level synthetic slide living in HBM (generated on the device, never on the host)."""
+class DeviceWSI:
+    """Single-level slide whose level-0 RGB image lives in HBM: the IWSI attribute / method contract of the reference
+    (core/wsi/iwsi.py:9-124) plus `device_image` / `pitch` for the kernels.  Subclasses provide `_load_image()`."""
 
-    def __init__(self, spec: SyntheticSlideSpec, *, path: str | None = None, ctx: Context | None = None):
-        self.spec = spec
-        self.path = path or f"synthetic_{spec.width}x{spec.height}_s{spec.seed}.synth"
-        self.w, self.h = spec.width, spec.height
+    def __init__(self, path: str, width: int, height: int, mpp: float, *, ctx: Context | None = None):
+        self.path = path
+        self.w, self.h = int(width), int(height)
         self.nlvl, self.ds, self.dims = 1, [1.0], [(self.w, self.h)]
         self.meta: dict = {}
-        self.mpp = validate_mpp(float(spec.mpp), source="manual")
+        self.mpp = validate_mpp(float(mpp), source="manual")
         self.mag = infer_mag(self.mpp)
         self._ctx = ctx
         self._image = None
         self._pitch = 0
 
+    def _load_image(self):
+        raise NotImplementedError
+
     # ---- device side ----
     @property
     def device_image(self):
-        """(H, pitch) uint8 CUDA tensor holding RGB HWC rows; rendered on first use."""
+        """(H, pitch) uint8 CUDA tensor holding RGB HWC rows; produced on first use."""
         if self._image is None:
-            self._image, self._pitch = render_device(self.spec, 0, 0, self.w, self.h, ctx=self._ctx)
+            self._image, self._pitch = self._load_image()
         return self._image
 
     @property
@@ -136,3 +139,61 @@ class SyntheticWSI:
 
     def cleanup(self) -> None:
         self._image = None
+
+
+class SyntheticWSI(DeviceWSI):
+    """Synthetic slide generated on the device (never materialised on the host)."""
+
+    def __init__(self, spec: SyntheticSlideSpec, *, path: str | None = None, ctx: Context | None = None):
+        super().__init__(path or f"synthetic_{spec.width}x{spec.height}_s{spec.seed}.synth", spec.width, spec.height, spec.mpp, ctx=ctx)
+        self.spec = spec
+
+    def _load_image(self):
+        return render_device(self.spec, 0, 0, self.w, self.h, ctx=self._ctx)
+
+
+class ArrayWSI(DeviceWSI):
+    """A host RGB array (or an image file PIL can open: the reference's ImageWSI case, core/wsi/image_wsi.py, mpp mandatory)
+    uploaded to HBM once; afterwards every step of the path runs on the device copy."""
+
+    def __init__(self, source, *, mpp: float, path: str | None = None, ctx: Context | None = None):
+        if mpp is None or mpp <= 0:
+            raise ValueError("mpp parameter is required for standard images")
+        if isinstance(source, np.ndarray):
+            arr = source
+        else:
+            from PIL import Image
+
+            path = path or str(source)
+            arr = np.asarray(Image.open(source).convert("RGB"))
+        if arr.ndim != 3 or arr.shape[2] != 3 or arr.dtype != np.uint8:
+            raise ValueError(f"expected an (H, W, 3) uint8 RGB array, got {arr.dtype} {arr.shape}")
+        super().__init__(path or f"array_{arr.shape[1]}x{arr.shape[0]}", arr.shape[1], arr.shape[0], mpp, ctx=ctx)
+        self._host = np.ascontiguousarray(arr)
+
+    def _load_image(self):
+        import torch
+
+        pitch = (self.w * 3 + 15) // 16 * 16
+        buf = torch.zeros((self.h, pitch), dtype=torch.uint8, device="cuda")
+        buf[:, :self.w * 3] = torch.from_numpy(self._host.reshape(self.h, self.w * 3)).cuda()
+        return buf, pitch
+
+
+class DeviceWSILoader:
+    """WSILoader (services/interfaces.py:34-40) for the runner: `.synth` descriptors -> SyntheticWSI, image files -> ArrayWSI."""
+
+    def open(self, slide):
+        from pathlib import Path
+
+        p = Path(slide.path)
+        if p.suffix.lower() == ".synth":
+            from atlaspatch_b200.ref_backend import read_synth_descriptor
+            from atlaspatch_b200.synthetic import make_spec
+
+            d = read_synth_descriptor(p)
+            mpp = slide.mpp if getattr(slide, "mpp", None) is not None else d["mpp"]
+            return SyntheticWSI(make_spec(d["width"], d["height"], d["seed"], mpp=mpp), path=str(p))
+        if getattr(slide, "mpp", None) is None:
+            raise ValueError(f"{p.name}: mpp is required for standard images")
+        return ArrayWSI(p, mpp=slide.mpp)

@@ -133,6 +133,37 @@ def append_features(path: str | os.PathLike, name: str, feats: np.ndarray, *, fe
     return int(arr.shape[0])
 
 
+def save_patch_images(wsi, coords: np.ndarray, image_dir: str | os.PathLike, stem: str, *, patch_size: int) -> int:
+    """--save-images (services/storage.py:163-248, services/extraction.py:105-113): one PNG per coordinate row,
+    `<image_dir>/<stem>_x{X}_y{Y}.png`, the read resized to the patch size with cv2.resize when it differs, written by a pool of
+    max(2, min(8, cpu_count)) threads with at most 4 x workers saves pending."""
+    import concurrent.futures as fut
+    from collections import deque
+
+    from PIL import Image
+
+    image_dir = Path(image_dir)
+    image_dir.mkdir(parents=True, exist_ok=True)
+    workers = max(2, min(8, os.cpu_count() or 4))
+    pending: deque = deque()
+    n = 0
+    with fut.ThreadPoolExecutor(max_workers=workers, thread_name_prefix="patch-img") as pool:
+        for x, y, rw, rh, lv in np.asarray(coords).reshape(-1, 5).tolist():
+            patch = wsi.extract((int(x), int(y)), int(lv), (int(rw), int(rh)), mode="array")
+            if patch.shape[0] != patch_size or patch.shape[1] != patch_size:
+                import cv2
+
+                patch = cv2.resize(patch, (patch_size, patch_size))
+            out = image_dir / f"{stem}_x{int(x)}_y{int(y)}.png"
+            pending.append(pool.submit(lambda a, o: Image.fromarray(a).save(str(o)), np.ascontiguousarray(patch), out))
+            n += 1
+            if len(pending) >= workers * 4:
+                pending.popleft().result()
+        while pending:
+            pending.popleft().result()
+    return n
+
+
 def write_result(path: str | os.PathLike, result, *, wsi, cfg, write_batch: int = 8192, feature_batch: int = 32, h5=None) -> Path:
     """ExtractionResult (services.py) -> the reference's H5: coords first, then one dataset per embedded feature set.
     File attributes as services/extraction.py:146-164 passes them: filename = the slide's file name, then wsi.metadata_attrs()

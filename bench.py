@@ -430,6 +430,18 @@ def aux_c3_slides(ctx, rank, world, local_rank, peaks):
             "max_rel_err_vs_golden": golden_err, "tolerance": 1e-3}
 
 
+def c4_slide_spec():
+    """82000 x 80000 slide covered by tissue except for three holes: 512 px patches at stride 256 give ~100 k coordinates
+    (BASELINE.json configs[4]: "100k-patch slide")."""
+    from atlaspatch_b200.synthetic import SyntheticSlideSpec
+
+    W, H = 82000, 80000
+    cw, ch = (W + 15) >> 4, (H + 15) >> 4
+    blobs = ((cw // 2, ch // 2, int(0.75 * cw), int(0.75 * ch), 64, 0),)        # an ellipse that contains the whole rectangle
+    holes = ((cw // 3, ch // 3, ch // 12), (2 * cw // 3, ch // 2, ch // 16), (cw // 2, 4 * ch // 5, ch // 20))
+    return SyntheticSlideSpec(W, H, 5, 0.5, blobs, holes)
+
+
 def aux_c4_intra_slide(ctx, rank, world, local_rank, peaks, cap):
     """BASELINE.json configs[4]: ONE synthetic slide, 512 px patches at stride 256 (overlap) -> ~100 k patches, dinov2_giant.  Every
     rank holds the slide and the coordinate list, embeds its contiguous row range (sharding.row_range) and the (N, 1536) fp32
@@ -446,7 +458,7 @@ def aux_c4_intra_slide(ctx, rank, world, local_rank, peaks, cap):
     name = "dinov2_giant"
     ext = _encoder_for(name, 512, GOLDEN_CASES[name]["weight_seed"])
     golden_err = _golden_check(ext, name)
-    wsi = SyntheticWSI(make_spec(90000, 80000, 5))
+    wsi = SyntheticWSI(c4_slide_spec())
     wsi.device_image
     svc = B200PatchExtractionService(ExtractionConfig(patch_size=512, target_magnification=20, step_size=256))
     res = svc.extract(wsi, _capped_mask(wsi.spec), slide=Slide(Path(wsi.path), mpp=0.5))
@@ -457,7 +469,7 @@ def aux_c4_intra_slide(ctx, rank, world, local_rank, peaks, cap):
     ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows[:127].contiguous(), read_size=512)   # warm
     local, ms = _cuda_time(lambda: ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows, read_size=512))
     n_local = int(rows.shape[0])
-    out = {"workload": "one synthetic 90000x80000 slide, 512px patches stride 256, dinov2_giant (ViT-g/14, SwiGLU, 40 layers), rows split "
+    out = {"workload": f"one synthetic {wsi.w}x{wsi.h} slide (tissue nearly everywhere), 512px patches stride 256, dinov2_giant (ViT-g/14, SwiGLU, 40 layers), rows split "
                        "by contiguous range over the ranks", "coords_total": int(n_all), "rows_per_rank_cap": int(cap)}
     gather_ms, identical = None, None
     if world > 1:
