@@ -66,8 +66,10 @@ _SIGNATURES = {
     "ap_sam2_finalize": (C.c_int, [_P]),
     "ap_sam2_forward": (C.c_int, [_P, _P, _P, _P, _P]),
     "ap_sam2_predict_host": (C.c_int, [_P, _P, _P, _P]),
+    "ap_sam2_predict_batch_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ap_sam2_debug_copy": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "ap_gemm_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ap_gemm_f16_split": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ap_layernorm_f16": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_float, _P, C.c_int, C.c_int, _P]),
     "ap_attention_f16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
 }

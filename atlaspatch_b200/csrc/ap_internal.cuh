@@ -26,7 +26,10 @@ struct ap_ctx {
     int fold_ln = 1;              // LayerNorm folded into the GEMMs around it: 0 off, 1 automatic (<= 32 layers), 2 on (read at
                                   // ap_encoder_finalize; "fold_ln"; encoder.cu)
     int sam_tensor_cores = 1;     // SAM2 linears on mma.sync: 1 split-fp16 operands (3 MMAs, fp32-like), 2 plain fp16 (1 MMA), 0 fp32 SIMT
-    int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split weights: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
+    int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split operands: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
+    int precise_kind = 0;         // what is split there: 0 the weights, 1 the A operands of qkv / out_proj / mlp.0 (+ mlp.3's weights)
+                                  // ("precise_kind"; encoder.cu: ap_encoder_finalize; measured: profiles/r02_dinov2_giant_precision.log)
+    int precise_aw_layers = 0;    // with kind 0: leading layers whose qkv / out_proj / mlp.0 ALSO get split A operands (3 products per term)
     int pdl = 1;                  // programmatic dependent launch for the encoder kernel chain (ap_set_option "pdl")
     int cls_only_last_layer = 1;  // last layer: attention / out_proj / MLP only for the class-token row (ap_set_option)
     int attn_mode = 2;       // 2: tcgen05 attention when 16 <= S_pad <= 256, 1: warp-MMA (mma.sync) kernel
@@ -142,11 +145,19 @@ struct GemmPlan {
     CUtensorMap map_w;       // box = bn rows of W (single-CTA tiles)
     CUtensorMap map_w_half;  // box = bn/2 rows of W (each CTA of a cta_group::2 pair loads half)
     int M, N, K, epilogue;
-    int Ka;         // width of A in memory (K % Ka == 0; K > Ka when W holds hi/lo split weights)
+    int Ka;         // width of A in memory
+    // Split operands (DESIGN.md "precision"): the contraction runs over `segs` segments of Kseg columns; segment s multiplies
+    // A columns [a_seg[s] Kseg, +Kseg) with W columns [w_seg[s] Kseg, +Kseg).  W-split (W = [W_hi | W_lo], A stored once):
+    // a_seg = {0, 0}, w_seg = {0, 1}.  A-split (A = [A_hi | A_lo], W stored once): a_seg = {0, 1}, w_seg = {0, 0}.
+    int segs, Kseg;
+    int a_seg[3], w_seg[3];
     int bn;         // N tile (256 or 128)
     int cta_group;  // 2: CTA pair owns a 256 x 256 tile; 1: one CTA owns a 128 x bn tile
 };
 int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue, int Ka = 0);
+// split: AP_SPLIT_NONE, AP_SPLIT_W (W holds [hi | lo], 2 Kbase wide), AP_SPLIT_A (A holds [hi | lo]), AP_SPLIT_AW (both: 3 segments)
+enum { AP_SPLIT_NONE = 0, AP_SPLIT_W = 1, AP_SPLIT_A = 2, AP_SPLIT_AW = 3 };
+int ap_gemm_plan_split(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int Kbase, int epilogue, int split);
 // Patch-embed epilogue parameters: output row remap (b*T + t -> b*(T+1) + 1 + t) and +pos[1+t].
 struct GemmExtra {
     const float* pos = nullptr;  // [(T+1), N] fp32 or null
@@ -168,8 +179,9 @@ struct GemmExtra {
 int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const float* resid, void* out,
                 const GemmExtra* extra, cudaStream_t stream);
 
+// y_f16 rows are y_ld halfs apart (0 = D); with split_lo the row holds [hi | lo] (y_ld >= 2 D): lo = fp16(y - hi)
 int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const float* gamma, const float* beta,
-                     float eps, __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream);
+                     float eps, __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream, int y_ld = 0, int split_lo = 0);
 int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, cudaStream_t stream);
 // tcgen05 attention (S <= 257): TMA descriptors over the packed QKV buffer [rows, 3 * heads * 64]
 struct AttnPlan {
@@ -182,16 +194,18 @@ struct AttnPlan {
     int xkey;            // extra key token folded in as a rank-1 update (257-token sequences: the class token), else -1
 };
 int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int rows, int S, int heads);
-int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream);
+// out rows are out_ld halfs apart (0 = heads * 64); with split_lo a row holds [hi | lo] (out_ld >= 2 * heads * 64)
+int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream, int out_ld = 0,
+                        int split_lo = 0);
 int ap_preprocess_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords,
                       int64_t n, int input_patch, int image, int patch, __half* out, int64_t out_row_stride,
                       const int* centre, int dup, const int32_t* lin_s, const int16_t* lin_w, cudaStream_t stream);
 int ap_build_linear_tables(ap_ctx* ctx, int n_src, int n_dst, std::vector<int32_t>& taps, std::vector<int16_t>& weights);
 // DINOv2 preprocess (transformers BitImageProcessorFast): antialias bicubic resize + centre crop + im2col (preprocess_resize.cu)
-int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, std::vector<int32_t>& tap_min, std::vector<int32_t>& tap_cnt,
-                           std::vector<int16_t>& tap_w, int* max_taps, int* precision);
+int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, int kind, std::vector<int32_t>& tap_min,
+                           std::vector<int32_t>& tap_cnt, std::vector<int32_t>& tap_w, int* max_taps, int* precision);
 int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords, int64_t n,
-                             int input_patch, int image, int patch, const int32_t* tap_min, const int32_t* tap_cnt, const int16_t* tap_w,
+                             int input_patch, int image, int patch, const int32_t* tap_min, const int32_t* tap_cnt, const int32_t* tap_w,
                              int max_taps, int precision, int max_src_rows, __half* out, int64_t out_row_stride, const int* centre,
                              cudaStream_t stream);
 // class-token query only; image b's output row is out[b * out_row_stride] (1: compact rows, S: row 0 of every image's block)

@@ -49,6 +49,8 @@ struct AttnArgs {
     int xkey;            // extra key token (XK kernels), else -1
     int S_pad;           // nk rounded up to 16
     int variant;         // diagnostics
+    int out_ld;          // halfs between output rows (heads * 64, or 2 x that when the row holds [hi | lo])
+    int split_lo;        // also write lo = fp16(o - fp16(o)) at column offset heads * 64 (A-operand split of out_proj)
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -418,7 +420,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const float inv = 1.0f / l;
             const float wa = alpha * inv, wb = beta * inv;
             const float wx = p_x * wa;   // weight of the extra key's value row (its score was normalised with half A's maximum)
-            uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * S + a.q0 + q_row) * D + h * 64);
+            uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * S + a.q0 + q_row) * a.out_ld + h * 64);
             const uint4* vx = XK ? reinterpret_cast<const uint4*>(xrow + 2 * D) : nullptr;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {       // 32 output columns at a time
@@ -450,7 +452,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                 v[2 * e + 1] = fmaf(f.y, wxx, v[2 * e + 1]);
                             }
                         }
-                        dst[hh * 4 + j] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                        const uint4 hi4 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                        dst[hh * 4 + j] = hi4;
+                        if (a.split_lo) {
+                            const uint32_t hw[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+                            uint32_t lw[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                                lw[e] = pack_h2(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+                            }
+                            dst[(D >> 3) + hh * 4 + j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);   // + D halfs = D / 8 uint4
+                        }
                     }
                 }
             }
@@ -499,7 +512,8 @@ int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int row
     return ap_make_tmap_f16_2d(ctx, &plan->map_kv, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D, plan->S_pad, 64);
 }
 
-int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream) {
+int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, int S, int heads, cudaStream_t stream, int out_ld,
+                        int split_lo) {
     if (B == 0) return AP_OK;
     const int S_pad = plan->S_pad;
     const size_t n_qt = (plan->nq + 127) / 128;
@@ -509,6 +523,9 @@ int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, i
     AttnArgs a;
     a.B = B; a.S = S; a.heads = heads; a.q0 = plan->q0; a.nq = plan->nq; a.k0 = plan->k0; a.nk = plan->nk; a.xkey = plan->xkey;
     a.S_pad = S_pad; a.variant = ctx->attn_variant;
+    a.out_ld = out_ld > 0 ? out_ld : heads * 64;
+    a.split_lo = split_lo;
+    AP_REQUIRE(ctx, a.out_ld >= (split_lo ? 2 : 1) * heads * 64 && a.out_ld % 8 == 0, "attention: output row stride %d too small", a.out_ld);
     int rc;
     {
         ProfScope prof(ctx, stream, AP_K_ATTENTION);

@@ -79,6 +79,16 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         ctx->attn_mode = value;
         return AP_OK;
     }
+    if (!strcmp(key, "precise_kind")) {
+        AP_REQUIRE(ctx, value >= 0 && value <= 1, "precise_kind must be 0 or 1");
+        ctx->precise_kind = value;
+        return AP_OK;
+    }
+    if (!strcmp(key, "precise_aw_layers")) {
+        AP_REQUIRE(ctx, value >= 0, "precise_aw_layers must be >= 0");
+        ctx->precise_aw_layers = value;
+        return AP_OK;
+    }
     if (!strcmp(key, "pdl")) {
         ctx->pdl = value != 0;
         return AP_OK;

@@ -22,6 +22,8 @@ struct LayerWeights {
     GemmPlan p_qkv, p_o, p_1, p_2;
     GemmPlan pc_o, pc_1, pc_2;  // last layer only: class-token rows (M = images)
     int split = 0;  // bit mask of GEMMs whose weights are stored as [hi | lo] fp16 pairs (K doubled): 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
+    int asplit = 0; // bit mask of GEMMs whose A operand is stored as [hi | lo] instead (1 qkv, 2 out_proj, 4 mlp.0): the LayerNorm /
+                    // attention epilogue that produces it also writes lo = fp16(a - fp16(a)); weights stay single fp16
 };
 
 }  // namespace
@@ -33,8 +35,7 @@ struct ap_encoder {
     int kpe = 0;      // 3 * patch * patch
     int kpe_pad = 0;  // kpe rounded up to the GEMM's 64-wide K block (588 -> 640 for patch 14); pad columns stay zero
     // preprocess 1 (BitImageProcessorFast): tap tables of the input_patch -> resize_to antialias bicubic resize
-    int32_t *tap_min = nullptr, *tap_cnt = nullptr;
-    int16_t* tap_w = nullptr;
+    int32_t *tap_min = nullptr, *tap_cnt = nullptr, *tap_w = nullptr;
     int max_taps = 0, tap_precision = 0, max_src_rows = 0;
     int centre[3] = {0, 0, 0};  // integer pixel centre per channel = round(255 * mean_c)
     int max_batch = 0;
@@ -51,6 +52,7 @@ struct ap_encoder {
     std::vector<LayerWeights> layers;
     // workspaces
     __half *a_pe = nullptr, *y1 = nullptr, *y2 = nullptr, *qkv = nullptr, *hbuf = nullptr;
+    __half *y1s = nullptr, *y2s = nullptr;   // [rows, 2 D]: LayerNorm / attention outputs as [hi | lo] pairs (A-split layers)
     float* x = nullptr;
     // class-token-only tail of the last layer
     __half *yc_attn = nullptr, *yc_ln = nullptr, *hc = nullptr;
@@ -175,8 +177,8 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     int rc;
     const int32_t* lin_s = nullptr;
     const int16_t* lin_w = nullptr;
-    if (e->d.preprocess == 1) {
-        AP_REQUIRE(ctx, read_size == e->d.input_patch, "encoder: reads larger than the patch are not implemented for the resizing (DINOv2) preprocess");
+    if (e->d.preprocess >= 1) {
+        AP_REQUIRE(ctx, read_size == e->d.input_patch, "encoder: reads larger than the patch are not implemented for the resizing preprocesses");
         if ((rc = ap_preprocess_resize_run(ctx, slide, W, H, pitch, coords, nb, e->d.input_patch, e->d.image_size, e->d.patch, e->tap_min,
                                            e->tap_cnt, e->tap_w, e->max_taps, e->tap_precision, e->max_src_rows, e->a_pe, e->kpe_pad,
                                            e->centre, st)))
@@ -212,7 +214,9 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     for (size_t li = 0; li < e->layers.size(); ++li) {
         auto& L = e->layers[li];
         GemmPlan p;
-        if (!fold && (rc = ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
+        if (!fold && (rc = (L.asplit & 1) ? ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1s, nullptr, rows, D, st, 2 * D, 1)
+                                          : ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st)))
+            return rc;
         p = L.p_qkv; p.M = rows;
         cons.stats_in = e->stats1;
         if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, fold ? &cons : nullptr, st))) return rc;
@@ -233,12 +237,16 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
             if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->xc, e->xc, nullptr, st))) return rc;
             return ap_layernorm_run(ctx, e->xc, D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
         }
-        if (e->attn_tc && ctx->attn_mode == 2) {
+        if (L.asplit & 2) {   // out_proj reads [hi | lo] attention outputs (finalize only sets this bit with the tcgen05 kernel)
+            if ((rc = ap_attention_tc_run(ctx, &e->p_attn, e->y2s, nb, T1, e->d.heads, st, 2 * D, 1))) return rc;
+        } else if (e->attn_tc && ctx->attn_mode == 2) {
             if ((rc = ap_attention_tc_run(ctx, &e->p_attn, e->y2, nb, T1, e->d.heads, st))) return rc;
         } else if ((rc = ap_attention_run(ctx, e->qkv, e->y2, nb, T1, e->d.heads, st))) return rc;
         p = L.p_o; p.M = rows;
         if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->x, e->x, fold ? &prod2 : nullptr, st))) return rc;
-        if (!fold && (rc = ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1, nullptr, rows, D, st))) return rc;
+        if (!fold && (rc = (L.asplit & 4) ? ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1s, nullptr, rows, D, st, 2 * D, 1)
+                                          : ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1, nullptr, rows, D, st)))
+            return rc;
         p = L.p_1; p.M = rows;
         cons.stats_in = e->stats2;
         if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hbuf, fold ? &cons : nullptr, st))) return rc;
@@ -255,10 +263,10 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     if (!ctx || !desc || !out_enc) return AP_EINVAL;
     DeviceGuard guard(ctx);
     *out_enc = nullptr;
-    AP_REQUIRE(ctx, desc->preprocess == 0 || desc->preprocess == 1, "encoder: unknown preprocess %d", desc->preprocess);
+    AP_REQUIRE(ctx, desc->preprocess >= 0 && desc->preprocess <= 2, "encoder: unknown preprocess %d", desc->preprocess);
     AP_REQUIRE(ctx, desc->mlp_kind == 0 || desc->mlp_kind == 1, "encoder: unknown mlp_kind %d", desc->mlp_kind);
-    AP_REQUIRE(ctx, desc->patch == 16 || desc->patch == 32 || (desc->preprocess == 1 && desc->patch >= 4 && desc->patch <= 16),
-               "encoder: conv patch %d unsupported (16 / 32 with the crop preprocess, 4..16 with the resizing preprocess)", desc->patch);
+    AP_REQUIRE(ctx, desc->patch == 16 || desc->patch == 32 || (desc->preprocess >= 1 && desc->patch >= 4 && desc->patch <= 32),
+               "encoder: conv patch %d unsupported (16 / 32 with the crop preprocess, 4..32 with the resizing preprocesses)", desc->patch);
     AP_REQUIRE(ctx, desc->preprocess == 0 || desc->resize_to >= desc->image_size, "encoder: resize_to %d < image_size %d", desc->resize_to,
                desc->image_size);
     AP_REQUIRE(ctx, desc->mlp_kind == 0 || (2 * desc->mlp) % 256 == 0, "encoder: SwiGLU needs 2 * mlp %% 256 == 0 (mlp %d)", desc->mlp);
@@ -266,7 +274,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     AP_REQUIRE(ctx, desc->hidden % desc->heads == 0 && desc->hidden / desc->heads == 64,
                "encoder: head_dim must be 64 (hidden %d, heads %d)", desc->hidden, desc->heads);
     AP_REQUIRE(ctx, desc->hidden % 128 == 0 && desc->mlp % 128 == 0, "encoder: hidden/mlp must be multiples of 128");
-    AP_REQUIRE(ctx, desc->preprocess == 1 || desc->input_patch >= desc->image_size,
+    AP_REQUIRE(ctx, desc->preprocess >= 1 || desc->input_patch >= desc->image_size,
                "encoder: input_patch %d < image_size %d (needs an up-sampling resize)", desc->input_patch, desc->image_size);
     AP_REQUIRE(ctx, desc->layers >= 1, "encoder: layers must be >= 1");
     ap_encoder* e = new ap_encoder();
@@ -387,7 +395,21 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         AP_GET(wo, p + "self_attention.out_proj.weight", (size_t)D * D) AP_GET(bo, p + "self_attention.out_proj.bias", D)
         AP_GET(w1, p + "mlp.0.weight", (size_t)M1 * D) AP_GET(b1, p + "mlp.0.bias", M1)
         AP_GET(w2, p + "mlp.3.weight", (size_t)D * M) AP_GET(b2, p + "mlp.3.bias", D)
-        L.split = i < e->precise_layers ? (ctx->precise_mask & 15) : 0;
+        // precise layers: W-split everywhere (kind 0), or -- where the activations' rounding dominates the error, i.e. the deep
+        // DINOv2 giant (DESIGN.md "precision": per layer the A operands cost ~4x the weights' share of the squared error) -- the
+        // A operands of in_proj / out_proj / mlp.0 as [hi | lo] pairs and only mlp.3's weights split (kind 1).  A-split needs the
+        // LayerNorm kernels (not the folded form) and the tcgen05 attention epilogue; the class-token tail of the last layer keeps
+        // single operands.
+        const bool a_kind = ctx->precise_kind == 1;
+        const bool a_ok = !e->fold_ln && (T1 <= 257) && ctx->attn_mode == 2 && !(i + 1 == e->d.layers && ctx->cls_only_last_layer);
+        const int pm = ctx->precise_mask & 15;
+        if (a_kind) {            // A operands of qkv / out_proj / mlp.0 split, weights of mlp.3 split
+            L.asplit = (i < e->precise_layers && a_ok) ? (pm & 7) : 0;
+            L.split = i < e->precise_layers ? (pm & ~L.asplit) : 0;
+        } else {                 // weights split; in the first precise_aw_layers layers the A operands as well (three products per term)
+            L.split = i < e->precise_layers ? pm : 0;
+            L.asplit = (i < e->precise_layers && i < ctx->precise_aw_layers && a_ok) ? (pm & 7) : 0;
+        }
         std::vector<float> wq(*wqkv), bq(*bqkv), wf(*w1), bf1(*b1);
         if (e->fold_ln) {
             fold_ln_affine(wq, bq, *ln1g, *ln1b, (size_t)3 * D, D);
@@ -415,6 +437,13 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         (rc = dev_alloc(e, (void**)&e->y1, rows * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2, rows * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->qkv, rows * 3 * D * 2)) || (rc = dev_alloc(e, (void**)&e->hbuf, rows * M * 2)))
         return rc;
+    bool any_asplit = false;
+    for (auto& L : e->layers) any_asplit |= L.asplit != 0;
+    if (any_asplit) {
+        if ((rc = dev_alloc(e, (void**)&e->y1s, rows * 2 * D * 2)) || (rc = dev_alloc(e, (void**)&e->y2s, rows * 2 * D * 2))) return rc;
+        AP_CHECK_CUDA(ctx, cudaMemset(e->y1s, 0, rows * 2 * D * 2));
+        AP_CHECK_CUDA(ctx, cudaMemset(e->y2s, 0, rows * 2 * D * 2));
+    }
     {
         std::vector<float> ones(D, 1.0f), zeros(D, 0.0f);
         if ((rc = upload_f32(e, &e->ones, ones)) || (rc = upload_f32(e, &e->zeros, zeros)) ||
@@ -444,9 +473,13 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     const int epi1 = e->d.mlp_kind == 1 ? AP_EPI_BIAS_SWIGLU_F16 : AP_EPI_BIAS_GELU_F16;
     for (auto& L : e->layers) {
         const int sq = (L.split & 1) ? 2 : 1, so = (L.split & 2) ? 2 : 1, s1 = (L.split & 4) ? 2 : 1, s2 = (L.split & 8) ? 2 : 1;
-        if ((rc = ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, sq * D, AP_EPI_BIAS_F16, D)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, so * D, AP_EPI_BIAS_RESID_F32, D)) ||
-            (rc = ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M1, s1 * D, epi1, D)) ||
+        auto mode = [&](int bit) { return ((L.asplit & bit) ? AP_SPLIT_A : 0) | ((L.split & bit) ? AP_SPLIT_W : 0); };
+        if ((rc = (L.asplit & 1) ? ap_gemm_plan_split(ctx, &L.p_qkv, e->y1s, L.w_qkv, MB * T1, 3 * D, D, AP_EPI_BIAS_F16, mode(1))
+                                 : ap_gemm_plan(ctx, &L.p_qkv, e->y1, L.w_qkv, MB * T1, 3 * D, sq * D, AP_EPI_BIAS_F16, D)) ||
+            (rc = (L.asplit & 2) ? ap_gemm_plan_split(ctx, &L.p_o, e->y2s, L.w_o, MB * T1, D, D, AP_EPI_BIAS_RESID_F32, mode(2))
+                                 : ap_gemm_plan(ctx, &L.p_o, e->y2, L.w_o, MB * T1, D, so * D, AP_EPI_BIAS_RESID_F32, D)) ||
+            (rc = (L.asplit & 4) ? ap_gemm_plan_split(ctx, &L.p_1, e->y1s, L.w_1, MB * T1, M1, D, epi1, mode(4))
+                                 : ap_gemm_plan(ctx, &L.p_1, e->y1, L.w_1, MB * T1, M1, s1 * D, epi1, D)) ||
             (rc = ap_gemm_plan(ctx, &L.p_2, e->hbuf, L.w_2, MB * T1, D, s2 * M, AP_EPI_BIAS_RESID_F32, M)))
             return rc;
         if (&L == &e->layers.back() &&
@@ -462,10 +495,10 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     }
 
     // ---- tap tables of the resizing preprocess ----------------------------------------------------------------
-    if (e->d.preprocess == 1) {
-        std::vector<int32_t> tmin, tcnt;
-        std::vector<int16_t> tw;
-        if ((rc = ap_build_resize_tables(ctx, e->d.input_patch, e->d.resize_to, e->d.image_size, tmin, tcnt, tw, &e->max_taps, &e->tap_precision)))
+    if (e->d.preprocess >= 1) {
+        std::vector<int32_t> tmin, tcnt, tw;
+        if ((rc = ap_build_resize_tables(ctx, e->d.input_patch, e->d.resize_to, e->d.image_size, e->d.preprocess == 2 ? 1 : 0, tmin, tcnt, tw,
+                                         &e->max_taps, &e->tap_precision)))
             return rc;
         for (int tr = 0; tr < e->d.image_size / P; ++tr) {
             const int last = tr * P + P - 1;
@@ -473,11 +506,11 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
             if (nr > e->max_src_rows) e->max_src_rows = nr;
         }
         if ((rc = dev_alloc(e, (void**)&e->tap_min, tmin.size() * 4)) || (rc = dev_alloc(e, (void**)&e->tap_cnt, tcnt.size() * 4)) ||
-            (rc = dev_alloc(e, (void**)&e->tap_w, tw.size() * 2)))
+            (rc = dev_alloc(e, (void**)&e->tap_w, tw.size() * 4)))
             return rc;
         AP_CHECK_CUDA(ctx, cudaMemcpy(e->tap_min, tmin.data(), tmin.size() * 4, cudaMemcpyHostToDevice));
         AP_CHECK_CUDA(ctx, cudaMemcpy(e->tap_cnt, tcnt.data(), tcnt.size() * 4, cudaMemcpyHostToDevice));
-        AP_CHECK_CUDA(ctx, cudaMemcpy(e->tap_w, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
+        AP_CHECK_CUDA(ctx, cudaMemcpy(e->tap_w, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     }
 
     // ---- host-patch path: double-buffered pinned staging + its own streams -------------------------------
@@ -543,7 +576,7 @@ extern "C" int ap_encoder_preprocess(ap_encoder* e, const uint8_t* slide_dev, in
                "encoder_preprocess: read size %d unsupported for patch size %d", read_size, e->d.input_patch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    if (e->d.preprocess == 1)
+    if (e->d.preprocess >= 1)
         rc = ap_preprocess_resize_run(ctx, slide_dev, W, H, pitch, coords_dev, n, e->d.input_patch, e->d.image_size, e->d.patch, e->tap_min,
                                       e->tap_cnt, e->tap_w, e->max_taps, e->tap_precision, e->max_src_rows, e->a_pe, e->kpe_pad, e->centre, st);
     else {

@@ -128,7 +128,8 @@ __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__
 template <int VEC>  // D = VEC * 128
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t x_row_stride, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, __half* __restrict__ y16, float* __restrict__ y32, int rows) {
+                 const float* __restrict__ beta, float eps, __half* __restrict__ y16, float* __restrict__ y32, int rows, int y_ld,
+                 int split_lo) {
     constexpr int D = VEC * 128;
     ptx::pdl_wait();
     ptx::pdl_launch_dependents();
@@ -170,7 +171,15 @@ layernorm_kernel(const float* __restrict__ x, int64_t x_row_stride, const float*
             uint2 u;
             u.x = *reinterpret_cast<uint32_t*>(&h0);
             u.y = *reinterpret_cast<uint32_t*>(&h1);
-            reinterpret_cast<uint2*>(y16 + static_cast<int64_t>(warp) * D)[lane + 32 * i] = u;
+            reinterpret_cast<uint2*>(y16 + static_cast<int64_t>(warp) * y_ld)[lane + 32 * i] = u;
+            if (split_lo) {   // A-operand split (DESIGN.md "precision"): the row holds [hi | lo], lo = fp16(y - hi)
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                __half2 l0 = __floats2half2_rn(o0 - f0.x, o1 - f0.y), l1 = __floats2half2_rn(o2 - f1.x, o3 - f1.y);
+                uint2 ul;
+                ul.x = *reinterpret_cast<uint32_t*>(&l0);
+                ul.y = *reinterpret_cast<uint32_t*>(&l1);
+                reinterpret_cast<uint2*>(y16 + static_cast<int64_t>(warp) * y_ld + D)[lane + 32 * i] = ul;
+            }
         } else {
             reinterpret_cast<float4*>(y32 + static_cast<int64_t>(warp) * D)[lane + 32 * i] = make_float4(o0, o1, o2, o3);
         }
@@ -514,7 +523,9 @@ int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, i
 }
 
 int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
-                     __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream) {
+                     __half* y_f16, float* y_f32, int rows, int D, cudaStream_t stream, int y_ld, int split_lo) {
+    if (y_ld <= 0) y_ld = D;
+    AP_REQUIRE(ctx, y_ld % 4 == 0 && y_ld >= (split_lo ? 2 * D : D), "layernorm: output row stride %d too small", y_ld);
     AP_REQUIRE(ctx, D % 128 == 0 && D <= 1536, "layernorm: D=%d unsupported (multiple of 128, <= 1536)", D);
     AP_REQUIRE(ctx, x_row_stride % 4 == 0, "layernorm: row stride %lld not a multiple of 4", (long long)x_row_stride);
     if (rows == 0) return AP_OK;
@@ -523,7 +534,7 @@ int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const fl
 #define AP_LN_CASE(V)                                                                                               \
     case V:                                                                                                         \
         AP_CHECK_CUDA(ctx, ap_launch_pdl(layernorm_kernel<V>, dim3(blocks), dim3(256), 0, stream, 1, ctx->pdl != 0, x, x_row_stride, gamma, \
-                                         beta, eps, y_f16, y_f32, rows));                                                  \
+                                         beta, eps, y_f16, y_f32, rows, y_ld, split_lo));                                  \
         break;
     switch (D / 128) {
         AP_LN_CASE(1) AP_LN_CASE(2) AP_LN_CASE(3) AP_LN_CASE(4) AP_LN_CASE(5) AP_LN_CASE(6) AP_LN_CASE(8) AP_LN_CASE(10)

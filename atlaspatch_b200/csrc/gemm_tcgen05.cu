@@ -54,8 +54,8 @@ struct EpiParams {
     const float* pos;
     int tokens_per_image;
     float alpha;
-    int a_k_blocks;  // A has this many 64-wide K blocks; block kb of the contraction reads A block kb % a_k_blocks
-                     // (hi/lo split weights: W = [W_hi | W_lo] over 2K while A is stored once)
+    int seg_blocks;  // 64-wide K blocks per segment; block kb of the contraction is block kb % seg_blocks of segment kb / seg_blocks
+    int a_map, w_map;  // 2 bits per segment: which Kseg-wide column range of A / W that segment reads (split operands, GemmPlan)
     int debug;  // diagnostics only (ap_set_option "gemm_debug"): 1 = no epilogue math/stores, 2 = no MMA issue, 4 = no TMA loads
     // LayerNorm folding (GemmExtra in ap_internal.cuh)
     __half* out_h;
@@ -378,18 +378,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int m0 = (tile / tiles_n) * TILE_M + cta_rank * 128;
                 const int n0 = (tile % tiles_n) * BN + cta_rank * L::B_ROWS;
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    const int seg = kb / ep.seg_blocks, blk = kb - seg * ep.seg_blocks;
+                    const int ka = (((ep.a_map >> (2 * seg)) & 3) * ep.seg_blocks + blk) * BK;
+                    const int kw = (((ep.w_map >> (2 * seg)) & 3) * ep.seg_blocks + blk) * BK;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     if (ep.debug & 4) {
                         if (cta_rank == 0) ptx::mbar_arrive(&full_bar[stage]);
                     } else if (CG == 1) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], L::A_STAGE + L::B_STAGE);
-                        ptx::tma_load_2d(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], (kb % ep.a_k_blocks) * BK, m0);
-                        ptx::tma_load_2d(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kb * BK, n0);
+                        ptx::tma_load_2d(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], ka, m0);
+                        ptx::tma_load_2d(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kw, n0);
                     } else {
                         // both CTAs' bytes are accounted on the leader's barrier (peer bit cleared in the address)
                         if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (L::A_STAGE + L::B_STAGE));
-                        ptx::tma_load_2d_2sm(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], (kb % ep.a_k_blocks) * BK, m0);
-                        ptx::tma_load_2d_2sm(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kb * BK, n0);
+                        ptx::tma_load_2d_2sm(smem + L::A_OFF + stage * L::A_STAGE, &map_a, &full_bar[stage], ka, m0);
+                        ptx::tma_load_2d_2sm(smem + L::B_OFF + stage * L::B_STAGE, &map_w, &full_bar[stage], kw, n0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -553,22 +556,50 @@ int dispatch_epi(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream
 
 }  // namespace
 
+namespace {
+int plan_common(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int epilogue, int Kw);
+}
+
+// K = width of W; Ka = width of A (K % Ka == 0): K > Ka means W holds K / Ka column segments (hi/lo split weights) that all
+// multiply the same A.
 int ap_gemm_plan(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int K, int epilogue, int Ka) {
     if (Ka <= 0) Ka = K;
     AP_REQUIRE(ctx, M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
-    AP_REQUIRE(ctx, K % BK == 0 && Ka % BK == 0 && K % Ka == 0, "gemm: K=%d (A width %d) must be multiples of %d, K %% Ka == 0", K, Ka, BK);
+    AP_REQUIRE(ctx, K % BK == 0 && Ka % BK == 0 && K % Ka == 0 && K / Ka <= 3, "gemm: K=%d (A width %d) must be multiples of %d, K = 1..3 x Ka", K, Ka, BK);
+    plan->segs = K / Ka; plan->Kseg = Ka; plan->K = K; plan->Ka = Ka;
+    for (int i = 0; i < 3; ++i) { plan->a_seg[i] = 0; plan->w_seg[i] = i < plan->segs ? i : 0; }
+    return plan_common(ctx, plan, A, W, M, N, epilogue, K);
+}
+
+int ap_gemm_plan_split(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int Kbase, int epilogue, int split) {
+    AP_REQUIRE(ctx, M > 0 && N > 0 && Kbase > 0 && Kbase % BK == 0, "gemm: bad problem %dx%dx%d", M, N, Kbase);
+    AP_REQUIRE(ctx, split >= AP_SPLIT_NONE && split <= AP_SPLIT_AW, "gemm: unknown split mode %d", split);
+    static const int segs[4] = {1, 2, 2, 3};
+    static const int am[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 1, 0}, {0, 1, 0}};   // A_hi W_hi + A_lo W_hi (+ A_hi W_lo)
+    static const int wm[4][3] = {{0, 0, 0}, {0, 1, 0}, {0, 0, 0}, {0, 0, 1}};
+    plan->segs = segs[split]; plan->Kseg = Kbase; plan->K = segs[split] * Kbase;
+    plan->Ka = (split & AP_SPLIT_A) ? 2 * Kbase : Kbase;
+    for (int i = 0; i < 3; ++i) { plan->a_seg[i] = am[split][i]; plan->w_seg[i] = wm[split][i]; }
+    return plan_common(ctx, plan, A, W, M, N, epilogue, (split & AP_SPLIT_W) ? 2 * Kbase : Kbase);
+}
+
+namespace {
+int plan_common(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int epilogue, int Kw) {
+    const int K = plan->K, Ka = plan->Ka;
     AP_REQUIRE(ctx, N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
     AP_REQUIRE(ctx, epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
     AP_REQUIRE(ctx, epilogue != AP_EPI_BIAS_SWIGLU_F16 || N % 256 == 0, "gemm: SwiGLU epilogue needs N %% 256 == 0 (N=%d)", N);
-    plan->M = M; plan->N = N; plan->K = K; plan->Ka = Ka; plan->epilogue = epilogue;
+    (void)K;
+    plan->M = M; plan->N = N; plan->epilogue = epilogue;
     plan->bn = (N % 256 == 0) ? 256 : 128;
     plan->cta_group = (plan->bn == 256 && ctx->gemm_cta_group == 2) ? 2 : 1;
     int rc = ap_make_tmap_f16_2d(ctx, &plan->map_a, A, (uint64_t)M, (uint64_t)Ka, (uint64_t)Ka, 128, BK);
     if (rc) return rc;
-    rc = ap_make_tmap_f16_2d(ctx, &plan->map_w, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, plan->bn, BK);
+    rc = ap_make_tmap_f16_2d(ctx, &plan->map_w, W, (uint64_t)N, (uint64_t)Kw, (uint64_t)Kw, plan->bn, BK);
     if (rc) return rc;
-    return ap_make_tmap_f16_2d(ctx, &plan->map_w_half, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, plan->bn / 2, BK);
+    return ap_make_tmap_f16_2d(ctx, &plan->map_w_half, W, (uint64_t)N, (uint64_t)Kw, (uint64_t)Kw, plan->bn / 2, BK);
 }
+}  // namespace
 
 int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const float* resid, void* out,
                 const GemmExtra* extra, cudaStream_t stream) {
@@ -580,7 +611,9 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
     ep.tokens_per_image = extra ? extra->tokens_per_image : 0;
     ep.alpha = extra ? extra->alpha : 1.0f;
     ep.debug = ctx->gemm_debug;
-    ep.a_k_blocks = plan->Ka / BK;
+    ep.seg_blocks = plan->Kseg / BK;
+    ep.a_map = plan->a_seg[0] | (plan->a_seg[1] << 2) | (plan->a_seg[2] << 4);
+    ep.w_map = plan->w_seg[0] | (plan->w_seg[1] << 2) | (plan->w_seg[2] << 4);
     ep.out_h = extra ? extra->out_h : nullptr;
     ep.stats_out = extra ? extra->stats_out : nullptr;
     ep.stats_in = extra ? extra->stats_in : nullptr;
@@ -606,5 +639,18 @@ extern "C" int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, co
     GemmPlan plan;
     int rc = ap_gemm_plan(ctx, &plan, A_dev, W_dev, M, N, K, epilogue, K);
     if (rc) return rc;
+    return ap_gemm_run(ctx, &plan, bias_dev, resid_dev, out_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// The same GEMM with split fp16 operands (DESIGN.md "precision"): split 1: W_dev is [N, 2K] = [W_hi | W_lo]; split 2: A_dev is
+// [M, 2K] = [A_hi | A_lo]; split 3: both (three products per term: A_hi W_hi + A_lo W_hi + A_hi W_lo, ~22 significant bits).
+extern "C" int ap_gemm_f16_split(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
+                                 void* out_dev, int M, int N, int K, int epilogue, int split, void* stream) {
+    if (!ctx) return AP_EINVAL;
+    DeviceGuard guard(ctx);
+    GemmPlan plan;
+    int rc = ap_gemm_plan_split(ctx, &plan, A_dev, W_dev, M, N, K, epilogue, split);
+    if (rc) return rc;
+    AP_REQUIRE(ctx, N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
     return ap_gemm_run(ctx, &plan, bias_dev, resid_dev, out_dev, nullptr, static_cast<cudaStream_t>(stream));
 }

@@ -14,6 +14,8 @@
 // One CTA per (patch b, token row tr): the P cropped output rows of that token row need source rows [ymin, ymax) of the
 // patch; they are staged in shared memory (zeros outside the slide, like IWSI.extract), resampled horizontally for the `image`
 // cropped columns only, then vertically, and written as `g` im2col rows (k = c P^2 + ky P + kx).
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "ap_internal.cuh"
@@ -24,7 +26,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 preprocess_resize_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64_t pitch, const int32_t* __restrict__ coords,
                          int input_patch, int image, int P, const int32_t* __restrict__ tap_min, const int32_t* __restrict__ tap_cnt,
-                         const int16_t* __restrict__ tap_w, int max_taps, int precision, __half* __restrict__ out,
+                         const int32_t* __restrict__ tap_w, int max_taps, int precision, __half* __restrict__ out,
                          int64_t out_row_stride, int3 centre) {
     extern __shared__ __align__(16) uint8_t smem[];
     ptx::pdl_wait();
@@ -57,10 +59,10 @@ preprocess_resize_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H
         const int r = i / h_stride, rem = i - r * h_stride;
         const int ox = rem / 3, c = rem - ox * 3;
         const int xm = tap_min[ox], n = tap_cnt[ox];
-        const int16_t* w = tap_w + ox * max_taps;
+        const int32_t* w = tap_w + ox * max_taps;
         const uint8_t* s = src + r * src_stride + xm * 3 + c;
         int acc = round_add;
-        for (int k = 0; k < n; ++k) acc += static_cast<int>(w[k]) * static_cast<int>(s[k * 3]);
+        for (int k = 0; k < n; ++k) acc += w[k] * static_cast<int>(s[k * 3]);
         hbuf[i] = static_cast<uint8_t>(min(max(acc >> precision, 0), 255));
     }
     __syncthreads();
@@ -73,10 +75,10 @@ preprocess_resize_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H
         const int ky = rem / P, kx = rem - ky * P;
         const int oy = oy0 + ky, ox = tc * P + kx;
         const int ym = tap_min[oy], n = tap_cnt[oy];
-        const int16_t* w = tap_w + oy * max_taps;
+        const int32_t* w = tap_w + oy * max_taps;
         const uint8_t* s = hbuf + (ym - ymin) * h_stride + ox * 3 + c;
         int acc = round_add;
-        for (int t = 0; t < n; ++t) acc += static_cast<int>(w[t]) * static_cast<int>(s[t * h_stride]);
+        for (int t = 0; t < n; ++t) acc += w[t] * static_cast<int>(s[t * h_stride]);
         const int pix = min(max(acc >> precision, 0), 255);
         const int cen = c == 0 ? centre.x : (c == 1 ? centre.y : centre.z);
         out[(static_cast<int64_t>(b) * g * g + tr * g + tc) * out_row_stride + k] = __float2half_rn(static_cast<float>(pix - cen) * (1.0f / 256.0f));
@@ -93,13 +95,19 @@ double cubic_aa(double x) {  // Keys cubic, a = -0.5 (ATen HelperInterpCubic::aa
 
 }  // namespace
 
-// Tap tables of the n_in -> n_out antialias resize for the `image` output indices that survive the centre crop
-// (ATen _compute_index_ranges_int16_weights; the precision is chosen over ALL n_out outputs, as ATen does).
-int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, std::vector<int32_t>& tap_min, std::vector<int32_t>& tap_cnt,
-                           std::vector<int16_t>& tap_w, int* max_taps, int* precision) {
+// Tap tables of the n_in -> n_out antialias resize for the `image` output indices that survive the centre crop.
+//   kind 0: ATen's uint8 bicubic (a = -0.5, support 2): _compute_index_ranges_int16_weights, the precision is chosen over ALL
+//           n_out outputs so that the largest weight fits int16 (transformers' BitImageProcessorFast, DINOv2);
+//   kind 1: Pillow's own BILINEAR (triangle, support 1): precompute_coeffs + normalize_coeffs_8bpc, fixed 22-bit int32
+//           coefficients (torchvision's ImageClassification preset on the PIL image the reference hands it; crop offset
+//           int(round((n_out - image) / 2.0)) as torchvision's center_crop computes it).
+int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, int kind, std::vector<int32_t>& tap_min, std::vector<int32_t>& tap_cnt,
+                           std::vector<int32_t>& tap_w, int* max_taps, int* precision) {
     AP_REQUIRE(ctx, n_in > 0 && n_out >= image && image > 0, "resize tables: bad sizes %d -> %d crop %d", n_in, n_out, image);
+    AP_REQUIRE(ctx, kind == 0 || kind == 1, "resize tables: unknown filter kind %d", kind);
     const double scale = static_cast<double>(n_in) / n_out;
-    const double support = scale >= 1.0 ? 2.0 * scale : 2.0;
+    const double fsup = kind == 0 ? 2.0 : 1.0;
+    const double support = scale >= 1.0 ? fsup * scale : fsup;
     const double invscale = scale >= 1.0 ? 1.0 / scale : 1.0;
     std::vector<std::vector<double>> ws(n_out);
     std::vector<int> mins(n_out);
@@ -115,22 +123,25 @@ int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, std::vec
         double total = 0.0;
         ws[i].resize(xsize);
         for (int j = 0; j < xsize; ++j) {
-            ws[i][j] = cubic_aa((j + xmin - center + 0.5) * invscale);
+            const double t = (j + xmin - center + 0.5) * invscale;
+            ws[i][j] = kind == 0 ? cubic_aa(t) : std::max(0.0, 1.0 - std::fabs(t));
             total += ws[i][j];
         }
         for (int j = 0; j < xsize; ++j) {
-            ws[i][j] /= total;
+            if (total != 0.0) ws[i][j] /= total;
             if (ws[i][j] > wt_max) wt_max = ws[i][j];
         }
         mins[i] = xmin;
         if (xsize > taps) taps = xsize;
     }
-    int prec = 0;
-    for (prec = 0; prec < 22; ++prec) {
-        const int next = static_cast<int>(0.5 + wt_max * (1 << (prec + 1)));
-        if (next >= (1 << 15)) break;
-    }
-    const int off = (n_out - image) / 2;  // transformers center_crop: top = (h - crop) // 2
+    int prec = 22;                         // Pillow: PRECISION_BITS = 32 - 8 - 2
+    if (kind == 0)
+        for (prec = 0; prec < 22; ++prec) {
+            const int next = static_cast<int>(0.5 + wt_max * (1 << (prec + 1)));
+            if (next >= (1 << 15)) break;
+        }
+    // transformers center_crop: top = (h - crop) // 2; torchvision center_crop: int(round((h - crop) / 2.0)) (half to even)
+    const int off = kind == 0 ? (n_out - image) / 2 : static_cast<int>(std::nearbyint((n_out - image) / 2.0));
     tap_min.assign(image, 0);
     tap_cnt.assign(image, 0);
     tap_w.assign(static_cast<size_t>(image) * taps, 0);
@@ -140,7 +151,7 @@ int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, std::vec
         tap_cnt[o] = static_cast<int>(ws[i].size());
         for (size_t j = 0; j < ws[i].size(); ++j) {
             const double v = ws[i][j] * (1 << prec);
-            tap_w[static_cast<size_t>(o) * taps + j] = static_cast<int16_t>(v + (ws[i][j] >= 0 ? 0.5 : -0.5));
+            tap_w[static_cast<size_t>(o) * taps + j] = static_cast<int32_t>(v + (ws[i][j] >= 0 ? 0.5 : -0.5));
         }
     }
     *max_taps = taps;
@@ -149,10 +160,10 @@ int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, std::vec
 }
 
 int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords, int64_t n,
-                             int input_patch, int image, int patch, const int32_t* tap_min, const int32_t* tap_cnt, const int16_t* tap_w,
+                             int input_patch, int image, int patch, const int32_t* tap_min, const int32_t* tap_cnt, const int32_t* tap_w,
                              int max_taps, int precision, int max_src_rows, __half* out, int64_t out_row_stride, const int* centre,
                              cudaStream_t stream) {
-    AP_REQUIRE(ctx, image % patch == 0 && patch <= 16, "preprocess(resize): bad geometry image %d patch %d", image, patch);
+    AP_REQUIRE(ctx, image % patch == 0 && patch <= 32, "preprocess(resize): bad geometry image %d patch %d", image, patch);
     if (n == 0) return AP_OK;
     const int g = image / patch;
     const size_t smem = ((static_cast<size_t>(max_src_rows) * input_patch * 3 + 15) & ~static_cast<size_t>(15)) +

@@ -485,6 +485,71 @@ extern "C" int ap_sam2_predict_host(ap_sam2* s, const uint8_t* image_host, float
     return AP_OK;
 }
 
+// A batch of thumbnails (the reference's predict_batch: SAM2ImagePredictor.set_image_batch + predict_batch, one whole-image box per
+// image, services/segmentation.py:142-180).  The model's activation buffers hold one image; the batch is pipelined instead: image
+// i + 1 is uploaded on a copy stream while image i runs, its logits are downloaded while image i + 1 runs.  Outputs are binary-
+// thresholded by the caller; logits_host: n x [1024, 1024] floats, lowres_host: n x [256, 256] floats or NULL.
+extern "C" int ap_sam2_predict_batch_host(ap_sam2* s, const uint8_t* images_host, int n, float* logits_host, float* lowres_host) {
+    if (!s || (n > 0 && (!images_host || !logits_host))) return AP_EINVAL;
+    DeviceGuard guard(s->ctx);
+    ap_ctx* ctx = s->ctx;
+    if (!s->finalized) return ap_set_error(ctx, AP_ESTATE, "sam2: ap_sam2_finalize has not been called");
+    if (n <= 0) return AP_OK;
+    const size_t img_bytes = static_cast<size_t>(IMG) * IMG * 3, lg_n = static_cast<size_t>(IMG) * IMG, lo_n = 256 * 256;
+    uint8_t* img[2] = {s->img_dev, nullptr};
+    float* lg[2] = {buf(s, "logits", lg_n), buf(s, "logits_b", lg_n)};
+    float* lo[2] = {buf(s, "lowres_out", lo_n), buf(s, "lowres_out_b", lo_n)};
+    if (!lg[0] || !lg[1] || !lo[0] || !lo[1]) return AP_ENOMEM;
+    AP_CHECK_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&img[1]), img_bytes));
+    cudaStream_t s_copy = nullptr, s_run = nullptr;
+    cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    int rc = AP_OK;
+    auto ck = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == AP_OK) rc = ap_set_error(ctx, AP_ECUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    ck(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking), "cudaStreamCreate");
+    ck(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; i < 2; ++i) {
+        ck(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming), "cudaEventCreate");
+        ck(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming), "cudaEventCreate");
+        ck(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    if (rc == AP_OK) {
+        ck(cudaMemcpyAsync(img[0], images_host, img_bytes, cudaMemcpyHostToDevice, s_copy), "upload");
+        ck(cudaEventRecord(up[0], s_copy), "record");
+        for (int i = 0; i < n && rc == AP_OK; ++i) {
+            const int b = i & 1;
+            if (i + 1 < n) {   // next image in flight while this one runs (its buffer was last read by forward i - 1)
+                if (i >= 1) ck(cudaStreamWaitEvent(s_copy, done[b ^ 1], 0), "wait");
+                ck(cudaMemcpyAsync(img[b ^ 1], images_host + static_cast<size_t>(i + 1) * img_bytes, img_bytes, cudaMemcpyHostToDevice, s_copy), "upload");
+                ck(cudaEventRecord(up[b ^ 1], s_copy), "record");
+            }
+            ck(cudaStreamWaitEvent(s_run, up[b], 0), "wait");
+            if (i >= 2) ck(cudaStreamWaitEvent(s_run, drained[b], 0), "wait");   // logits buffer b has been downloaded
+            if (rc != AP_OK) break;
+            int frc = ap_sam2_forward(s, img[b], lg[b], lo[b], s_run);
+            if (frc) { rc = frc; break; }
+            ck(cudaEventRecord(done[b], s_run), "record");
+            ck(cudaStreamWaitEvent(s_copy, done[b], 0), "wait");
+            ck(cudaMemcpyAsync(logits_host + static_cast<size_t>(i) * lg_n, lg[b], lg_n * sizeof(float), cudaMemcpyDeviceToHost, s_copy), "download");
+            if (lowres_host) ck(cudaMemcpyAsync(lowres_host + static_cast<size_t>(i) * lo_n, lo[b], lo_n * sizeof(float), cudaMemcpyDeviceToHost, s_copy), "download");
+            ck(cudaEventRecord(drained[b], s_copy), "record");
+        }
+    }
+    if (s_run) cudaStreamSynchronize(s_run);
+    if (s_copy) cudaStreamSynchronize(s_copy);
+    for (int i = 0; i < 2; ++i) {
+        if (up[i]) cudaEventDestroy(up[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+        if (drained[i]) cudaEventDestroy(drained[i]);
+    }
+    if (s_copy) cudaStreamDestroy(s_copy);
+    if (s_run) cudaStreamDestroy(s_run);
+    cudaFree(img[1]);
+    return rc;
+}
+
 extern "C" int ap_sam2_debug_copy(ap_sam2* s, const char* buffer_name, float* host_out, int64_t numel) {
     if (!s || !buffer_name || !host_out) return AP_EINVAL;
     DeviceGuard guard(s->ctx);

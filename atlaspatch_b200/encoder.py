@@ -44,7 +44,8 @@ class B200FeatureExtractor:
 
     torchvision ViTs (models/patch/vit.py) take a torchvision state_dict and the ImageClassification preset (centre crop);
     `dinov2_*` (models/patch/dinov2.py) take a transformers Dinov2Model state_dict and the BitImageProcessorFast preprocess
-    (bicubic-antialias resize to 256, centre crop 224)."""
+    (bicubic-antialias resize to 256, centre crop 224).  `input_patch` is the --patch-size of the run (the size of the patches
+    handed to extract_batch / cut by embed_coords)."""
 
     def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int | None = None, image_size: int = 224,
                  max_batch: int = 127, device: int = 0, config: tuple | None = None, registry_name: str | None = None,
@@ -61,6 +62,10 @@ class B200FeatureExtractor:
                 raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS) + sorted(DINOV2_CONFIGS)}")
             patch, layers, heads, hidden, mlp = cfg
             input_patch = 256 if input_patch is None else input_patch
+            if int(input_patch) != 256:
+                # --patch-size other than the preset's resize_size: torchvision resizes the PIL patch to 256 with Pillow's BILINEAR
+                # before the 224 crop (models/patch/base.py:170 -> [tv]transforms/_presets.py:58-64); done in the CUDA preprocess
+                preprocess, resize_to = 2, 256
         self._patch, self._grid = int(patch), int(image_size) // int(patch)
         self.name = registry_name or name   # H5 dataset name: features/<name> (services/storage.py:250-337)
         self.embedding_dim = int(hidden)

@@ -48,6 +48,17 @@ class B200Sam2Predictor:
                                                          low.ctypes.data_as(C.c_void_p)))
         return (logits, low) if return_lowres else logits
 
+    def predict_logits_batch(self, images_u8) -> np.ndarray:
+        """(n, 1024, 1024, 3) uint8 -> (n, 1024, 1024) float32 logits: the reference's predict_batch (services/segmentation.py:142-180)."""
+        a = np.ascontiguousarray(np.stack([np.asarray(i) for i in images_u8]) if not isinstance(images_u8, np.ndarray) else images_u8)
+        if a.ndim != 4 or a.shape[1:] != (1024, 1024, 3) or a.dtype != np.uint8:
+            raise ValueError(f"expected uint8 (n,1024,1024,3), got {a.dtype} {a.shape}")
+        logits = np.empty((a.shape[0], 1024, 1024), dtype=np.float32)
+        if a.shape[0]:
+            self.ctx.check(self.ctx.lib.ap_sam2_predict_batch_host(self._h, a.ctypes.data_as(C.c_void_p), int(a.shape[0]),
+                                                                   logits.ctypes.data_as(C.c_void_p), None))
+        return logits
+
     def debug_buffer(self, name: str, shape) -> np.ndarray:
         out = np.empty(shape, dtype=np.float32)
         self.ctx.check(self.ctx.lib.ap_sam2_debug_copy(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.size))

@@ -74,4 +74,30 @@ class B200SegmentationService:
         return Mask(data=mask.astype(np.float32), source_shape=(int(mask.shape[0]), int(mask.shape[1])))
 
     def segment_batch(self, wsis: Sequence) -> list[Mask]:
-        return [self.segment_thumbnail(w) for w in wsis]
+        """services/segmentation.py:216-229: thumbnails are prepared by up to 8 threads (device thumbnail kernel + Pillow cap), then
+        the batch goes through the predictor's batch call (`predict_logits_batch` of a bound B200Sam2Predictor method when the
+        callable has one, else image by image)."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        if self.predict_logits is None:
+            raise NotImplementedError("no SAM2 predictor bound; pass predict_logits=B200Sam2Predictor(...).predict_logits")
+        wsis = list(wsis)
+        if not wsis:
+            return []
+        workers = max(1, min(8, len(wsis), os.cpu_count() or 8))
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="thumb") as ex:
+            thumbs = list(ex.map(lambda w: np.array(self._prepare_thumbnail(w).convert("RGB"), copy=True), wsis))
+        ins, shapes = zip(*(resize_for_sam(t) for t in thumbs))
+        owner = getattr(self.predict_logits, "__self__", None)
+        if owner is not None and hasattr(owner, "predict_logits_batch"):
+            logits = owner.predict_logits_batch(np.stack(ins))
+        else:
+            logits = [np.asarray(self.predict_logits(i), dtype=np.float32) for i in ins]
+        out = []
+        for lg, orig in zip(logits, shapes):
+            mask = (np.asarray(lg) > self.mask_threshold).astype(np.float32)
+            if mask.shape[:2] != orig:
+                mask = resize_mask(mask, orig)
+            out.append(Mask(data=mask.astype(np.float32), source_shape=(int(mask.shape[0]), int(mask.shape[1]))))
+        return out

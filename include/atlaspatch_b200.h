@@ -141,8 +141,12 @@ typedef struct ap_vit_desc {
     int preprocess;   /* 0: centre crop of the input patch to image_size (torchvision preset whose resize == input_patch);
                          1: transformers BitImageProcessorFast as configured by the DINOv2 checkpoints
                             (atlas_patch/models/patch/dinov2.py:20-25,49): uint8 bicubic-antialias resize of the
-                            input_patch^2 patch to resize_to^2, centre crop to image_size, rescale + normalise */
-    int resize_to;    /* 256 (preprocess 1) */
+                            input_patch^2 patch to resize_to^2, centre crop to image_size, rescale + normalise;
+                         2: torchvision's ImageClassification preset for an input patch whose size differs from resize_to
+                            (atlas_patch/models/patch/base.py:42-45,170: PIL image -> Image.resize(BILINEAR) = Pillow's antialiased
+                            triangle filter in 22-bit fixed point -> centre crop -> /255 -> normalise); input_patch == resize_to needs
+                            no resize and uses preprocess 0 */
+    int resize_to;    /* 256 (preprocess 1, 2) */
     int mlp_kind;     /* 0: Linear - GELU - Linear, mlp = hidden features;
                          1: SwiGLU (Dinov2SwiGLUFFN): "mlp.0" = weights_in with 2 * mlp rows interleaved as AP_EPI_BIAS_SWIGLU_F16
                             expects, "mlp.3" = weights_out [hidden, mlp] */
@@ -198,6 +202,10 @@ int ap_sam2_finalize(ap_sam2* s);
 int ap_sam2_forward(ap_sam2* s, const uint8_t* image_dev, float* logits_dev, float* lowres_dev, void* stream);
 /* Same with host buffers (synchronous). */
 int ap_sam2_predict_host(ap_sam2* s, const uint8_t* image_host, float* logits_host, float* lowres_host);
+/* A batch of n thumbnails, replacing predict_batch (atlas_patch/services/segmentation.py:142-180: set_image_batch + predict_batch
+ * with one whole-image box each): images_host n x [1024,1024,3] uint8, logits_host n x [1024,1024], lowres_host n x [256,256] or
+ * NULL.  Uploads / downloads of neighbouring images overlap the forward passes (two streams, double-buffered). */
+int ap_sam2_predict_batch_host(ap_sam2* s, const uint8_t* images_host, int n, float* logits_host, float* lowres_host);
 /* Parity tests: copy a named intermediate activation ("patch_embed", "blk0".."blk11", "fpn0".."fpn2", "feat_s0", "feat_s1",
  * "keys", "queries", "upscaled", "low_res") to the host. */
 int ap_sam2_debug_copy(ap_sam2* s, const char* buffer_name, float* host_out, int64_t numel);
@@ -214,6 +222,12 @@ int ap_sam2_debug_copy(ap_sam2* s, const char* buffer_name, float* host_out, int
  * K % 64 == 0, N % 128 == 0. */
 int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,
                 const float* resid_dev, void* out_dev, int M, int N, int K, int epilogue, void* stream);
+/* The same contraction with fp16 hi/lo SPLIT operands, fp32-like precision on the tensor cores (what the "precise" encoder layers
+ * and conv_proj use): split 1: W_dev is [N, 2K] = [W_hi | W_lo]; 2: A_dev is [M, 2K] = [A_hi | A_lo]; 3: both (A_hi W_hi +
+ * A_lo W_hi + A_hi W_lo); 0: plain.  x = hi + lo with hi = fp16(x), lo = fp16(x - hi). */
+int ap_gemm_f16_split(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
+                      void* out_dev, int M, int N, int K, int epilogue, int split, void* stream);
+
 /* y fp16 [rows, D] = LayerNorm(x fp32 [rows, D]; gamma, beta, eps), x row stride in elements. */
 int ap_layernorm_f16(ap_ctx* ctx, const float* x_dev, int64_t x_row_stride, const float* gamma_dev,
                      const float* beta_dev, float eps, void* y_dev, int rows, int D, void* stream);

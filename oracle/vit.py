@@ -25,22 +25,29 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
 def preprocess(patches: Sequence[np.ndarray], *, crop: int = 224, resize: int = 256) -> torch.Tensor:
-    """ImageClassification(crop_size=224, resize_size=256, bilinear) preset, [tv]_presets.py:39-65.
+    """ImageClassification(crop_size=224, resize_size=256, bilinear) preset on the PIL image the reference's PatchDataset builds
+    (models/patch/base.py:42-45; [tv]_presets.py:39-65).
 
-    For (256,256,3) patches the resize is a no-op ([tv]transforms/functional.py:470-471), so this is
-    centre-crop [16:240) -> /255 -> (x-mean)/std.  Other sizes go through torchvision's resize.
+    For (256,256,3) patches the resize is a no-op ([tv]transforms/functional.py:470-471), so this is centre-crop [16:240) ->
+    /255 -> (x-mean)/std.  Other sizes are resized by Pillow (Image.resize(BILINEAR): antialiased triangle filter, 8-bit fixed
+    point) -- NOT by torch's tensor resize, whose int16 coefficients round differently.
     """
+    from PIL import Image
+
     out = []
     mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
     std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
     for p in patches:
-        t = torch.from_numpy(np.ascontiguousarray(p)).permute(2, 0, 1)  # uint8 CHW
-        h, w = t.shape[1:]
+        a = np.ascontiguousarray(p)
+        h, w = a.shape[:2]
         if min(h, w) != resize:
-            from torchvision.transforms import functional as TF
-
-            t = TF.resize(t, [resize], interpolation=TF.InterpolationMode.BILINEAR, antialias=True)
-            h, w = t.shape[1:]
+            if h <= w:
+                nh, nw = resize, int(resize * w / h)
+            else:
+                nh, nw = int(resize * h / w), resize
+            a = np.asarray(Image.fromarray(a).resize((nw, nh), Image.Resampling.BILINEAR))
+            h, w = nh, nw
+        t = torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1)  # uint8 CHW
         top, left = int(round((h - crop) / 2.0)), int(round((w - crop) / 2.0))
         t = t[:, top:top + crop, left:left + crop]
         t = t.to(torch.float32) / 255.0

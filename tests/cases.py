@@ -142,6 +142,25 @@ def feature_patches() -> list[np.ndarray]:
     return out
 
 
+# --patch-size other than 256 with the torchvision ViTs (the preset resizes the PIL patch to 256 with Pillow's BILINEAR first)
+VIT_RESIZE_CASES = dict(weight_seed=4242, slide=dict(width=4096, height=4096, seed=14, mpp=0.5), n=4, sizes=(224, 512))
+
+
+def vit_resize_coords(P: int) -> np.ndarray:
+    s = VIT_RESIZE_CASES["slide"]
+    rng = np.random.default_rng(500 + P)
+    n = VIT_RESIZE_CASES["n"]
+    xy = np.stack([rng.integers(0, s["width"] - P, n), rng.integers(0, s["height"] - P, n)], 1)
+    xy[-1] = (s["width"] - P // 2, s["height"] - P // 3)          # overhang
+    return np.concatenate([xy, np.full((n, 2), P), np.zeros((n, 1))], 1).astype(np.int32)
+
+
+def vit_resize_patches(P: int) -> list[np.ndarray]:
+    s = VIT_RESIZE_CASES["slide"]
+    spec = make_spec(s["width"], s["height"], s["seed"], mpp=s["mpp"])
+    return [render_region_host(spec, int(x), int(y), P, P) for x, y in vit_resize_coords(P)[:, :2]]
+
+
 def sam2_input_image() -> np.ndarray:
     """The 1024 x 1024 uint8 image the segmentation service would hand to SAM2 for the 8192^2 synthetic slide (seed 0)."""
     from atlaspatch_b200.synthetic import sam2_benchmark_image

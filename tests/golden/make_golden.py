@@ -136,7 +136,7 @@ def main() -> None:
     (OUT / "versions.json").write_text(json.dumps(versions, indent=1) + "\n")
 
 
-if __name__ == "__main__" and not ({"--sam2", "--sam2-large", "--filter", "--dinov2", "--thumb-general"} & set(sys.argv)):
+if __name__ == "__main__" and not ({"--sam2", "--sam2-large", "--filter", "--dinov2", "--thumb-general", "--vit-resize"} & set(sys.argv)):
     os.environ.setdefault("OMP_NUM_THREADS", "8")
     main()
 
@@ -238,3 +238,31 @@ def make_thumb_general_golden() -> None:
 
 if __name__ == "__main__" and "--thumb-general" in sys.argv:
     make_thumb_general_golden()
+
+
+def make_vit_resize_golden() -> None:
+    """--patch-size 224 / 512 with vit_b_16: the reference's own PatchFeatureExtractor (models/patch/base.py:76-107) on the torchvision
+    preset, which resizes the PIL patch to 256 (Pillow BILINEAR) before the 224 crop.  Seeded weights, fp32 CPU."""
+    import torch
+    from torchvision import models
+
+    from atlas_patch.models.patch.base import PatchFeatureExtractor
+    from oracle.weights import vit_state_dict
+    from tests.cases import VIT_RESIZE_CASES, vit_resize_patches
+
+    sd = vit_state_dict("vit_b_16", seed=VIT_RESIZE_CASES["weight_seed"])
+    model = models.vit_b_16(weights=None)
+    model.heads = torch.nn.Identity()
+    model.load_state_dict(sd, strict=True)
+    ext = PatchFeatureExtractor(name="vit_b_16", model=model, embedding_dim=768, preprocess=models.ViT_B_16_Weights.IMAGENET1K_V1.transforms(),
+                                device=torch.device("cpu"), dtype=torch.float32, num_workers=0)
+    out = {}
+    for P in VIT_RESIZE_CASES["sizes"]:
+        patches = vit_resize_patches(P)
+        out[f"feats_{P}"] = ext.extract_batch(patches, batch_size=4)
+        print(f"vit_b_16 patch {P}: {out[f'feats_{P}'].shape}")
+    np.savez_compressed(OUT / "vit_b_16_resize_feats.npz", **out)
+
+
+if __name__ == "__main__" and "--vit-resize" in sys.argv:
+    make_vit_resize_golden()

@@ -146,6 +146,41 @@ def test_patch32_vits_match_oracle(name):
     ext.cleanup()
 
 
+@pytest.mark.parametrize("P", [224, 512, 300])
+def test_vit_preset_with_other_patch_sizes(P, golden_dir):
+    """--patch-size != 256 with vit_b_16 (legal in the reference): the preset resizes the PIL patch to 256 with Pillow's BILINEAR
+    (models/patch/base.py:170).  Pixels the encoder sees: bit-exact vs the integer restatement (pinned against Pillow); features:
+    <= 1e-3 vs golden rows produced by the reference's own PatchFeatureExtractor (224, 512) / the fp32 oracle (300)."""
+    import torch
+
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec, render_region_host
+    from oracle import resize_aa as ra
+    from tests.cases import VIT_RESIZE_CASES, vit_resize_coords
+
+    s = VIT_RESIZE_CASES["slide"]
+    wsi = SyntheticWSI(make_spec(s["width"], s["height"], s["seed"], mpp=s["mpp"]))
+    rows = vit_resize_coords(P)
+    rows_dev = torch.from_numpy(rows).cuda()
+    patches = [render_region_host(wsi.spec, int(x), int(y), P, P) for x, y in rows[:, :2]]
+    sd = vit_state_dict("vit_b_16", seed=VIT_RESIZE_CASES["weight_seed"])
+    ext = B200FeatureExtractor("vit_b_16", sd, input_patch=P, max_batch=3)
+    pix = ext.preprocess_pixels(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows_dev[:3])
+    for i in range(3):
+        assert np.array_equal(pix[i], ra.vit_preset_pixels(patches[i])), i
+    got = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows_dev).cpu().numpy()
+    if P in VIT_RESIZE_CASES["sizes"]:
+        want = np.load(golden_dir / "vit_b_16_resize_feats.npz")[f"feats_{P}"]
+    else:
+        want = ov.extract_features(patches, sd, "vit_b_16")
+    rel = _rel(got, want)
+    print("vit_b_16 patch", P, "rel err per row:", rel)
+    assert rel.max() < REL_TOL, rel
+    assert np.abs(ext.extract_batch(patches, batch_size=2) - got).max() < 1e-5       # host-patch entry, same result
+    ext.cleanup()
+
+
 def test_mag40_read_2x_box_resize_matches_oracle():
     """a11 with read size = 2 x patch size (40x slide, 20x patches): coords rows carry read_w = 512; the reference reads
     512 x 512 and cv2.resize()s to 256 (feature_embedding.py:88-95).  Oracle: cv2 itself + the fp32 ViT."""

@@ -58,6 +58,36 @@ def test_gemm_tcgen05(ctx, M, N, K, epi, cg):
     assert err <= tol * max(scale, 1.0), f"max abs err {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (1000, 768, 768), (257 * 3, 4608, 1536)])
+def test_gemm_split_operands(ctx, M, N, K):
+    """hi/lo split operands: each split removes that operand's fp16 rounding, so the error against the fp32 product of the ORIGINAL
+    fp32 operands must fall: none > W-split ~ A-split > both (~fp32)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = (A.double() @ W.double().T + bias.double())
+
+    def split(x):
+        hi = x.half()
+        return hi, (x - hi.float()).half()
+
+    A_hi, A_lo = split(A)
+    W_hi, W_lo = split(W)
+    ops = {0: (A_hi, W_hi), 1: (A_hi, torch.cat([W_hi, W_lo], 1)), 2: (torch.cat([A_hi, A_lo], 1), W_hi),
+           3: (torch.cat([A_hi, A_lo], 1), torch.cat([W_hi, W_lo], 1))}
+    err = {}
+    for mode, (a, w) in ops.items():
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+        ctx.check(ctx.lib.ap_gemm_f16_split(ctx.handle, _p(a.contiguous()), _p(w.contiguous()), _p(bias), None, _p(out), M, N, K, 3, mode, _stream()))
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        err[mode] = ((out.double() - ref).norm() / ref.norm()).item()
+    print("split-operand GEMM rel-l2 errors:", err)
+    assert err[0] < 5e-4 and err[1] < 0.8 * err[0] and err[2] < 0.8 * err[0] and err[3] < 0.05 * err[0], err
+    assert 0.7 < err[1] / err[2] < 1.4, err          # the two operands contribute alike
+
+
 def test_gemm_rejects_bad_shapes(ctx):
     from atlaspatch_b200._lib import AtlasB200Error
 

@@ -72,6 +72,29 @@ def test_segmentation_service_end_to_end(predictor):
     assert np.array_equal(got, oc.coords_from_mask(mask.data, **kw))
 
 
+def test_batch_prediction_equals_single_predictions(predictor):
+    """predict_batch / segment_batch (services/segmentation.py:142-180,216-229): the pipelined batch entry returns, image by image,
+    exactly what the single-image entry returns, and the service threads the thumbnails."""
+    from atlaspatch_b200.segmentation import B200SegmentationService
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec
+
+    img = sam2_input_image()
+    imgs = np.stack([img, img[::-1].copy(), img[:, ::-1].copy(), img])
+    single = [predictor.predict_logits(i) for i in imgs]
+    batch = predictor.predict_logits_batch(imgs)
+    assert batch.shape == (4, 1024, 1024)
+    for a, b in zip(single, batch):
+        assert np.array_equal(a, b)
+    assert predictor.predict_logits_batch(np.zeros((0, 1024, 1024, 3), np.uint8)).shape == (0, 1024, 1024)
+    svc = B200SegmentationService(predictor.predict_logits)
+    wsis = [SyntheticWSI(make_spec(4096, 4096, s)) for s in (1, 2, 3)]
+    masks = svc.segment_batch(wsis)
+    for w, m in zip(wsis, masks):
+        one = svc.segment_thumbnail(w)
+        assert m.source_shape == one.source_shape == (256, 256) and np.array_equal(m.data, one.data)
+
+
 def test_hiera_large_matches_live_hf_model():
     """BASELINE.json configs[2]: SAM2 Hiera-L (embed 144, blocks 2/6/36/4, windows 8/4/16/8, global blocks 23/33/43) on the
     1024 x 1024 thumbnail, mask IoU against the fp32 restatement."""

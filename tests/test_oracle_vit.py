@@ -79,3 +79,36 @@ def test_cv2_exact_2x_resize_is_box_mean():
     s = a.astype(np.uint32)
     want = ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n", [224, 512, 300, 100, 257, 768])
+def test_pillow_bilinear_restatement_is_bit_exact(n):
+    """oracle/resize_aa.py: resize_pil_bilinear (what the CUDA preprocess implements for --patch-size != 256) against Pillow itself."""
+    from PIL import Image
+
+    from oracle import resize_aa as ra
+
+    img = np.random.default_rng(n).integers(0, 256, (n, n, 3), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img).resize((256, 256), Image.Resampling.BILINEAR))
+    assert np.array_equal(ra.resize_pil_bilinear(img, 256, 256), want)
+
+
+@pytest.mark.parametrize("P", [224, 512])
+def test_oracle_matches_reference_golden_for_other_patch_sizes(P, golden_dir):
+    """tests/golden/vit_b_16_resize_feats.npz: produced by the reference's PatchFeatureExtractor + torchvision preset on PIL patches."""
+    from tests.cases import VIT_RESIZE_CASES, vit_resize_patches
+
+    g = np.load(golden_dir / "vit_b_16_resize_feats.npz")[f"feats_{P}"]
+    sd = vit_state_dict("vit_b_16", seed=VIT_RESIZE_CASES["weight_seed"])
+    patches = vit_resize_patches(P)
+    got = ov.extract_features(patches, sd, "vit_b_16")
+    rel = np.linalg.norm(got - g, axis=1) / np.linalg.norm(g, axis=1)
+    assert rel.max() < 2e-5, rel
+    # and the integer restatement of the preset's pixels equals what torchvision normalises
+    from oracle import resize_aa as ra
+
+    x = ov.preprocess(patches[:2])
+    mean, std = np.asarray(ov.IMAGENET_MEAN, np.float32), np.asarray(ov.IMAGENET_STD, np.float32)
+    for i in range(2):
+        px = ra.vit_preset_pixels(patches[i]).astype(np.float32) / 255.0
+        assert np.allclose(((px - mean) / std).transpose(2, 0, 1), x[i].numpy(), atol=1e-6)
