@@ -29,11 +29,13 @@ struct ap_ctx {
     int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split operands: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
     int precise_kind = 0;         // what is split there: 0 the weights, 1 the A operands of qkv / out_proj / mlp.0 (+ mlp.3's weights)
                                   // ("precise_kind"; encoder.cu: ap_encoder_finalize; measured: profiles/r02_dinov2_giant_precision.log)
-    int precise_aw_layers = 0;    // with kind 0: leading layers whose qkv / out_proj / mlp.0 ALSO get split A operands (3 products per term)
+    int precise_aw_layers = -1;   // with kind 0: leading layers whose qkv / out_proj / mlp.0 ALSO get split A operands (3 products per term);
+                                  // -1 = automatic (8 for encoders deeper than 32 layers, else 0)
     int pdl = 1;                  // programmatic dependent launch for the encoder kernel chain (ap_set_option "pdl")
     int cls_only_last_layer = 1;  // last layer: attention / out_proj / MLP only for the class-token row (ap_set_option)
     int attn_mode = 2;       // 2: tcgen05 attention when 16 <= S_pad <= 256, 1: warp-MMA (mma.sync) kernel
     int attn_variant = 0;    // diagnostics
+    int attn_emu = 0;        // attention (<= 208 keys): exponential PAIRS per 16 evaluated on the FMA pipe instead of MUFU (0, 4, 6, 8)
     int gemm_debug = 0;      // diagnostics: see EpiParams::debug
     int gemm_cta_group = 2;  // default GEMM flavour (ap_set_option "gemm_cta_group"; env AP_GEMM_CTA_GROUP)
     // optional per-launch CUDA-event timing (ap_profile_*): bench.py's live roofline measurement

@@ -478,6 +478,426 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
 }
 
+
+// =====================================================================================================================================
+// Round 2, "tile stream with a free-standing O": the pipeline used whenever two score tiles AND one output tile fit tensor memory
+// (2 * S_pad + 64 + 16 <= 512 columns, i.e. up to 208 keys: the 197-token ViT/16 sequence, the 50-token ViT/32 one).
+//
+// What the profiles of the kernel above said (profiles/r02_attention_notes.md): nothing is saturated, every softmax warpgroup walks
+// the serial chain  S-MMA -> softmax -> P.V -> O read-out -> S-MMA  (9 500 clk per tile) because O lives INSIDE the score buffer
+// (dead upper half of S), so the next S cannot be issued into a buffer before its O has been read out.  Here
+//   * O gets its own 64 columns [416, 480) and is drained by a DEDICATED epilogue warpgroup (warps 12-15), so a score buffer is
+//     free again as soon as P.V has been issued: the MMA thread issues  P.V_i, L_i, S_{i+2}  back to back (tcgen05.mma executes in
+//     issue order, so S_{i+2} may overwrite P_i behind P.V_i without a barrier in between);
+//   * the MMA warp runs its loop warp-uniformly and one ELECTED lane issues, so descriptor arithmetic stays on the uniform datapath
+//     (from a `lane == 0` branch the 30 MMAs of a tile took 2 850 clk to issue: an R2UR round trip per operand);
+//   * the softmax is two passes over TMEM in 64-column loads: a tcgen05.wait::ld costs ~120 clk of warp time however little it has to
+//     wait for (tools/attn6_trace.py: 7 x 32-column pieces took 1 340 clk for pass 1 alone), so prefetching does not help, only fewer
+//     waits do; packed fma.rn.f32x2 for the scale / shift and the row sum, FMNMX3 for the maximum; the row sums reach the epilogue
+//     warps through shared memory (a row-sum MMA against a tile of ones was tried: 13 N = 16 MMAs cost the tensor pipe ~600 clk / tile);
+//   * a fraction of the exponentials (EMU of every 32) is evaluated on the FMA pipe instead of the MUFU (Cody-Waite: 2^x =
+//     2^floor(x) * p(x - floor(x)), p = degree-3 minimax, exponent spliced in with one shift-add): MUFU does 4 lanes / clk / scheduler,
+//     i.e. 8 clk per warp instruction, and two softmax warps share each scheduler's unit;
+//   * the second query tile of a 197-token job holds 69 rows: on odd jobs it is loaded as tokens [nq - 128, nq) instead of
+//     [128, 256), which moves its valid rows (and the MUFU work) from lane quarters 0-2 to quarters 1-3.
+// Warps: 0 TMA (Q, K), 3 TMA (V), 1 MMA issuer, 2 TMEM allocator, 4-7 / 8-11 softmax warpgroups (score buffer 0 / 1), 12-15 epilogue.
+constexpr int ATC6_THREADS = 512;
+// diagnostics (variant bit 128): block 0 records clock64() at the hand-over points of its first tiles; tools/attn6_trace.py prints them
+constexpr int ATC6_TRACE_N = 256;
+__device__ long long g_attn6_trace[4][ATC6_TRACE_N];
+#define ATC6_TRACE(role, slot)                                                                               \
+    do {                                                                                                     \
+        if (trace && (slot) < ATC6_TRACE_N) g_attn6_trace[role][slot] = clock64();                           \
+    } while (0)
+constexpr int ATC6_O_COL = 416;
+
+__device__ __forceinline__ uint64_t pk2f(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2f(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2f(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2f(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2f_rm(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float ex2_mufu(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// 2^x for two values x <= 0 on the FMA pipe.  t = x + 1.5 * 2^23 rounded DOWN keeps floor(x) in the low mantissa bits; f = x - floor(x)
+// in [0, 1); p(f) = 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5, a sixth of the fp16 rounding P gets anyway); the
+// exponent is spliced in by adding floor(x) << 23 to the bits of p.  x is clamped to >= -32 (P < 2^-24 rounds to zero in fp16 anyway).
+__device__ __forceinline__ void ex2_emu2(uint64_t x, float& p0, float& p1) {
+    float x0, x1;
+    upk2f(x, x0, x1);
+    x = pk2f(fmaxf(x0, -32.f), fmaxf(x1, -32.f));
+    const float magic = 12582912.f;   // 1.5 * 2^23
+    const uint64_t t = add2f_rm(x, pk2f(magic, magic));
+    const uint64_t nfl = fma2f(t, pk2f(-1.f, -1.f), pk2f(magic, magic));   // -(floor x), exact
+    const uint64_t f = add2f(x, nfl);
+    const float c3 = 0.0780240297f, c2 = 0.2260670662f, c1 = 0.6958339810f, c0 = 0.9999251366f;   // max rel. error 7.5e-5 on [0, 1]
+    uint64_t p = fma2f(f, pk2f(c3, c3), pk2f(c2, c2));
+    p = fma2f(p, f, pk2f(c1, c1));
+    p = fma2f(p, f, pk2f(c0, c0));
+    float q0, q1, t0, t1;
+    upk2f(p, q0, q1);
+    upk2f(t, t0, t1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+template <int W>
+__device__ __forceinline__ void tmem_ld_w(uint32_t taddr, uint32_t (&r)[W]) {
+    if constexpr (W == 64) ptx::tmem_ld_32x64(taddr, r);
+    else if constexpr (W == 32) ptx::tmem_ld_32x32(taddr, r);
+    else ptx::tmem_ld_32x16(taddr, r);
+}
+// pass 1 over W score columns starting at key c0: four running maxima (FMNMX3 chains)
+template <int W, bool MASK>
+__device__ __forceinline__ void sm6_max_piece(uint32_t t_src, int c0, int nk, float (&m)[4]) {
+    uint32_t r[W];
+    tmem_ld_w<W>(t_src, r);
+    ptx::tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < W; j += 8) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (!MASK) {
+                m[e] = fmaxf(m[e], fmaxf(__uint_as_float(r[j + 2 * e]), __uint_as_float(r[j + 2 * e + 1])));
+            } else {
+                if (c0 + j + 2 * e < nk) m[e] = fmaxf(m[e], __uint_as_float(r[j + 2 * e]));
+                if (c0 + j + 2 * e + 1 < nk) m[e] = fmaxf(m[e], __uint_as_float(r[j + 2 * e + 1]));
+            }
+        }
+    }
+}
+// pass 2 over W score columns: P = 2^(s * scale - m * scale) -> fp16 pairs -> W / 2 TMEM columns at t_dst; the fp32 values are summed
+// into lsum (packed pair of partial sums).  EMU of every 16 pairs take the FMA-pipe exponential, spread evenly between the MUFU ones.
+template <int W, bool MASK, int EMU>
+__device__ __forceinline__ void sm6_exp_piece(uint32_t t_src, uint32_t t_dst, int c0, int nk, uint64_t scale2, uint64_t negms2, uint64_t& lsum) {
+    uint32_t r[W];
+    tmem_ld_w<W>(t_src, r);
+    ptx::tc_wait_ld();
+#pragma unroll
+    for (int g = 0; g < W / 16; ++g) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = g * 8 + jj;          // pair index inside the piece
+            const uint64_t x = fma2f(pk2f(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), scale2, negms2);
+            float p0, p1;
+            if ((((j & 15) + 1) * EMU) / 16 > ((j & 15) * EMU) / 16) {
+                ex2_emu2(x, p0, p1);
+            } else {
+                float x0, x1;
+                upk2f(x, x0, x1);
+                p0 = ex2_mufu(x0);
+                p1 = ex2_mufu(x1);
+            }
+            if (MASK) {
+                p0 = (c0 + 2 * j < nk) ? p0 : 0.f;
+                p1 = (c0 + 2 * j + 1 < nk) ? p1 : 0.f;
+            }
+            lsum = add2f(lsum, pk2f(p0, p1));
+            pk[jj] = pack_h2(p0, p1);
+        }
+        ptx::tmem_st_32x8(t_dst + g * 8, pk);
+    }
+}
+
+template <int EMU, int NC>   // NC > 0: S_pad = 16 * NC at compile time (fully unrolled MMA issue), 0: run-time S_pad
+__global__ void __launch_bounds__(ATC6_THREADS, 1)
+attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, __half* __restrict__ out,
+                     const AttnArgs a) {
+    const int S_pad = NC > 0 ? NC * 16 : a.S_pad;               // <= 208
+    extern __shared__ uint8_t smem_raw_att[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_att) + 1023) & ~uintptr_t(1023));
+    const int heads = a.heads, S = a.S;
+    const int D = heads * 64;
+    const int kv_bytes = S_pad * 128;
+    const int n_qt = (a.nq + 127) / 128;                        // 1 or 2 query tiles per job
+    const int q_bytes = n_qt * Q_TILE_BYTES;
+    const int stage_bytes = q_bytes + 2 * kv_bytes;             // per job stage: [Q tiles | K | V], a multiple of 1024
+    float* lsm = reinterpret_cast<float*>(smem + 2 * stage_bytes);   // [4 tiles in flight][128 rows] row sums, softmax -> epilogue
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes + 2048);
+    uint64_t* qk_full = bars;        // [2 stages] TMA -> MMA   (Q tiles + K)
+    uint64_t* qk_empty = bars + 2;   // [2 stages] MMA -> TMA   (the job's S MMAs have retired)
+    uint64_t* v_full = bars + 4;     // [2 stages] TMA -> MMA   (V)
+    uint64_t* v_empty = bars + 6;    // [2 stages] MMA -> TMA   (the job's P.V MMAs have retired)
+    uint64_t* s_full = bars + 8;     // [2 buffers] MMA -> softmax
+    uint64_t* p_full = bars + 10;    // [2 buffers] softmax -> MMA
+    uint64_t* o_full = bars + 12;    // MMA -> epilogue
+    uint64_t* o_empty = bars + 13;   // epilogue -> MMA
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_jobs = a.B * heads;
+    const int my_jobs = blockIdx.x < n_jobs ? (n_jobs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int n_tiles = my_jobs * n_qt;
+    const bool flip = n_qt == 2 && !(a.variant & 64);
+    const bool trace = (a.variant & 128) && blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 4 || warp == 8 || warp == 12);
+    // first token (inside the query window) of tile g of this CTA's jt-th job, and the first row of the tile that is this tile's to
+    // compute (rows below it repeat tokens of tile 0)
+    auto tile_tok0 = [&](int jt, int g) -> int { return (g == 1 && flip && (jt & 1)) ? a.nq - 128 : g * 128; };
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&map_q);
+        ptx::prefetch_tmap(&map_kv);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&qk_full[i], 1);
+            ptx::mbar_init(&qk_empty[i], 1);
+            ptx::mbar_init(&v_full[i], 1);
+            ptx::mbar_init(&v_empty[i], 1);
+            ptx::mbar_init(&s_full[i], 1);
+            ptx::mbar_init(&p_full[i], 4);
+        }
+        ptx::mbar_init(o_full, 1);
+        ptx::mbar_init(o_empty, 4);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc<1>(tmem_ptr_smem, 512);
+        ptx::tmem_relinquish<1>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
+
+    if (warp < 4) {
+      if (warp == 0 || warp == 3) {
+        if (lane == 0) {
+            for (int jt = 0; jt < my_jobs; ++jt) {
+                const int job = blockIdx.x + jt * gridDim.x;
+                const int st = jt & 1;
+                const uint32_t sph = (jt >> 1) & 1;
+                const int b = job / heads, h = job - b * heads;
+                uint8_t* sb = smem + st * stage_bytes;
+                if (warp == 0) {
+                    ptx::mbar_wait(&qk_empty[st], sph ^ 1, 61);
+                    ptx::mbar_arrive_expect_tx(&qk_full[st], n_qt * Q_TILE_BYTES + kv_bytes);
+                    ptx::tma_load_2d(sb + q_bytes, &map_kv, &qk_full[st], D + h * 64, b * S + a.k0);
+                    for (int g = 0; g < n_qt; ++g)
+                        ptx::tma_load_2d(sb + g * Q_TILE_BYTES, &map_q, &qk_full[st], h * 64, b * S + a.q0 + tile_tok0(jt, g));
+                } else {
+                    ptx::mbar_wait(&v_empty[st], sph ^ 1, 62);
+                    ptx::mbar_arrive_expect_tx(&v_full[st], kv_bytes);
+                    ptx::tma_load_2d(sb + q_bytes + kv_bytes, &map_kv, &v_full[st], 2 * D + h * 64, b * S + a.k0);
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        // The WHOLE warp walks the loop (waits included) and one elected lane issues: with warp-uniform control flow the descriptor
+        // arithmetic stays on the uniform datapath.  Issued from a `lane == 0` branch every operand of every tcgen05.mma went through an
+        // R2UR first and the 30 MMAs of a tile took 2 850 clk to ISSUE (tools/attn6_trace.py) -- longer than they take to execute.
+        if (n_tiles > 0) {
+            const uint32_t idesc_s = ptx::make_idesc_f16(128, S_pad);
+            const uint32_t idesc_o = ptx::make_idesc_f16(128, 64, false, true);
+            const int k_steps_pv = S_pad / 16;
+            auto issue_s = [&](int i) {       // S_i = Q_g K^T into score buffer i & 1
+                const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
+                uint8_t* sb = smem + st * stage_bytes;
+                if (g == 0) ptx::mbar_wait(&qk_full[st], (jt >> 1) & 1, 63);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes));
+                    const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + g * Q_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::tc_mma_f16<1>(tmem_base + buf * S_pad, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                    ptx::tc_commit<1>(&s_full[buf]);
+                    if (g == n_qt - 1) ptx::tc_commit<1>(&qk_empty[st]);   // Q and K of this stage are free once the S MMAs retire
+                }
+                __syncwarp();
+            };
+            issue_s(0);
+            if (n_tiles > 1) issue_s(1);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
+                uint8_t* sb = smem + st * stage_bytes;
+                ATC6_TRACE(2, 4 * i);
+                if (g == 0) ptx::mbar_wait(&v_full[st], (jt >> 1) & 1, 64);
+                ptx::mbar_wait(&p_full[buf], (i >> 1) & 1, 65);
+                ATC6_TRACE(2, 4 * i + 1);
+                ptx::mbar_wait(o_empty, (i & 1) ^ 1, 66);              // O / L of tile i - 1 have been read out
+                ATC6_TRACE(2, 4 * i + 2);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes + kv_bytes), 64);
+                    const uint32_t p_addr = tmem_base + buf * S_pad;
+                    if (NC > 0) {
+#pragma unroll
+                        for (int ks = 0; ks < (NC > 0 ? NC : 1); ++ks) {   // 16 keys per step: 8 TMEM columns of P, two 8-key groups (2 KB) of V
+                            ptx::tc_mma_f16_ts(tmem_base + ATC6_O_COL, p_addr + ks * 8, v_desc + ks * 128, idesc_o, ks != 0 ? 1u : 0u);
+                        }
+                    } else {
+                        for (int ks = 0; ks < k_steps_pv; ++ks) {
+                            ptx::tc_mma_f16_ts(tmem_base + ATC6_O_COL, p_addr + ks * 8, v_desc + ks * 128, idesc_o, ks != 0 ? 1u : 0u);
+                        }
+                    }
+                    ptx::tc_commit<1>(o_full);
+                    if (g == n_qt - 1) ptx::tc_commit<1>(&v_empty[st]);
+                }
+                __syncwarp();
+                // the score buffer is free as soon as P.V_i is in the pipe: tcgen05.mma executes in issue order
+                if (i + 2 < n_tiles) issue_s(i + 2);
+                ATC6_TRACE(2, 4 * i + 3);
+            }
+        }
+      }
+    } else if (warp < 12) {
+        // ---------------- softmax warpgroups ----------------
+        const int wg = (warp - 4) >> 2;   // = score buffer
+        const int q = warp & 3;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + wg * S_pad;
+        const float scale = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e)
+        const uint64_t scale2 = pk2f(scale, scale);
+        for (int i = wg; i < n_tiles; i += 2) {
+            const int jt = i / n_qt, g = i - jt * n_qt;
+            const uint32_t ph = (i >> 1) & 1;
+            const int tok0 = tile_tok0(jt, g);
+            // rows of this warp: tokens tok0 + 32 q .. + 31; the tile's own tokens are [g * 128, nq)
+            const bool warp_has_rows = tok0 + q * 32 + 31 >= g * 128 && tok0 + q * 32 < a.nq;
+            ATC6_TRACE(wg, 4 * (i >> 1));
+            ptx::mbar_wait(&s_full[wg], ph, 67);
+            ATC6_TRACE(wg, 4 * (i >> 1) + 1);
+            ptx::tc_fence_after();
+            if (warp_has_rows) {
+                // ---- pass 1: row maximum ----
+                float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                int c0 = 0;
+#pragma unroll
+                for (; c0 + 64 <= S_pad; c0 += 64) {
+                    if (c0 + 64 <= a.nk) sm6_max_piece<64, false>(t_row + c0, c0, a.nk, m);
+                    else sm6_max_piece<64, true>(t_row + c0, c0, a.nk, m);
+                }
+                if (S_pad - c0 >= 32) {
+                    if (c0 + 32 <= a.nk) sm6_max_piece<32, false>(t_row + c0, c0, a.nk, m);
+                    else sm6_max_piece<32, true>(t_row + c0, c0, a.nk, m);
+                    c0 += 32;
+                }
+                if (S_pad - c0 >= 16) {
+                    if (c0 + 16 <= a.nk) sm6_max_piece<16, false>(t_row + c0, c0, a.nk, m);
+                    else sm6_max_piece<16, true>(t_row + c0, c0, a.nk, m);
+                }
+                ATC6_TRACE(wg, 4 * (i >> 1) + 2);
+                const float nms = -fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * scale;
+                const uint64_t negms2 = pk2f(nms, nms);
+                // ---- pass 2: P (fp16) over the first half of the score columns, row sum ----
+                uint64_t lsum = pk2f(0.f, 0.f);
+                c0 = 0;
+#pragma unroll
+                for (; c0 + 64 <= S_pad; c0 += 64) {
+                    if (c0 + 64 <= a.nk) sm6_exp_piece<64, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                    else sm6_exp_piece<64, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                }
+                if (S_pad - c0 >= 32) {
+                    if (c0 + 32 <= a.nk) sm6_exp_piece<32, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                    else sm6_exp_piece<32, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                    c0 += 32;
+                }
+                if (S_pad - c0 >= 16) {
+                    if (c0 + 16 <= a.nk) sm6_exp_piece<16, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                    else sm6_exp_piece<16, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                }
+                float l0, l1;
+                upk2f(lsum, l0, l1);
+                lsm[(i & 3) * 128 + q * 32 + lane] = l0 + l1;      // read by the epilogue warp of the same lane quarter after o_full
+                ptx::tc_wait_st();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&p_full[wg]);
+            ATC6_TRACE(wg, 4 * (i >> 1) + 3);
+        }
+    } else {
+        // ---------------- epilogue warpgroup: O / L -> fp16 -> global ----------------
+        const int q = warp & 3;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int i = 0; i < n_tiles; ++i) {
+            const int jt = i / n_qt, g = i - jt * n_qt;
+            const int job = blockIdx.x + jt * gridDim.x;
+            const int b = job / heads, h = job - b * heads;
+            const int tok = tile_tok0(jt, g) + q * 32 + lane;     // token inside the query window
+            ATC6_TRACE(3, 4 * i);
+            ptx::mbar_wait(o_full, i & 1, 68);
+            ATC6_TRACE(3, 4 * i + 1);
+            ptx::tc_fence_after();
+            uint32_t o[64];
+            ptx::tmem_ld_32x32(t_row + ATC6_O_COL, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+            ptx::tmem_ld_32x32(t_row + ATC6_O_COL + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+            const float lsum = lsm[(i & 3) * 128 + q * 32 + lane];
+            ptx::tc_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_relaxed(o_empty);    // the values are in registers: P.V of the next tile may overwrite O
+            ATC6_TRACE(3, 4 * i + 2);
+            if (tok >= g * 128 && tok < a.nq) {
+                const float inv = 1.0f / lsum;
+                uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * S + a.q0 + tok) * a.out_ld + h * 64);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * j + e]) * inv;
+                    const uint4 hi4 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                    dst[j] = hi4;
+                    if (a.split_lo) {
+                        const uint32_t hw[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+                        uint32_t lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                            lw[e] = pack_h2(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+                        }
+                        dst[(D >> 3) + j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);   // + D halfs = D / 8 uint4
+                    }
+                }
+            }
+            ATC6_TRACE(3, 4 * i + 3);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+template <int EMU, int NC>
+int launch_attn6(ap_ctx* ctx, const AttnPlan* plan, __half* out, const AttnArgs& a, int grid, cudaStream_t stream) {
+    auto kern = attention_tc6_kernel<EMU, NC>;
+    const size_t n_qt = (a.nq + 127) / 128;
+    const size_t smem = 2 * (n_qt * (size_t)Q_TILE_BYTES + 2 * (size_t)a.S_pad * 128) + 2048 + 15 * 8 + 16 + 1024;
+    static PerDeviceOnce attr;   // per instantiation
+    if (attr.need(ctx->device)) {
+        const int max_smem = 2 * (2 * Q_TILE_BYTES + 2 * 208 * 128) + 2048 + 15 * 8 + 16 + 1024;
+        AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr.done(ctx->device);
+    }
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(kern, dim3(grid), dim3(ATC6_THREADS), smem, stream, 1, ctx->pdl != 0, plan->map_q, plan->map_kv, out, a));
+    return AP_OK;
+}
+
 template <int NC, bool XK>
 int launch_attn(ap_ctx* ctx, const AttnPlan* plan, const __half* qkv, __half* out, const AttnArgs& a, int grid, size_t smem,
                 cudaStream_t stream) {
@@ -530,7 +950,15 @@ int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, i
     {
         ProfScope prof(ctx, stream, AP_K_ATTENTION);
         const bool generic = (ctx->attn_variant & 16) != 0;
-        if (plan->xkey >= 0) {
+        if (plan->xkey < 0 && S_pad <= 208 && plan->nq <= 256 && !(ctx->attn_variant & 32)) {   // two score tiles + a free-standing O fit TMEM
+            const int emu = ctx->attn_emu;
+            if (S_pad == 208 && !generic) {     // 197 tokens (ViT/16 @ 224)
+                rc = emu == 0 ? launch_attn6<0, 13>(ctx, plan, out, a, grid, stream) : emu <= 4 ? launch_attn6<4, 13>(ctx, plan, out, a, grid, stream)
+                     : emu <= 6 ? launch_attn6<6, 13>(ctx, plan, out, a, grid, stream) : launch_attn6<8, 13>(ctx, plan, out, a, grid, stream);
+            } else {
+                rc = emu == 0 ? launch_attn6<0, 0>(ctx, plan, out, a, grid, stream) : launch_attn6<6, 0>(ctx, plan, out, a, grid, stream);
+            }
+        } else if (plan->xkey >= 0) {
             if (S_pad == 256 && !generic) rc = launch_attn<16, true>(ctx, plan, plan->qkv, out, a, grid, smem, stream);
             else rc = launch_attn<0, true>(ctx, plan, plan->qkv, out, a, grid, smem, stream);
         } else if (S_pad == 208 && !generic) {   // 197 tokens (ViT/16 @ 224): register-resident single-pass softmax
@@ -541,5 +969,13 @@ int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, i
         if (rc) return rc;
         AP_CHECK_LAUNCH(ctx, "attention_tc_kernel");
     }
+    return AP_OK;
+}
+
+// diagnostics, not part of the public header: the clock64() trace block 0 of attention_tc6_kernel records with attn_variant bit 128
+extern "C" int ap_debug_attn6_trace(ap_ctx* ctx, long long* host_out) {
+    DeviceGuard guard(ctx);
+    AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    AP_CHECK_CUDA(ctx, cudaMemcpyFromSymbol(host_out, g_attn6_trace, sizeof(long long) * 4 * ATC6_TRACE_N));
     return AP_OK;
 }

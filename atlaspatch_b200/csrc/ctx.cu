@@ -85,7 +85,7 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         return AP_OK;
     }
     if (!strcmp(key, "precise_aw_layers")) {
-        AP_REQUIRE(ctx, value >= 0, "precise_aw_layers must be >= 0");
+        AP_REQUIRE(ctx, value >= -1, "precise_aw_layers must be >= -1 (-1 = automatic)");
         ctx->precise_aw_layers = value;
         return AP_OK;
     }
@@ -115,6 +115,11 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
     if (!strcmp(key, "precise_mask")) {   // read at ap_encoder_finalize
         AP_REQUIRE(ctx, value >= 0 && value <= 15, "precise_mask must be in [0, 15]");
         ctx->precise_mask = value;
+        return AP_OK;
+    }
+    if (!strcmp(key, "attn_emu")) {
+        AP_REQUIRE(ctx, value >= 0 && value <= 8, "attn_emu must be in [0, 8]");
+        ctx->attn_emu = value;
         return AP_OK;
     }
     if (!strcmp(key, "attn_variant")) {

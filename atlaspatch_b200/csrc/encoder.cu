@@ -285,10 +285,12 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     e->kpe = 3 * desc->patch * desc->patch;
     e->kpe_pad = (e->kpe + 63) / 64 * 64;
     e->max_batch = desc->max_batch > 0 ? desc->max_batch : 127;
-    // default: 1 layer (DESIGN.md "precision"); 20 for models deeper than 32 layers (DINOv2 giant: 40 layers of fp16 roundings put
-    // its worst golden row -- an 83 % black overhang patch -- at 1.31e-3 with 1 split layer, 1.09e-3 with 8, 0.97e-3 with 20; every
-    // golden row has to be inside 1e-3 at the default, tools/dinov2_precision.py)
-    const int default_precise = desc->layers > 32 ? 20 : 1;
+    // default: 1 layer with hi/lo split weights (DESIGN.md "precision").  Models deeper than 32 layers (DINOv2 giant: 40 layers of
+    // fp16 roundings) get 8 leading layers in which the weights AND the A operands of qkv / out_proj / mlp.0 are split (three
+    // products per term, ctx->precise_aw_layers): worst golden row 7.9e-4 (83 % black overhang patch), against 1.19e-3 with 20
+    // weight-only layers and 9.1e-4 with 4 + 4 (gpurun_out/r02/giant_precision11.log -> profiles/r02_dinov2_giant_precision.log).
+    // Every golden row has to be inside 1e-3 at the default.
+    const int default_precise = desc->layers > 32 ? 8 : 1;
     e->precise_layers = desc->precise_layers < 0 ? default_precise : (desc->precise_layers > desc->layers ? desc->layers : desc->precise_layers);
     if ((e->tokens + 1) > 272) {
         delete e;
@@ -408,7 +410,8 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
             L.split = i < e->precise_layers ? (pm & ~L.asplit) : 0;
         } else {                 // weights split; in the first precise_aw_layers layers the A operands as well (three products per term)
             L.split = i < e->precise_layers ? pm : 0;
-            L.asplit = (i < e->precise_layers && i < ctx->precise_aw_layers && a_ok) ? (pm & 7) : 0;
+            const int aw = ctx->precise_aw_layers >= 0 ? ctx->precise_aw_layers : (e->d.layers > 32 ? 8 : 0);
+            L.asplit = (i < e->precise_layers && i < aw && a_ok) ? (pm & 7) : 0;
         }
         std::vector<float> wq(*wqkv), bq(*bqkv), wf(*w1), bf1(*b1);
         if (e->fold_ln) {

@@ -91,7 +91,7 @@ def test_matches_transformers_golden(name):
     rel = np.linalg.norm(got - g["feats"], axis=1) / np.linalg.norm(g["feats"], axis=1)
     print(name, "default precise_layers: max rel", rel.max(), "mean", rel.mean())
     ext.cleanup()
-    # every golden row, at the library's default setting, under the stated tolerance.  For the 40-layer giant the default is 20
-    # leading layers with hi/lo split weights (+50 % GEMM FLOPs): the last case row is 83 % black overhang (hundreds of
-    # near-identical tokens -> coherent rounding errors) and sits at 1.09e-3 with 8 split layers.
+    # every golden row, at the library's default setting, under the stated tolerance.  For the 40-layer giant the default is 8
+    # leading layers with hi/lo split weights AND split A operands: the last case row is 83 % black overhang (hundreds of
+    # near-identical tokens -> coherent rounding errors) and sits at 7.9e-4 there.
     assert rel.max() < 1e-3, rel

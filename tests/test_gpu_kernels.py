@@ -112,6 +112,9 @@ def test_layernorm(ctx, rows, D):
     assert (out.float() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
+DEFAULT_ATTN_EMU = 0   # library default of ap_set_option("attn_emu")
+
+
 # (64, 197, 12), (30, 257, 16): several jobs per CTA (the two-buffer tile pipeline wraps its stages / phases many times);
 # (200, 50, 12), (300, 130, 2): one / two query tiles with fewer than 128 keys; 257 = 256 MMA keys + the class token as the extra key
 @pytest.mark.parametrize("amp", [1.5, 6.0])
@@ -132,19 +135,25 @@ def test_attention(ctx, B, S, heads, amp):
     assert (got - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("variant", [16])   # 16: the generic run-time (two-pass) kernel instead of the register-resident instantiations
-@pytest.mark.parametrize("B,S,heads", [(64, 197, 12), (30, 257, 16), (3, 197, 4)])
-def test_attention_kernel_variants(ctx, B, S, heads, variant):
+# variant 16: the generic run-time (two-pass) kernel instead of the register-resident instantiations; 32: the round-1/2 pipeline with
+# O inside the score buffer instead of the free-standing-O pipeline (<= 208 keys); 64: no flipped second query tile;
+# emu: exponential pairs per 16 evaluated by the FMA-pipe polynomial instead of MUFU
+@pytest.mark.parametrize("variant,emu", [(16, 0), (32, 0), (48, 0), (64, 0), (0, 0), (0, 4), (0, 6), (0, 8), (64, 8)])
+@pytest.mark.parametrize("B,S,heads,amp", [(64, 197, 12, 2.0), (30, 257, 16, 2.0), (3, 197, 4, 2.0), (200, 50, 12, 6.0), (300, 130, 2, 6.0),
+                                           (150, 197, 12, 6.0), (7, 208, 3, 1.0), (9, 193, 5, 3.0)])
+def test_attention_kernel_variants(ctx, B, S, heads, amp, variant, emu):
     D = heads * 64
     g = torch.Generator(device="cuda").manual_seed(B + S + heads)
-    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 2.0).half()
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * amp).half()
     out = torch.full((B * S, D), float("nan"), device="cuda", dtype=torch.float16)
     ctx.set_option("attn_variant", variant)
+    ctx.set_option("attn_emu", emu)
     try:
         ctx.check(ctx.lib.ap_attention_f16(ctx.handle, _p(qkv), _p(out), B, S, heads, _stream()))
         torch.cuda.synchronize()
     finally:
         ctx.set_option("attn_variant", 0)
+        ctx.set_option("attn_emu", DEFAULT_ATTN_EMU)
     q, k, v = qkv.float().view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, D)
     assert torch.isfinite(out.float()).all()

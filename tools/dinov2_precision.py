@@ -47,4 +47,4 @@ for kind, pl, aw in levels:      # kind : precise layers : leading layers with A
     del ext
     torch.cuda.empty_cache()
 ctx.set_option("precise_kind", 0)
-ctx.set_option("precise_aw_layers", 0)
+ctx.set_option("precise_aw_layers", -1)
