@@ -617,6 +617,86 @@ __device__ __forceinline__ void sm6_exp_piece(uint32_t t_src, uint32_t t_dst, in
     }
 }
 
+// ONE pass over W score columns: piece maximum, then P = 2^((s - m_ref) * scale) against the row's running REFERENCE maximum m_ref.
+// m_ref is the exact maximum of the first piece; a later piece only moves it when its own maximum exceeds m_ref by more than 8 in
+// the log2 domain (P would leave [0, 2^8], still far inside fp16), and then the P columns already written are rescaled in TMEM
+// (rare: needs a 256-fold jump of the row's largest probability after the first 64 keys).  Reading the scores once instead of twice
+// is what matters: a warp moves ~51 B/clk TMEM -> registers (2.5 clk per column) and pays ~123 clk per tcgen05.wait::ld
+// (profiles/r02_ldtm_microbench.log), so a second pass over 208 columns costs ~1 000 clk per tile before any arithmetic.
+template <int W, bool MASK, bool FIRST, int EMU>
+__device__ __forceinline__ void sm6_piece(uint32_t t_row, int c0, int nk, float scale, uint64_t scale2, float& m_ref, uint64_t& lsum) {
+    uint32_t r[W];
+    tmem_ld_w<W>(t_row + c0, r);
+    ptx::tc_wait_ld();
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < W; j += 8) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (!MASK) {
+                m[e] = fmaxf(m[e], fmaxf(__uint_as_float(r[j + 2 * e]), __uint_as_float(r[j + 2 * e + 1])));
+            } else {
+                if (c0 + j + 2 * e < nk) m[e] = fmaxf(m[e], __uint_as_float(r[j + 2 * e]));
+                if (c0 + j + 2 * e + 1 < nk) m[e] = fmaxf(m[e], __uint_as_float(r[j + 2 * e + 1]));
+            }
+        }
+    }
+    const float pm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+    if (FIRST) {
+        m_ref = pm;
+    } else {
+        const bool need = pm * scale > fmaf(m_ref, scale, 8.0f);
+        if (__any_sync(0xffffffffu, need)) {      // rare path: move the reference, rescale what this row has written so far
+            ptx::tc_wait_st();                    // the P columns written so far must have landed before they are read back
+            const float new_ref = need ? pm : m_ref;
+            const float f = ex2_mufu((m_ref - new_ref) * scale);          // 1 for the rows that keep their reference
+            const __half2 f2 = __float2half2_rn(f);
+            for (int pc = 0; pc < (c0 >> 1); pc += 16) {                   // c0 is a multiple of 32: whole 16-column groups of packed P
+                uint32_t pr[16];
+                ptx::tmem_ld_32x16(t_row + pc, pr);
+                ptx::tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const __half2 v = __hmul2(*reinterpret_cast<const __half2*>(&pr[j]), f2);
+                    pr[j] = *reinterpret_cast<const uint32_t*>(&v);
+                }
+                ptx::tmem_st_32x16(t_row + pc, pr);
+            }
+            float l0, l1;
+            upk2f(lsum, l0, l1);
+            lsum = pk2f(l0 * f, l1 * f);
+            m_ref = new_ref;
+        }
+    }
+    const float nms = -m_ref * scale;
+    const uint64_t negms2 = pk2f(nms, nms);
+#pragma unroll
+    for (int g = 0; g < W / 16; ++g) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = g * 8 + jj;          // pair index inside the piece
+            const uint64_t x = fma2f(pk2f(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), scale2, negms2);
+            float p0, p1;
+            if ((((j & 15) + 1) * EMU) / 16 > ((j & 15) * EMU) / 16) {
+                ex2_emu2(x, p0, p1);
+            } else {
+                float x0, x1;
+                upk2f(x, x0, x1);
+                p0 = ex2_mufu(x0);
+                p1 = ex2_mufu(x1);
+            }
+            if (MASK) {
+                p0 = (c0 + 2 * j < nk) ? p0 : 0.f;
+                p1 = (c0 + 2 * j + 1 < nk) ? p1 : 0.f;
+            }
+            lsum = add2f(lsum, pk2f(p0, p1));
+            pk[jj] = pack_h2(p0, p1);
+        }
+        ptx::tmem_st_32x8(t_row + (c0 >> 1) + g * 8, pk);
+    }
+}
+
 template <int EMU, int NC>   // NC > 0: S_pad = 16 * NC at compile time (fully unrolled MMA issue), 0: run-time S_pad
 __global__ void __launch_bounds__(ATC6_THREADS, 1)
 attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, __half* __restrict__ out,
@@ -780,42 +860,72 @@ attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             ATC6_TRACE(wg, 4 * (i >> 1) + 1);
             ptx::tc_fence_after();
             if (warp_has_rows) {
-                // ---- pass 1: row maximum ----
-                float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                int c0 = 0;
-#pragma unroll
-                for (; c0 + 64 <= S_pad; c0 += 64) {
-                    if (c0 + 64 <= a.nk) sm6_max_piece<64, false>(t_row + c0, c0, a.nk, m);
-                    else sm6_max_piece<64, true>(t_row + c0, c0, a.nk, m);
-                }
-                if (S_pad - c0 >= 32) {
-                    if (c0 + 32 <= a.nk) sm6_max_piece<32, false>(t_row + c0, c0, a.nk, m);
-                    else sm6_max_piece<32, true>(t_row + c0, c0, a.nk, m);
-                    c0 += 32;
-                }
-                if (S_pad - c0 >= 16) {
-                    if (c0 + 16 <= a.nk) sm6_max_piece<16, false>(t_row + c0, c0, a.nk, m);
-                    else sm6_max_piece<16, true>(t_row + c0, c0, a.nk, m);
-                }
-                ATC6_TRACE(wg, 4 * (i >> 1) + 2);
-                const float nms = -fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * scale;
-                const uint64_t negms2 = pk2f(nms, nms);
-                // ---- pass 2: P (fp16) over the first half of the score columns, row sum ----
+                float m_ref;
                 uint64_t lsum = pk2f(0.f, 0.f);
-                c0 = 0;
-#pragma unroll
-                for (; c0 + 64 <= S_pad; c0 += 64) {
-                    if (c0 + 64 <= a.nk) sm6_exp_piece<64, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
-                    else sm6_exp_piece<64, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
-                }
-                if (S_pad - c0 >= 32) {
-                    if (c0 + 32 <= a.nk) sm6_exp_piece<32, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
-                    else sm6_exp_piece<32, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
-                    c0 += 32;
-                }
-                if (S_pad - c0 >= 16) {
-                    if (c0 + 16 <= a.nk) sm6_exp_piece<16, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
-                    else sm6_exp_piece<16, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                int c0 = 0;
+                if (a.variant & 512) {
+                    // ---- two passes (diagnostics): exact row maximum first ----
+                    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    for (; c0 + 64 <= S_pad; c0 += 64) {
+                        if (c0 + 64 <= a.nk) sm6_max_piece<64, false>(t_row + c0, c0, a.nk, m);
+                        else sm6_max_piece<64, true>(t_row + c0, c0, a.nk, m);
+                    }
+                    if (S_pad - c0 >= 32) {
+                        if (c0 + 32 <= a.nk) sm6_max_piece<32, false>(t_row + c0, c0, a.nk, m);
+                        else sm6_max_piece<32, true>(t_row + c0, c0, a.nk, m);
+                        c0 += 32;
+                    }
+                    if (S_pad - c0 >= 16) {
+                        if (c0 + 16 <= a.nk) sm6_max_piece<16, false>(t_row + c0, c0, a.nk, m);
+                        else sm6_max_piece<16, true>(t_row + c0, c0, a.nk, m);
+                    }
+                    ATC6_TRACE(wg, 4 * (i >> 1) + 2);
+                    const float nms = -fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * scale;
+                    const uint64_t negms2 = pk2f(nms, nms);
+                    c0 = 0;
+                    for (; c0 + 64 <= S_pad; c0 += 64) {
+                        if (c0 + 64 <= a.nk) sm6_exp_piece<64, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                        else sm6_exp_piece<64, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                    }
+                    if (S_pad - c0 >= 32) {
+                        if (c0 + 32 <= a.nk) sm6_exp_piece<32, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                        else sm6_exp_piece<32, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                        c0 += 32;
+                    }
+                    if (S_pad - c0 >= 16) {
+                        if (c0 + 16 <= a.nk) sm6_exp_piece<16, false, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                        else sm6_exp_piece<16, true, EMU>(t_row + c0, t_row + (c0 >> 1), c0, a.nk, scale2, negms2, lsum);
+                    }
+                } else {
+                    // ---- one pass with a lazily moved reference maximum (sm6_piece) ----
+                    if (S_pad >= 64) {
+                        if (64 <= a.nk) sm6_piece<64, false, true, EMU>(t_row, 0, a.nk, scale, scale2, m_ref, lsum);
+                        else sm6_piece<64, true, true, EMU>(t_row, 0, a.nk, scale, scale2, m_ref, lsum);
+                        c0 = 64;
+                        for (; c0 + 64 <= S_pad; c0 += 64) {
+                            if (c0 + 64 <= a.nk) sm6_piece<64, false, false, EMU>(t_row, c0, a.nk, scale, scale2, m_ref, lsum);
+                            else sm6_piece<64, true, false, EMU>(t_row, c0, a.nk, scale, scale2, m_ref, lsum);
+                        }
+                        if (S_pad - c0 >= 32) {
+                            if (c0 + 32 <= a.nk) sm6_piece<32, false, false, EMU>(t_row, c0, a.nk, scale, scale2, m_ref, lsum);
+                            else sm6_piece<32, true, false, EMU>(t_row, c0, a.nk, scale, scale2, m_ref, lsum);
+                            c0 += 32;
+                        }
+                        if (S_pad - c0 >= 16) {
+                            if (c0 + 16 <= a.nk) sm6_piece<16, false, false, EMU>(t_row, c0, a.nk, scale, scale2, m_ref, lsum);
+                            else sm6_piece<16, true, false, EMU>(t_row, c0, a.nk, scale, scale2, m_ref, lsum);
+                        }
+                    } else if (S_pad >= 32) {
+                        if (32 <= a.nk) sm6_piece<32, false, true, EMU>(t_row, 0, a.nk, scale, scale2, m_ref, lsum);
+                        else sm6_piece<32, true, true, EMU>(t_row, 0, a.nk, scale, scale2, m_ref, lsum);
+                        if (S_pad >= 48) {
+                            if (48 <= a.nk) sm6_piece<16, false, false, EMU>(t_row, 32, a.nk, scale, scale2, m_ref, lsum);
+                            else sm6_piece<16, true, false, EMU>(t_row, 32, a.nk, scale, scale2, m_ref, lsum);
+                        }
+                    } else {
+                        if (16 <= a.nk) sm6_piece<16, false, true, EMU>(t_row, 0, a.nk, scale, scale2, m_ref, lsum);
+                        else sm6_piece<16, true, true, EMU>(t_row, 0, a.nk, scale, scale2, m_ref, lsum);
+                    }
                 }
                 float l0, l1;
                 upk2f(lsum, l0, l1);
