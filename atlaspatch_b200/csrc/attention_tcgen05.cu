@@ -165,47 +165,67 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         __syncwarp();
       } else if (warp == 1) {
-        if (lane == 0 && n_tiles > 0) {
+        // The whole warp polls and one ELECTED lane issues: warp-uniform control flow keeps the descriptor arithmetic on the uniform
+        // datapath (issued from a `lane == 0` branch every tcgen05.mma operand needed an R2UR round trip: ~70 clk per MMA, see
+        // attention_tc6_kernel).  The polled results are made uniform with a vote, since lanes may observe a barrier flip at different times.
+        if (n_tiles > 0) {
             const uint32_t idesc_s = ptx::make_idesc_f16(128, S_pad);
             const uint32_t idesc_o = ptx::make_idesc_f16(128, 64, false, true);
             const int k_steps_pv = S_pad / 16;
             // ---- tile i: S = Q_g K^T into buffer i & 1 ----
             auto s_ready = [&](int i) -> bool {
                 const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
-                if (g == 0 && !ptx::mbar_try_wait(&qk_full[st], (jt >> 1) & 1)) return false;
-                return ptx::mbar_try_wait(&o_empty[buf], (((i >> 1) & 1) ^ 1));   // the buffer's previous tile has been drained
+                bool ok = true;
+                if (g == 0) ok = ptx::mbar_try_wait(&qk_full[st], (jt >> 1) & 1);
+                if (ok) ok = ptx::mbar_try_wait(&o_empty[buf], (((i >> 1) & 1) ^ 1));   // the buffer's previous tile has been drained
+                return __all_sync(0xffffffffu, ok);
             };
             auto issue_s = [&](int i) {
                 const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
                 uint8_t* sb = smem + st * stage_bytes;
                 ptx::tc_fence_after();
-                const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes));
-                const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + g * Q_TILE_BYTES));
+                if (ptx::elect_one()) {
+                    const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes));
+                    const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + g * Q_TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::tc_mma_f16<1>(tmem_base + buf * 256, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-                ptx::tc_commit<1>(&s_full[buf]);
-                if (g == n_qt - 1) ptx::tc_commit<1>(&qk_empty[st]);   // Q and K of this stage are free once the S MMAs retire
+                    for (int k = 0; k < 4; ++k)
+                        ptx::tc_mma_f16<1>(tmem_base + buf * 256, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                    ptx::tc_commit<1>(&s_full[buf]);
+                    if (g == n_qt - 1) ptx::tc_commit<1>(&qk_empty[st]);   // Q and K of this stage are free once the S MMAs retire
+                }
+                __syncwarp();
             };
             // ---- tile i: O = P V ----
             auto pv_ready = [&](int i) -> bool {
                 const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
-                if (g == 0 && !ptx::mbar_try_wait(&v_full[st], (jt >> 1) & 1)) return false;
-                return ptx::mbar_try_wait(&p_full[buf], (i >> 1) & 1);
+                bool ok = true;
+                if (g == 0) ok = ptx::mbar_try_wait(&v_full[st], (jt >> 1) & 1);
+                if (ok) ok = ptx::mbar_try_wait(&p_full[buf], (i >> 1) & 1);
+                return __all_sync(0xffffffffu, ok);
             };
             auto issue_pv = [&](int i) {
                 const int jt = i / n_qt, g = i - jt * n_qt, st = jt & 1, buf = i & 1;
                 uint8_t* sb = smem + st * stage_bytes;
                 ptx::tc_fence_after();
-                const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes + kv_bytes), 64);
-                constexpr int NA = (NC + 1) / 2;
-                for (int ks = 0; ks < k_steps_pv; ++ks) {   // 16 keys per step: 8 TMEM columns of P, two 8-key groups (2 KB) of V
-                    const bool half_b = NC > 0 && ks >= NA;   // second half of the keys accumulates into O_b
-                    ptx::tc_mma_f16_ts(tmem_base + buf * 256 + (half_b ? 192 : 128), tmem_base + buf * 256 + ks * 8, v_desc + ks * 128,
-                                       idesc_o, (ks != 0 && !(NC > 0 && ks == NA)) ? 1u : 0u);
+                if (ptx::elect_one()) {
+                    const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes + kv_bytes), 64);
+                    constexpr int NA = (NC + 1) / 2;
+                    if (NC > 0) {
+#pragma unroll
+                        for (int ks = 0; ks < (NC > 0 ? NC : 1); ++ks) {   // 16 keys per step: 8 TMEM columns of P, two 8-key groups (2 KB) of V
+                            const bool half_b = ks >= NA;                   // second half of the keys accumulates into O_b
+                            ptx::tc_mma_f16_ts(tmem_base + buf * 256 + (half_b ? 192 : 128), tmem_base + buf * 256 + ks * 8, v_desc + ks * 128,
+                                               idesc_o, (ks != 0 && ks != NA) ? 1u : 0u);
+                        }
+                    } else {
+                        for (int ks = 0; ks < k_steps_pv; ++ks)
+                            ptx::tc_mma_f16_ts(tmem_base + buf * 256 + 128, tmem_base + buf * 256 + ks * 8, v_desc + ks * 128, idesc_o,
+                                               ks != 0 ? 1u : 0u);
+                    }
+                    ptx::tc_commit<1>(&o_full[buf]);
+                    if (g == n_qt - 1) ptx::tc_commit<1>(&v_empty[st]);
                 }
-                ptx::tc_commit<1>(&o_full[buf]);
-                if (g == n_qt - 1) ptx::tc_commit<1>(&v_empty[st]);
+                __syncwarp();
             };
             long long t0 = clock64();
             while (!s_ready(0)) spin_guard(t0, 21);
@@ -216,11 +236,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 while (!pv_done || !s_done) {
                     if (!s_done && s_ready(i + 1)) { issue_s(i + 1); s_done = true; }
                     if (!pv_done && pv_ready(i)) { issue_pv(i); pv_done = true; }
-                    spin_guard(t0, 22);
+                    if (lane == 0) spin_guard(t0, 22);
                 }
             }
         }
-        __syncwarp();
       }
     } else {
         const int wg = (warp - 4) >> 2;   // softmax warpgroup = TMEM buffer
