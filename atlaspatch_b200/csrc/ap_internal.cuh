@@ -25,7 +25,9 @@ struct ap_ctx {
     void* encode_tiled = nullptr;
     int fold_ln = 1;              // LayerNorm folded into the GEMMs around it: 0 off, 1 automatic (<= 32 layers), 2 on (read at
                                   // ap_encoder_finalize; "fold_ln"; encoder.cu)
-    int sam_tensor_cores = 1;     // SAM2 linears on mma.sync: 1 split-fp16 operands (3 MMAs, fp32-like), 2 plain fp16 (1 MMA), 0 fp32 SIMT
+    int sam_tensor_cores = 3;     // SAM2 linears: 3 tcgen05 GEMM with split-fp16 operands (A_hi W_hi + A_lo W_hi + A_hi W_lo), 1 the same
+                                  // three products on mma.sync, 2 plain fp16 on mma.sync (1 MMA, not pinnable), 0 fp32 SIMT
+    void* sam_state = nullptr;    // sam2_kernels.cu: split-weight cache + scratch of the tcgen05 linears (sam_state_free)
     int precise_mask = 15;        // which GEMMs of the precise layers get hi/lo split operands: 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
     int precise_kind = 0;         // what is split there: 0 the weights, 1 the A operands of qkv / out_proj / mlp.0 (+ mlp.3's weights)
                                   // ("precise_kind"; encoder.cu: ap_encoder_finalize; measured: profiles/r02_dinov2_giant_precision.log)
@@ -59,6 +61,7 @@ struct ProfScope {
 };
 
 int ap_set_error(ap_ctx* ctx, int code, const char* fmt, ...);
+void sam_state_free(ap_ctx* ctx);   // sam2_kernels.cu
 
 // Every C-ABI entry runs on ITS context's device whatever the calling thread's current device is (another thread, or torch having
 // switched devices since ap_init), and leaves the caller's current device as it found it.

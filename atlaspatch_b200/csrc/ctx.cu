@@ -109,7 +109,8 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
         return AP_OK;
     }
     if (!strcmp(key, "sam_tensor_cores")) {
-        ctx->sam_tensor_cores = value;   // 0: fp32 SIMT, 1: split-fp16 (3 MMAs, fp32-like), 2: plain fp16 operands (1 MMA)
+        AP_REQUIRE(ctx, value >= 0 && value <= 3, "sam_tensor_cores must be 0..3");
+        ctx->sam_tensor_cores = value;   // 3: tcgen05 split GEMM, 1: mma.sync split-fp16, 2: mma.sync plain fp16, 0: fp32 SIMT
         return AP_OK;
     }
     if (!strcmp(key, "precise_mask")) {   // read at ap_encoder_finalize
@@ -135,6 +136,7 @@ extern "C" int ap_set_option(ap_ctx* ctx, const char* key, int value) {
 
 extern "C" int ap_destroy(ap_ctx* ctx) {
     if (ctx) {
+        sam_state_free(ctx);
         for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
         for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     }

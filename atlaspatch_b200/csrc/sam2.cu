@@ -138,6 +138,7 @@ extern "C" int ap_sam2_destroy(ap_sam2* s) {
     if (!s) return AP_OK;
     DeviceGuard guard(s->ctx);
     cudaDeviceSynchronize();
+    sam_state_free(s->ctx);   // the split-weight cache is keyed by this model's (about to be freed) weight pointers
     for (void* p : s->allocs) cudaFree(p);
     if (s->img_dev) cudaFree(s->img_dev);
     delete s;

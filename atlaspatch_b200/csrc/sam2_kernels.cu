@@ -6,6 +6,8 @@
 // Layout everywhere: tokens x channels, row-major ("NHWC").
 #include "ap_internal.cuh"
 #include "ptx.cuh"
+#include <unordered_map>
+
 #include "sam2_internal.cuh"
 
 namespace {
@@ -440,11 +442,172 @@ inline unsigned blocks_for(int64_t n, int t = 256) { return static_cast<unsigned
 
 #define SAM_LAUNCH_CHECK(ctx, what) AP_CHECK_LAUNCH(ctx, what)
 
+// ---- linears on the tcgen05 GEMM (gemm_tcgen05.cu) -----------------------------------------------------------------------------------
+// The activations of this path are fp32 and its oracle amplifies a per-layer error ~1000x over Hiera's 48 blocks, so
+// every product keeps ~22 significant bits: x = hi + lo (two fp16), A_hi W_hi + A_lo W_hi + A_hi W_lo as ONE GEMM whose contraction
+// runs over three K segments (GemmPlan: AP_SPLIT_AW), fp32 accumulation in TMEM.
+//   1. sam_split_a_kernel: A fp32 [M, lda] -> [A_hi | A_lo] fp16 [M, 2 K_pad]   (K padded to the GEMM's 64-column TMA box with zeros)
+//   2. gemm_tcgen05_kernel: x [W_hi | W_lo] fp16 [N_pad, 2 K_pad] (split once per weight, scaled by 256 so that lo stays normal;
+//      the epilogue multiplies by 1/256), bias, fp32 out (+ residual when the output needs no de-padding / activation)
+//   3. sam_finish_kernel: activation / accumulate / de-padding when N is not a multiple of 128 or an activation follows
+namespace {
+
+struct SamWSplit {
+    __half* w = nullptr;      // [N_pad, 2 K_pad]
+    float* bias = nullptr;    // [N_pad]
+    int N_pad = 0, K_pad = 0;
+};
+struct SamState {
+    std::unordered_map<const void*, SamWSplit> weights;
+    void* a_buf = nullptr; size_t a_cap = 0;      // split A operand
+    void* o_buf = nullptr; size_t o_cap = 0;      // padded fp32 output
+};
+
+constexpr float SAM_W_SCALE = 256.f;
+
+__global__ void sam_split_w_kernel(const float* __restrict__ W, const float* __restrict__ bias, __half* __restrict__ out, float* __restrict__ bias_out,
+                                   int N, int K, int N_pad, int K_pad) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx < N_pad) bias_out[idx] = (idx < N && bias) ? bias[idx] : 0.f;
+    if (idx >= static_cast<int64_t>(N_pad) * K_pad) return;
+    const int n = static_cast<int>(idx / K_pad), k = static_cast<int>(idx - static_cast<int64_t>(n) * K_pad);
+    const float w = (n < N && k < K) ? W[static_cast<int64_t>(n) * K + k] * SAM_W_SCALE : 0.f;
+    const __half hi = __float2half_rn(w);
+    out[static_cast<int64_t>(n) * 2 * K_pad + k] = hi;
+    out[static_cast<int64_t>(n) * 2 * K_pad + K_pad + k] = __float2half_rn(w - __half2float(hi));
+}
+
+// 8 consecutive k per thread: two float4 in, one uint4 of hi and one of lo out
+__global__ void __launch_bounds__(256)
+sam_split_a_kernel(const float* __restrict__ A, int lda, __half* __restrict__ out, int M, int K, int K_pad) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int kc = K_pad >> 3;
+    if (idx >= static_cast<int64_t>(M) * kc) return;
+    const int m = static_cast<int>(idx / kc), k = static_cast<int>(idx - static_cast<int64_t>(m) * kc) * 8;
+    float v[8];
+    if (k + 8 <= K) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(A + static_cast<int64_t>(m) * lda + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(A + static_cast<int64_t>(m) * lda + k + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = k + e < K ? A[static_cast<int64_t>(m) * lda + k + e] : 0.f;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    __half* row = out + static_cast<int64_t>(m) * 2 * K_pad;
+    *reinterpret_cast<uint4*>(row + k) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(row + K_pad + k) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__device__ __forceinline__ float sam_act(float v, int act) {
+    if (act == SAM_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    if (act == SAM_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+__global__ void sam_finish_kernel(const float* __restrict__ tmp, int ldt, float* __restrict__ C, int ldc, int M, int N, int act, int accumulate) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int nc = N >> 2;   // N % 4 == 0 (checked by the launcher)
+    if (idx >= static_cast<int64_t>(M) * nc) return;
+    const int m = static_cast<int>(idx / nc), n = static_cast<int>(idx - static_cast<int64_t>(m) * nc) * 4;
+    float4 v = *reinterpret_cast<const float4*>(tmp + static_cast<int64_t>(m) * ldt + n);
+    v.x = sam_act(v.x, act); v.y = sam_act(v.y, act); v.z = sam_act(v.z, act); v.w = sam_act(v.w, act);
+    float4* dst = reinterpret_cast<float4*>(C + static_cast<int64_t>(m) * ldc + n);
+    if (accumulate) {
+        const float4 c = *dst;
+        v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+    }
+    *dst = v;
+}
+
+int sam_scratch(ap_ctx* ctx, void** buf, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return AP_OK;
+    // the stream that still uses the old buffer has to drain before it is freed; growth happens a handful of times per model
+    AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(buf, bytes);
+    if (e != cudaSuccess) return ap_set_error(ctx, AP_ENOMEM, "sam2: cudaMalloc(%zu) for the tensor-core linears failed: %s", bytes, cudaGetErrorString(e));
+    *cap = bytes;
+    return AP_OK;
+}
+
+int sam_linear_tcgen05(ap_ctx* ctx, const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, int act,
+                       int accumulate, cudaStream_t st) {
+    if (!ctx->sam_state) ctx->sam_state = new SamState();
+    SamState* ss = static_cast<SamState*>(ctx->sam_state);
+    const int K_pad = (K + 63) / 64 * 64, N_pad = (N + 127) / 128 * 128;
+    auto it = ss->weights.find(W);
+    if (it == ss->weights.end()) {     // first use of this weight: split it once
+        SamWSplit ws;
+        ws.N_pad = N_pad; ws.K_pad = K_pad;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws.w), static_cast<size_t>(N_pad) * 2 * K_pad * sizeof(__half));
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ws.bias), static_cast<size_t>(N_pad) * sizeof(float));
+        if (e != cudaSuccess) return ap_set_error(ctx, AP_ENOMEM, "sam2: cudaMalloc for split weights failed: %s", cudaGetErrorString(e));
+        const int64_t n = static_cast<int64_t>(N_pad) * K_pad;
+        sam_split_w_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(W, bias, ws.w, ws.bias, N, K, N_pad, K_pad);
+        SAM_LAUNCH_CHECK(ctx, "sam_split_w_kernel");
+        it = ss->weights.emplace(W, ws).first;
+    }
+    const SamWSplit& ws = it->second;
+    AP_REQUIRE(ctx, ws.N_pad == N_pad && ws.K_pad == K_pad, "sam2: weight %p reused with another shape", static_cast<const void*>(W));
+    int rc = sam_scratch(ctx, &ss->a_buf, &ss->a_cap, static_cast<size_t>(M) * 2 * K_pad * sizeof(__half));
+    if (rc) return rc;
+    {
+        const int64_t n = static_cast<int64_t>(M) * (K_pad >> 3);
+        sam_split_a_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(A, lda, static_cast<__half*>(ss->a_buf), M, K, K_pad);
+        SAM_LAUNCH_CHECK(ctx, "sam_split_a_kernel");
+    }
+    const bool direct = N == N_pad && ldc == N && act == SAM_ACT_NONE;
+    float* out = C;
+    if (!direct) {
+        rc = sam_scratch(ctx, &ss->o_buf, &ss->o_cap, static_cast<size_t>(M) * N_pad * sizeof(float));
+        if (rc) return rc;
+        out = static_cast<float*>(ss->o_buf);
+    }
+    GemmPlan plan;
+    rc = ap_gemm_plan_split(ctx, &plan, ss->a_buf, ws.w, M, N_pad, K_pad, (direct && accumulate) ? AP_EPI_BIAS_RESID_F32 : AP_EPI_BIAS_F32, AP_SPLIT_AW);
+    if (rc) return rc;
+    GemmExtra ex;
+    ex.alpha = 1.0f / SAM_W_SCALE;
+    rc = ap_gemm_run(ctx, &plan, ws.bias, (direct && accumulate) ? C : nullptr, out, &ex, st);
+    if (rc) return rc;
+    if (!direct) {
+        const int64_t n = static_cast<int64_t>(M) * (N >> 2);
+        sam_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(out, N_pad, C, ldc, M, N, act, accumulate);
+        SAM_LAUNCH_CHECK(ctx, "sam_finish_kernel");
+    }
+    return AP_OK;
+}
+
+}  // namespace
+
+void sam_state_free(ap_ctx* ctx) {
+    if (!ctx || !ctx->sam_state) return;
+    SamState* ss = static_cast<SamState*>(ctx->sam_state);
+    cudaDeviceSynchronize();
+    for (auto& kv : ss->weights) { cudaFree(kv.second.w); cudaFree(kv.second.bias); }
+    if (ss->a_buf) cudaFree(ss->a_buf);
+    if (ss->o_buf) cudaFree(ss->o_buf);
+    delete ss;
+    ctx->sam_state = nullptr;
+}
+
 int sam_linear(ap_ctx* ctx, const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, int act,
                int accumulate, cudaStream_t st) {
     if (M == 0) return AP_OK;
     const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0 && lda % 4 == 0 && K % 4 == 0;
-    if (ctx->sam_tensor_cores && aligned && M >= 64) {
+    // tcgen05 GEMM: whole 128-row tiles are worth it from a few hundred rows on; the 9-token decoder linears stay on the SIMT kernel
+    if (ctx->sam_tensor_cores == 3 && aligned && M >= 256 && N % 4 == 0 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0)
+        return sam_linear_tcgen05(ctx, A, lda, W, bias, C, ldc, M, N, K, act, accumulate, st);
+    if (ctx->sam_tensor_cores && ctx->sam_tensor_cores != 3 && aligned && M >= 64) {
         static PerDeviceOnce attr;
         if (attr.need(ctx->device)) {
             AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
