@@ -391,6 +391,153 @@ sam_attention_kernel(const float* __restrict__ q, int q_stride, const float* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention on the tensor cores with fp32-like operands (round 2).  Same contract as sam_attention_kernel.  Flash-attention
+// structure on mma.sync.m16n8k16: CTA = 64 queries of one (batch, head) = 4 warps x 16 rows; keys in tiles of 64 with an online
+// softmax in the accumulator registers.  Every operand is an fp16 pair x = hi + lo (the oracle's random Hiera amplifies a per-layer
+// error ~1000x, see sam_linear_tcgen05) and every product three MMAs:  S = Q_hi K_hi + Q_lo K_hi + Q_hi K_lo,
+// O += P_hi V_hi + P_lo V_hi + P_hi V_lo.  q / k / v are fp32 in global memory and are split while they are staged into shared
+// memory; the softmax scale (times log2 e) is folded into Q.  HDS = head_dim padded to 16, in k16 steps (72 -> 5, 96 -> 6, 32 -> 2,
+// 16 -> 1); padded columns are zero.  head_dim 72 at 4096 x 4096 tokens: 2.7 ms (SIMT) -> see profiles/r02_sam2_hiera_l_launches.md.
+// (tcgen05 would want a TMEM-resident O with online rescaling and fp16 Q / K / V buffers; this path runs once per slide.)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int HDS>
+__global__ void __launch_bounds__(128)
+sam_attention_tc_kernel(const float* __restrict__ q, int q_stride, const float* __restrict__ k, const float* __restrict__ v, int kv_stride,
+                        float* __restrict__ out, int out_stride, int Lq, int Lk, int heads, int hd, float scale_log2) {
+    constexpr int HDP = HDS * 16, PITCH = HDP + 8;           // halfs per smem row; +16 B keeps ldmatrix conflict-free
+    constexpr int NT_O = HDP / 8;                            // n8 tiles of the output
+    extern __shared__ __align__(16) __half sm_att[];
+    __half* sQh = sm_att;                    // [64][PITCH]
+    __half* sQl = sQh + 64 * PITCH;
+    __half* sKh = sQl + 64 * PITCH;
+    __half* sKl = sKh + 64 * PITCH;
+    __half* sVh = sKl + 64 * PITCH;
+    __half* sVl = sVh + 64 * PITCH;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* qb = q + static_cast<int64_t>(b) * Lq * q_stride + h * hd;
+    const float* kb = k + static_cast<int64_t>(b) * Lk * kv_stride + h * hd;
+    const float* vb = v + static_cast<int64_t>(b) * Lk * kv_stride + h * hd;
+    // stage a [64][hd] fp32 tile as hi / lo fp16, 4 columns per thread and step (hd % 4 == 0, 16-byte aligned rows: checked by the launcher)
+    auto stage = [&](const float* base, int64_t stride, int row0, int nrows, float mul, __half* dh, __half* dl) {
+        constexpr int C4 = HDP / 4;
+        for (int i = tid; i < 64 * C4; i += 128) {
+            const int r = i / C4, c = (i - r * C4) * 4;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < nrows && c < hd) x = __ldg(reinterpret_cast<const float4*>(base + static_cast<int64_t>(row0 + r) * stride + c));
+            x.x *= mul; x.y *= mul; x.z *= mul; x.w *= mul;
+            const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            const __half2 l0 = __floats2half2_rn(x.x - f0.x, x.y - f0.y), l1 = __floats2half2_rn(x.z - f1.x, x.w - f1.y);
+            *reinterpret_cast<uint2*>(dh + r * PITCH + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            *reinterpret_cast<uint2*>(dl + r * PITCH + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+    };
+    stage(qb, q_stride, q0, Lq, scale_log2, sQh, sQl);
+    __syncthreads();
+    // Q fragments of this warp's 16 rows (A operand, row-major): ldmatrix x4 per k16 step
+    uint32_t qh[HDS][4], ql[HDS][4];
+    {
+        const int r = warp * 16 + (lane & 15), cofs = (lane >> 4) * 8;
+#pragma unroll
+        for (int ks = 0; ks < HDS; ++ks) {
+            ptx::ldmatrix_x4(ptx::smem_u32(sQh + r * PITCH + ks * 16 + cofs), qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3]);
+            ptx::ldmatrix_x4(ptx::smem_u32(sQl + r * PITCH + ks * 16 + cofs), ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3]);
+        }
+    }
+    float o[NT_O][4];
+#pragma unroll
+    for (int j = 0; j < NT_O; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // rows g and g + 8 of the warp's 16 (g = lane / 4)
+    for (int k0 = 0; k0 < Lk; k0 += 64) {
+        __syncthreads();                                            // the previous tile's K / V are no longer read
+        stage(kb, kv_stride, k0, Lk, 1.f, sKh, sKl);
+        stage(vb, kv_stride, k0, Lk, 1.f, sVh, sVl);
+        __syncthreads();
+        // ---- S = Q K^T for 64 keys: 8 n8 tiles ----
+        float sc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < HDS; ++ks) {
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {       // two n8 tiles (16 keys) per ldmatrix x4: rows = keys, 16 consecutive k
+                const int kr = jp * 16 + (lane & 7) + ((lane >> 4) << 3), kc = ks * 16 + ((lane >> 3) & 1) * 8;
+                uint32_t bh[4], bl[4];
+                ptx::ldmatrix_x4(ptx::smem_u32(sKh + kr * PITCH + kc), bh[0], bh[1], bh[2], bh[3]);
+                ptx::ldmatrix_x4(ptx::smem_u32(sKl + kr * PITCH + kc), bl[0], bl[1], bl[2], bl[3]);
+                ptx::mma_m16n8k16_f16(sc[2 * jp], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bh[0], bh[1]);
+                ptx::mma_m16n8k16_f16(sc[2 * jp], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], bh[0], bh[1]);
+                ptx::mma_m16n8k16_f16(sc[2 * jp], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bl[0], bl[1]);
+                ptx::mma_m16n8k16_f16(sc[2 * jp + 1], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bh[2], bh[3]);
+                ptx::mma_m16n8k16_f16(sc[2 * jp + 1], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], bh[2], bh[3]);
+                ptx::mma_m16n8k16_f16(sc[2 * jp + 1], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bl[2], bl[3]);
+            }
+        }
+        // ---- online softmax (log2 domain): thread holds keys 8 j + 2 (lane % 4) + {0, 1} of rows g (c0, c1) and g + 8 (c2, c3) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int key = k0 + 8 * j + 2 * (lane & 3);
+            if (key >= Lk) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+            if (key + 1 >= Lk) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
+            mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);     // finite: every tile holds >= 1 valid key
+        const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);   // 0 on the first tile
+        m0 = mn0; m1 = mn1;
+        float s0 = 0.f, s1 = 0.f;
+        uint32_t ph[4][4], pl[4][4];                                // A fragments of P for the 4 k16 steps over the 64 keys
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = exp2f(sc[j][0] - mn0), p1 = exp2f(sc[j][1] - mn0), p2 = exp2f(sc[j][2] - mn1), p3 = exp2f(sc[j][3] - mn1);
+            s0 += p0 + p1; s1 += p2 + p3;
+            const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(p0 - f01.x, p1 - f01.y), l23 = __floats2half2_rn(p2 - f23.x, p3 - f23.y);
+            const int ks = j >> 1, hi_half = (j & 1) * 2;          // n8 tile 2 ks -> a0 / a1, tile 2 ks + 1 -> a2 / a3
+            ph[ks][hi_half] = *reinterpret_cast<const uint32_t*>(&h01); ph[ks][hi_half + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+            pl[ks][hi_half] = *reinterpret_cast<const uint32_t*>(&l01); pl[ks][hi_half + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+        }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        l0 = l0 * al0 + s0; l1 = l1 * al1 + s1;
+#pragma unroll
+        for (int j = 0; j < NT_O; ++j) { o[j][0] *= al0; o[j][1] *= al0; o[j][2] *= al1; o[j][3] *= al1; }
+        // ---- O += P V: B operand = V^T, taken from the [key][hd] tile with transposing ldmatrix ----
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int jp = 0; jp < NT_O / 2; ++jp) {     // two n8 tiles (16 head-dim columns) per ldmatrix x4.trans
+                const int vr = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, vc = jp * 16 + (lane >> 4) * 8;
+                uint32_t bh[4], bl[4];
+                ptx::ldmatrix_x4_trans(ptx::smem_u32(sVh + vr * PITCH + vc), bh[0], bh[1], bh[2], bh[3]);
+                ptx::ldmatrix_x4_trans(ptx::smem_u32(sVl + vr * PITCH + vc), bl[0], bl[1], bl[2], bl[3]);
+                ptx::mma_m16n8k16_f16(o[2 * jp], ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], bh[0], bh[1]);
+                ptx::mma_m16n8k16_f16(o[2 * jp], pl[ks][0], pl[ks][1], pl[ks][2], pl[ks][3], bh[0], bh[1]);
+                ptx::mma_m16n8k16_f16(o[2 * jp], ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], bl[0], bl[1]);
+                ptx::mma_m16n8k16_f16(o[2 * jp + 1], ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], bh[2], bh[3]);
+                ptx::mma_m16n8k16_f16(o[2 * jp + 1], pl[ks][0], pl[ks][1], pl[ks][2], pl[ks][3], bh[2], bh[3]);
+                ptx::mma_m16n8k16_f16(o[2 * jp + 1], ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], bl[2], bl[3]);
+            }
+        }
+    }
+    const int g = lane >> 2, r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+    for (int j = 0; j < NT_O; ++j) {
+        const int c = 8 * j + 2 * (lane & 3);
+        if (c < hd) {
+            if (r0 < Lq) *reinterpret_cast<float2*>(out + (static_cast<int64_t>(b) * Lq + r0) * out_stride + h * hd + c) = make_float2(o[j][0] * i0, o[j][1] * i0);
+            if (r1 < Lq) *reinterpret_cast<float2*>(out + (static_cast<int64_t>(b) * Lq + r1) * out_stride + h * hd + c) = make_float2(o[j][2] * i1, o[j][3] * i1);
+        }
+    }
+}
+
 // y = a + b (b broadcast over rows when b_rows == 1)
 __global__ void sam_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n, int D, int b_rows) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -652,9 +799,37 @@ int sam_maxpool2(ap_ctx* ctx, const float* x, int ld, float* y, int nB, int H, i
     SAM_LAUNCH_CHECK(ctx, "sam_maxpool2_kernel");
     return AP_OK;
 }
+namespace {
+template <int HDS>
+int launch_sam_attention_tc(ap_ctx* ctx, const float* q, int q_stride, const float* k, const float* v, int kv_stride, float* out, int out_stride,
+                            int nB, int Lq, int Lk, int heads, int hd, float scale, cudaStream_t st) {
+    constexpr size_t smem = sizeof(__half) * 6 * 64 * (HDS * 16 + 8);
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
+        AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_attention_tc_kernel<HDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr.done(ctx->device);
+    }
+    dim3 grid((Lq + 63) / 64, heads, nB);
+    sam_attention_tc_kernel<HDS><<<grid, 128, smem, st>>>(q, q_stride, k, v, kv_stride, out, out_stride, Lq, Lk, heads, hd,
+                                                          scale * 1.44269504088896340736f);
+    SAM_LAUNCH_CHECK(ctx, "sam_attention_tc_kernel");
+    return AP_OK;
+}
+}  // namespace
+
 int sam_attention(ap_ctx* ctx, const float* q, int q_stride, const float* k, const float* v, int kv_stride, float* out, int out_stride, int nB,
                   int Lq, int Lk, int heads, int hd, float scale, cudaStream_t st) {
     AP_REQUIRE(ctx, hd >= 1 && hd <= 128, "sam attention: head_dim %d unsupported", hd);
+    const bool vec_ok = hd % 4 == 0 && q_stride % 4 == 0 && kv_stride % 4 == 0 && out_stride % 2 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    if (ctx->sam_tensor_cores && vec_ok && Lk >= 1) {
+        const int hds = (hd + 15) / 16;
+        if (hds == 5) return launch_sam_attention_tc<5>(ctx, q, q_stride, k, v, kv_stride, out, out_stride, nB, Lq, Lk, heads, hd, scale, st);
+        if (hds == 6) return launch_sam_attention_tc<6>(ctx, q, q_stride, k, v, kv_stride, out, out_stride, nB, Lq, Lk, heads, hd, scale, st);
+        if (hds == 2) return launch_sam_attention_tc<2>(ctx, q, q_stride, k, v, kv_stride, out, out_stride, nB, Lq, Lk, heads, hd, scale, st);
+        if (hds == 1) return launch_sam_attention_tc<1>(ctx, q, q_stride, k, v, kv_stride, out, out_stride, nB, Lq, Lk, heads, hd, scale, st);
+    }
     const size_t smem = sizeof(float) * (static_cast<size_t>(AQ + 2 * AK) * (hd + 1) + AQ * (AK + 1) + 3 * AQ);
     static PerDeviceOnce attr;
     if (attr.need(ctx->device)) {
