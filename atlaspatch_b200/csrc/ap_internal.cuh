@@ -180,6 +180,9 @@ struct GemmExtra {
     int ln_parts = 0;
     int ln_dim = 0;                  // length of the normalised rows (hidden size)
     float ln_eps = 0.f;
+    // AP_EPI_BIAS_F32 only: destination row stride in floats (0 = N), real columns (0 = N; the GEMM's N may be padded to 128),
+    // activation on the fp32 result (0 none, 1 GELU erf, 2 ReLU)
+    int out_ld = 0, n_valid = 0, act = 0;
 };
 int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const float* resid, void* out,
                 const GemmExtra* extra, cudaStream_t stream);

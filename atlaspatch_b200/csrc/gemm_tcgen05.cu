@@ -63,6 +63,8 @@ struct EpiParams {
     const float2* stats_in;
     int ln_parts;
     float ln_inv_dim, ln_eps;
+    // AP_EPI_BIAS_F32 only (the SAM2 linears): output row stride, number of real columns (<= N), activation (0 none, 1 GELU erf, 2 ReLU)
+    int out_ld, n_valid, act;
 };
 
 // Per-row scale of the consumer epilogues: with gamma folded into the weights AND their rows centred (sum_k W''[n, k] = 0, which
@@ -218,7 +220,22 @@ __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], cons
                 v[it].x += pp.x; v[it].y += pp.y; v[it].z += pp.z; v[it].w += pp.w;
             }
         }
-        if (row < M) *(reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * N + col0) + p) = v[it];
+        if (EPI == AP_EPI_BIAS_F32 && ep.act != 0) {   // fp32 activations of the SAM2 path (exact erf GELU / ReLU)
+            if (ep.act == 1) {
+                v[it].x = 0.5f * v[it].x * (1.f + erff(v[it].x * 0.70710678118654752440f));
+                v[it].y = 0.5f * v[it].y * (1.f + erff(v[it].y * 0.70710678118654752440f));
+                v[it].z = 0.5f * v[it].z * (1.f + erff(v[it].z * 0.70710678118654752440f));
+                v[it].w = 0.5f * v[it].w * (1.f + erff(v[it].w * 0.70710678118654752440f));
+            } else {
+                v[it] = make_float4(fmaxf(v[it].x, 0.f), fmaxf(v[it].y, 0.f), fmaxf(v[it].z, 0.f), fmaxf(v[it].w, 0.f));
+            }
+        }
+        if (EPI == AP_EPI_BIAS_F32) {     // row stride and column bound of the destination may differ from the (padded) GEMM N
+            if (row < M && col0 + p * 4 < ep.n_valid)
+                *(reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * ep.out_ld + col0) + p) = v[it];
+        } else if (row < M) {
+            *(reinterpret_cast<float4*>(static_cast<float*>(ep.out) + out_row * N + col0) + p) = v[it];
+        }
         if (fold) {   // the next GEMM's A operand: raw x in fp16 (its LayerNorm is finished in that GEMM's epilogue) + row statistics
             if (row < M)
                 *reinterpret_cast<uint2*>(ep.out_h + out_row * N + col0 + p * 4) =
@@ -620,6 +637,12 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
     ep.ln_parts = extra ? extra->ln_parts : 0;
     ep.ln_inv_dim = extra && extra->ln_dim > 0 ? 1.0f / static_cast<float>(extra->ln_dim) : 0.f;
     ep.ln_eps = extra ? extra->ln_eps : 0.f;
+    ep.out_ld = extra && extra->out_ld > 0 ? extra->out_ld : plan->N;
+    ep.n_valid = extra && extra->n_valid > 0 ? extra->n_valid : plan->N;
+    ep.act = extra ? extra->act : 0;
+    AP_REQUIRE(ctx, (ep.out_ld == plan->N && ep.n_valid == plan->N && ep.act == 0) || (plan->epilogue == AP_EPI_BIAS_F32 && ep.out_h == nullptr &&
+                        ep.tokens_per_image == 0 && ep.n_valid % 4 == 0 && ep.out_ld % 4 == 0 && ep.n_valid <= plan->N),
+               "gemm: out_ld / n_valid / act belong to the plain fp32-output epilogue");
     const bool f32_out = plan->epilogue == AP_EPI_BIAS_RESID_F32 || plan->epilogue == AP_EPI_BIAS_F32;
     AP_REQUIRE(ctx, (ep.out_h == nullptr) == (ep.stats_out == nullptr) && (ep.out_h == nullptr || f32_out),
                "gemm: out_h / stats_out belong together and to the fp32-output epilogues");

@@ -589,6 +589,48 @@ inline unsigned blocks_for(int64_t n, int t = 256) { return static_cast<unsigned
 
 #define SAM_LAUNCH_CHECK(ctx, what) AP_CHECK_LAUNCH(ctx, what)
 
+// Linears with a handful of rows (the 9 decoder tokens): one warp per output column, lanes split K, the rows' partial sums are
+// reduced with shuffles.  The 64 x 64-tile SIMT kernel ran these on N / 64 CTAs with a serial K loop: 58 us per launch, 52 per forward.
+template <int MAXM>
+__global__ void __launch_bounds__(256)
+sam_linear_rows_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ C,
+                       int ldc, int M, int N, int K, int act, int accumulate) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float acc[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+    const float* wrow = W + static_cast<int64_t>(n) * K;
+    for (int k = lane * 4; k < K; k += 128) {        // K % 4 == 0, 16-byte aligned rows (checked by the launcher)
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k));
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < M) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(A + static_cast<int64_t>(m) * lda + k));
+                acc[m] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[m]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+    }
+    if (lane == 0) {
+        const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < M) {
+                float v = acc[m] + bv;
+                if (act == SAM_ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+                else if (act == SAM_ACT_RELU) v = fmaxf(v, 0.f);
+                float* dst = C + static_cast<int64_t>(m) * ldc + n;
+                *dst = accumulate ? *dst + v : v;
+            }
+        }
+    }
+}
+
 // ---- linears on the tcgen05 GEMM (gemm_tcgen05.cu) -----------------------------------------------------------------------------------
 // The activations of this path are fp32 and its oracle amplifies a per-layer error ~1000x over Hiera's 48 blocks, so
 // every product keeps ~22 significant bits: x = hi + lo (two fp16), A_hi W_hi + A_lo W_hi + A_hi W_lo as ONE GEMM whose contraction
@@ -712,7 +754,11 @@ int sam_linear_tcgen05(ap_ctx* ctx, const float* A, int lda, const float* W, con
         sam_split_a_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(A, lda, static_cast<__half*>(ss->a_buf), M, K, K_pad);
         SAM_LAUNCH_CHECK(ctx, "sam_split_a_kernel");
     }
-    const bool direct = N == N_pad && ldc == N && act == SAM_ACT_NONE;
+    // without accumulation the GEMM's fp32 epilogue writes C directly (its own row stride, column bound and activation); the
+    // accumulating linears (mlp.proj_out) go through the residual epilogue when the shapes allow it, else through a padded temporary
+    const bool direct_plain = !accumulate;
+    const bool direct_resid = accumulate && N == N_pad && ldc == N && act == SAM_ACT_NONE;
+    const bool direct = direct_plain || direct_resid;
     float* out = C;
     if (!direct) {
         rc = sam_scratch(ctx, &ss->o_buf, &ss->o_cap, static_cast<size_t>(M) * N_pad * sizeof(float));
@@ -720,11 +766,15 @@ int sam_linear_tcgen05(ap_ctx* ctx, const float* A, int lda, const float* W, con
         out = static_cast<float*>(ss->o_buf);
     }
     GemmPlan plan;
-    rc = ap_gemm_plan_split(ctx, &plan, ss->a_buf, ws.w, M, N_pad, K_pad, (direct && accumulate) ? AP_EPI_BIAS_RESID_F32 : AP_EPI_BIAS_F32, AP_SPLIT_AW);
+    rc = ap_gemm_plan_split(ctx, &plan, ss->a_buf, ws.w, M, N_pad, K_pad, direct_resid ? AP_EPI_BIAS_RESID_F32 : AP_EPI_BIAS_F32, AP_SPLIT_AW);
     if (rc) return rc;
     GemmExtra ex;
     ex.alpha = 1.0f / SAM_W_SCALE;
-    rc = ap_gemm_run(ctx, &plan, ws.bias, (direct && accumulate) ? C : nullptr, out, &ex, st);
+    if (direct_plain) {
+        ex.out_ld = ldc; ex.n_valid = N;
+        ex.act = act == SAM_ACT_GELU ? 1 : act == SAM_ACT_RELU ? 2 : 0;
+    }
+    rc = ap_gemm_run(ctx, &plan, ws.bias, direct_resid ? C : nullptr, out, &ex, st);
     if (rc) return rc;
     if (!direct) {
         const int64_t n = static_cast<int64_t>(M) * (N >> 2);
@@ -754,7 +804,12 @@ int sam_linear(ap_ctx* ctx, const float* A, int lda, const float* W, const float
     // tcgen05 GEMM: whole 128-row tiles are worth it from a few hundred rows on; the 9-token decoder linears stay on the SIMT kernel
     if (ctx->sam_tensor_cores == 3 && aligned && M >= 256 && N % 4 == 0 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0)
         return sam_linear_tcgen05(ctx, A, lda, W, bias, C, ldc, M, N, K, act, accumulate, st);
-    if (ctx->sam_tensor_cores && ctx->sam_tensor_cores != 3 && aligned && M >= 64) {
+    if (aligned && M <= 16) {
+        sam_linear_rows_kernel<16><<<(N + 7) / 8, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K, act, accumulate);
+        SAM_LAUNCH_CHECK(ctx, "sam_linear_rows_kernel");
+        return AP_OK;
+    }
+    if (ctx->sam_tensor_cores && aligned && M >= 64) {
         static PerDeviceOnce attr;
         if (attr.need(ctx->device)) {
             AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(sam_linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
