@@ -221,11 +221,9 @@ __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], cons
             }
         }
         if (EPI == AP_EPI_BIAS_F32 && ep.act != 0) {   // fp32 activations of the SAM2 path (exact erf GELU / ReLU)
-            if (ep.act == 1) {
-                v[it].x = 0.5f * v[it].x * (1.f + erff(v[it].x * 0.70710678118654752440f));
-                v[it].y = 0.5f * v[it].y * (1.f + erff(v[it].y * 0.70710678118654752440f));
-                v[it].z = 0.5f * v[it].z * (1.f + erff(v[it].z * 0.70710678118654752440f));
-                v[it].w = 0.5f * v[it].w * (1.f + erff(v[it].w * 0.70710678118654752440f));
+            if (ep.act == 1) {      // the packed-FMA GELU of the fp16 epilogues: max abs error 9.2e-8 against float64 erf
+                gelu_erf2(v[it].x, v[it].y);
+                gelu_erf2(v[it].z, v[it].w);
             } else {
                 v[it] = make_float4(fmaxf(v[it].x, 0.f), fmaxf(v[it].y, 0.f), fmaxf(v[it].z, 0.f), fmaxf(v[it].w, 0.f));
             }
