@@ -49,7 +49,13 @@ class B200FeatureExtractor:
 
     def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int | None = None, image_size: int = 224,
                  max_batch: int = 127, device: int = 0, config: tuple | None = None, registry_name: str | None = None,
-                 precise_layers: int = -1):
+                 precise_layers: int = -1, precision: str = "fast"):
+        """precision: "fast" = the library defaults (typical rows 5.5e-4 of the fp32 path, p99 9.3e-4; rows with
+        two large flat regions -- a patch hanging 40 % over the slide edge next to white background -- touch 1.0e-3);
+        "strict" = LayerNorm kernels instead of folding, two leading layers with split weights AND split A operands: max 8.1e-4 on
+        the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log) for ~20 % more GEMM work."""
+        if precision not in ("fast", "strict"):
+            raise ValueError("precision must be 'fast' or 'strict'")
         preprocess, resize_to, mlp_kind = 0, 0, 0
         if config is None and name in DINOV2_CONFIGS:
             patch, layers, heads, hidden, mlp, swiglu = DINOV2_CONFIGS[name]
@@ -73,6 +79,8 @@ class B200FeatureExtractor:
         self.max_batch = int(max_batch)
         self.ctx = Context.get(device)
         lib = self.ctx.lib
+        if precision == "strict" and precise_layers < 2:
+            precise_layers = max(2, 8 if layers > 32 else 2)
         desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
                        input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=1e-6,
                        mean=(C.c_float * 3)(*IMAGENET_MEAN), std=(C.c_float * 3)(*IMAGENET_STD), preprocess=preprocess,
@@ -87,7 +95,15 @@ class B200FeatureExtractor:
                 t = state_dict[key]
                 a = t.detach().to("cpu").float().contiguous().numpy() if hasattr(t, "detach") else np.ascontiguousarray(t, np.float32)
                 self.ctx.check(lib.ap_encoder_set_tensor(h, key.encode(), a.ctypes.data_as(C.c_void_p), a.size))
-            self.ctx.check(lib.ap_encoder_finalize(h))
+            if precision == "strict":     # the three settings are read at finalize; they are context-wide, so put the defaults back
+                self.ctx.set_option("fold_ln", 0)
+                self.ctx.set_option("precise_aw_layers", 2)
+            try:
+                self.ctx.check(lib.ap_encoder_finalize(h))
+            finally:
+                if precision == "strict":
+                    self.ctx.set_option("fold_ln", 1)
+                    self.ctx.set_option("precise_aw_layers", -1)
         except Exception:
             lib.ap_encoder_destroy(h)
             self._h = None

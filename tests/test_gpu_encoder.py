@@ -85,6 +85,31 @@ def test_vit_b_16_many_patches_ragged_and_overhang():
     ext.cleanup()
 
 
+def test_strict_precision_preset_on_the_hardest_rows():
+    """The rows with the largest error of the 1 024-row survey (tools/vit_outliers.py): patches hanging ~40 % over the slide edge
+    next to white background -- two large flat regions, i.e. hundreds of identical tokens whose rounding errors add up coherently.
+    The default setting sits at the tolerance there (0.95 - 1.01e-3 in the survey); precision="strict" has to keep clear of it."""
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec, render_region_host
+
+    spec = make_spec(6000, 5000, seed=41)
+    wsi = SyntheticWSI(spec)
+    xy = [(5853, 1456), (-108, 36), (2146, -114), (5794, 4813), (644, -98), (518, 4844), (3923, 4860), (-73, -114), (4947, 2568), (3698, 1150)]
+    coords = torch.tensor([[x, y, 256, 256, 0] for x, y in xy], dtype=torch.int32, device="cuda")
+    sd = vit_state_dict("vit_b_16", seed=1234)
+    want = ov.extract_features([render_region_host(spec, x, y, 256, 256) for x, y in xy], sd, "vit_b_16")
+    rels = {}
+    for precision in ("fast", "strict"):
+        ext = B200FeatureExtractor("vit_b_16", sd, max_batch=16, precision=precision)
+        rels[precision] = _rel(ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, coords).cpu().numpy(), want)
+        ext.cleanup()
+    print("fast", rels["fast"], "strict", rels["strict"])
+    assert rels["strict"].max() < 9.0e-4, rels["strict"]
+    assert rels["fast"][-2:].max() < 7.0e-4, rels["fast"]          # ordinary tissue / background rows
+    assert rels["fast"].max() < 1.1e-3, rels["fast"]                # documented: the flat-region rows touch the 1e-3 bar (DESIGN.md 5)
+
+
 def test_cls_only_last_layer_and_attention_flavours_agree():
     """Algorithmic shortcuts must not change results: class-token-only last layer vs full last layer, and
     tcgen05 attention vs the warp-MMA attention kernel."""
