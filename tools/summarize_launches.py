@@ -1,4 +1,4 @@
-"""profiles/r01_launches_summary.md from an `ncu --metrics gpu__time_duration.sum --csv` launch list."""
+"""profiles/rNN_launches_summary.md from an `ncu --metrics gpu__time_duration.sum --csv` launch list."""
 import collections
 import csv
 import re
