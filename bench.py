@@ -35,8 +35,11 @@ GEMM_FLOP_PER_PATCH = 2 * (197 * GEMM_MAC_PER_TOKEN_LAYER * 12 + 196 * 768 * 768
 ATTN_FLOP_PER_PATCH = 2 * 12 * 12 * 2 * 197 * 197 * 64
 MODEL_FLOP_PER_PATCH = GEMM_FLOP_PER_PATCH + ATTN_FLOP_PER_PATCH  # 35.13 GFLOP
 PATCH_BYTES = 256 * 256 * 3
-# patches per forward chunk: 127 x 197 tokens = 98 CTA-pair row tiles -> 294 / 882 / 1176 tiles = 3.97 / 11.9 / 15.9 waves of 74 pairs
-CHUNK = 127
+# patches per forward chunk: 508 x 197 tokens = 391 CTA-pair row tiles -> 1173 / 3519 / 4692 tiles = 15.9 / 47.6 / 63.4 waves of 74 pairs.
+# Chunk sweep of round 2 (gpurun_out/r02/bench36_*, same box): 127: 22.95 k patches/s (e2e 22.9 k), 254: 24.1 k (23.7 k), 508: 24.9 k (24.0 k),
+# 762: 24.9 k (23.2 k), 1016: 25.2 k (22.9 k): fewer launch gaps and residual-stream tails per patch; beyond 508 the host-patch (e2e) path
+# loses its H2D / compute overlap granularity.
+CHUNK = 508
 
 
 def parse_args():
@@ -45,7 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--batch", type=int, default=2032, help="patches per step (b200 arm); 16 forward chunks of 127")
+    ap.add_argument("--batch", type=int, default=2032, help="patches per step (b200 arm); 4 forward chunks of 508")
     ap.add_argument("--chunk", type=int, default=CHUNK, help="patches per forward chunk (workspace size)")
     ap.add_argument("--width", type=int, default=80000)
     ap.add_argument("--height", type=int, default=60000)
@@ -376,7 +379,7 @@ def aux_c2_sam2(ctx, rank, world):
     return out
 
 
-def _encoder_for(name, patch, seed, chunk=127):
+def _encoder_for(name, patch, seed, chunk=254):
     import torch
 
     from atlaspatch_b200.encoder import B200FeatureExtractor
@@ -700,13 +703,15 @@ def main_b200(args):
         patches_timed = args.steps * B
     achieved_tflops = (patches_timed * GEMM_FLOP_PER_PATCH) / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all 49 launches per 127-patch chunk: conv_proj, in_proj, out_proj, mlp.0, mlp.3)",
+        "bound": "tensor", "kernel": f"gemm_tcgen05_kernel (all 49 launches per {args.chunk}-patch chunk: conv_proj, in_proj, out_proj, mlp.0, mlp.3)",
         "achieved": achieved_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": (achieved_tflops / peaks["tflops_sustained"]) if achieved_tflops else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 49 GEMM launches of one 127-patch chunk (ncu,
-        # profiles/r01_ncu_gemm_dram_traffic.csv: 103.7 MB read + 64.7 MB written); algorithmic bytes A + W + out (+ resid + the fp16
-        # copy of the residual stream the folded LayerNorm needs) average 233 MB per launch, the difference is served by L2
-        "traffic": 168.4e6, "traffic_unit": "B/launch (ncu, profiles/r01_ncu_gemm_dram_traffic.csv)",
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 49 GEMM launches of one forward chunk (ncu,
+        # profiles/r02_ncu_gemm_dram_traffic.csv at the default 508-patch chunk: 405.2 MB read + 418.7 MB written; at 127 patches
+        # 103.7 + 64.7 MB, profiles/r01_ncu_gemm_dram_traffic.csv); algorithmic bytes A + W + out (+ resid + the fp16 copy of the
+        # residual stream the folded LayerNorm needs) average 233 MB per launch per 127 patches, the difference is served by L2
+        "traffic": (824.0e6 if args.chunk == 508 else 168.4e6 * args.chunk / 127.0),
+        "traffic_unit": "B/launch (ncu, profiles/r02_ncu_gemm_dram_traffic.csv; other chunk sizes: scaled from the 127-patch capture)",
         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
         "algorithmic_flop_per_launch": GEMM_FLOP_PER_PATCH * patches_timed / max(gemm_n, 1),
         "avg_launch_ms": gemm_ms / max(gemm_n, 1), "launches_timed": gemm_n // max(stride, 1) if stride else gemm_n,
