@@ -48,9 +48,12 @@ class B200FeatureExtractor:
     handed to extract_batch / cut by embed_coords)."""
 
     def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int | None = None, image_size: int = 224,
-                 max_batch: int = 127, device: int = 0, config: tuple | None = None, registry_name: str | None = None,
+                 max_batch: int = 254, device: int = 0, config: tuple | None = None, registry_name: str | None = None,
                  precise_layers: int = -1, precision: str = "fast"):
-        """precision: "fast" = the library defaults (typical rows 5.5e-4 of the fp32 path, p99 9.3e-4; rows with
+        """max_batch: patches per forward chunk = size of the activation workspaces (ViT-B/16: ~1 GB at 254).  Larger chunks amortise
+        launch gaps and the tails of the HBM-bound residual GEMMs: 127 -> 254 -> 508 patches gave 22.9 -> 24.1 -> 24.9 k patches/s for
+        ViT-B/16 (bench.py uses 508), +2-5 % for ViT-L / DINOv2.
+        precision: "fast" = the library defaults (typical rows 5.5e-4 of the fp32 path, p99 9.3e-4; rows with
         two large flat regions -- a patch hanging 40 % over the slide edge next to white background -- touch 1.0e-3);
         "strict" = LayerNorm kernels instead of folding, two leading layers with split weights AND split A operands: max 8.1e-4 on
         the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log) for ~20 % more GEMM work."""
