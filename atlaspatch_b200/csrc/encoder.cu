@@ -620,7 +620,7 @@ extern "C" int ap_encoder_embed_patches_host(ap_encoder* e, const uint8_t* const
                 memcpy(out_features_host + ps * D, e->pin_out[buf], (size_t)pnb * D * 4);
             }
             {   // gather the (possibly scattered) host patches into pinned memory
-                const int nthreads = nb >= 32 ? 4 : 1;
+                const int nthreads = nb >= 256 ? 8 : nb >= 32 ? 4 : 1;   // 100 MB per 508-patch chunk: the first chunk's gather is not overlapped
                 auto work = [&](int t) {
                     for (int i = t; i < nb; i += nthreads) memcpy(e->pin_in[buf] + (size_t)i * patch_bytes, patches_host[s + i], patch_bytes);
                 };
