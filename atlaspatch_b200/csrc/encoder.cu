@@ -7,6 +7,7 @@
 // Residual stream, LayerNorm and softmax are fp32; GEMM operands are fp16 with fp32 accumulation.
 #include <map>
 #include <string>
+#include <cstdlib>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -620,7 +621,16 @@ extern "C" int ap_encoder_embed_patches_host(ap_encoder* e, const uint8_t* const
                 memcpy(out_features_host + ps * D, e->pin_out[buf], (size_t)pnb * D * 4);
             }
             {   // gather the (possibly scattered) host patches into pinned memory
-                const int nthreads = nb >= 256 ? 8 : nb >= 32 ? 4 : 1;   // 100 MB per 508-patch chunk: the first chunk's gather is not overlapped
+                // 100 MB per 508-patch chunk, and the first chunk's gather is not overlapped with anything: up to 8 threads, but never more
+                // than this process' share of the host cores (one process per GPU: torchrun exports LOCAL_WORLD_SIZE)
+                static const int max_threads = [] {
+                    const char* lw = getenv("LOCAL_WORLD_SIZE");
+                    const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
+                    const int hc = static_cast<int>(std::thread::hardware_concurrency());
+                    const int share = hc > 0 ? hc / ranks : 4;
+                    return share < 1 ? 1 : share > 8 ? 8 : share;
+                }();
+                const int nthreads = nb >= 256 ? max_threads : nb >= 32 ? (max_threads < 4 ? max_threads : 4) : 1;
                 auto work = [&](int t) {
                     for (int i = t; i < nb; i += nthreads) memcpy(e->pin_in[buf] + (size_t)i * patch_bytes, patches_host[s + i], patch_bytes);
                 };
