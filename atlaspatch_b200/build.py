@@ -14,7 +14,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libatlaspatch_b200.so"
 STAMP = PKG / ".build_stamp"
 
-SOURCES = ["ctx.cu", "gemm_tcgen05.cu", "encoder_kernels.cu", "preprocess_resize.cu", "attention_tcgen05.cu", "encoder.cu", "coords.cu", "patch_filter.cu", "slide_kernels.cu", "sam2_kernels.cu", "sam2.cu"]
+SOURCES = ["ctx.cu", "gemm_tcgen05.cu", "encoder_kernels.cu", "preprocess_resize.cu", "attention_tcgen05.cu", "attention_units.cu", "encoder.cu", "coords.cu", "patch_filter.cu", "slide_kernels.cu", "sam2_kernels.cu", "sam2.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-cudart", "static",

@@ -136,12 +136,13 @@ def test_attention(ctx, B, S, heads, amp):
 
 
 # variant 16: the generic run-time (two-pass) kernel instead of the register-resident instantiations; 32: the round-1/2 pipeline with
-# O inside the score buffer instead of the free-standing-O pipeline (<= 208 keys); 64: no flipped second query tile; 512: two-pass softmax (exact row maximum first) instead of
+# O inside the score buffer instead of the free-standing-O pipeline (<= 208 keys); 64: no flipped second query tile; 2048 / 1024: force the key-block-unit pipeline (attention_units.cu) /
+# the whole-tile pipeline (attention_tc6_kernel) whatever the sequence length; 512: two-pass softmax (exact row maximum first) instead of
 # the one-pass softmax with a lazily moved reference maximum;
 # emu: exponential pairs per 16 evaluated by the FMA-pipe polynomial instead of MUFU
-@pytest.mark.parametrize("variant,emu", [(16, 0), (32, 0), (48, 0), (64, 0), (0, 0), (0, 4), (0, 6), (0, 8), (64, 8), (512, 0), (512, 4)])
+@pytest.mark.parametrize("variant,emu", [(16, 0), (32, 0), (48, 0), (64, 0), (0, 0), (0, 4), (0, 6), (0, 8), (64, 8), (512, 0), (512, 4), (2048, 0), (2048, 4), (2112, 0), (1024, 0), (1024, 4)])
 @pytest.mark.parametrize("B,S,heads,amp", [(64, 197, 12, 2.0), (30, 257, 16, 2.0), (3, 197, 4, 2.0), (200, 50, 12, 6.0), (300, 130, 2, 6.0),
-                                           (150, 197, 12, 6.0), (7, 208, 3, 1.0), (9, 193, 5, 3.0)])
+                                           (150, 197, 12, 6.0), (7, 208, 3, 1.0), (9, 193, 5, 3.0), (40, 256, 4, 6.0), (33, 144, 3, 6.0)])
 def test_attention_kernel_variants(ctx, B, S, heads, amp, variant, emu):
     D = heads * 64
     g = torch.Generator(device="cuda").manual_seed(B + S + heads)

@@ -8,8 +8,8 @@ from atlaspatch_b200._lib import Context
 ctx = Context.get(0)
 P = lambda t: C.c_void_p(t.data_ptr())
 torch.manual_seed(0)
-cases = [(32, 0), (512, 0), (0, 0), (64, 0), (0, 2), (0, 4), (0, 6), (0, 8)]
-for (B, S, heads) in [(127, 197, 12), (127, 197, 16), (508, 50, 12)]:
+cases = [(32, 0), (0, 0), (64, 0), (0, 4), (2048, 0), (2048, 4)]
+for (B, S, heads) in [(127, 197, 12), (508, 197, 12), (127, 256, 16), (508, 50, 12)]:
     D = heads * 64
     qkv = torch.randn(B * S, 3 * D, device="cuda").half()
     q, k, v = qkv[: 8 * S].double().view(8, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
