@@ -194,6 +194,7 @@ int ap_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, 
 // tcgen05 attention (S <= 257): TMA descriptors over the packed QKV buffer [rows, 3 * heads * 64]
 struct AttnPlan {
     CUtensorMap map_q;   // box 128 rows x 64
+    CUtensorMap map_q16; // box 16 rows x 64: the third query tile of a 257-token sequence holds one row (attention_units.cu)
     CUtensorMap map_kv;  // box S_pad rows x 64
     const __half* qkv;   // the packed QKV buffer the maps describe
     int S_pad;           // MMA keys rounded up to 16

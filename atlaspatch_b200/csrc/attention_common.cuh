@@ -26,6 +26,18 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float dot8_h(const uint4& a, const uint4& b, float acc) {
+    const __half2* pa = reinterpret_cast<const __half2*>(&a);
+    const __half2* pb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 x = __half22float2(pa[i]), y = __half22float2(pb[i]);
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+    }
+    return acc;
+}
+
 __device__ __forceinline__ uint64_t pk2f(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));

@@ -41,18 +41,6 @@
 namespace {
 
 constexpr int ATC_THREADS = 384;
-__device__ __forceinline__ float dot8_h(const uint4& a, const uint4& b, float acc) {
-    const __half2* pa = reinterpret_cast<const __half2*>(&a);
-    const __half2* pb = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 x = __half22float2(pa[i]), y = __half22float2(pb[i]);
-        acc = fmaf(x.x, y.x, acc);
-        acc = fmaf(x.y, y.y, acc);
-    }
-    return acc;
-}
-
 // Bounded polling on two conditions at once (the MMA thread): a protocol bug must become a trap, never a hung GPU.
 __device__ __forceinline__ void spin_guard(long long t0, int tag) {
     if (clock64() - t0 > 6000000000LL) {
@@ -988,6 +976,8 @@ int ap_attention_tc_plan(ap_ctx* ctx, AttnPlan* plan, const __half* qkv, int row
     plan->S_pad = (plan->nk + 15) / 16 * 16;
     int rc = ap_make_tmap_f16_2d(ctx, &plan->map_q, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D, 128, 64);
     if (rc) return rc;
+    rc = ap_make_tmap_f16_2d(ctx, &plan->map_q16, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D, 16, 64);
+    if (rc) return rc;
     return ap_make_tmap_f16_2d(ctx, &plan->map_kv, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D, plan->S_pad, 64);
 }
 
@@ -1012,9 +1002,12 @@ int ap_attention_tc_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, int B, i
         // which pipeline: key-block units (attention_units.cu) where they win -- one key block (<= 128 keys: 46.8 us against 53.3 us at 50
         // tokens) and 209..256 keys (69.7 us against 90.6 us at 256) -- whole tiles with a free-standing O for 129..208 keys (197 tokens:
         // 46.6 us against 56.9 us: two 128 / 80-key units per tile cost more hand-overs than they hide); attn_variant 2048 / 1024 force one
-        const bool units_ok = plan->xkey < 0 && S_pad <= 256 && plan->nq <= 256;
+        // the 257-token DINOv2 sequence on the units kernel (extra key + a short third query tile): correct, but its six units per job make
+        // it slower than the round-1 pipeline (146.5 us against 125.5 us at 127 images x 16 heads) -- on request only
+        const bool units_xk = plan->xkey >= 0 && S_pad == 256 && plan->nq == 257 && plan->q0 == 0 && (ctx->attn_variant & 2048);
+        const bool units_ok = (plan->xkey < 0 && S_pad <= 256 && plan->nq <= 256) || units_xk;
         const bool tc6_ok = plan->xkey < 0 && S_pad <= 208 && plan->nq <= 256;
-        const bool want_units = (ctx->attn_variant & 2048) || (!(ctx->attn_variant & 1024) && (S_pad <= 128 || S_pad > 208));
+        const bool want_units = (ctx->attn_variant & 2048) || units_xk || (!(ctx->attn_variant & 1024) && (S_pad <= 128 || S_pad > 208));
         if (units_ok && !(ctx->attn_variant & 32) && (want_units || !tc6_ok)) {
             rc = ap_attention_units_run(ctx, plan, out, a, grid, stream);
         } else if (plan->xkey < 0 && S_pad <= 208 && plan->nq <= 256 && !(ctx->attn_variant & 32)) {   // two score tiles + a free-standing O fit TMEM

@@ -35,7 +35,7 @@ struct UnitRare {
 // fetches -- but the call makes ptxas spill 240 B around it and the kernel got slower: 75.8 -> 96.7 us at 256 keys.)
 template <int W, bool MASK, bool FIRST, bool BLOCK_B, int EMU>
 __device__ __forceinline__ void unit_piece(uint32_t t_buf, int c, int key0, int nk, float scale, uint64_t scale2, float& m_ref, uint64_t& lsum,
-                                           const UnitRare& rare) {
+                                           const UnitRare& rare, float extra, float& p_x) {
     uint32_t r[W];
     tmem_ld_w<W>(t_buf + c, r);
     ptx::tc_wait_ld();
@@ -55,7 +55,9 @@ __device__ __forceinline__ void unit_piece(uint32_t t_buf, int c, int key0, int 
     }
     const float pm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
     if (FIRST) {
-        m_ref = pm;
+        m_ref = fmaxf(pm, extra);          // extra: score of the key outside the MMA window (-inf without one)
+        p_x = ex2_mufu(fmaf(extra, scale, -m_ref * scale));
+        lsum = pk2f(p_x, 0.f);
     } else {
         const bool need = pm * scale > fmaf(m_ref, scale, 8.0f);
         if (__any_sync(0xffffffffu, need)) {      // rare path: move the reference, rescale what this row has produced so far
@@ -92,6 +94,7 @@ __device__ __forceinline__ void unit_piece(uint32_t t_buf, int c, int key0, int 
             float l0, l1;
             upk2f(lsum, l0, l1);
             lsum = pk2f(l0 * f, l1 * f);
+            p_x *= f;
             m_ref = new_ref;
         }
     }
@@ -127,33 +130,36 @@ __device__ __forceinline__ void unit_piece(uint32_t t_buf, int c, int key0, int 
 // all pieces of one unit (len score columns at t_buf, first key key0): 64-column loads, the remainder in 16-column loads
 template <bool BLOCK_B, int EMU>
 __device__ __forceinline__ void unit_softmax(uint32_t t_buf, int len, int key0, int nk, float scale, uint64_t scale2, float& m_ref, uint64_t& lsum,
-                                             const UnitRare& rare) {
+                                             const UnitRare& rare, float extra, float& p_x) {
     int c = 0;
     if (!BLOCK_B) {     // the row's first piece defines the reference maximum
         if (len >= 64) {
-            if (key0 + 64 <= nk) unit_piece<64, false, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare);
-            else unit_piece<64, true, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare);
+            if (key0 + 64 <= nk) unit_piece<64, false, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
+            else unit_piece<64, true, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
             c = 64;
         } else {
-            if (key0 + 16 <= nk) unit_piece<16, false, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare);
-            else unit_piece<16, true, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare);
+            if (key0 + 16 <= nk) unit_piece<16, false, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
+            else unit_piece<16, true, true, false, EMU>(t_buf, 0, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
             c = 16;
         }
     }
     for (; c + 64 <= len; c += 64) {
-        if (key0 + c + 64 <= nk) unit_piece<64, false, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare);
-        else unit_piece<64, true, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare);
+        if (key0 + c + 64 <= nk) unit_piece<64, false, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
+        else unit_piece<64, true, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
     }
     for (; c + 16 <= len; c += 16) {
-        if (key0 + c + 16 <= nk) unit_piece<16, false, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare);
-        else unit_piece<16, true, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare);
+        if (key0 + c + 16 <= nk) unit_piece<16, false, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
+        else unit_piece<16, true, false, BLOCK_B, EMU>(t_buf, c, key0, nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
     }
 }
 
-template <int EMU>
+// XK: one EXTRA key token `xkey` outside the MMA key window is folded in as a rank-1 update (its score is a 64-term dot product per row
+// on the CUDA cores and joins the first piece's maximum, its value row is added to O in the epilogue): the 257-token DINOv2 sequence =
+// 256 patch keys through the MMA + the class token.  Its 257th query rides in a third query tile that is loaded as a 16-row box.
+template <int EMU, bool XK>
 __global__ void __launch_bounds__(ATU_THREADS, 1)
-attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, __half* __restrict__ out,
-                       const AttnArgs a) {
+attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_q16,
+                       const __grid_constant__ CUtensorMap map_kv, const __half* __restrict__ qkv, __half* __restrict__ out, const AttnArgs a) {
     const int S_pad = a.S_pad;                                   // <= 256
     const int ka = S_pad < ATU_KB ? S_pad : ATU_KB, kb = S_pad - ka;   // keys of block a / block b (multiples of 16; kb may be 0)
     const int KBLK = kb > 0 ? 2 : 1;                             // key blocks = units per query tile
@@ -162,14 +168,15 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const int heads = a.heads, S = a.S;
     const int D = heads * 64;
     const int kv_bytes = S_pad * 128;
-    const int n_qt = (a.nq + 127) / 128;                        // 1 or 2 query tiles per job
-    const int q_bytes = n_qt * Q_TILE_BYTES;
+    const int n_qt = (a.nq + 127) / 128;                        // 1 or 2 query tiles per job, 3 for the 257 queries of XK
+    const int q_bytes = n_qt == 3 ? 2 * Q_TILE_BYTES + 2048 : n_qt * Q_TILE_BYTES;   // third tile: 16 rows (one is real)
     const int stage_bytes = q_bytes + 2 * kv_bytes;             // per job stage: [Q tiles | K | V], a multiple of 1024
     // row sums, softmax -> epilogue: [8 tiles][128 rows].  Eight slots, not four: with one key block per tile (<= 128 keys) the MMA warp
     // may be blocked at P.V of tile T (waiting for the read-out of tile T - 2) while S of tile T + 2 is already out, so the softmax of
     // T + 2 can finish before the epilogue has read the sums of T - 2 -- (T + 2) & 3 == (T - 2) & 3 was a real race for 50-token sequences
     float* lsm = reinterpret_cast<float*>(smem + 2 * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes + 4096);
+    float* pxs = lsm + 8 * 128;                                  // [8 tiles][128 rows] probability of the extra key (XK)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes + 8192);
     uint64_t* qk_full = bars;        // [2 stages] TMA -> MMA   (Q tiles + K)
     uint64_t* qk_empty = bars + 2;   // [2 stages] MMA -> TMA   (the job's S MMAs have retired)
     uint64_t* v_full = bars + 4;     // [2 stages] TMA -> MMA   (V)
@@ -195,6 +202,7 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&map_q);
+        ptx::prefetch_tmap(&map_q16);
         ptx::prefetch_tmap(&map_kv);
     }
     if (warp == 1 && lane == 0) {
@@ -235,10 +243,11 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 uint8_t* sb = smem + st * stage_bytes;
                 if (warp == 0) {
                     ptx::mbar_wait(&qk_empty[st], sph ^ 1, 91);
-                    ptx::mbar_arrive_expect_tx(&qk_full[st], n_qt * Q_TILE_BYTES + kv_bytes);
+                    ptx::mbar_arrive_expect_tx(&qk_full[st], q_bytes + kv_bytes);
                     ptx::tma_load_2d(sb + q_bytes, &map_kv, &qk_full[st], D + h * 64, b * S + a.k0);
-                    for (int g = 0; g < n_qt; ++g)
+                    for (int g = 0; g < n_qt && g < 2; ++g)
                         ptx::tma_load_2d(sb + g * Q_TILE_BYTES, &map_q, &qk_full[st], h * 64, b * S + a.q0 + tile_tok0(jt, g));
+                    if (n_qt == 3) ptx::tma_load_2d(sb + 2 * Q_TILE_BYTES, &map_q16, &qk_full[st], h * 64, b * S + a.q0 + 256);
                 } else {
                     ptx::mbar_wait(&v_empty[st], sph ^ 1, 92);
                     ptx::mbar_arrive_expect_tx(&v_full[st], kv_bytes);
@@ -310,7 +319,7 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const float scale = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e)
         const uint64_t scale2 = pk2f(scale, scale);
-        float m_ref = 0.f;
+        float m_ref = 0.f, p_x = 0.f;
         uint64_t lsum = pk2f(0.f, 0.f);
         for (int c = 0; c < n_units; ++c) {
             const int tile = unit_tile(c);
@@ -325,19 +334,31 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             rare.oa_done = &oa_done[wg];
             rare.phase = (tile >> 1) & 1;
             rare.t_o = t_lane + ATU_O_COL + 64 * wg;
+            float extra = -INFINITY;
+            if (XK && blk == 0 && warp_has_rows) {   // score of the extra key: 64-term dot product on the CUDA cores (L2-resident rows)
+                const int job = blockIdx.x + jt * gridDim.x;
+                const int b = job / heads, h = job - b * heads;
+                const int qr = tok0 + q * 32 + lane < a.nq ? tok0 + q * 32 + lane : a.nq - 1;
+                const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<int64_t>(b) * S + a.q0 + qr) * 3 * D + h * 64);
+                const uint4* kp = reinterpret_cast<const uint4*>(qkv + (static_cast<int64_t>(b) * S + a.xkey) * 3 * D + D + h * 64);
+                float s_x = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) s_x = dot8_h(__ldg(qp + cc), __ldg(kp + cc), s_x);
+                extra = s_x;
+            }
             ptx::mbar_wait(&s_full[buf], (c / 3) & 1, 98);
             ptx::tc_fence_after();
             if (warp_has_rows) {
                 if (blk == 0) {
-                    lsum = pk2f(0.f, 0.f);
-                    unit_softmax<false, EMU>(t_buf, ka, 0, a.nk, scale, scale2, m_ref, lsum, rare);
+                    unit_softmax<false, EMU>(t_buf, ka, 0, a.nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
                 } else {
-                    unit_softmax<true, EMU>(t_buf, kb, ATU_KB, a.nk, scale, scale2, m_ref, lsum, rare);
+                    unit_softmax<true, EMU>(t_buf, kb, ATU_KB, a.nk, scale, scale2, m_ref, lsum, rare, extra, p_x);
                 }
                 if (blk == KBLK - 1) {
                     float l0, l1;
                     upk2f(lsum, l0, l1);
                     lsm[(tile & 7) * 128 + q * 32 + lane] = l0 + l1;      // read by the epilogue warp of the same lane quarter after o_full
+                    if (XK) pxs[(tile & 7) * 128 + q * 32 + lane] = p_x;
                 }
                 ptx::tc_wait_st();
             }
@@ -359,6 +380,7 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             uint32_t o[64];
             ptx::tmem_ld_32x64(t_lane + ATU_O_COL + 64 * wg, o);
             const float lsum = lsm[(i & 7) * 128 + q * 32 + lane];
+            const float px = XK ? pxs[(i & 7) * 128 + q * 32 + lane] : 0.f;
             ptx::tc_wait_ld();
             ptx::tc_fence_before();
             __syncwarp();
@@ -366,11 +388,24 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             if (tok >= g * 128 && tok < a.nq) {
                 const float inv = 1.0f / lsum;
                 uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * S + a.q0 + tok) * a.out_ld + h * 64);
+                const uint4* vx = XK ? reinterpret_cast<const uint4*>(qkv + (static_cast<int64_t>(b) * S + a.xkey) * 3 * D + 2 * D + h * 64) : nullptr;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float v[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * j + e]) * inv;
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * j + e]);
+                    if (XK) {                   // + p_x * (value row of the extra key)
+                        const uint4 u = __ldg(vx + j);
+                        const __half2* hv = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(hv[e]);
+                            v[2 * e] = fmaf(f.x, px, v[2 * e]);
+                            v[2 * e + 1] = fmaf(f.y, px, v[2 * e + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] *= inv;
                     const uint4 hi4 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
                     dst[j] = hi4;
                     if (a.split_lo) {
@@ -396,28 +431,34 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
 }
 
-template <int EMU>
+template <int EMU, bool XK>
 int launch_units(ap_ctx* ctx, const AttnPlan* plan, __half* out, const AttnArgs& a, int grid, cudaStream_t stream) {
-    auto kern = attention_units_kernel<EMU>;
+    auto kern = attention_units_kernel<EMU, XK>;
     const size_t n_qt = (a.nq + 127) / 128;
-    const size_t smem = 2 * (n_qt * (size_t)Q_TILE_BYTES + 2 * (size_t)a.S_pad * 128) + 4096 + 21 * 8 + 16 + 1024;
+    const size_t q_bytes = n_qt == 3 ? 2 * (size_t)Q_TILE_BYTES + 2048 : n_qt * (size_t)Q_TILE_BYTES;
+    const size_t smem = 2 * (q_bytes + 2 * (size_t)a.S_pad * 128) + 8192 + 21 * 8 + 16 + 1024;
     static PerDeviceOnce attr;   // per instantiation
     if (attr.need(ctx->device)) {
-        const int max_smem = 2 * (2 * Q_TILE_BYTES + 2 * 256 * 128) + 4096 + 21 * 8 + 16 + 1024;
+        const int max_smem = 2 * (2 * Q_TILE_BYTES + 2048 + 2 * 256 * 128) + 8192 + 21 * 8 + 16 + 1024;
         AP_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr.done(ctx->device);
     }
-    AP_CHECK_CUDA(ctx, ap_launch_pdl(kern, dim3(grid), dim3(ATU_THREADS), smem, stream, 1, ctx->pdl != 0, plan->map_q, plan->map_kv, out, a));
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(kern, dim3(grid), dim3(ATU_THREADS), smem, stream, 1, ctx->pdl != 0, plan->map_q, plan->map_q16, plan->map_kv, plan->qkv, out, a));
     return AP_OK;
 }
 
 }  // namespace
 
-// plan->xkey < 0, S_pad <= 256, at most two query tiles (nq <= 256)
+// plan->xkey < 0: S_pad <= 256 keys, at most two query tiles (nq <= 256).  plan->xkey >= 0: the 257-token case (256 MMA keys + the extra
+// key, q0 = 0, nq = 257).
 int ap_attention_units_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, const AttnArgs& a, int grid, cudaStream_t stream) {
     const int emu = ctx->attn_emu;
-    if (emu == 0) return launch_units<0>(ctx, plan, out, a, grid, stream);
-    if (emu <= 2) return launch_units<2>(ctx, plan, out, a, grid, stream);
-    if (emu <= 4) return launch_units<4>(ctx, plan, out, a, grid, stream);
-    return launch_units<6>(ctx, plan, out, a, grid, stream);
+    if (plan->xkey >= 0) {
+        AP_REQUIRE(ctx, a.S_pad == 256 && a.nq == 257 && a.q0 == 0, "attention(units): extra key needs 256 MMA keys and 257 queries");
+        return emu == 0 ? launch_units<0, true>(ctx, plan, out, a, grid, stream) : launch_units<4, true>(ctx, plan, out, a, grid, stream);
+    }
+    if (emu == 0) return launch_units<0, false>(ctx, plan, out, a, grid, stream);
+    if (emu <= 2) return launch_units<2, false>(ctx, plan, out, a, grid, stream);
+    if (emu <= 4) return launch_units<4, false>(ctx, plan, out, a, grid, stream);
+    return launch_units<6, false>(ctx, plan, out, a, grid, stream);
 }
