@@ -24,6 +24,14 @@ constexpr int ATU_THREADS = 512;
 constexpr int ATU_O_COL = 384;       // O tile of warpgroup w at columns [384 + 64 w, +64)
 constexpr int ATU_KB = 128;          // keys per block = columns per score buffer
 
+// diagnostics (attn_variant bit 128): block 0 records clock64() at the hand-over points of its first units (tools/attn_units_trace.py)
+constexpr int ATU_TRACE_N = 256;
+__device__ long long g_attn_units_trace[4][ATU_TRACE_N];
+#define ATU_TRACE(role, slot)                                                                                  \
+    do {                                                                                                       \
+        if (trace && (slot) < ATU_TRACE_N) g_attn_units_trace[role][slot] = clock64();                         \
+    } while (0)
+
 struct UnitRare {
     uint64_t* oa_done;     // P_a.V_a of this tile has retired (only waited for on the rare path)
     uint32_t phase;
@@ -194,6 +202,7 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const int n_tiles = my_jobs * n_qt;
     const int n_units = n_tiles * KBLK;
     const bool flip = n_qt == 2 && !(a.variant & 64);
+    const bool trace = (a.variant & 128) && blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 4 || warp == 8 || warp == 12);
     auto tile_tok0 = [&](int jt, int g) -> int { return (g == 1 && flip && (jt & 1)) ? a.nq - 128 : g * 128; };
     // unit c of the stream -> (query tile, key block): pairs of tiles interleave their blocks, a trailing single tile runs a, b
     const int full_units = KBLK == 2 ? (n_tiles >> 1) * 4 : n_units;
@@ -294,8 +303,11 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     ptx::mbar_wait(&v_full[st], (jt >> 1) & 1, 94);
                     v_waited = jt + 1;
                 }
+                ATU_TRACE(2, 4 * c);
                 ptx::mbar_wait(&p_full[buf], (c / 3) & 1, 96);
+                ATU_TRACE(2, 4 * c + 1);
                 if (blk == 0 && tile >= 2) ptx::mbar_wait(&o_empty[wg], ((tile >> 1) - 1) & 1, 97);   // this warpgroup's previous O has been read out
+                ATU_TRACE(2, 4 * c + 2);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                     const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sb + q_bytes + kv_bytes + blk * ATU_KB * 128), 64);
@@ -309,6 +321,7 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 __syncwarp();
                 if (c + 3 < n_units) issue_s(c + 3);     // behind P.V of unit c in the pipe: may overwrite its P
+                ATU_TRACE(2, 4 * c + 3);
             }
         }
       }
@@ -346,7 +359,9 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 for (int cc = 0; cc < 8; ++cc) s_x = dot8_h(__ldg(qp + cc), __ldg(kp + cc), s_x);
                 extra = s_x;
             }
+            ATU_TRACE(wg, 4 * c);
             ptx::mbar_wait(&s_full[buf], (c / 3) & 1, 98);
+            ATU_TRACE(wg, 4 * c + 1);
             ptx::tc_fence_after();
             if (warp_has_rows) {
                 if (blk == 0) {
@@ -365,6 +380,7 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p_full[buf]);
+            ATU_TRACE(wg, 4 * c + 2);
         }
     } else {
         // ---------------- epilogue warpgroup: O / row sum -> fp16 -> global ----------------
@@ -375,7 +391,9 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const int job = blockIdx.x + jt * gridDim.x;
             const int b = job / heads, h = job - b * heads;
             const int tok = tile_tok0(jt, g) + q * 32 + lane;     // token inside the query window
+            ATU_TRACE(3, 4 * i);
             ptx::mbar_wait(&o_full[wg], (i >> 1) & 1, 99);
+            ATU_TRACE(3, 4 * i + 1);
             ptx::tc_fence_after();
             uint32_t o[64];
             ptx::tmem_ld_32x64(t_lane + ATU_O_COL + 64 * wg, o);
@@ -385,6 +403,7 @@ attention_units_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_relaxed(&o_empty[wg]);   // the values are in registers: the warpgroup's next tile may overwrite O
+            ATU_TRACE(3, 4 * i + 2);
             if (tok >= g * 128 && tok < a.nq) {
                 const float inv = 1.0f / lsum;
                 uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * S + a.q0 + tok) * a.out_ld + h * 64);
@@ -461,4 +480,12 @@ int ap_attention_units_run(ap_ctx* ctx, const AttnPlan* plan, __half* out, const
     if (emu <= 2) return launch_units<2, false>(ctx, plan, out, a, grid, stream);
     if (emu <= 4) return launch_units<4, false>(ctx, plan, out, a, grid, stream);
     return launch_units<6, false>(ctx, plan, out, a, grid, stream);
+}
+
+// diagnostics, not part of the public header: the clock64() trace block 0 of attention_units_kernel records with attn_variant bit 128
+extern "C" int ap_debug_attn_units_trace(ap_ctx* ctx, long long* host_out) {
+    DeviceGuard guard(ctx);
+    AP_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    AP_CHECK_CUDA(ctx, cudaMemcpyFromSymbol(host_out, g_attn_units_trace, sizeof(long long) * 4 * ATU_TRACE_N));
+    return AP_OK;
 }
