@@ -110,6 +110,25 @@ def test_strict_precision_preset_on_the_hardest_rows():
     assert rels["fast"].max() < 1.1e-3, rels["fast"]                # documented: the flat-region rows touch the 1e-3 bar
 
 
+def test_host_patch_path_ramp_up_schedule_matches_small_chunks():
+    """extract_batch with large workspaces ramps its chunk sizes up (127, max_batch - 127, max_batch, ...; encoder.cu:
+    ap_encoder_embed_patches_host); rows are independent, so the features must equal those of a small-chunk run bit for bit."""
+    from atlaspatch_b200.encoder import B200FeatureExtractor
+    from atlaspatch_b200.synthetic import make_spec, render_region_host
+
+    sd = vit_state_dict("vit_test_tiny", seed=3)
+    spec = make_spec(3000, 2000, seed=21)
+    rng = np.random.default_rng(8)
+    patches = [render_region_host(spec, int(rng.integers(0, 2700)), int(rng.integers(0, 1700)), 256, 256) for _ in range(700)]
+    outs = []
+    for mb in (64, 254, 300):
+        ext = B200FeatureExtractor("vit_test_tiny", sd, max_batch=mb)
+        outs.append(ext.extract_batch(patches))
+        ext.cleanup()
+    assert outs[0].shape == (700, 256) and np.isfinite(outs[0]).all()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
 def test_cls_only_last_layer_and_attention_flavours_agree():
     """Algorithmic shortcuts must not change results: class-token-only last layer vs full last layer, and
     tcgen05 attention vs the warp-MMA attention kernel."""
