@@ -250,6 +250,12 @@ extern "C" int ap_sam2_finalize(ap_sam2* s) {
         SAM_TRY(upload(s, n + "__wt", wt));
         SAM_TRY(upload(s, n + "__bt", bt));
     }
+    {   // patch-embed weights [C0][3][7][7] as a [C0][148] matrix (147 taps + a zero column) for the im2col + GEMM form of the convolution
+        SAM_PTR(w, H(s, "vision_encoder.backbone.patch_embed.projection.weight", static_cast<size_t>(C0) * 147))
+        std::vector<float> w148(static_cast<size_t>(C0) * 148, 0.f);
+        for (int c = 0; c < C0; ++c) std::copy(w->begin() + static_cast<size_t>(c) * 147, w->begin() + static_cast<size_t>(c + 1) * 147, w148.begin() + static_cast<size_t>(c) * 148);
+        SAM_TRY(upload(s, "__pe_w148", w148));
+    }
     for (auto& kv : s->host) SAM_TRY(upload(s, kv.first, kv.second));
     s->host.clear();
     AP_CHECK_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&s->img_dev), static_cast<size_t>(IMG) * IMG * 3));
@@ -278,7 +284,16 @@ extern "C" int ap_sam2_forward(ap_sam2* s, const uint8_t* image_dev, float* logi
         SAM_PTR(w, W(s, "vision_encoder.backbone.patch_embed.projection.weight"))
         SAM_PTR(b, W(s, "vision_encoder.backbone.patch_embed.projection.bias"))
         SAM_PTR(pos, W(s, "__pos"))
-        SAM_TRY(sam_patch_embed(ctx, image_dev, IMG, IMG, w, b, pos, cur, C0, mean, stdv, st));
+        if (ctx->sam_tensor_cores == 3) {   // im2col + the tcgen05 split GEMM, then + positional embedding
+            SAM_PTR(w148, W(s, "__pe_w148"))
+            float* cols = buf(s, "pe_cols", static_cast<size_t>(Hc) * Wc * 148);
+            if (!cols) return AP_ENOMEM;
+            SAM_TRY(sam_patch_im2col(ctx, image_dev, IMG, IMG, cols, mean, stdv, st));
+            SAM_TRY(sam_linear(ctx, cols, 148, w148, b, cur, C0, Hc * Wc, C0, 148, SAM_ACT_NONE, 0, st));
+            SAM_TRY(sam_add(ctx, cur, pos, cur, static_cast<int64_t>(Hc) * Wc * C0, C0, 0, st));
+        } else {
+            SAM_TRY(sam_patch_embed(ctx, image_dev, IMG, IMG, w, b, pos, cur, C0, mean, stdv, st));
+        }
     }
     const float* stage_out[4] = {nullptr, nullptr, nullptr, nullptr};
     int stage_hw[4] = {0, 0, 0, 0};
@@ -311,20 +326,28 @@ extern "C" int ap_sam2_forward(ap_sam2* s, const uint8_t* image_dev, float* logi
             }
             int nB = 1, Lk = T, nWx = 1, nWy = 1;
             const float* win = ln;
+            const bool fuse_windows = ws > 0 && ctx->sam_tensor_cores == 3 && dim_in % 4 == 0;   // window_partition inside the operand staging
             if (ws > 0) {
                 nWy = (Hc + ws - 1) / ws; nWx = (Wc + ws - 1) / ws;
                 nB = nWy * nWx; Lk = ws * ws;
-                float* wb = buf(s, "win", static_cast<size_t>(nB) * Lk * dim_in);
-                if (!wb) return AP_ENOMEM;
-                SAM_TRY(sam_window_gather(ctx, ln, wb, Hc, Wc, dim_in, ws, nWy, nWx, st));
-                win = wb;
+                if (!fuse_windows) {
+                    float* wb = buf(s, "win", static_cast<size_t>(nB) * Lk * dim_in);
+                    if (!wb) return AP_ENOMEM;
+                    SAM_TRY(sam_window_gather(ctx, ln, wb, Hc, Wc, dim_in, ws, nWy, nWx, st));
+                    win = wb;
+                }
             }
             const int ntok = nB * Lk;
             float* qkv = buf(s, "qkv", static_cast<size_t>(ntok) * 3 * dim_out);
             if (!qkv) return AP_ENOMEM;
             {
                 SAM_PTR(w, W(s, p + "attn.qkv.weight")) SAM_PTR(bb, W(s, p + "attn.qkv.bias"))
-                SAM_TRY(sam_linear(ctx, win, dim_in, w, bb, qkv, 3 * dim_out, ntok, 3 * dim_out, dim_in, SAM_ACT_NONE, 0, st));
+                if (fuse_windows) {
+                    const SamGather g{Hc, Wc, ws, nWx};
+                    SAM_TRY(sam_linear_windows(ctx, ln, dim_in, g, w, bb, qkv, 3 * dim_out, ntok, 3 * dim_out, dim_in, st));
+                } else {
+                    SAM_TRY(sam_linear(ctx, win, dim_in, w, bb, qkv, 3 * dim_out, ntok, 3 * dim_out, dim_in, SAM_ACT_NONE, 0, st));
+                }
             }
             const float* q = qkv;
             int q_stride = 3 * dim_out, Lq = Lk, ws_out = ws;

@@ -228,6 +228,29 @@ sam_patch_embed_kernel(const uint8_t* __restrict__ img, int H, int W, const floa
     out[idx] = acc + pos[idx];
 }
 
+// im2col of the patch-embed convolution (7 x 7, stride 4, padding 3 on the NORMALISED image: out-of-range taps are 0, not "black"):
+// cols[(oy * Wo + ox)][(ci * 7 + ky) * 7 + kx], 148 columns per row (147 taps + one zero column: the tensor-core linears want K % 4 == 0).
+// The convolution then runs as a tcgen05 GEMM with split operands like every other linear (1.75 ms -> 0.15 ms for 1024 x 1024).
+__global__ void __launch_bounds__(256)
+sam_patch_im2col_kernel(const uint8_t* __restrict__ img, int H, int W, float* __restrict__ cols, float3 mean, float3 inv_std) {
+    const int Ho = H / 4, Wo = W / 4;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(Ho) * Wo * 148) return;
+    const int k = static_cast<int>(idx % 148);
+    const int p = static_cast<int>(idx / 148);
+    float v = 0.f;
+    if (k < 147) {
+        const int ci = k / 49, r = k - ci * 49, ky = r / 7, kx = r - ky * 7;
+        const int oy = p / Wo, ox = p - oy * Wo;
+        const int y = oy * 4 - 3 + ky, x = ox * 4 - 3 + kx;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const float mu = ci == 0 ? mean.x : ci == 1 ? mean.y : mean.z, is = ci == 0 ? inv_std.x : ci == 1 ? inv_std.y : inv_std.z;
+            v = (static_cast<float>(img[(static_cast<int64_t>(y) * W + x) * 3 + ci]) * (1.0f / 255.0f) - mu) * is;
+        }
+    }
+    cols[idx] = v;
+}
+
 // [H, W, C] -> windows [nWy * nWx, ws * ws, C], zero padded at the bottom / right (window_partition).
 __global__ void sam_window_gather_kernel(const float* __restrict__ x, float* __restrict__ win, int H, int W, int C, int ws, int nWy, int nWx) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -668,13 +691,23 @@ __global__ void sam_split_w_kernel(const float* __restrict__ W, const float* __r
 
 // 8 consecutive k per thread: two float4 in, one uint4 of hi and one of lo out
 __global__ void __launch_bounds__(256)
-sam_split_a_kernel(const float* __restrict__ A, int lda, __half* __restrict__ out, int M, int K, int K_pad) {
+sam_split_a_kernel(const float* __restrict__ A, int lda, __half* __restrict__ out, int M, int K, int K_pad, SamGather g) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int kc = K_pad >> 3;
     if (idx >= static_cast<int64_t>(M) * kc) return;
-    const int m = static_cast<int>(idx / kc), k = static_cast<int>(idx - static_cast<int64_t>(m) * kc) * 8;
+    const int row = static_cast<int>(idx / kc), k = static_cast<int>(idx - static_cast<int64_t>(row) * kc) * 8;
+    int m = row;
+    if (g.ws > 0) {      // window_partition: (window, iy, ix) -> (y, x), zero rows for the padding of the last windows
+        const int ix = row % g.ws, t1 = row / g.ws, iy = t1 % g.ws, wi = t1 / g.ws;
+        const int wx = wi % g.nWx, wy = wi / g.nWx;
+        const int y = wy * g.ws + iy, x = wx * g.ws + ix;
+        m = (y < g.H && x < g.W) ? y * g.W + x : -1;
+    }
     float v[8];
-    if (k + 8 <= K) {
+    if (m < 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    } else if (k + 8 <= K) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(A + static_cast<int64_t>(m) * lda + k));
         const float4 b = __ldg(reinterpret_cast<const float4*>(A + static_cast<int64_t>(m) * lda + k + 4));
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -691,9 +724,9 @@ sam_split_a_kernel(const float* __restrict__ A, int lda, __half* __restrict__ ou
         hi[e] = *reinterpret_cast<const uint32_t*>(&h);
         lo[e] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    __half* row = out + static_cast<int64_t>(m) * 2 * K_pad;
-    *reinterpret_cast<uint4*>(row + k) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(row + K_pad + k) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    __half* orow = out + static_cast<int64_t>(row) * 2 * K_pad;
+    *reinterpret_cast<uint4*>(orow + k) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(orow + K_pad + k) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 __device__ __forceinline__ float sam_act(float v, int act) {
@@ -729,7 +762,7 @@ int sam_scratch(ap_ctx* ctx, void** buf, size_t* cap, size_t bytes) {
 }
 
 int sam_linear_tcgen05(ap_ctx* ctx, const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, int act,
-                       int accumulate, cudaStream_t st) {
+                       int accumulate, cudaStream_t st, const SamGather* gather = nullptr) {
     if (!ctx->sam_state) ctx->sam_state = new SamState();
     SamState* ss = static_cast<SamState*>(ctx->sam_state);
     const int K_pad = (K + 63) / 64 * 64, N_pad = (N + 127) / 128 * 128;
@@ -751,7 +784,8 @@ int sam_linear_tcgen05(ap_ctx* ctx, const float* A, int lda, const float* W, con
     if (rc) return rc;
     {
         const int64_t n = static_cast<int64_t>(M) * (K_pad >> 3);
-        sam_split_a_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(A, lda, static_cast<__half*>(ss->a_buf), M, K, K_pad);
+        const SamGather g = gather ? *gather : SamGather{0, 0, 0, 0};
+        sam_split_a_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(A, lda, static_cast<__half*>(ss->a_buf), M, K, K_pad, g);
         SAM_LAUNCH_CHECK(ctx, "sam_split_a_kernel");
     }
     // without accumulation the GEMM's fp32 epilogue writes C directly (its own row stride, column bound and activation); the
@@ -797,6 +831,15 @@ void sam_state_free(ap_ctx* ctx) {
     ctx->sam_state = nullptr;
 }
 
+// qkv linear of a windowed block with window_partition fused into the operand staging (tcgen05 path only; the caller checks the mode)
+int sam_linear_windows(ap_ctx* ctx, const float* A, int lda, const SamGather& g, const float* W, const float* bias, float* C, int ldc, int M, int N,
+                       int K, cudaStream_t st) {
+    AP_REQUIRE(ctx, ctx->sam_tensor_cores == 3 && M >= 256 && lda % 4 == 0 && K % 4 == 0 && N % 4 == 0 && ldc % 4 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+               "sam_linear_windows: shape / alignment not supported by the tensor-core linear");
+    return sam_linear_tcgen05(ctx, A, lda, W, bias, C, ldc, M, N, K, SAM_ACT_NONE, 0, st, &g);
+}
+
 int sam_linear(ap_ctx* ctx, const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, int act,
                int accumulate, cudaStream_t st) {
     if (M == 0) return AP_OK;
@@ -837,6 +880,12 @@ int sam_patch_embed(ap_ctx* ctx, const uint8_t* img, int H, int W, const float* 
     sam_patch_embed_kernel<<<blocks_for(static_cast<int64_t>(H / 4) * (W / 4) * C), 256, 0, st>>>(
         img, H, W, w, bias, pos, out, C, make_float3(mean[0], mean[1], mean[2]), make_float3(1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]));
     SAM_LAUNCH_CHECK(ctx, "sam_patch_embed_kernel");
+    return AP_OK;
+}
+int sam_patch_im2col(ap_ctx* ctx, const uint8_t* img, int H, int W, float* cols, const float* mean, const float* stdv, cudaStream_t st) {
+    sam_patch_im2col_kernel<<<blocks_for(static_cast<int64_t>(H / 4) * (W / 4) * 148), 256, 0, st>>>(
+        img, H, W, cols, make_float3(mean[0], mean[1], mean[2]), make_float3(1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]));
+    SAM_LAUNCH_CHECK(ctx, "sam_patch_im2col_kernel");
     return AP_OK;
 }
 int sam_window_gather(ap_ctx* ctx, const float* x, float* win, int H, int W, int C, int ws, int nWy, int nWx, cudaStream_t st) {
