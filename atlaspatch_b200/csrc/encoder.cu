@@ -25,6 +25,7 @@ struct LayerWeights {
     int split = 0;  // bit mask of GEMMs whose weights are stored as [hi | lo] fp16 pairs (K doubled): 1 qkv, 2 out_proj, 4 mlp.0, 8 mlp.3
     int asplit = 0; // bit mask of GEMMs whose A operand is stored as [hi | lo] instead (1 qkv, 2 out_proj, 4 mlp.0): the LayerNorm /
                     // attention epilogue that produces it also writes lo = fp16(a - fp16(a)); weights stay single fp16
+    bool fold1 = false, fold2 = false;  // LayerNorm 1 / 2 of this layer folded into in_proj / mlp.0 (not where that GEMM's A operand is split)
 };
 
 }  // namespace
@@ -215,12 +216,12 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     for (size_t li = 0; li < e->layers.size(); ++li) {
         auto& L = e->layers[li];
         GemmPlan p;
-        if (!fold && (rc = (L.asplit & 1) ? ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1s, nullptr, rows, D, st, 2 * D, 1)
+        if (!L.fold1 && (rc = (L.asplit & 1) ? ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1s, nullptr, rows, D, st, 2 * D, 1)
                                           : ap_layernorm_run(ctx, e->x, D, L.ln1_g, L.ln1_b, e->d.ln_eps, e->y1, nullptr, rows, D, st)))
             return rc;
         p = L.p_qkv; p.M = rows;
         cons.stats_in = e->stats1;
-        if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, fold ? &cons : nullptr, st))) return rc;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, L.fold1 ? &cons : nullptr, st))) return rc;
         if (li + 1 == e->layers.size() && ctx->cls_only_last_layer) {
             // Only x[:, 0] survives the final LayerNorm (models/patch/base.py:100 -> torchvision forward `x[:, 0]`): the last
             // layer's attention needs every token's K/V but only the class-token query, and out_proj / MLP only that row.
@@ -229,7 +230,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
             p = L.pc_o; p.M = nb;
             if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->xc, e->xc, nullptr, st))) return rc;
             // with folding mlp.0 already carries gamma / beta: the tail's explicit LayerNorm only normalises
-            if ((rc = ap_layernorm_run(ctx, e->xc, D, fold ? e->ones : L.ln2_g, fold ? e->zeros : L.ln2_b, e->d.ln_eps, e->yc_ln, nullptr, nb,
+            if ((rc = ap_layernorm_run(ctx, e->xc, D, L.fold2 ? e->ones : L.ln2_g, L.fold2 ? e->zeros : L.ln2_b, e->d.ln_eps, e->yc_ln, nullptr, nb,
                                        D, st)))
                 return rc;
             p = L.pc_1; p.M = nb;
@@ -245,12 +246,12 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         } else if ((rc = ap_attention_run(ctx, e->qkv, e->y2, nb, T1, e->d.heads, st))) return rc;
         p = L.p_o; p.M = rows;
         if ((rc = ap_gemm_run(ctx, &p, L.b_o, e->x, e->x, fold ? &prod2 : nullptr, st))) return rc;
-        if (!fold && (rc = (L.asplit & 4) ? ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1s, nullptr, rows, D, st, 2 * D, 1)
+        if (!L.fold2 && (rc = (L.asplit & 4) ? ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1s, nullptr, rows, D, st, 2 * D, 1)
                                           : ap_layernorm_run(ctx, e->x, D, L.ln2_g, L.ln2_b, e->d.ln_eps, e->y1, nullptr, rows, D, st)))
             return rc;
         p = L.p_1; p.M = rows;
         cons.stats_in = e->stats2;
-        if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hbuf, fold ? &cons : nullptr, st))) return rc;
+        if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hbuf, L.fold2 ? &cons : nullptr, st))) return rc;
         p = L.p_2; p.M = rows;
         if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->x, e->x, fold ? &prod1 : nullptr, st))) return rc;
     }
@@ -383,9 +384,10 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         if ((rc = upload_f32(e, &e->lnf_g, *g))) return rc;
         if ((rc = upload_f32(e, &e->lnf_b, *b))) return rc;
     }
-    // 1 (default) = automatic: on for encoders of up to 32 layers; the 40-layer DINOv2 giant has no precision budget left for reading
-    // the un-normalised residual stream in fp16 (its black-overhang case row goes from 0.97e-3 to 1.03e-3), so it keeps the LayerNorm
-    // kernels.  0 = off, 2 = on regardless of depth.
+    // LayerNorm folding is decided per layer and per LayerNorm: a GEMM whose A operand is split into [hi | lo] needs the LayerNorm kernel
+    // that writes that pair, every other in_proj / mlp.0 reads the raw residual stream.  0 = off, 1 (default) = automatic, 2 = on.
+    // Automatic (1) leaves encoders deeper than 32 layers unfolded as before: measured on the giant, folding its 32 plain layers trades
+    // 27 ms of LayerNorm kernels for 59 ms of heavier producer / consumer epilogues per 1 016 patches (1 370 -> 1 375 patches/s: nothing).
     e->fold_ln = ctx->fold_ln == 2 || (ctx->fold_ln == 1 && e->d.layers <= 32);
     e->ln_parts = D / ((D % 256 == 0 ? 256 : 128) / 2);   // one partial per bn/2-column block of the N = D producer GEMMs
     e->layers.resize(e->d.layers);
@@ -404,7 +406,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         // LayerNorm kernels (not the folded form) and the tcgen05 attention epilogue; the class-token tail of the last layer keeps
         // single operands.
         const bool a_kind = ctx->precise_kind == 1;
-        const bool a_ok = !e->fold_ln && (T1 <= 257) && ctx->attn_mode == 2 && !(i + 1 == e->d.layers && ctx->cls_only_last_layer);
+        const bool a_ok = (T1 <= 257) && ctx->attn_mode == 2 && !(i + 1 == e->d.layers && ctx->cls_only_last_layer);
         const int pm = ctx->precise_mask & 15;
         if (a_kind) {            // A operands of qkv / out_proj / mlp.0 split, weights of mlp.3 split
             L.asplit = (i < e->precise_layers && a_ok) ? (pm & 7) : 0;
@@ -414,11 +416,11 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
             const int aw = ctx->precise_aw_layers >= 0 ? ctx->precise_aw_layers : (e->d.layers > 32 ? 8 : 0);
             L.asplit = (i < e->precise_layers && i < aw && a_ok) ? (pm & 7) : 0;
         }
+        L.fold1 = e->fold_ln && !(L.asplit & 1);
+        L.fold2 = e->fold_ln && !(L.asplit & 4);
         std::vector<float> wq(*wqkv), bq(*bqkv), wf(*w1), bf1(*b1);
-        if (e->fold_ln) {
-            fold_ln_affine(wq, bq, *ln1g, *ln1b, (size_t)3 * D, D);
-            fold_ln_affine(wf, bf1, *ln2g, *ln2b, (size_t)M1, D);
-        }
+        if (L.fold1) fold_ln_affine(wq, bq, *ln1g, *ln1b, (size_t)3 * D, D);
+        if (L.fold2) fold_ln_affine(wf, bf1, *ln2g, *ln2b, (size_t)M1, D);
         if ((rc = upload_f32(e, &L.ln1_g, *ln1g)) || (rc = upload_f32(e, &L.ln1_b, *ln1b)) ||
             (rc = upload_f32(e, &L.ln2_g, *ln2g)) || (rc = upload_f32(e, &L.ln2_b, *ln2b)) ||
             (rc = upload_f32(e, &L.b_qkv, bq)) || (rc = upload_f32(e, &L.b_o, *bo)) ||

@@ -55,8 +55,8 @@ class B200FeatureExtractor:
         ViT-B/16 (bench.py uses 508), +2-5 % for ViT-L / DINOv2.
         precision: "fast" = the library defaults (typical rows 5.5e-4 of the fp32 path, p99 9.3e-4; rows with
         two large flat regions -- a patch hanging 40 % over the slide edge next to white background -- touch 1.0e-3);
-        "strict" = LayerNorm kernels instead of folding, two leading layers with split weights AND split A operands: max 8.1e-4 on
-        the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log) for ~20 % more GEMM work."""
+        "strict" = two leading layers with split weights AND split A operands (they run their LayerNorm kernels, the other layers stay
+        folded): max 8.7e-4 on the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log), 21.1 k against 24.1 k patches/s."""
         if precision not in ("fast", "strict"):
             raise ValueError("precision must be 'fast' or 'strict'")
         preprocess, resize_to, mlp_kind = 0, 0, 0
@@ -83,7 +83,7 @@ class B200FeatureExtractor:
         self.ctx = Context.get(device)
         lib = self.ctx.lib
         if precision == "strict" and precise_layers < 2:
-            precise_layers = max(2, 8 if layers > 32 else 2)
+            precise_layers = 2 if layers <= 32 else 12
         desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
                        input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=1e-6,
                        mean=(C.c_float * 3)(*IMAGENET_MEAN), std=(C.c_float * 3)(*IMAGENET_STD), preprocess=preprocess,
@@ -98,14 +98,12 @@ class B200FeatureExtractor:
                 t = state_dict[key]
                 a = t.detach().to("cpu").float().contiguous().numpy() if hasattr(t, "detach") else np.ascontiguousarray(t, np.float32)
                 self.ctx.check(lib.ap_encoder_set_tensor(h, key.encode(), a.ctypes.data_as(C.c_void_p), a.size))
-            if precision == "strict":     # the three settings are read at finalize; they are context-wide, so put the defaults back
-                self.ctx.set_option("fold_ln", 0)
-                self.ctx.set_option("precise_aw_layers", 2)
+            if precision == "strict":     # read at finalize; context-wide, so put the default back.  The layers whose A operands are
+                self.ctx.set_option("precise_aw_layers", 2 if layers <= 32 else 12)   # split run their LayerNorm kernels, the rest stay folded
             try:
                 self.ctx.check(lib.ap_encoder_finalize(h))
             finally:
                 if precision == "strict":
-                    self.ctx.set_option("fold_ln", 1)
                     self.ctx.set_option("precise_aw_layers", -1)
         except Exception:
             lib.ap_encoder_destroy(h)

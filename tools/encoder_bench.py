@@ -1,6 +1,6 @@
 """Device-timed throughput of any registered encoder on an HBM-resident synthetic slide (embed_coords fast path).
 
-    python tools/encoder_bench.py dinov2_large 224 [n_patches] [max_batch]
+    python tools/encoder_bench.py dinov2_large 224 [n_patches] [max_batch] [fast|strict]
 """
 import json
 import sys
@@ -19,12 +19,13 @@ GFLOP = {"vit_b_16": 35.13, "vit_l_16": 123.11, "dinov2_large": 162.02, "dinov2_
 name, P = sys.argv[1], int(sys.argv[2])
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 1016
 mb = int(sys.argv[4]) if len(sys.argv) > 4 else 127
+precision = sys.argv[5] if len(sys.argv) > 5 else "fast"     # "fast" | "strict" (B200FeatureExtractor precision preset)
 if name.startswith("dinov2"):
     from oracle.dinov2_hf import dinov2_state_dict as make_sd
 else:
     from oracle.weights import vit_state_dict as make_sd
 sd = make_sd(name, seed=1)
-ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=mb)
+ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=mb, precision=precision)
 del sd
 wsi = SyntheticWSI(make_spec(20000, 20000, 3))
 rng = np.random.default_rng(0)
