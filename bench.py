@@ -678,15 +678,25 @@ def main_b200(args):
     del ext, feats, coords_ring
     aux_cfg = {} if args.aux.strip().lower() in ("", "none") else {k.strip(): True for k in args.aux.split(",")}
     aux_out = {}
-    if "c2" in aux_cfg:
-        aux_out["c2"] = aux_c2_sam2(ctx, rank, world)
+    def _aux(key, fn, *a):
+        # The aux configs must not take the headline down with them.  On one GPU an exception is recorded in the line; with several
+        # ranks it propagates (the other ranks are inside the same collectives: swallowing it on one rank would hang the rest).
+        if key not in aux_cfg:
+            return
+        if world > 1:
+            aux_out[key] = fn(*a)
+            return
+        try:
+            aux_out[key] = fn(*a)
+        except Exception as exc:  # noqa: BLE001
+            aux_out[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    _aux("c2", aux_c2_sam2, ctx, rank, world)
     wsi.cleanup()
     del wsi, image
     torch.cuda.empty_cache()
-    if "c3" in aux_cfg:
-        aux_out["c3"] = aux_c3_slides(ctx, rank, world, local_rank, peaks)
-    if "c4" in aux_cfg:
-        aux_out["c4"] = aux_c4_intra_slide(ctx, rank, world, local_rank, peaks, args.c4_cap)
+    _aux("c3", aux_c3_slides, ctx, rank, world, local_rank, peaks)
+    _aux("c4", aux_c4_intra_slide, ctx, rank, world, local_rank, peaks, args.c4_cap)
 
     if rank != 0:
         if world > 1:
