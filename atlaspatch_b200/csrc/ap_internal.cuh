@@ -219,6 +219,9 @@ int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64
                              cudaStream_t stream);
 // class-token query only; image b's output row is out[b * out_row_stride] (1: compact rows, S: row 0 of every image's block)
 int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, int out_row_stride, cudaStream_t stream);
+// [CLS || mean(patch tokens)] of the final-LayerNorm'd sequence: x [n_images, tokens1, D] fp32 -> out [n_images, 2 D] fp32
+int ap_cls_mean_pool_run(ap_ctx* ctx, const float* x, int n_images, int tokens1, int D, const float* gamma, const float* beta, float eps,
+                         float* out, cudaStream_t stream);
 int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, int64_t src_row_stride, int D, cudaStream_t stream);
 int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D, __half* xh,
                     float2* stats, int parts, cudaStream_t stream);

@@ -34,6 +34,7 @@ struct ap_encoder {
     ap_ctx* ctx = nullptr;
     ap_vit_desc d{};
     int tokens = 0;   // patches per image (196)
+    int out_dim = 0;  // features per patch: hidden (class token) or 2 * hidden ([class || mean of patch tokens], desc.pool == 1)
     int kpe = 0;      // 3 * patch * patch
     int kpe_pad = 0;  // kpe rounded up to the GEMM's 64-wide K block (588 -> 640 for patch 14); pad columns stay zero
     // preprocess 1 (BitImageProcessorFast): tap tables of the input_patch -> resize_to antialias bicubic resize
@@ -222,7 +223,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         p = L.p_qkv; p.M = rows;
         cons.stats_in = e->stats1;
         if ((rc = ap_gemm_run(ctx, &p, L.b_qkv, nullptr, e->qkv, L.fold1 ? &cons : nullptr, st))) return rc;
-        if (li + 1 == e->layers.size() && ctx->cls_only_last_layer) {
+        if (li + 1 == e->layers.size() && ctx->cls_only_last_layer && e->d.pool == 0) {
             // Only x[:, 0] survives the final LayerNorm (models/patch/base.py:100 -> torchvision forward `x[:, 0]`): the last
             // layer's attention needs every token's K/V but only the class-token query, and out_proj / MLP only that row.
             if ((rc = ap_cls_attention_run(ctx, e->qkv, e->yc_attn, nb, T1, e->d.heads, 1, st))) return rc;
@@ -255,6 +256,8 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         p = L.p_2; p.M = rows;
         if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->x, e->x, fold ? &prod1 : nullptr, st))) return rc;
     }
+    if (e->d.pool == 1)   // final LayerNorm on every token, then [class || mean of the patch tokens] (midnight.py:57-61)
+        return ap_cls_mean_pool_run(ctx, e->x, nb, T1, D, e->lnf_g, e->lnf_b, e->d.ln_eps, out_feats, st);
     // final LayerNorm on the class-token rows only -> fp32 features
     return ap_layernorm_run(ctx, e->x, static_cast<int64_t>(T1) * D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
 }
@@ -265,7 +268,8 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     if (!ctx || !desc || !out_enc) return AP_EINVAL;
     DeviceGuard guard(ctx);
     *out_enc = nullptr;
-    AP_REQUIRE(ctx, desc->preprocess >= 0 && desc->preprocess <= 2, "encoder: unknown preprocess %d", desc->preprocess);
+    AP_REQUIRE(ctx, desc->preprocess >= 0 && desc->preprocess <= 3, "encoder: unknown preprocess %d", desc->preprocess);
+    AP_REQUIRE(ctx, desc->pool == 0 || desc->pool == 1, "encoder: unknown pool %d (0 class token, 1 [class || mean of patch tokens])", desc->pool);
     AP_REQUIRE(ctx, desc->mlp_kind == 0 || desc->mlp_kind == 1, "encoder: unknown mlp_kind %d", desc->mlp_kind);
     AP_REQUIRE(ctx, desc->patch == 16 || desc->patch == 32 || (desc->preprocess >= 1 && desc->patch >= 4 && desc->patch <= 32),
                "encoder: conv patch %d unsupported (16 / 32 with the crop preprocess, 4..32 with the resizing preprocesses)", desc->patch);
@@ -284,6 +288,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     e->d = *desc;
     const int g = desc->image_size / desc->patch;
     e->tokens = g * g;
+    e->out_dim = desc->pool == 1 ? 2 * desc->hidden : desc->hidden;
     e->kpe = 3 * desc->patch * desc->patch;
     e->kpe_pad = (e->kpe + 63) / 64 * 64;
     e->max_batch = desc->max_batch > 0 ? desc->max_batch : 127;
@@ -319,7 +324,7 @@ extern "C" int ap_encoder_destroy(ap_encoder* e) {
     return AP_OK;
 }
 
-extern "C" int ap_encoder_embedding_dim(const ap_encoder* e) { return e ? e->d.hidden : 0; }
+extern "C" int ap_encoder_embedding_dim(const ap_encoder* e) { return e ? e->out_dim : 0; }
 
 extern "C" int ap_encoder_set_tensor(ap_encoder* e, const char* name, const float* data_host, int64_t numel) {
     if (!e || !name || !data_host || numel <= 0) return AP_EINVAL;
@@ -406,7 +411,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         // LayerNorm kernels (not the folded form) and the tcgen05 attention epilogue; the class-token tail of the last layer keeps
         // single operands.
         const bool a_kind = ctx->precise_kind == 1;
-        const bool a_ok = (T1 <= 257) && ctx->attn_mode == 2 && !(i + 1 == e->d.layers && ctx->cls_only_last_layer);
+        const bool a_ok = (T1 <= 257) && ctx->attn_mode == 2 && !(i + 1 == e->d.layers && ctx->cls_only_last_layer && e->d.pool == 0);
         const int pm = ctx->precise_mask & 15;
         if (a_kind) {            // A operands of qkv / out_proj / mlp.0 split, weights of mlp.3 split
             L.asplit = (i < e->precise_layers && a_ok) ? (pm & 7) : 0;
@@ -503,7 +508,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     // ---- tap tables of the resizing preprocess ----------------------------------------------------------------
     if (e->d.preprocess >= 1) {
         std::vector<int32_t> tmin, tcnt, tw;
-        if ((rc = ap_build_resize_tables(ctx, e->d.input_patch, e->d.resize_to, e->d.image_size, e->d.preprocess == 2 ? 1 : 0, tmin, tcnt, tw,
+        if ((rc = ap_build_resize_tables(ctx, e->d.input_patch, e->d.resize_to, e->d.image_size, e->d.preprocess - 1, tmin, tcnt, tw,
                                          &e->max_taps, &e->tap_precision)))
             return rc;
         for (int tr = 0; tr < e->d.image_size / P; ++tr) {
@@ -524,9 +529,9 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     const size_t patch_bytes = IP * IP * 3;
     for (int i = 0; i < 2; ++i) {
         AP_CHECK_CUDA(ctx, cudaMallocHost((void**)&e->pin_in[i], (size_t)MB * patch_bytes));
-        AP_CHECK_CUDA(ctx, cudaMallocHost((void**)&e->pin_out[i], (size_t)MB * D * 4));
+        AP_CHECK_CUDA(ctx, cudaMallocHost((void**)&e->pin_out[i], (size_t)MB * e->out_dim * 4));
         if ((rc = dev_alloc(e, (void**)&e->dev_patches[i], (size_t)MB * patch_bytes)) ||
-            (rc = dev_alloc(e, (void**)&e->dev_feats[i], (size_t)MB * D * 4)))
+            (rc = dev_alloc(e, (void**)&e->dev_feats[i], (size_t)MB * e->out_dim * 4)))
             return rc;
         AP_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
         AP_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
@@ -561,7 +566,7 @@ extern "C" int ap_encoder_embed_coords(ap_encoder* e, const uint8_t* slide_dev, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int64_t s = 0; s < n; s += e->max_batch) {
         const int nb = static_cast<int>(n - s < e->max_batch ? n - s : e->max_batch);
-        int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, read_size, out_features_dev + s * e->d.hidden, st);
+        int rc = forward_chunk(e, slide_dev, W, H, pitch, coords_dev + s * 5, nb, read_size, out_features_dev + s * e->out_dim, st);
         if (rc) return rc;
     }
     return AP_OK;
@@ -606,7 +611,7 @@ extern "C" int ap_encoder_embed_patches_host(ap_encoder* e, const uint8_t* const
     AP_REQUIRE(ctx, n >= 0, "embed_patches_host: n < 0");
     if (n == 0) return AP_OK;
     AP_REQUIRE(ctx, patches_host && out_features_host, "embed_patches_host: NULL pointer");
-    const int MB = e->max_batch, D = e->d.hidden;
+    const int MB = e->max_batch, D = e->out_dim;
     const size_t IP = e->d.input_patch, patch_bytes = IP * IP * 3;
     // Chunk schedule: the first chunk's gather + H2D is not overlapped with anything, so with large workspaces the pipeline ramps up:
     // 127 patches, then max_batch - 127 (together one full chunk, so what follows stays aligned to max_batch), then full chunks.  With

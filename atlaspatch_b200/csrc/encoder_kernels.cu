@@ -187,6 +187,86 @@ layernorm_kernel(const float* __restrict__ x, int64_t x_row_stride, const float*
 }
 
 // =====================================================================================================
+// [CLS || mean(patch tokens)] head (atlas_patch/models/patch/midnight.py:57-61, virchow.py:57-61): the final LayerNorm applied to
+// EVERY token of the residual stream, then  out[b] = [ LN(x[b, 0]) , mean_{t >= 1} LN(x[b, t]) ]  (2 D floats per image).
+// One CTA per image; each warp normalises whole rows held in registers (as layernorm_kernel) and sums the normalised values of its
+// rows; gamma / beta are applied to the mean once (the LayerNorm's affine map commutes with it).  The 8 warp partials are added
+// in warp order, so the result does not depend on scheduling.  HBM-bound: tokens * D * 4 bytes read once per image.
+// =====================================================================================================
+template <int VEC>  // D = VEC * 128
+__global__ void __launch_bounds__(256)
+cls_mean_pool_kernel(const float* __restrict__ x, int tokens1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float eps, float* __restrict__ out) {
+    constexpr int D = VEC * 128;
+    __shared__ float4 s_acc[VEC * 32];
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xb = x + static_cast<int64_t>(blockIdx.x) * tokens1 * D;
+    float* ob = out + static_cast<int64_t>(blockIdx.x) * 2 * D;
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    float4 acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // warp 0 starts at the class token (t = 0), which is written out instead of accumulated; patch tokens are dealt round-robin
+    for (int t = warp; t < tokens1; t += 8) {
+        const float4* xr = reinterpret_cast<const float4*>(xb + static_cast<int64_t>(t) * D);
+        float4 v[VEC];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            v[i] = xr[lane + 32 * i];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.0f / D);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+        if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float4 g = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+                reinterpret_cast<float4*>(ob)[lane + 32 * i] =
+                    make_float4(v[i].x * rstd * g.x + bb.x, v[i].y * rstd * g.y + bb.y, v[i].z * rstd * g.z + bb.z, v[i].w * rstd * g.w + bb.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                acc[i].x += v[i].x * rstd; acc[i].y += v[i].y * rstd; acc[i].z += v[i].z * rstd; acc[i].w += v[i].w * rstd;
+            }
+        }
+    }
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float4 a = acc[i];
+                if (w > 0) {
+                    const float4 p = s_acc[lane + 32 * i];
+                    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+                }
+                s_acc[lane + 32 * i] = a;
+            }
+        }
+        __syncthreads();
+    }
+    const float inv = 1.0f / static_cast<float>(tokens1 - 1);
+    for (int j = threadIdx.x; j < VEC * 32; j += 256) {
+        const float4 a = s_acc[j], g = __ldg(g4 + j), bb = __ldg(b4 + j);
+        reinterpret_cast<float4*>(ob + D)[j] = make_float4(a.x * inv * g.x + bb.x, a.y * inv * g.y + bb.y, a.z * inv * g.z + bb.z, a.w * inv * g.w + bb.w);
+    }
+}
+
+// =====================================================================================================
 // Multi-head self-attention, head_dim 64, sequence S <= 272 (197 for ViT/16@224, 257 for ViT/14@224).
 // nn.MultiheadAttention semantics (torchvision EncoderBlock.self_attention): softmax((q/sqrt(d)) k^T) v.
 // One CTA per (head, image): Q, K, V head slices staged once in (XOR-swizzled) smem with cp.async,
@@ -543,6 +623,27 @@ int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const fl
     }
 #undef AP_LN_CASE
     AP_CHECK_LAUNCH(ctx, "layernorm_kernel");
+    return AP_OK;
+}
+
+int ap_cls_mean_pool_run(ap_ctx* ctx, const float* x, int n_images, int tokens1, int D, const float* gamma, const float* beta, float eps,
+                         float* out, cudaStream_t stream) {
+    AP_REQUIRE(ctx, D % 128 == 0 && D <= 1536, "cls_mean pool: D=%d unsupported (multiple of 128, <= 1536)", D);
+    AP_REQUIRE(ctx, tokens1 >= 2, "cls_mean pool: needs at least one patch token (tokens %d)", tokens1);
+    if (n_images == 0) return AP_OK;
+    ProfScope prof(ctx, stream, AP_K_LAYERNORM);
+#define AP_POOL_CASE(V)                                                                                                          \
+    case V:                                                                                                                      \
+        AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_mean_pool_kernel<V>, dim3(n_images), dim3(256), 0, stream, 1, ctx->pdl != 0, x, tokens1, gamma, \
+                                         beta, eps, out));                                                                       \
+        break;
+    switch (D / 128) {
+        AP_POOL_CASE(1) AP_POOL_CASE(2) AP_POOL_CASE(3) AP_POOL_CASE(4) AP_POOL_CASE(5) AP_POOL_CASE(6) AP_POOL_CASE(8) AP_POOL_CASE(10)
+        AP_POOL_CASE(12)
+        default: return ap_set_error(ctx, AP_EINVAL, "cls_mean pool: D=%d not instantiated", D);
+    }
+#undef AP_POOL_CASE
+    AP_CHECK_LAUNCH(ctx, "cls_mean_pool_kernel");
     return AP_OK;
 }
 

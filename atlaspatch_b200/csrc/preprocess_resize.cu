@@ -100,11 +100,13 @@ double cubic_aa(double x) {  // Keys cubic, a = -0.5 (ATen HelperInterpCubic::aa
 //           n_out outputs so that the largest weight fits int16 (transformers' BitImageProcessorFast, DINOv2);
 //   kind 1: Pillow's own BILINEAR (triangle, support 1): precompute_coeffs + normalize_coeffs_8bpc, fixed 22-bit int32
 //           coefficients (torchvision's ImageClassification preset on the PIL image the reference hands it; crop offset
-//           int(round((n_out - image) / 2.0)) as torchvision's center_crop computes it).
+//           int(round((n_out - image) / 2.0)) as torchvision's center_crop computes it);
+//   kind 2: ATen's uint8 bilinear with antialias (triangle, support 1; int16 weights with the precision rule of kind 0): what
+//           transformers' ViTImageProcessorFast runs for `resample = 2` checkpoints (atlas_patch/models/patch/phikon.py:15-21,46).
 int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, int kind, std::vector<int32_t>& tap_min, std::vector<int32_t>& tap_cnt,
                            std::vector<int32_t>& tap_w, int* max_taps, int* precision) {
     AP_REQUIRE(ctx, n_in > 0 && n_out >= image && image > 0, "resize tables: bad sizes %d -> %d crop %d", n_in, n_out, image);
-    AP_REQUIRE(ctx, kind == 0 || kind == 1, "resize tables: unknown filter kind %d", kind);
+    AP_REQUIRE(ctx, kind >= 0 && kind <= 2, "resize tables: unknown filter kind %d", kind);
     const double scale = static_cast<double>(n_in) / n_out;
     const double fsup = kind == 0 ? 2.0 : 1.0;
     const double support = scale >= 1.0 ? fsup * scale : fsup;
@@ -135,13 +137,13 @@ int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, int kind
         if (xsize > taps) taps = xsize;
     }
     int prec = 22;                         // Pillow: PRECISION_BITS = 32 - 8 - 2
-    if (kind == 0)
+    if (kind != 1)
         for (prec = 0; prec < 22; ++prec) {
             const int next = static_cast<int>(0.5 + wt_max * (1 << (prec + 1)));
             if (next >= (1 << 15)) break;
         }
     // transformers center_crop: top = (h - crop) // 2; torchvision center_crop: int(round((h - crop) / 2.0)) (half to even)
-    const int off = kind == 0 ? (n_out - image) / 2 : static_cast<int>(std::nearbyint((n_out - image) / 2.0));
+    const int off = kind != 1 ? (n_out - image) / 2 : static_cast<int>(std::nearbyint((n_out - image) / 2.0));
     tap_min.assign(image, 0);
     tap_cnt.assign(image, 0);
     tap_w.assign(static_cast<size_t>(image) * taps, 0);

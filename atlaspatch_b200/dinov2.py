@@ -23,6 +23,17 @@ DINOV2_CONFIGS = {
     "dinov2_giant": (14, 40, 24, 1536, 4096, True),
     "dinov2_test_tiny": (14, 2, 4, 256, 1024, False),
     "dinov2_test_tiny_swiglu": (14, 2, 6, 384, 1024, True),
+    # hub encoders with the same Dinov2Model architecture: kaiko-ai/midnight (models/patch/midnight.py:12,44: ViT-g/14, feature =
+    # [class || mean of patch tokens]) and owkin/phikon-v2 (models/patch/phikon.py:90-93: ViT-L/16)
+    "midnight": (14, 40, 24, 1536, 4096, True),
+    "phikon_v2": (16, 24, 16, 1024, 4096, False),
+    "midnight_test_tiny": (14, 2, 6, 384, 1024, True),
+    "phikon_v2_test_tiny": (16, 2, 4, 256, 1024, False),
+}
+# name -> (patch, layers, heads, hidden, mlp): transformers ViTModel checkpoints (owkin/phikon, models/patch/phikon.py:41-44)
+HF_VIT_CONFIGS = {
+    "phikon_v1": (16, 12, 12, 768, 3072),
+    "phikon_v1_test_tiny": (16, 2, 4, 256, 512),
 }
 SWIGLU_BLOCK = 16
 
@@ -105,4 +116,32 @@ def convert_dinov2_state_dict(sd: Mapping[str, object], *, layers: int, swiglu: 
             w_out, b_out = _np(sd[s + "mlp.fc2.weight"]), _np(sd[s + "mlp.fc2.bias"])
         out[d + "mlp.3.weight"] = w_out * ls2[:, None]
         out[d + "mlp.3.bias"] = b_out * ls2
+    return out
+
+
+def convert_hf_vit_state_dict(sd: Mapping[str, object], *, layers: int) -> dict[str, np.ndarray]:
+    """transformers ViTModel names (what `ViTModel.from_pretrained("owkin/phikon", add_pooling_layer=False)` gives the reference,
+    models/patch/phikon.py:41-44) -> engine names.  Same pre-LayerNorm block as torchvision's (layernorm_before / attention /
+    layernorm_after / intermediate GELU / output), query / key / value stacked into one in_proj; no LayerScale, learned position
+    embedding used as stored (224 px checkpoints, 14 x 14 grid)."""
+    sd = {k[len("vit."):] if k.startswith("vit.") else k: v for k, v in sd.items()}
+    out: dict[str, np.ndarray] = {}
+    out["conv_proj.weight"] = _np(sd["embeddings.patch_embeddings.projection.weight"])
+    out["conv_proj.bias"] = _np(sd["embeddings.patch_embeddings.projection.bias"])
+    out["class_token"] = _np(sd["embeddings.cls_token"]).reshape(1, 1, -1)
+    pos = _np(sd["embeddings.position_embeddings"])
+    out["encoder.pos_embedding"] = pos.reshape(1, pos.shape[-2], pos.shape[-1])
+    out["encoder.ln.weight"], out["encoder.ln.bias"] = _np(sd["layernorm.weight"]), _np(sd["layernorm.bias"])
+    for i in range(layers):
+        s, d = f"encoder.layer.{i}.", f"encoder.layers.encoder_layer_{i}."
+        out[d + "ln_1.weight"], out[d + "ln_1.bias"] = _np(sd[s + "layernorm_before.weight"]), _np(sd[s + "layernorm_before.bias"])
+        out[d + "ln_2.weight"], out[d + "ln_2.bias"] = _np(sd[s + "layernorm_after.weight"]), _np(sd[s + "layernorm_after.bias"])
+        out[d + "self_attention.in_proj_weight"] = np.concatenate(
+            [_np(sd[s + f"attention.attention.{n}.weight"]) for n in ("query", "key", "value")], axis=0)
+        out[d + "self_attention.in_proj_bias"] = np.concatenate(
+            [_np(sd[s + f"attention.attention.{n}.bias"]) for n in ("query", "key", "value")], axis=0)
+        out[d + "self_attention.out_proj.weight"] = _np(sd[s + "attention.output.dense.weight"])
+        out[d + "self_attention.out_proj.bias"] = _np(sd[s + "attention.output.dense.bias"])
+        out[d + "mlp.0.weight"], out[d + "mlp.0.bias"] = _np(sd[s + "intermediate.dense.weight"]), _np(sd[s + "intermediate.dense.bias"])
+        out[d + "mlp.3.weight"], out[d + "mlp.3.bias"] = _np(sd[s + "output.dense.weight"]), _np(sd[s + "output.dense.bias"])
     return out

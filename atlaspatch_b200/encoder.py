@@ -13,7 +13,7 @@ from typing import Mapping, Sequence
 import numpy as np
 
 from atlaspatch_b200._lib import Context, VitDesc, current_stream_ptr
-from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, convert_dinov2_state_dict
+from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, HF_VIT_CONFIGS, convert_dinov2_state_dict, convert_hf_vit_state_dict
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -26,6 +26,25 @@ VIT_CONFIGS = {
     "vit_l_32": (32, 24, 16, 1024, 4096),
     # vit_h_14 (models/patch/vit.py:14) has head_dim 80: not built -- the attention kernels are head_dim 64
     "vit_test_tiny": (16, 2, 4, 256, 512),
+}
+
+# Hub encoders of the reference that run on the same kernels with their own preprocess / head.  The
+# processor settings are the published contents of each repo's preprocessor_config.json (no network here: restated, not fetched).
+#   preprocess: ap_vit_desc.preprocess (1 ATen uint8 bicubic-antialias, 2 Pillow BILINEAR, 3 ATen uint8 bilinear-antialias)
+#   pool: 0 class token, 1 [class || mean of patch tokens]
+_HALF = (0.5, 0.5, 0.5)
+FAMILY_RECIPES = {
+    # kaiko-ai/midnight (models/patch/midnight.py:15-25,55-61): torchvision Resize(224) on the PIL patch, CenterCrop(224),
+    # Normalize(0.5, 0.5); feature = cat(last_hidden_state[:, 0], last_hidden_state[:, 1:].mean(1)) -> 3072
+    "midnight": dict(preprocess=2, resize_to=224, mean=_HALF, std=_HALF, pool=1, ln_eps=1e-6, default_patch=224),
+    "midnight_test_tiny": dict(preprocess=2, resize_to=224, mean=_HALF, std=_HALF, pool=1, ln_eps=1e-6, default_patch=224),
+    # owkin/phikon-v2 (models/patch/phikon.py:90-93,103-105): BitImageProcessor(fast) shortest_edge 224 bicubic, crop 224, ImageNet
+    "phikon_v2": dict(preprocess=1, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
+    "phikon_v2_test_tiny": dict(preprocess=1, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
+    # owkin/phikon (models/patch/phikon.py:41-46,54-56): ViTImageProcessor(fast) 224 x 224 resample 2 (bilinear), ImageNet; ViTModel
+    # with layer_norm_eps 1e-12
+    "phikon_v1": dict(preprocess=3, resize_to=224, pool=0, ln_eps=1e-12, default_patch=224),
+    "phikon_v1_test_tiny": dict(preprocess=3, resize_to=224, pool=0, ln_eps=1e-12, default_patch=224),
 }
 
 
@@ -59,16 +78,24 @@ class B200FeatureExtractor:
         folded): max 8.7e-4 on the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log), 21.1 k against 24.1 k patches/s."""
         if precision not in ("fast", "strict"):
             raise ValueError("precision must be 'fast' or 'strict'")
-        preprocess, resize_to, mlp_kind = 0, 0, 0
-        if config is None and name in DINOV2_CONFIGS:
-            patch, layers, heads, hidden, mlp, swiglu = DINOV2_CONFIGS[name]
-            state_dict = convert_dinov2_state_dict(state_dict, layers=layers, swiglu=swiglu, image_size=image_size, patch=patch)
-            preprocess, resize_to, mlp_kind = 1, 256, int(swiglu)
-            input_patch = 224 if input_patch is None else input_patch
+        preprocess, resize_to, mlp_kind, pool, ln_eps = 0, 0, 0, 0, 1e-6
+        mean, std = IMAGENET_MEAN, IMAGENET_STD
+        recipe = FAMILY_RECIPES.get(name, {}) if config is None else {}
+        if config is None and (name in DINOV2_CONFIGS or name in HF_VIT_CONFIGS):
+            if name in DINOV2_CONFIGS:
+                patch, layers, heads, hidden, mlp, swiglu = DINOV2_CONFIGS[name]
+                state_dict = convert_dinov2_state_dict(state_dict, layers=layers, swiglu=swiglu, image_size=image_size, patch=patch)
+            else:
+                (patch, layers, heads, hidden, mlp), swiglu = HF_VIT_CONFIGS[name], False
+                state_dict = convert_hf_vit_state_dict(state_dict, layers=layers)
+            preprocess, resize_to, mlp_kind = recipe.get("preprocess", 1), recipe.get("resize_to", 256), int(swiglu)
+            pool, ln_eps = recipe.get("pool", 0), recipe.get("ln_eps", 1e-6)
+            mean, std = recipe.get("mean", IMAGENET_MEAN), recipe.get("std", IMAGENET_STD)
+            input_patch = recipe.get("default_patch", 224) if input_patch is None else input_patch
         else:
             cfg = config or VIT_CONFIGS.get(name)
             if cfg is None:
-                raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS) + sorted(DINOV2_CONFIGS)}")
+                raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS) + sorted(DINOV2_CONFIGS) + sorted(HF_VIT_CONFIGS)}")
             patch, layers, heads, hidden, mlp = cfg
             input_patch = 256 if input_patch is None else input_patch
             if int(input_patch) != 256:
@@ -77,7 +104,8 @@ class B200FeatureExtractor:
                 preprocess, resize_to = 2, 256
         self._patch, self._grid = int(patch), int(image_size) // int(patch)
         self.name = registry_name or name   # H5 dataset name: features/<name> (services/storage.py:250-337)
-        self.embedding_dim = int(hidden)
+        self.embedding_dim = int(hidden) * (2 if pool == 1 else 1)
+        self._mean = tuple(float(m) for m in mean)
         self.input_patch = int(input_patch)
         self.max_batch = int(max_batch)
         self.ctx = Context.get(device)
@@ -85,9 +113,9 @@ class B200FeatureExtractor:
         if precision == "strict" and precise_layers < 2:
             precise_layers = 2 if layers <= 32 else 12
         desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
-                       input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=1e-6,
-                       mean=(C.c_float * 3)(*IMAGENET_MEAN), std=(C.c_float * 3)(*IMAGENET_STD), preprocess=preprocess,
-                       resize_to=resize_to, mlp_kind=mlp_kind)
+                       input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=ln_eps,
+                       mean=(C.c_float * 3)(*mean), std=(C.c_float * 3)(*std), preprocess=preprocess,
+                       resize_to=resize_to, mlp_kind=mlp_kind, pool=pool)
         h = C.c_void_p()
         self.ctx.check(lib.ap_encoder_create(self.ctx.handle, C.byref(desc), C.byref(h)))
         self._h = h
@@ -153,7 +181,7 @@ class B200FeatureExtractor:
         assert cols.value == kp
         a = buf[:n * g * g, :3 * p * p].float().cpu().numpy() * 256.0           # (n g g, 3 p p) = pixel - centre
         a = a.reshape(n, g, g, 3, p, p).transpose(0, 1, 4, 2, 5, 3).reshape(n, g * p, g * p, 3)
-        centre = np.rint(255.0 * np.asarray(IMAGENET_MEAN)).astype(np.float32)
+        centre = np.rint(255.0 * np.asarray(self._mean, dtype=np.float64)).astype(np.float32)   # encoder.cu: lrint(255 * mean_c)
         return np.rint(a + centre).astype(np.uint8)
 
     # ---- device-resident fast path -----------------------------------------------------------------

@@ -5,8 +5,9 @@
 
 The hook signature is the reference's CustomRegistryHook (atlas_patch/models/patch/custom.py:92-146).  Weights come
 from torchvision exactly as the reference's own `vit_b_16` builder resolves them (models/patch/base.py:126-180); the
-forward runs on the sm_100a kernels.  `b200_dinov2_large` / `b200_dinov2_giant` load transformers' Dinov2Model like the
-reference's DinoV2Encoder (models/patch/dinov2.py).  A CUDA device is mandatory: there is no CPU fallback.
+forward runs on the sm_100a kernels.  `b200_dinov2_*` load transformers' Dinov2Model like the reference's DinoV2Encoder
+(models/patch/dinov2.py); `b200_midnight`, `b200_phikon_v1`, `b200_phikon_v2` load the hub checkpoints like models/patch/midnight.py and
+phikon.py.  A CUDA device is mandatory: there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -60,6 +61,34 @@ def _build_dinov2(name: str, device, patch_size: int | None) -> B200FeatureExtra
     return B200FeatureExtractor(name, model.state_dict(), input_patch=patch, device=idx, registry_name=f"b200_{name}")
 
 
+# Hub encoders on the same kernels: name -> (hub id, loader), loaded exactly as the reference's classes do
+_HUB = {"midnight": "kaiko-ai/midnight",        # models/patch/midnight.py:12,44  AutoModel (Dinov2Model ViT-g/14), [class || mean] -> 3072
+        "phikon_v1": "owkin/phikon",            # models/patch/phikon.py:41-44    ViTModel(add_pooling_layer=False) -> 768
+        "phikon_v2": "owkin/phikon-v2"}         # models/patch/phikon.py:90-92    AutoModel (Dinov2Model ViT-L/16) -> 1024
+
+
+def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
+    """Weights as the reference loads them; each family's preprocess (torchvision Resize / CenterCrop / Normalize(0.5) for midnight,
+    the checkpoints' fast image processors for phikon) and head run in the CUDA path (encoder.py: FAMILY_RECIPES)."""
+    import os
+
+    import torch
+
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("atlaspatch_b200 encoders need a CUDA device (B200); no CPU fallback exists")
+    if name == "phikon_v1":
+        from transformers import ViTModel
+
+        model = ViTModel.from_pretrained(_HUB[name], add_pooling_layer=False)
+    else:
+        from transformers import AutoModel
+
+        model = AutoModel.from_pretrained(_HUB[name])
+    idx = torch.device(device).index or 0
+    patch = int(patch_size or os.environ.get("ATLASPATCH_B200_PATCH_SIZE", 224))
+    return B200FeatureExtractor(name, model.state_dict(), input_patch=patch, device=idx, registry_name=f"b200_{name}")
+
+
 def resolve_feature_dtype(device, precision: str):
     """services/feature_embedding.py:28-39: the reference's dtype policy (float16 is downgraded to float32 on CPU devices)."""
     import torch
@@ -80,3 +109,5 @@ def register_feature_extractors(registry, device, dtype, num_workers) -> None:
         registry.register(f"b200_{name}", lambda n=name: _build(n, device))
     for name in _DINOV2:
         registry.register(f"b200_{name}", lambda n=name: _build_dinov2(n, device, None))
+    for name in _HUB:
+        registry.register(f"b200_{name}", lambda n=name: _build_hub(n, device, None))

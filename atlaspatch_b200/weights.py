@@ -76,8 +76,15 @@ DINOV2_SPECS = {
     # tiny configs used only by fast unit tests
     "dinov2_test_tiny": (2, 4, 256, False),
     "dinov2_test_tiny_swiglu": (2, 6, 384, True),
+    # other hub encoders of the reference with the Dinov2Model architecture: kaiko-ai/midnight (ViT-g/14, atlas_patch/models/patch/
+    # midnight.py:12,44) and owkin/phikon-v2 (ViT-L/16, phikon.py:90-93)
+    "midnight": (40, 24, 1536, True),
+    "phikon_v2": (24, 16, 1024, False),
+    "midnight_test_tiny": (2, 6, 384, True),
+    "phikon_v2_test_tiny": (2, 4, 256, False),
 }
 PATCH = 14
+DINOV2_PATCH = {"phikon_v2": 16, "phikon_v2_test_tiny": 16}   # conv patch where it is not 14
 
 
 def swiglu_hidden(d: int) -> int:
@@ -85,11 +92,12 @@ def swiglu_hidden(d: int) -> int:
     return (int(int(d * 4) * 2 / 3) + 7) // 8 * 8
 
 
-def dinov2_state_dict(name: str, seed: int = 0, image_size: int = 518) -> dict[str, torch.Tensor]:
+def dinov2_state_dict(name: str, seed: int = 0, image_size: int = 518, patch: int | None = None) -> dict[str, torch.Tensor]:
     """Seeded weights in transformers' Dinov2Model key layout (numpy PCG64, independent of the torch build).  Biases, LayerNorm
     affine parameters, LayerScale and the class token are perturbed away from their init so that dropping one fails parity."""
     layers, heads, d, swiglu = DINOV2_SPECS[name]
     rng = np.random.default_rng(seed)
+    PATCH = int(patch or DINOV2_PATCH.get(name, 14))
     g = image_size // PATCH
 
     def normal(shape, std):
@@ -132,6 +140,51 @@ def dinov2_state_dict(name: str, seed: int = 0, image_size: int = 518) -> dict[s
     sd["layernorm.bias"] = normal((d,), 0.05)
     return sd
 
+
+
+# ---- transformers ViTModel key layout (owkin/phikon: atlas_patch/models/patch/phikon.py:41-46, add_pooling_layer=False) ----
+HF_VIT_SPECS = {
+    # name: (patch, layers, heads, hidden, mlp)
+    "phikon_v1": (16, 12, 12, 768, 3072),
+    "phikon_v1_test_tiny": (16, 2, 4, 256, 512),
+}
+
+
+def hf_vit_state_dict(name: str, seed: int = 0, image_size: int = 224) -> dict[str, torch.Tensor]:
+    """Seeded weights in transformers' ViTModel key layout; every bias / LayerNorm parameter away from its init value."""
+    patch, layers, heads, d, mlp = HF_VIT_SPECS[name]
+    rng = np.random.default_rng(seed)
+    g = image_size // patch
+
+    def normal(shape, std):
+        return torch.from_numpy((rng.standard_normal(shape, dtype=np.float32) * np.float32(std)))
+
+    def uniform(shape, bound):
+        return torch.from_numpy(rng.uniform(-bound, bound, shape).astype(np.float32))
+
+    sd: dict[str, torch.Tensor] = {}
+    sd["embeddings.cls_token"] = normal((1, 1, d), 0.02)
+    sd["embeddings.position_embeddings"] = normal((1, g * g + 1, d), 0.02)
+    sd["embeddings.patch_embeddings.projection.weight"] = normal((d, 3, patch, patch), math.sqrt(1.0 / (3 * patch * patch)))
+    sd["embeddings.patch_embeddings.projection.bias"] = normal((d,), 0.02)
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        sd[p + "layernorm_before.weight"] = 1.0 + normal((d,), 0.1)
+        sd[p + "layernorm_before.bias"] = normal((d,), 0.05)
+        for nm in ("query", "key", "value"):
+            sd[p + f"attention.attention.{nm}.weight"] = uniform((d, d), math.sqrt(6.0 / (d + 3 * d)))
+            sd[p + f"attention.attention.{nm}.bias"] = normal((d,), 0.02)
+        sd[p + "attention.output.dense.weight"] = uniform((d, d), math.sqrt(1.0 / d))
+        sd[p + "attention.output.dense.bias"] = normal((d,), 0.02)
+        sd[p + "layernorm_after.weight"] = 1.0 + normal((d,), 0.1)
+        sd[p + "layernorm_after.bias"] = normal((d,), 0.05)
+        sd[p + "intermediate.dense.weight"] = uniform((mlp, d), math.sqrt(6.0 / (d + mlp)))
+        sd[p + "intermediate.dense.bias"] = normal((mlp,), 0.02)
+        sd[p + "output.dense.weight"] = uniform((d, mlp), math.sqrt(6.0 / (d + mlp)))
+        sd[p + "output.dense.bias"] = normal((d,), 0.02)
+    sd["layernorm.weight"] = 1.0 + normal((d,), 0.1)
+    sd["layernorm.bias"] = normal((d,), 0.05)
+    return sd
 
 
 # ---- SAM2 (transformers Sam2Model key layout; 'tiny' = the model the reference ships, 'large' = BASELINE.json configs[2]) ----

@@ -145,11 +145,18 @@ typedef struct ap_vit_desc {
                          2: torchvision's ImageClassification preset for an input patch whose size differs from resize_to
                             (atlas_patch/models/patch/base.py:42-45,170: PIL image -> Image.resize(BILINEAR) = Pillow's antialiased
                             triangle filter in 22-bit fixed point -> centre crop -> /255 -> normalise); input_patch == resize_to needs
-                            no resize and uses preprocess 0 */
-    int resize_to;    /* 256 (preprocess 1, 2) */
+                            no resize and uses preprocess 0;
+                         3: transformers ViTImageProcessorFast with resample = 2 (atlas_patch/models/patch/phikon.py:15-21,46 for
+                            owkin/phikon): uint8 bilinear-antialias resize (ATen's separable uint8 kernel, triangle filter) of the
+                            input_patch^2 patch to resize_to^2, centre crop to image_size (none when equal), rescale + normalise */
+    int resize_to;    /* 256 (preprocess 1, 2); 224 (preprocess 3) */
     int mlp_kind;     /* 0: Linear - GELU - Linear, mlp = hidden features;
                          1: SwiGLU (Dinov2SwiGLUFFN): "mlp.0" = weights_in with 2 * mlp rows interleaved as AP_EPI_BIAS_SWIGLU_F16
                             expects, "mlp.3" = weights_out [hidden, mlp] */
+    int pool;         /* 0: feature = final LayerNorm of the class token (torchvision heads -> Identity, base.py:100; transformers
+                            last_hidden_state[:, 0], dinov2.py:60-62), hidden floats per patch;
+                         1: [class || mean of the patch tokens] of the final-LayerNorm'd sequence, 2 * hidden floats per patch
+                            (atlas_patch/models/patch/midnight.py:57-61, virchow.py:57-61) */
 } ap_vit_desc;
 
 int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc);

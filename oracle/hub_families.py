@@ -1,0 +1,110 @@
+"""TEST INFRASTRUCTURE ONLY.  CPU oracle for the hub encoders of SURVEY.md section 8(f) rank 4 that run on the DINOv2 / ViT kernels:
+
+* `midnight`  (atlas_patch/models/patch/midnight.py:12-25,44,55-61): `AutoModel.from_pretrained("kaiko-ai/midnight")` = a
+  transformers Dinov2Model (ViT-g/14, SwiGLU), torchvision `Resize(224) -> CenterCrop(224) -> ToTensor -> Normalize(0.5, 0.5)` on
+  the PIL patch, feature = cat(last_hidden_state[:, 0], last_hidden_state[:, 1:].mean(1))  -> 2 x 1536.
+* `phikon_v2` (phikon.py:90-93,103-105): `AutoModel.from_pretrained("owkin/phikon-v2")` = Dinov2Model (ViT-L/16, 224 px) with the
+  repo's BitImageProcessor (fast: shortest_edge 224 bicubic, crop 224, ImageNet mean / std), feature = last_hidden_state[:, 0].
+* `phikon_v1` (phikon.py:41-46,54-56): `ViTModel.from_pretrained("owkin/phikon", add_pooling_layer=False)` with the repo's
+  ViTImageProcessor (fast: 224 x 224, resample 2 = bilinear, ImageNet mean / std), feature = last_hidden_state[:, 0].
+
+There is no network: the oracle builds the classes those hub files resolve to, from the published contents of their config.json /
+preprocessor_config.json (restated from memory of the public repos -- parity of the *settings* is unpinned; parity of the
+*arithmetic* is pinned against transformers / torchvision run in this container on the same settings), with seeded weights.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from atlaspatch_b200.weights import DINOV2_PATCH, DINOV2_SPECS, HF_VIT_SPECS, dinov2_state_dict, hf_vit_state_dict  # noqa: F401
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def _family(name: str) -> str:
+    for fam in ("midnight", "phikon_v2", "phikon_v1"):
+        if name.startswith(fam):
+            return fam
+    raise KeyError(name)
+
+
+def state_dict(name: str, seed: int = 0) -> dict[str, torch.Tensor]:
+    """Seeded weights in the key layout of the model class the reference loads (224 px position grids)."""
+    if _family(name) == "phikon_v1":
+        return hf_vit_state_dict(name, seed=seed, image_size=224)
+    return dinov2_state_dict(name, seed=seed, image_size=224)
+
+
+def build_model(name: str, sd: dict[str, torch.Tensor]):
+    fam = _family(name)
+    if fam == "phikon_v1":
+        from transformers import ViTConfig, ViTModel
+
+        patch, layers, heads, d, mlp = HF_VIT_SPECS[name]
+        cfg = ViTConfig(hidden_size=d, num_hidden_layers=layers, num_attention_heads=heads, intermediate_size=mlp, patch_size=patch,
+                        image_size=224, hidden_act="gelu", layer_norm_eps=1e-12, qkv_bias=True)
+        model = ViTModel(cfg, add_pooling_layer=False).eval()
+    else:
+        from transformers import Dinov2Config, Dinov2Model
+
+        layers, heads, d, swiglu = DINOV2_SPECS[name]
+        cfg = Dinov2Config(hidden_size=d, num_hidden_layers=layers, num_attention_heads=heads, mlp_ratio=4, patch_size=DINOV2_PATCH.get(name, 14),
+                           image_size=224, use_swiglu_ffn=swiglu, layer_norm_eps=1e-6, qkv_bias=True, layerscale_value=1.0)
+        model = Dinov2Model(cfg).eval()
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    return model
+
+
+def make_preprocess(name: str):
+    """PIL image -> (3, 224, 224) float32, built from the same classes the reference builds."""
+    fam = _family(name)
+    if fam == "midnight":                                   # midnight.py:15-25
+        from torchvision import transforms
+
+        return transforms.Compose([transforms.Resize(224), transforms.CenterCrop(224), transforms.ToTensor(),
+                                   transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
+    import transformers
+
+    if fam == "phikon_v2":
+        proc = transformers.BitImageProcessor(do_resize=True, size={"shortest_edge": 224}, resample=3, do_center_crop=True,
+                                              crop_size={"height": 224, "width": 224}, do_rescale=True, rescale_factor=1 / 255,
+                                              do_normalize=True, image_mean=list(IMAGENET_MEAN), image_std=list(IMAGENET_STD), do_convert_rgb=True)
+    else:
+        proc = transformers.ViTImageProcessor(do_resize=True, size={"height": 224, "width": 224}, resample=2, do_rescale=True,
+                                              rescale_factor=1 / 255, do_normalize=True, image_mean=list(IMAGENET_MEAN),
+                                              image_std=list(IMAGENET_STD))
+    return lambda pil: proc(images=pil, return_tensors="pt")["pixel_values"].squeeze(0)       # phikon.py:15-21
+
+
+def pixels(name: str, patch: np.ndarray) -> np.ndarray:
+    """The uint8 (224, 224, 3) pixels the family's preprocess normalises, by the integer restatements of oracle/resize_aa.py."""
+    from oracle import resize_aa as ra
+
+    fam = _family(name)
+    if fam == "midnight":
+        return ra.vit_preset_pixels(patch, resize_to=224, crop=224)
+    if fam == "phikon_v2":
+        return ra.dinov2_pixels(patch, resize_to=224, crop=224) if patch.shape[0] != 224 else patch
+    return ra.hf_vit_pixels(patch, 224)
+
+
+@torch.inference_mode()
+def extract_features(patches: Sequence[np.ndarray], sd: dict[str, torch.Tensor], name: str, batch_size: int = 8) -> np.ndarray:
+    """The reference's extract_batch for these families (base.py:76-107 with each class's forward_fn), fp32 on the CPU."""
+    from PIL import Image
+
+    model = build_model(name, sd)
+    pre = make_preprocess(name)
+    cls_mean = _family(name) == "midnight"
+    outs = []
+    for i in range(0, len(patches), batch_size):
+        x = torch.stack([pre(Image.fromarray(np.asarray(p))) for p in patches[i:i + batch_size]])
+        h = model(pixel_values=x).last_hidden_state
+        outs.append(torch.cat([h[:, 0], h[:, 1:].mean(1)], dim=-1) if cls_mean else h[:, 0])
+    d = model.config.hidden_size * (2 if cls_mean else 1)
+    return torch.cat(outs).to(torch.float32).numpy() if outs else np.empty((0, d), dtype=np.float32)

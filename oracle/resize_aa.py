@@ -26,17 +26,24 @@ def _cubic(x: float, a: float = -0.5) -> float:
     return 0.0
 
 
-def aa_weights(n_in: int, n_out: int):
-    """(xmin[n_out], xsize[n_out], list of int64 weight arrays, precision)."""
+def _triangle(x: float) -> float:   # ATen HelperInterpLinear::aa_filter
+    x = abs(x)
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def aa_weights(n_in: int, n_out: int, mode: str = "bicubic"):
+    """(xmin[n_out], xsize[n_out], list of int64 weight arrays, precision).  mode "bilinear": the triangle filter with
+    interp_size 2 (support 1) through the same index / precision arithmetic (ViTImageProcessorFast with resample = 2: phikon.py)."""
+    filt, half = (_cubic, 2.0) if mode == "bicubic" else (_triangle, 1.0)
     scale = n_in / n_out
-    support = 2.0 * scale if scale >= 1.0 else 2.0
+    support = half * scale if scale >= 1.0 else half
     invscale = 1.0 / scale if scale >= 1.0 else 1.0
     xmins, sizes, ws = [], [], []
     for i in range(n_out):
         center = scale * (i + 0.5)
         xmin = max(int(center - support + 0.5), 0)
         xsize = min(int(center + support + 0.5), n_in) - xmin
-        w = np.array([_cubic((j + xmin - center + 0.5) * invscale) for j in range(xsize)], dtype=np.float64)
+        w = np.array([filt((j + xmin - center + 0.5) * invscale) for j in range(xsize)], dtype=np.float64)
         w = w / w.sum()
         xmins.append(xmin)
         sizes.append(xsize)
@@ -50,9 +57,9 @@ def aa_weights(n_in: int, n_out: int):
     return np.asarray(xmins), np.asarray(sizes), w16, prec
 
 
-def _resize_axis(a: np.ndarray, n_out: int, axis: int) -> np.ndarray:
+def _resize_axis(a: np.ndarray, n_out: int, axis: int, mode: str = "bicubic") -> np.ndarray:
     a = np.moveaxis(a, axis, 0).astype(np.int64)
-    xmins, sizes, w16, prec = aa_weights(a.shape[0], n_out)
+    xmins, sizes, w16, prec = aa_weights(a.shape[0], n_out, mode)
     out = np.empty((n_out,) + a.shape[1:], dtype=np.int64)
     for i in range(n_out):
         acc = np.tensordot(w16[i], a[xmins[i]:xmins[i] + sizes[i]], axes=(0, 0)) + (1 << (prec - 1))
@@ -60,10 +67,15 @@ def _resize_axis(a: np.ndarray, n_out: int, axis: int) -> np.ndarray:
     return np.moveaxis(out, 0, axis).astype(np.uint8)
 
 
-def resize_aa(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+def resize_aa(img: np.ndarray, out_h: int, out_w: int, mode: str = "bicubic") -> np.ndarray:
     """HWC uint8 -> (out_h, out_w, C) uint8; an axis whose size does not change is not resampled."""
-    t = _resize_axis(img, out_w, 1) if img.shape[1] != out_w else img
-    return _resize_axis(t, out_h, 0) if img.shape[0] != out_h else t
+    t = _resize_axis(img, out_w, 1, mode) if img.shape[1] != out_w else img
+    return _resize_axis(t, out_h, 0, mode) if img.shape[0] != out_h else t
+
+
+def hf_vit_pixels(patch: np.ndarray, size: int = 224) -> np.ndarray:
+    """uint8 (size, size, 3) that ViTImageProcessorFast (resize to size x size, resample 2 = bilinear, no crop) normalises."""
+    return resize_aa(patch, size, size, "bilinear") if patch.shape[0] != size or patch.shape[1] != size else patch
 
 
 def dinov2_pixels(patch: np.ndarray, resize_to: int = 256, crop: int = 224) -> np.ndarray:

@@ -1,0 +1,93 @@
+"""GPU: hub encoder families of SURVEY.md section 8(f) rank 4 on the DINOv2 / ViT kernels through the C ABI -- midnight ([class || mean
+of patch tokens] head, Pillow BILINEAR preset, atlas_patch/models/patch/midnight.py), phikon_v1 (transformers ViTModel + uint8
+bilinear-antialias processor, phikon.py:41-56) and phikon_v2 (Dinov2Model ViT-L/16 + bicubic processor, phikon.py:90-105):
+preprocess pixels bit-exact vs the integer restatements (pinned on the CPU against the reference's own preprocess objects),
+features within 1e-3 relative of transformers' models run in fp32 on the CPU with the same seeded weights."""
+import numpy as np
+import pytest
+
+from oracle import hub_families as hf
+
+pytestmark = pytest.mark.gpu
+
+
+def _slide():
+    from atlaspatch_b200.slide import SyntheticWSI
+    from atlaspatch_b200.synthetic import make_spec
+
+    return SyntheticWSI(make_spec(4096, 3072, 11, mpp=0.5))
+
+
+@pytest.mark.parametrize("name,P", [("midnight_test_tiny", 224), ("midnight_test_tiny", 256), ("midnight_test_tiny", 512),
+                                    ("phikon_v1_test_tiny", 224), ("phikon_v1_test_tiny", 256), ("phikon_v1_test_tiny", 300),
+                                    ("phikon_v2_test_tiny", 224), ("phikon_v2_test_tiny", 256)])
+def test_tiny_family_pixels_bit_exact_and_features(name, P):
+    import torch
+
+    from atlaspatch_b200.encoder import FAMILY_RECIPES, B200FeatureExtractor
+    from atlaspatch_b200.synthetic import render_region_host
+
+    wsi = _slide()
+    rng = np.random.default_rng(P + len(name))
+    n = 9
+    xy = np.stack([rng.integers(0, wsi.w - P, n), rng.integers(0, wsi.h - P, n)], 1)
+    xy[-1] = (wsi.w - P // 2, wsi.h - P // 3)                                   # overhang: zero padding like IWSI.extract
+    rows = np.concatenate([xy, np.full((n, 2), P), np.zeros((n, 1))], 1).astype(np.int32)
+    patches = [render_region_host(wsi.spec, int(x), int(y), P, P) for x, y in xy]
+    sd = hf.state_dict(name, seed=6)
+    ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=4)            # 9 patches -> three forward chunks
+    pool = FAMILY_RECIPES[name]["pool"]
+    assert ext.embedding_dim == sd["layernorm.weight"].numel() * (2 if pool == 1 else 1)
+    rows_dev = torch.from_numpy(rows).cuda()
+    pix = ext.preprocess_pixels(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows_dev[-4:])
+    for i in range(4):
+        assert np.array_equal(pix[i], hf.pixels(name, patches[n - 4 + i])), i
+    want = hf.extract_features(patches, sd, name)
+    got = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows_dev).cpu().numpy()
+    assert got.shape == want.shape
+    rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+    print(name, P, "rel err per row:", rel)
+    assert rel.max() < 1e-3, rel
+    if pool == 1:                                                               # both halves separately: the mean half has a much smaller norm
+        d = got.shape[1] // 2
+        for half in (slice(0, d), slice(d, 2 * d)):
+            r = np.linalg.norm(got[:, half] - want[:, half], axis=1) / np.linalg.norm(want[:, half], axis=1)
+            assert r.max() < 1e-3, r
+    got_host = ext.extract_batch(patches, batch_size=4)                         # FeatureExtractor contract, host patches
+    assert got_host.shape == got.shape and np.abs(got_host - got).max() < 1e-5
+    assert ext.extract_batch([]).shape == (0, ext.embedding_dim)
+    ext.cleanup()
+
+
+def test_midnight_head_at_full_width():
+    """ViT-g width (hidden 1536, 24 heads, SwiGLU 4096) with 2 layers: the 3072-float [class || mean] rows of midnight.py:53-61."""
+    import torch
+
+    from atlaspatch_b200 import dinov2 as d2
+    from atlaspatch_b200 import weights as wt
+    from atlaspatch_b200.encoder import FAMILY_RECIPES, B200FeatureExtractor
+    from atlaspatch_b200.synthetic import render_region_host
+
+    name = "midnight_test_wide"
+    wt.DINOV2_SPECS[name] = (2, 24, 1536, True)
+    d2.DINOV2_CONFIGS[name] = (14, 2, 24, 1536, 4096, True)
+    FAMILY_RECIPES[name] = FAMILY_RECIPES["midnight"]
+    try:
+        wsi = _slide()
+        P, n = 224, 5
+        rng = np.random.default_rng(1)
+        xy = np.stack([rng.integers(0, wsi.w - P, n), rng.integers(0, wsi.h - P, n)], 1)
+        rows = np.concatenate([xy, np.full((n, 2), P), np.zeros((n, 1))], 1).astype(np.int32)
+        patches = [render_region_host(wsi.spec, int(x), int(y), P, P) for x, y in xy]
+        sd = hf.state_dict(name, seed=2)
+        want = hf.extract_features(patches, sd, name)
+        ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=4)
+        got = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, torch.from_numpy(rows).cuda()).cpu().numpy()
+        assert got.shape == want.shape == (n, 3072)
+        rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert rel.max() < 1e-3, rel
+        ext.cleanup()
+    finally:
+        wt.DINOV2_SPECS.pop(name, None)
+        d2.DINOV2_CONFIGS.pop(name, None)
+        FAMILY_RECIPES.pop(name, None)

@@ -1,0 +1,108 @@
+"""CPU: the hub encoder families of SURVEY.md section 8(f) rank 4 (midnight, phikon_v1, phikon_v2) -- the integer pixel restatements
+against the preprocess objects the reference builds, and the host-side recipe (weight conversion, LayerNorm eps, mean / std,
+[class || mean] head) evaluated with plain torch ops against transformers' own models on tiny configs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hub_families as hf
+from oracle import resize_aa
+
+FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny"]
+
+
+def _patch(P, seed=0):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (P // 8 + 1, P // 8 + 1, 3), dtype=np.uint8)
+    img = np.kron(base, np.ones((8, 8, 1), dtype=np.uint8))[:P, :P]                       # blocky structure + noise
+    return (img.astype(np.int32) + rng.integers(-20, 20, img.shape)).clip(0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 224, 224), (512, 512, 224, 224), (224, 224, 224, 224), (100, 130, 224, 224), (300, 257, 224, 200)])
+def test_bilinear_restatement_is_bit_exact_vs_torch(shape):
+    h, w, oh, ow = shape
+    img = np.random.default_rng(h * 7 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    t = torch.from_numpy(img).permute(2, 0, 1)[None]
+    ref = F.interpolate(t, size=(oh, ow), mode="bilinear", antialias=True, align_corners=False)[0].permute(1, 2, 0).numpy()
+    assert np.array_equal(resize_aa.resize_aa(img, oh, ow, "bilinear"), ref)
+
+
+@pytest.mark.parametrize("name", FAMILIES)
+@pytest.mark.parametrize("P", [224, 256, 512])
+def test_pixels_match_the_reference_preprocess(name, P):
+    from PIL import Image
+
+    from atlaspatch_b200.encoder import FAMILY_RECIPES, IMAGENET_MEAN, IMAGENET_STD
+
+    patch = _patch(P, seed=P)
+    got = hf.make_preprocess(name)(Image.fromarray(patch)).permute(1, 2, 0).numpy()
+    r = FAMILY_RECIPES[name]
+    mean, std = np.asarray(r.get("mean", IMAGENET_MEAN), np.float32), np.asarray(r.get("std", IMAGENET_STD), np.float32)
+    want = (hf.pixels(name, patch).astype(np.float32) / 255.0 - mean) / std
+    assert got.shape == want.shape == (224, 224, 3)
+    assert np.abs(got - want).max() < 2e-6
+
+
+def _engine_forward(x, w, *, patch, layers, heads, d, mlp, swiglu, eps, pool):
+    """The engine's tensor layout (torchvision names) evaluated with plain torch ops."""
+    from atlaspatch_b200.dinov2 import SWIGLU_BLOCK
+
+    B = x.shape[0]
+    t = F.conv2d(x, w["conv_proj.weight"], w["conv_proj.bias"], stride=patch).reshape(B, d, -1).permute(0, 2, 1)
+    t = torch.cat([w["class_token"].expand(B, -1, -1), t], dim=1) + w["encoder.pos_embedding"]
+    for i in range(layers):
+        p = f"encoder.layers.encoder_layer_{i}."
+        y = F.layer_norm(t, (d,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], eps=eps)
+        q, k, v = (y @ w[p + "self_attention.in_proj_weight"].T + w[p + "self_attention.in_proj_bias"]).split(d, dim=-1)
+        sh = lambda z: z.view(B, -1, heads, d // heads).transpose(1, 2)  # noqa: E731
+        a = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / (d // heads) ** 0.5, dim=-1) @ sh(v)
+        t = t + a.transpose(1, 2).reshape(B, -1, d) @ w[p + "self_attention.out_proj.weight"].T + w[p + "self_attention.out_proj.bias"]
+        y = F.layer_norm(t, (d,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], eps=eps)
+        h = y @ w[p + "mlp.0.weight"].T + w[p + "mlp.0.bias"]
+        if swiglu:
+            h = h.reshape(B, -1, mlp // SWIGLU_BLOCK, 2, SWIGLU_BLOCK)
+            h = (F.silu(h[..., 0, :]) * h[..., 1, :]).reshape(B, -1, mlp)
+        else:
+            h = F.gelu(h)
+        t = t + h @ w[p + "mlp.3.weight"].T + w[p + "mlp.3.bias"]
+    t = F.layer_norm(t, (d,), w["encoder.ln.weight"], w["encoder.ln.bias"], eps=eps)
+    return torch.cat([t[:, 0], t[:, 1:].mean(1)], dim=-1) if pool == 1 else t[:, 0]
+
+
+@pytest.mark.parametrize("name", FAMILIES)
+def test_recipe_and_converted_weights_reproduce_transformers(name):
+    from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, HF_VIT_CONFIGS, convert_dinov2_state_dict, convert_hf_vit_state_dict
+    from atlaspatch_b200.encoder import FAMILY_RECIPES, IMAGENET_MEAN, IMAGENET_STD
+
+    r = FAMILY_RECIPES[name]
+    sd = hf.state_dict(name, seed=4)
+    patches = [_patch(256, seed=s) for s in range(3)]
+    want = hf.extract_features(patches, sd, name)
+    if name in DINOV2_CONFIGS:
+        patch, layers, heads, d, mlp, swiglu = DINOV2_CONFIGS[name]
+        w = convert_dinov2_state_dict(sd, layers=layers, swiglu=swiglu, image_size=224, patch=patch)
+    else:
+        (patch, layers, heads, d, mlp), swiglu = HF_VIT_CONFIGS[name], False
+        w = convert_hf_vit_state_dict(sd, layers=layers)
+    w = {k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}
+    mean, std = np.asarray(r.get("mean", IMAGENET_MEAN), np.float32), np.asarray(r.get("std", IMAGENET_STD), np.float32)
+    x = np.stack([(hf.pixels(name, p).astype(np.float32) / 255.0 - mean) / std for p in patches]).transpose(0, 3, 1, 2)
+    with torch.inference_mode():
+        got = _engine_forward(torch.from_numpy(np.ascontiguousarray(x)), w, patch=patch, layers=layers, heads=heads, d=d, mlp=mlp,
+                              swiglu=swiglu, eps=r["ln_eps"], pool=r["pool"]).numpy()
+    assert got.shape == want.shape == (3, d * (2 if r["pool"] == 1 else 1))
+    rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert rel.max() < 2e-5, rel
+
+
+def test_full_size_configs_have_the_published_shapes():
+    """midnight = ViT-g/14 -> 3072 features (midnight.py:53), phikon_v1 768, phikon_v2 1024 (phikon.py:11-12)."""
+    from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, HF_VIT_CONFIGS
+    from atlaspatch_b200.encoder import FAMILY_RECIPES
+
+    assert DINOV2_CONFIGS["midnight"][3] * (2 if FAMILY_RECIPES["midnight"]["pool"] == 1 else 1) == 3072
+    assert HF_VIT_CONFIGS["phikon_v1"][3] == 768 and DINOV2_CONFIGS["phikon_v2"][3] == 1024
+    for name in ("midnight", "phikon_v1", "phikon_v2"):
+        cfg = DINOV2_CONFIGS.get(name) or HF_VIT_CONFIGS[name]
+        assert cfg[3] // cfg[2] == 64 and 224 % cfg[0] == 0 and (224 // cfg[0]) ** 2 + 1 <= 257      # what the attention kernels cover
