@@ -167,6 +167,7 @@ int ap_gemm_plan_split(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W
 struct GemmExtra {
     const float* pos = nullptr;  // [(T+1), N] fp32 or null
     int tokens_per_image = 0;    // T (0 = no remap)
+    int lead_tokens = 1;         // rows in front of each image's T patch rows: class token + register tokens (b*T + t -> b*(T+lead) + lead + t)
     float alpha = 1.0f;          // scale applied to the accumulator before bias
     // ---- LayerNorm folded into the GEMMs around it (encoder.cu "LN folding") -----------------------------------------------
     // producer side (fp32-output epilogues): also write the output as fp16 (the next GEMM's A operand) and, per output row,
@@ -220,8 +221,8 @@ int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64
 // class-token query only; image b's output row is out[b * out_row_stride] (1: compact rows, S: row 0 of every image's block)
 int ap_cls_attention_run(ap_ctx* ctx, const __half* qkv, __half* out, int B, int S, int heads, int out_row_stride, cudaStream_t stream);
 // [CLS || mean(patch tokens)] of the final-LayerNorm'd sequence: x [n_images, tokens1, D] fp32 -> out [n_images, 2 D] fp32
-int ap_cls_mean_pool_run(ap_ctx* ctx, const float* x, int n_images, int tokens1, int D, const float* gamma, const float* beta, float eps,
+int ap_cls_mean_pool_run(ap_ctx* ctx, const float* x, int n_images, int tokens1, int lead, int D, const float* gamma, const float* beta, float eps,
                          float* out, cudaStream_t stream);
 int ap_gather_rows_run(ap_ctx* ctx, const float* src, float* dst, int n_rows, int64_t src_row_stride, int D, cudaStream_t stream);
-int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D, __half* xh,
+int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, const float* regs, int lead, int n_images, int tokens, int D, __half* xh,
                     float2* stats, int parts, cudaStream_t stream);

@@ -34,6 +34,7 @@ struct ap_encoder {
     ap_ctx* ctx = nullptr;
     ap_vit_desc d{};
     int tokens = 0;   // patches per image (196)
+    int lead = 1;     // rows in front of each image's patch tokens: class token + desc.registers register tokens
     int out_dim = 0;  // features per patch: hidden (class token) or 2 * hidden ([class || mean of patch tokens], desc.pool == 1)
     int kpe = 0;      // 3 * patch * patch
     int kpe_pad = 0;  // kpe rounded up to the GEMM's 64-wide K block (588 -> 640 for patch 14); pad columns stay zero
@@ -48,7 +49,7 @@ struct ap_encoder {
     std::vector<void*> allocs;
     // packed weights
     __half* w_pe = nullptr;
-    float *b_pe = nullptr, *cls = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+    float *b_pe = nullptr, *cls = nullptr, *regs = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
     GemmPlan p_pe;
     AttnPlan p_attn;
     bool attn_tc = false;
@@ -175,7 +176,7 @@ int get_linear_tables(ap_encoder* e, int read_size, const int32_t** taps, const 
 int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int64_t pitch, const int32_t* coords, int nb,
                   int read_size, float* out_feats, cudaStream_t st) {
     ap_ctx* ctx = e->ctx;
-    const int D = e->d.hidden, T = e->tokens, T1 = T + 1;
+    const int D = e->d.hidden, T = e->tokens, T1 = T + e->lead;
     const int rows = nb * T1;
     int rc;
     const int32_t* lin_s = nullptr;
@@ -204,7 +205,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     prod1.ln_parts = prod2.ln_parts = cons.ln_parts = e->ln_parts;
     cons.ln_dim = D;
     cons.ln_eps = e->d.ln_eps;
-    if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, nb, T1, D, fold ? e->y1 : nullptr, fold ? e->stats1 : nullptr, e->ln_parts, st)))
+    if ((rc = ap_cls_rows_run(ctx, e->x, e->cls, e->pos, e->regs, e->lead, nb, T1, D, fold ? e->y1 : nullptr, fold ? e->stats1 : nullptr, e->ln_parts, st)))
         return rc;
     {
         GemmPlan p = e->p_pe;
@@ -212,6 +213,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         GemmExtra ex = fold ? prod1 : GemmExtra();
         ex.pos = e->pos;
         ex.tokens_per_image = T;
+        ex.lead_tokens = e->lead;
         if ((rc = ap_gemm_run(ctx, &p, e->b_pe, nullptr, e->x, &ex, st))) return rc;
     }
     for (size_t li = 0; li < e->layers.size(); ++li) {
@@ -257,7 +259,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->x, e->x, fold ? &prod1 : nullptr, st))) return rc;
     }
     if (e->d.pool == 1)   // final LayerNorm on every token, then [class || mean of the patch tokens] (midnight.py:57-61)
-        return ap_cls_mean_pool_run(ctx, e->x, nb, T1, D, e->lnf_g, e->lnf_b, e->d.ln_eps, out_feats, st);
+        return ap_cls_mean_pool_run(ctx, e->x, nb, T1, e->lead, D, e->lnf_g, e->lnf_b, e->d.ln_eps, out_feats, st);
     // final LayerNorm on the class-token rows only -> fp32 features
     return ap_layernorm_run(ctx, e->x, static_cast<int64_t>(T1) * D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
 }
@@ -269,6 +271,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     DeviceGuard guard(ctx);
     *out_enc = nullptr;
     AP_REQUIRE(ctx, desc->preprocess >= 0 && desc->preprocess <= 3, "encoder: unknown preprocess %d", desc->preprocess);
+    AP_REQUIRE(ctx, desc->registers >= 0 && desc->registers <= 8, "encoder: registers %d unsupported (0..8)", desc->registers);
     AP_REQUIRE(ctx, desc->pool == 0 || desc->pool == 1, "encoder: unknown pool %d (0 class token, 1 [class || mean of patch tokens])", desc->pool);
     AP_REQUIRE(ctx, desc->mlp_kind == 0 || desc->mlp_kind == 1, "encoder: unknown mlp_kind %d", desc->mlp_kind);
     AP_REQUIRE(ctx, desc->patch == 16 || desc->patch == 32 || (desc->preprocess >= 1 && desc->patch >= 4 && desc->patch <= 32),
@@ -289,6 +292,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     const int g = desc->image_size / desc->patch;
     e->tokens = g * g;
     e->out_dim = desc->pool == 1 ? 2 * desc->hidden : desc->hidden;
+    e->lead = 1 + desc->registers;
     e->kpe = 3 * desc->patch * desc->patch;
     e->kpe_pad = (e->kpe + 63) / 64 * 64;
     e->max_batch = desc->max_batch > 0 ? desc->max_batch : 127;
@@ -299,9 +303,9 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     // Every golden row has to be inside 1e-3 at the default.
     const int default_precise = desc->layers > 32 ? 8 : 1;
     e->precise_layers = desc->precise_layers < 0 ? default_precise : (desc->precise_layers > desc->layers ? desc->layers : desc->precise_layers);
-    if ((e->tokens + 1) > 272) {
+    if ((e->tokens + e->lead) > 272) {
         delete e;
-        return ap_set_error(ctx, AP_EINVAL, "encoder: sequence %d too long (<= 272)", g * g + 1);
+        return ap_set_error(ctx, AP_EINVAL, "encoder: sequence %d too long (<= 272)", g * g + 1 + desc->registers);
     }
     *out_enc = e;
     return AP_OK;
@@ -338,7 +342,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     DeviceGuard guard(e->ctx);
     ap_ctx* ctx = e->ctx;
     if (e->finalized) return AP_OK;
-    const int D = e->d.hidden, M = e->d.mlp, P = e->d.patch, T = e->tokens, T1 = T + 1, K = e->kpe, Kp = e->kpe_pad;
+    const int D = e->d.hidden, M = e->d.mlp, P = e->d.patch, T = e->tokens, T1 = T + e->lead, K = e->kpe, Kp = e->kpe_pad;
     const int M1 = e->d.mlp_kind == 1 ? 2 * M : M;  // rows of mlp.0 (SwiGLU: gates and values)
     const int MB = e->max_batch;
     int rc;
@@ -381,10 +385,14 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     }
     {
         AP_GET(c, "class_token", D)
-        AP_GET(p, "encoder.pos_embedding", (size_t)T1 * D)
+        AP_GET(p, "encoder.pos_embedding", (size_t)(T + 1) * D)   // class + patch positions; register tokens carry none
         AP_GET(g, "encoder.ln.weight", D)
         AP_GET(b, "encoder.ln.bias", D)
         if ((rc = upload_f32(e, &e->cls, *c))) return rc;
+        if (e->d.registers > 0) {
+            AP_GET(r, "register_tokens", (size_t)e->d.registers * D)
+            if ((rc = upload_f32(e, &e->regs, *r))) return rc;
+        }
         if ((rc = upload_f32(e, &e->pos, *p))) return rc;
         if ((rc = upload_f32(e, &e->lnf_g, *g))) return rc;
         if ((rc = upload_f32(e, &e->lnf_b, *b))) return rc;

@@ -96,16 +96,19 @@ preprocess_kernel(const uint8_t* __restrict__ slide, int64_t W, int64_t H, int64
 // x[b*tokens + 0, :] = class_token + pos[0, :]; with LayerNorm folding also the fp16 copy of the row and its statistics partials
 // (one warp per block of D / parts columns, fixed shuffle tree: same layout and reproducibility as the GEMM producers').
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
-                                int n_images, int tokens, int D, __half* __restrict__ xh, float2* __restrict__ stats, int parts) {
+                                const float* __restrict__ regs, int lead, int n_images, int tokens, int D, __half* __restrict__ xh,
+                                float2* __restrict__ stats, int parts) {
     ptx::pdl_wait();
     ptx::pdl_launch_dependents();
-    const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // one CTA per leading row: r = 0 the class token + its position, r >= 1 register token r - 1 (no position: transformers
+    // Dinov2WithRegistersEmbeddings inserts them after the position embedding has been added)
+    const int b = blockIdx.x / lead, r = blockIdx.x - b * lead, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (b >= n_images || w >= parts) return;
     const int slot = D / parts;
-    const int64_t row = static_cast<int64_t>(b) * tokens;
+    const int64_t row = static_cast<int64_t>(b) * tokens + r;
     float s = 0.f, q = 0.f;
     for (int d = w * slot + lane; d < (w + 1) * slot; d += 32) {
-        const float v = cls[d] + pos[d];
+        const float v = r == 0 ? cls[d] + pos[d] : regs[static_cast<int64_t>(r - 1) * D + d];
         x[row * D + d] = v;
         if (xh != nullptr) xh[row * D + d] = __float2half_rn(v);
         s += v;
@@ -195,7 +198,7 @@ layernorm_kernel(const float* __restrict__ x, int64_t x_row_stride, const float*
 // =====================================================================================================
 template <int VEC>  // D = VEC * 128
 __global__ void __launch_bounds__(256)
-cls_mean_pool_kernel(const float* __restrict__ x, int tokens1, const float* __restrict__ gamma, const float* __restrict__ beta,
+cls_mean_pool_kernel(const float* __restrict__ x, int tokens1, int lead, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float eps, float* __restrict__ out) {
     constexpr int D = VEC * 128;
     __shared__ float4 s_acc[VEC * 32];
@@ -209,8 +212,9 @@ cls_mean_pool_kernel(const float* __restrict__ x, int tokens1, const float* __re
     float4 acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // warp 0 starts at the class token (t = 0), which is written out instead of accumulated; patch tokens are dealt round-robin
-    for (int t = warp; t < tokens1; t += 8) {
+    // warp 0 starts at the class token (t = 0), which is written out instead of accumulated; register tokens (rows 1 .. lead - 1,
+    // virchow.py:110-114 `output[:, 5:]`) are skipped; patch tokens are dealt round-robin
+    for (int t = warp == 0 ? 0 : lead - 1 + warp; t < tokens1; t = (t == 0 ? lead + 7 : t + 8)) {
         const float4* xr = reinterpret_cast<const float4*>(xb + static_cast<int64_t>(t) * D);
         float4 v[VEC];
         float sum = 0.f;
@@ -259,7 +263,7 @@ cls_mean_pool_kernel(const float* __restrict__ x, int tokens1, const float* __re
         }
         __syncthreads();
     }
-    const float inv = 1.0f / static_cast<float>(tokens1 - 1);
+    const float inv = 1.0f / static_cast<float>(tokens1 - lead);
     for (int j = threadIdx.x; j < VEC * 32; j += 256) {
         const float4 a = s_acc[j], g = __ldg(g4 + j), bb = __ldg(b4 + j);
         reinterpret_cast<float4*>(ob + D)[j] = make_float4(a.x * inv * g.x + bb.x, a.y * inv * g.y + bb.y, a.z * inv * g.z + bb.z, a.w * inv * g.w + bb.w);
@@ -590,13 +594,14 @@ int ap_build_linear_tables(ap_ctx* ctx, int n_src, int n_dst, std::vector<int32_
     return AP_OK;
 }
 
-int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, int n_images, int tokens, int D, __half* xh,
+int ap_cls_rows_run(ap_ctx* ctx, float* x, const float* cls, const float* pos, const float* regs, int lead, int n_images, int tokens, int D, __half* xh,
                     float2* stats, int parts, cudaStream_t stream) {
     if (n_images == 0) return AP_OK;
+    AP_REQUIRE(ctx, lead >= 1 && (lead == 1 || regs != nullptr), "cls rows: %d leading rows need register tokens", lead);
     if (parts <= 0) parts = D % 128 == 0 ? D / 128 : 1;
     AP_REQUIRE(ctx, D % parts == 0 && parts <= 32, "cls rows: D=%d parts=%d unsupported", D, parts);
     ProfScope prof(ctx, stream, AP_K_OTHER);
-    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_rows_kernel, dim3(n_images), dim3(parts * 32), 0, stream, 1, ctx->pdl != 0, x, cls, pos, n_images,
+    AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_rows_kernel, dim3(n_images * lead), dim3(parts * 32), 0, stream, 1, ctx->pdl != 0, x, cls, pos, regs, lead, n_images,
                                      tokens, D, xh, stats, parts));
     AP_CHECK_LAUNCH(ctx, "cls_rows_kernel");
     return AP_OK;
@@ -626,15 +631,15 @@ int ap_layernorm_run(ap_ctx* ctx, const float* x, int64_t x_row_stride, const fl
     return AP_OK;
 }
 
-int ap_cls_mean_pool_run(ap_ctx* ctx, const float* x, int n_images, int tokens1, int D, const float* gamma, const float* beta, float eps,
+int ap_cls_mean_pool_run(ap_ctx* ctx, const float* x, int n_images, int tokens1, int lead, int D, const float* gamma, const float* beta, float eps,
                          float* out, cudaStream_t stream) {
     AP_REQUIRE(ctx, D % 128 == 0 && D <= 1536, "cls_mean pool: D=%d unsupported (multiple of 128, <= 1536)", D);
-    AP_REQUIRE(ctx, tokens1 >= 2, "cls_mean pool: needs at least one patch token (tokens %d)", tokens1);
+    AP_REQUIRE(ctx, lead >= 1 && tokens1 > lead, "cls_mean pool: needs at least one patch token (tokens %d, %d leading)", tokens1, lead);
     if (n_images == 0) return AP_OK;
     ProfScope prof(ctx, stream, AP_K_LAYERNORM);
 #define AP_POOL_CASE(V)                                                                                                          \
     case V:                                                                                                                      \
-        AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_mean_pool_kernel<V>, dim3(n_images), dim3(256), 0, stream, 1, ctx->pdl != 0, x, tokens1, gamma, \
+        AP_CHECK_CUDA(ctx, ap_launch_pdl(cls_mean_pool_kernel<V>, dim3(n_images), dim3(256), 0, stream, 1, ctx->pdl != 0, x, tokens1, lead, gamma, \
                                          beta, eps, out));                                                                       \
         break;
     switch (D / 128) {

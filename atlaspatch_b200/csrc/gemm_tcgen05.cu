@@ -53,6 +53,7 @@ struct EpiParams {
     void* out;
     const float* pos;
     int tokens_per_image;
+    int lead_tokens;   // class + register tokens in front of each image's patch tokens (1 without registers)
     float alpha;
     int seg_blocks;  // 64-wide K blocks per segment; block kb of the contraction is block kb % seg_blocks of segment kb / seg_blocks
     int a_map, w_map;  // 2 bits per segment: which Kseg-wide column range of A / W that segment reads (split operands, GemmPlan)
@@ -211,10 +212,10 @@ __device__ __forceinline__ void epilogue_group_f32(const uint32_t (&r)[32], cons
         int64_t out_row = row;
         if (EPI == AP_EPI_BIAS_RESID_F32) {
             v[it].x += rr[it].x; v[it].y += rr[it].y; v[it].z += rr[it].z; v[it].w += rr[it].w;
-        } else if (ep.tokens_per_image > 0) {   // conv_proj: token row -> sequence row (+1 class token per image), + pos
+        } else if (ep.tokens_per_image > 0) {   // conv_proj: token row -> sequence row (class [+ register] tokens lead each image), + pos
             const int b = row / ep.tokens_per_image;
             const int tk = row - b * ep.tokens_per_image;
-            out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + 1) + 1 + tk;
+            out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + ep.lead_tokens) + ep.lead_tokens + tk;
             if (ep.pos != nullptr && row < M) {
                 const float4 pp = __ldg(reinterpret_cast<const float4*>(ep.pos + static_cast<int64_t>(1 + tk) * N + col0) + p);
                 v[it].x += pp.x; v[it].y += pp.y; v[it].z += pp.z; v[it].w += pp.w;
@@ -262,7 +263,7 @@ __device__ __forceinline__ void epilogue_write_stats(const EpiParams& ep, int M,
             int64_t out_row = row;
             if (ep.tokens_per_image > 0) {
                 const int b = row / ep.tokens_per_image;
-                out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + 1) + 1 + (row - b * ep.tokens_per_image);
+                out_row = static_cast<int64_t>(b) * (ep.tokens_per_image + ep.lead_tokens) + ep.lead_tokens + (row - b * ep.tokens_per_image);
             }
             ep.stats_out[out_row * ep.ln_parts + col_block] = make_float2(s, q);
         }
@@ -624,6 +625,7 @@ int ap_gemm_run(ap_ctx* ctx, const GemmPlan* plan, const float* bias, const floa
     ep.bias = bias; ep.resid = resid; ep.out = out;
     ep.pos = extra ? extra->pos : nullptr;
     ep.tokens_per_image = extra ? extra->tokens_per_image : 0;
+    ep.lead_tokens = extra ? extra->lead_tokens : 1;
     ep.alpha = extra ? extra->alpha : 1.0f;
     ep.debug = ctx->gemm_debug;
     ep.seg_blocks = plan->Kseg / BK;

@@ -29,7 +29,15 @@ DINOV2_CONFIGS = {
     "phikon_v2": (16, 24, 16, 1024, 4096, False),
     "midnight_test_tiny": (14, 2, 6, 384, 1024, True),
     "phikon_v2_test_tiny": (16, 2, 4, 256, 1024, False),
+    # DINOv2 with 4 register tokens: histai/hibou-B / -L (models/patch/hibou.py:12-15, pooler_output = class token) and the
+    # facebookresearch dinov2_vitg14_reg that models/patch/openmidnight.py:49 fills with the OpenMidnight weights
+    "hibou_b": (14, 12, 12, 768, 3072, False),
+    "hibou_l": (14, 24, 16, 1024, 4096, False),
+    "openmidnight": (14, 40, 24, 1536, 4096, True),
+    "hibou_test_tiny": (14, 2, 4, 256, 1024, False),
+    "openmidnight_test_tiny": (14, 2, 6, 384, 1024, True),
 }
+DINOV2_REGISTERS = {"hibou_b": 4, "hibou_l": 4, "openmidnight": 4, "hibou_test_tiny": 4, "openmidnight_test_tiny": 4}
 # name -> (patch, layers, heads, hidden, mlp): transformers ViTModel checkpoints (owkin/phikon, models/patch/phikon.py:41-44)
 HF_VIT_CONFIGS = {
     "phikon_v1": (16, 12, 12, 768, 3072),
@@ -84,10 +92,20 @@ def swiglu_interleave(hidden_features: int) -> np.ndarray:
 
 
 def convert_dinov2_state_dict(sd: Mapping[str, object], *, layers: int, swiglu: bool, image_size: int = 224,
-                              patch: int = 14) -> dict[str, np.ndarray]:
-    """transformers Dinov2Model names -> engine names (the torchvision layout of encoder.py: vit_state_dict_names)."""
+                              patch: int = 14, registers: int = 0) -> dict[str, np.ndarray]:
+    """transformers Dinov2Model / Dinov2WithRegistersModel names -> engine names (the torchvision layout of encoder.py:
+    vit_state_dict_names).  Facebook's own key layout (torch.hub dinov2_*: cls_token, blocks.i.attn.qkv ...) is accepted too."""
+    if "cls_token" in sd and "embeddings.cls_token" not in sd:
+        sd = fb_to_hf_dinov2_names(sd, layers=layers, swiglu=swiglu)
     sd = {k[len("dinov2."):] if k.startswith("dinov2.") else k: v for k, v in sd.items()}
     out: dict[str, np.ndarray] = {}
+    if registers:
+        # Dinov2WithRegistersEmbeddings: [class + pos_0 ; registers (no position) ; patches + pos]; its position interpolation is the
+        # antialiased one, which is not restated here: the checkpoints this serves (224 px, 16 x 16 grid) need none
+        n_pos = _np(sd["embeddings.position_embeddings"]).shape[-2] - 1
+        if n_pos != (image_size // patch) ** 2:
+            raise ValueError(f"register-token checkpoints must carry the {image_size // patch}^2 position grid of the input (got {n_pos} positions)")
+        out["register_tokens"] = _np(sd["embeddings.register_tokens"]).reshape(registers, -1)
     out["conv_proj.weight"] = _np(sd["embeddings.patch_embeddings.projection.weight"])
     out["conv_proj.bias"] = _np(sd["embeddings.patch_embeddings.projection.bias"])
     out["class_token"] = _np(sd["embeddings.cls_token"]).reshape(1, 1, -1)
@@ -144,4 +162,30 @@ def convert_hf_vit_state_dict(sd: Mapping[str, object], *, layers: int) -> dict[
         out[d + "self_attention.out_proj.bias"] = _np(sd[s + "attention.output.dense.bias"])
         out[d + "mlp.0.weight"], out[d + "mlp.0.bias"] = _np(sd[s + "intermediate.dense.weight"]), _np(sd[s + "intermediate.dense.bias"])
         out[d + "mlp.3.weight"], out[d + "mlp.3.bias"] = _np(sd[s + "output.dense.weight"]), _np(sd[s + "output.dense.bias"])
+    return out
+
+
+def fb_to_hf_dinov2_names(sd: Mapping[str, object], *, layers: int, swiglu: bool) -> dict[str, object]:
+    """facebookresearch/dinov2 DinoVisionTransformer keys (what torch.hub's dinov2_vitg14_reg holds after models/patch/
+    openmidnight.py:49-63 loads the checkpoint into it; block_chunks = 0 as the hub entry points build it) -> transformers names.
+    Same tensors, same arithmetic: qkv rows are [q ; k ; v], SwiGLUFFNFused.w12 = weights_in (gate half first), w3 = weights_out."""
+    out: dict[str, object] = {"embeddings.cls_token": sd["cls_token"], "embeddings.position_embeddings": sd["pos_embed"],
+                              "embeddings.patch_embeddings.projection.weight": sd["patch_embed.proj.weight"],
+                              "embeddings.patch_embeddings.projection.bias": sd["patch_embed.proj.bias"],
+                              "layernorm.weight": sd["norm.weight"], "layernorm.bias": sd["norm.bias"]}
+    if "register_tokens" in sd:
+        out["embeddings.register_tokens"] = sd["register_tokens"]
+    for i in range(layers):
+        s, d = f"blocks.{i}.", f"encoder.layer.{i}."
+        for a, b in (("norm1", "norm1"), ("norm2", "norm2"), ("attn.proj", "attention.output.dense")):
+            out[d + b + ".weight"], out[d + b + ".bias"] = sd[s + a + ".weight"], sd[s + a + ".bias"]
+        qkv_w, qkv_b = _np(sd[s + "attn.qkv.weight"]), _np(sd[s + "attn.qkv.bias"])
+        D = qkv_w.shape[1]
+        for j, n in enumerate(("query", "key", "value")):
+            out[d + f"attention.attention.{n}.weight"] = qkv_w[j * D:(j + 1) * D]
+            out[d + f"attention.attention.{n}.bias"] = qkv_b[j * D:(j + 1) * D]
+        out[d + "layer_scale1.lambda1"], out[d + "layer_scale2.lambda1"] = sd[s + "ls1.gamma"], sd[s + "ls2.gamma"]
+        pairs = (("mlp.w12", "mlp.weights_in"), ("mlp.w3", "mlp.weights_out")) if swiglu else (("mlp.fc1", "mlp.fc1"), ("mlp.fc2", "mlp.fc2"))
+        for a, b in pairs:
+            out[d + b + ".weight"], out[d + b + ".bias"] = sd[s + a + ".weight"], sd[s + a + ".bias"]
     return out

@@ -13,7 +13,7 @@ from typing import Mapping, Sequence
 import numpy as np
 
 from atlaspatch_b200._lib import Context, VitDesc, current_stream_ptr
-from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, HF_VIT_CONFIGS, convert_dinov2_state_dict, convert_hf_vit_state_dict
+from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, DINOV2_REGISTERS, HF_VIT_CONFIGS, convert_dinov2_state_dict, convert_hf_vit_state_dict
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -33,6 +33,7 @@ VIT_CONFIGS = {
 #   preprocess: ap_vit_desc.preprocess (1 ATen uint8 bicubic-antialias, 2 Pillow BILINEAR, 3 ATen uint8 bilinear-antialias)
 #   pool: 0 class token, 1 [class || mean of patch tokens]
 _HALF = (0.5, 0.5, 0.5)
+_HIBOU_MEAN, _HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
 FAMILY_RECIPES = {
     # kaiko-ai/midnight (models/patch/midnight.py:15-25,55-61): torchvision Resize(224) on the PIL patch, CenterCrop(224),
     # Normalize(0.5, 0.5); feature = cat(last_hidden_state[:, 0], last_hidden_state[:, 1:].mean(1)) -> 3072
@@ -45,11 +46,22 @@ FAMILY_RECIPES = {
     # with layer_norm_eps 1e-12
     "phikon_v1": dict(preprocess=3, resize_to=224, pool=0, ln_eps=1e-12, default_patch=224),
     "phikon_v1_test_tiny": dict(preprocess=3, resize_to=224, pool=0, ln_eps=1e-12, default_patch=224),
+    # histai/hibou-B / -L (models/patch/hibou.py:51-54,67-69): BitImageProcessor(fast) shortest_edge 224 bicubic, crop 224, the
+    # repo's own mean / std; DINOv2 with 4 register tokens, feature = pooler_output (class token after the final LayerNorm)
+    "hibou_b": dict(preprocess=1, resize_to=224, mean=_HIBOU_MEAN, std=_HIBOU_STD, pool=0, ln_eps=1e-6, default_patch=224),
+    "hibou_l": dict(preprocess=1, resize_to=224, mean=_HIBOU_MEAN, std=_HIBOU_STD, pool=0, ln_eps=1e-6, default_patch=224),
+    "hibou_test_tiny": dict(preprocess=1, resize_to=224, mean=_HIBOU_MEAN, std=_HIBOU_STD, pool=0, ln_eps=1e-6, default_patch=224),
+    # SophontAI/OpenMidnight (models/patch/openmidnight.py:17-30,49): torchvision Resize((224, 224)) on the PIL patch, ImageNet
+    # mean / std; facebookresearch dinov2_vitg14_reg (4 register tokens, SwiGLU), feature = class token
+    "openmidnight": dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
+    "openmidnight_test_tiny": dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
 }
 
 
-def vit_state_dict_names(layers: int) -> list[str]:
+def vit_state_dict_names(layers: int, registers: int = 0) -> list[str]:
     names = ["conv_proj.weight", "conv_proj.bias", "class_token", "encoder.pos_embedding", "encoder.ln.weight", "encoder.ln.bias"]
+    if registers:
+        names.append("register_tokens")
     for i in range(layers):
         p = f"encoder.layers.encoder_layer_{i}."
         names += [p + s for s in ("ln_1.weight", "ln_1.bias", "self_attention.in_proj_weight", "self_attention.in_proj_bias",
@@ -78,13 +90,15 @@ class B200FeatureExtractor:
         folded): max 8.7e-4 on the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log), 21.1 k against 24.1 k patches/s."""
         if precision not in ("fast", "strict"):
             raise ValueError("precision must be 'fast' or 'strict'")
-        preprocess, resize_to, mlp_kind, pool, ln_eps = 0, 0, 0, 0, 1e-6
+        preprocess, resize_to, mlp_kind, pool, ln_eps, registers = 0, 0, 0, 0, 1e-6, 0
         mean, std = IMAGENET_MEAN, IMAGENET_STD
         recipe = FAMILY_RECIPES.get(name, {}) if config is None else {}
         if config is None and (name in DINOV2_CONFIGS or name in HF_VIT_CONFIGS):
             if name in DINOV2_CONFIGS:
                 patch, layers, heads, hidden, mlp, swiglu = DINOV2_CONFIGS[name]
-                state_dict = convert_dinov2_state_dict(state_dict, layers=layers, swiglu=swiglu, image_size=image_size, patch=patch)
+                registers = DINOV2_REGISTERS.get(name, 0)
+                state_dict = convert_dinov2_state_dict(state_dict, layers=layers, swiglu=swiglu, image_size=image_size, patch=patch,
+                                                       registers=registers)
             else:
                 (patch, layers, heads, hidden, mlp), swiglu = HF_VIT_CONFIGS[name], False
                 state_dict = convert_hf_vit_state_dict(state_dict, layers=layers)
@@ -115,12 +129,12 @@ class B200FeatureExtractor:
         desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
                        input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=ln_eps,
                        mean=(C.c_float * 3)(*mean), std=(C.c_float * 3)(*std), preprocess=preprocess,
-                       resize_to=resize_to, mlp_kind=mlp_kind, pool=pool)
+                       resize_to=resize_to, mlp_kind=mlp_kind, pool=pool, registers=registers)
         h = C.c_void_p()
         self.ctx.check(lib.ap_encoder_create(self.ctx.handle, C.byref(desc), C.byref(h)))
         self._h = h
         try:
-            for key in vit_state_dict_names(layers):
+            for key in vit_state_dict_names(layers, registers):
                 if key not in state_dict:
                     raise KeyError(f"state_dict is missing '{key}'")
                 t = state_dict[key]

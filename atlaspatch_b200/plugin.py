@@ -64,7 +64,10 @@ def _build_dinov2(name: str, device, patch_size: int | None) -> B200FeatureExtra
 # Hub encoders on the same kernels: name -> (hub id, loader), loaded exactly as the reference's classes do
 _HUB = {"midnight": "kaiko-ai/midnight",        # models/patch/midnight.py:12,44  AutoModel (Dinov2Model ViT-g/14), [class || mean] -> 3072
         "phikon_v1": "owkin/phikon",            # models/patch/phikon.py:41-44    ViTModel(add_pooling_layer=False) -> 768
-        "phikon_v2": "owkin/phikon-v2"}         # models/patch/phikon.py:90-92    AutoModel (Dinov2Model ViT-L/16) -> 1024
+        "phikon_v2": "owkin/phikon-v2",         # models/patch/phikon.py:90-92    AutoModel (Dinov2Model ViT-L/16) -> 1024
+        "hibou_b": "histai/hibou-B",            # models/patch/hibou.py:12-15,54  AutoModel(trust_remote_code): DINOv2 + 4 registers -> 768
+        "hibou_l": "histai/hibou-L",            #                                 -> 1024
+        "openmidnight": "SophontAI/OpenMidnight"}   # models/patch/openmidnight.py:49-63  torch.hub dinov2_vitg14_reg + checkpoint -> 1536
 
 
 def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
@@ -80,6 +83,17 @@ def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtracto
         from transformers import ViTModel
 
         model = ViTModel.from_pretrained(_HUB[name], add_pooling_layer=False)
+    elif name == "openmidnight":            # openmidnight.py:49-63, step for step; the state_dict stays in facebookresearch's key layout
+        from huggingface_hub import hf_hub_download
+
+        model = torch.hub.load("facebookresearch/dinov2", "dinov2_vitg14_reg", weights=None)
+        checkpoint = torch.load(hf_hub_download(repo_id=_HUB[name], filename="teacher_checkpoint_load.pt"), map_location="cpu")
+        model.pos_embed = torch.nn.parameter.Parameter(checkpoint["pos_embed"])
+        model.load_state_dict(checkpoint)
+    elif name.startswith("hibou"):
+        from transformers import AutoModel
+
+        model = AutoModel.from_pretrained(_HUB[name], trust_remote_code=True)
     else:
         from transformers import AutoModel
 

@@ -82,9 +82,16 @@ DINOV2_SPECS = {
     "phikon_v2": (24, 16, 1024, False),
     "midnight_test_tiny": (2, 6, 384, True),
     "phikon_v2_test_tiny": (2, 4, 256, False),
+    # DINOv2 with 4 register tokens: histai/hibou-B / -L (hibou.py:12-15) and the ViT-g/14 reg4 of openmidnight.py:49
+    "hibou_b": (12, 12, 768, False),
+    "hibou_l": (24, 16, 1024, False),
+    "openmidnight": (40, 24, 1536, True),
+    "hibou_test_tiny": (2, 4, 256, False),
+    "openmidnight_test_tiny": (2, 6, 384, True),
 }
 PATCH = 14
 DINOV2_PATCH = {"phikon_v2": 16, "phikon_v2_test_tiny": 16}   # conv patch where it is not 14
+DINOV2_REGISTERS = {"hibou_b": 4, "hibou_l": 4, "openmidnight": 4, "hibou_test_tiny": 4, "openmidnight_test_tiny": 4}
 
 
 def swiglu_hidden(d: int) -> int:
@@ -109,6 +116,8 @@ def dinov2_state_dict(name: str, seed: int = 0, image_size: int = 518, patch: in
     sd: dict[str, torch.Tensor] = {}
     sd["embeddings.cls_token"] = normal((1, 1, d), 0.02)
     sd["embeddings.mask_token"] = normal((1, d), 0.02)
+    if DINOV2_REGISTERS.get(name, 0):
+        sd["embeddings.register_tokens"] = normal((1, DINOV2_REGISTERS[name], d), 0.5)   # large against the 0.02 tokens: a dropped row shows
     sd["embeddings.position_embeddings"] = normal((1, g * g + 1, d), 0.02)
     sd["embeddings.patch_embeddings.projection.weight"] = normal((d, 3, PATCH, PATCH), math.sqrt(1.0 / (3 * PATCH * PATCH)))
     sd["embeddings.patch_embeddings.projection.bias"] = normal((d,), 0.02)

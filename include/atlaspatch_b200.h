@@ -156,7 +156,11 @@ typedef struct ap_vit_desc {
     int pool;         /* 0: feature = final LayerNorm of the class token (torchvision heads -> Identity, base.py:100; transformers
                             last_hidden_state[:, 0], dinov2.py:60-62), hidden floats per patch;
                          1: [class || mean of the patch tokens] of the final-LayerNorm'd sequence, 2 * hidden floats per patch
-                            (atlas_patch/models/patch/midnight.py:57-61, virchow.py:57-61) */
+                            (atlas_patch/models/patch/midnight.py:57-61, virchow.py:57-61); register tokens are left out of the
+                            mean (virchow.py:110-114, hoptimus.py:157-161) */
+    int registers;    /* register tokens between the class token and the patch tokens ("register_tokens" [registers, hidden], no
+                         position embedding: transformers Dinov2WithRegistersEmbeddings; hibou.py, openmidnight.py:49, the reg4 timm
+                         models of hoptimus.py): sequence = 1 + registers + (image_size / patch)^2 <= 272.  0 = none */
 } ap_vit_desc;
 
 int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc);

@@ -8,6 +8,14 @@
 * `phikon_v1` (phikon.py:41-46,54-56): `ViTModel.from_pretrained("owkin/phikon", add_pooling_layer=False)` with the repo's
   ViTImageProcessor (fast: 224 x 224, resample 2 = bilinear, ImageNet mean / std), feature = last_hidden_state[:, 0].
 
+* `hibou_b`, `hibou_l` (hibou.py:12-15,51-54,67-69): `AutoModel.from_pretrained("histai/hibou-*", trust_remote_code=True)` = DINOv2
+  with 4 register tokens (the architecture transformers ships as Dinov2WithRegistersModel), the repo's BitImageProcessor (fast:
+  shortest_edge 224 bicubic, crop 224, mean (0.7068, 0.5755, 0.722), std (0.195, 0.2316, 0.1816)), feature = pooler_output.
+* `openmidnight` (openmidnight.py:17-30,49-63): facebookresearch `dinov2_vitg14_reg` (ViT-g/14, 4 registers, SwiGLU) with the
+  checkpoint's 224 px position grid, torchvision `Resize((224, 224)) -> ToTensor -> Normalize(ImageNet)`, feature = model(x) = the
+  class token after the final LayerNorm.  facebookresearch/dinov2 is not importable offline; Dinov2WithRegistersModel is the same
+  architecture under transformers' key names (atlaspatch_b200/dinov2.py: fb_to_hf_dinov2_names maps one layout onto the other).
+
 There is no network: the oracle builds the classes those hub files resolve to, from the published contents of their config.json /
 preprocessor_config.json (restated from memory of the public repos -- parity of the *settings* is unpinned; parity of the
 *arithmetic* is pinned against transformers / torchvision run in this container on the same settings), with seeded weights.
@@ -19,14 +27,16 @@ from typing import Sequence
 import numpy as np
 import torch
 
-from atlaspatch_b200.weights import DINOV2_PATCH, DINOV2_SPECS, HF_VIT_SPECS, dinov2_state_dict, hf_vit_state_dict  # noqa: F401
+from atlaspatch_b200.weights import (DINOV2_PATCH, DINOV2_REGISTERS, DINOV2_SPECS, HF_VIT_SPECS, dinov2_state_dict,  # noqa: F401
+                                     hf_vit_state_dict)
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
+HIBOU_MEAN, HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
 
 
 def _family(name: str) -> str:
-    for fam in ("midnight", "phikon_v2", "phikon_v1"):
+    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight"):
         if name.startswith(fam):
             return fam
     raise KeyError(name)
@@ -49,12 +59,15 @@ def build_model(name: str, sd: dict[str, torch.Tensor]):
                         image_size=224, hidden_act="gelu", layer_norm_eps=1e-12, qkv_bias=True)
         model = ViTModel(cfg, add_pooling_layer=False).eval()
     else:
-        from transformers import Dinov2Config, Dinov2Model
+        from transformers import Dinov2Config, Dinov2Model, Dinov2WithRegistersConfig, Dinov2WithRegistersModel
 
         layers, heads, d, swiglu = DINOV2_SPECS[name]
-        cfg = Dinov2Config(hidden_size=d, num_hidden_layers=layers, num_attention_heads=heads, mlp_ratio=4, patch_size=DINOV2_PATCH.get(name, 14),
-                           image_size=224, use_swiglu_ffn=swiglu, layer_norm_eps=1e-6, qkv_bias=True, layerscale_value=1.0)
-        model = Dinov2Model(cfg).eval()
+        kw = dict(hidden_size=d, num_hidden_layers=layers, num_attention_heads=heads, mlp_ratio=4, patch_size=DINOV2_PATCH.get(name, 14),
+                  image_size=224, use_swiglu_ffn=swiglu, layer_norm_eps=1e-6, qkv_bias=True, layerscale_value=1.0)
+        if DINOV2_REGISTERS.get(name, 0):
+            model = Dinov2WithRegistersModel(Dinov2WithRegistersConfig(num_register_tokens=DINOV2_REGISTERS[name], **kw)).eval()
+        else:
+            model = Dinov2Model(Dinov2Config(**kw)).eval()
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected and not missing, (missing, unexpected)
     return model
@@ -68,9 +81,18 @@ def make_preprocess(name: str):
 
         return transforms.Compose([transforms.Resize(224), transforms.CenterCrop(224), transforms.ToTensor(),
                                    transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
+    if fam == "openmidnight":                               # openmidnight.py:17-30
+        from torchvision import transforms
+
+        return transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                                   transforms.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])
     import transformers
 
-    if fam == "phikon_v2":
+    if fam == "hibou":
+        proc = transformers.BitImageProcessor(do_resize=True, size={"shortest_edge": 224}, resample=3, do_center_crop=True,
+                                              crop_size={"height": 224, "width": 224}, do_rescale=True, rescale_factor=1 / 255,
+                                              do_normalize=True, image_mean=list(HIBOU_MEAN), image_std=list(HIBOU_STD), do_convert_rgb=True)
+    elif fam == "phikon_v2":
         proc = transformers.BitImageProcessor(do_resize=True, size={"shortest_edge": 224}, resample=3, do_center_crop=True,
                                               crop_size={"height": 224, "width": 224}, do_rescale=True, rescale_factor=1 / 255,
                                               do_normalize=True, image_mean=list(IMAGENET_MEAN), image_std=list(IMAGENET_STD), do_convert_rgb=True)
@@ -88,7 +110,9 @@ def pixels(name: str, patch: np.ndarray) -> np.ndarray:
     fam = _family(name)
     if fam == "midnight":
         return ra.vit_preset_pixels(patch, resize_to=224, crop=224)
-    if fam == "phikon_v2":
+    if fam == "openmidnight":
+        return ra.resize_pil_bilinear(patch, 224, 224)
+    if fam in ("phikon_v2", "hibou"):
         return ra.dinov2_pixels(patch, resize_to=224, crop=224) if patch.shape[0] != 224 else patch
     return ra.hf_vit_pixels(patch, 224)
 
@@ -104,7 +128,11 @@ def extract_features(patches: Sequence[np.ndarray], sd: dict[str, torch.Tensor],
     outs = []
     for i in range(0, len(patches), batch_size):
         x = torch.stack([pre(Image.fromarray(np.asarray(p))) for p in patches[i:i + batch_size]])
-        h = model(pixel_values=x).last_hidden_state
-        outs.append(torch.cat([h[:, 0], h[:, 1:].mean(1)], dim=-1) if cls_mean else h[:, 0])
+        out = model(pixel_values=x)
+        h = out.last_hidden_state
+        if _family(name) == "hibou":
+            outs.append(out.pooler_output)                                     # hibou.py:67-69
+        else:
+            outs.append(torch.cat([h[:, 0], h[:, 1:].mean(1)], dim=-1) if cls_mean else h[:, 0])
     d = model.config.hidden_size * (2 if cls_mean else 1)
     return torch.cat(outs).to(torch.float32).numpy() if outs else np.empty((0, d), dtype=np.float32)

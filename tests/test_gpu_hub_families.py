@@ -20,7 +20,9 @@ def _slide():
 
 @pytest.mark.parametrize("name,P", [("midnight_test_tiny", 224), ("midnight_test_tiny", 256), ("midnight_test_tiny", 512),
                                     ("phikon_v1_test_tiny", 224), ("phikon_v1_test_tiny", 256), ("phikon_v1_test_tiny", 300),
-                                    ("phikon_v2_test_tiny", 224), ("phikon_v2_test_tiny", 256)])
+                                    ("phikon_v2_test_tiny", 224), ("phikon_v2_test_tiny", 256),
+                                    ("hibou_test_tiny", 224), ("hibou_test_tiny", 256),                  # 4 register tokens: 261-token sequence
+                                    ("openmidnight_test_tiny", 224), ("openmidnight_test_tiny", 512)])
 def test_tiny_family_pixels_bit_exact_and_features(name, P):
     import torch
 
@@ -35,7 +37,12 @@ def test_tiny_family_pixels_bit_exact_and_features(name, P):
     rows = np.concatenate([xy, np.full((n, 2), P), np.zeros((n, 1))], 1).astype(np.int32)
     patches = [render_region_host(wsi.spec, int(x), int(y), P, P) for x, y in xy]
     sd = hf.state_dict(name, seed=6)
-    ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=4)            # 9 patches -> three forward chunks
+    sd_in = sd
+    if name.startswith("openmidnight"):     # the reference holds these weights in facebookresearch's key layout (openmidnight.py:49-63)
+        from tests.test_oracle_hub_families import hf_to_fb_names
+
+        sd_in = hf_to_fb_names(sd, 2, True)
+    ext = B200FeatureExtractor(name, sd_in, input_patch=P, max_batch=4)         # 9 patches -> three forward chunks
     pool = FAMILY_RECIPES[name]["pool"]
     assert ext.embedding_dim == sd["layernorm.weight"].numel() * (2 if pool == 1 else 1)
     rows_dev = torch.from_numpy(rows).cuda()
@@ -91,3 +98,44 @@ def test_midnight_head_at_full_width():
         wt.DINOV2_SPECS.pop(name, None)
         d2.DINOV2_CONFIGS.pop(name, None)
         FAMILY_RECIPES.pop(name, None)
+
+
+def test_class_mean_head_skips_register_tokens():
+    """[class || mean of the patch tokens] over a register-token sequence: virchow.py:110-114 `output[:, 5:]`, hoptimus.py:157-161
+    `output[:, m.num_prefix_tokens:]` -- the mean must leave the 4 register rows out."""
+    import torch
+    from PIL import Image
+
+    from atlaspatch_b200 import dinov2 as d2
+    from atlaspatch_b200 import weights as wt
+    from atlaspatch_b200.encoder import FAMILY_RECIPES, B200FeatureExtractor
+    from atlaspatch_b200.synthetic import render_region_host
+
+    name = "hibou_regpool_test"
+    wt.DINOV2_SPECS[name], wt.DINOV2_REGISTERS[name] = (2, 6, 384, True), 4
+    d2.DINOV2_CONFIGS[name], d2.DINOV2_REGISTERS[name] = (14, 2, 6, 384, 1024, True), 4
+    FAMILY_RECIPES[name] = dict(FAMILY_RECIPES["hibou_test_tiny"], pool=1)
+    try:
+        wsi = _slide()
+        P, n = 224, 6
+        rng = np.random.default_rng(4)
+        xy = np.stack([rng.integers(0, wsi.w - P, n), rng.integers(0, wsi.h - P, n)], 1)
+        rows = np.concatenate([xy, np.full((n, 2), P), np.zeros((n, 1))], 1).astype(np.int32)
+        patches = [render_region_host(wsi.spec, int(x), int(y), P, P) for x, y in xy]
+        sd = hf.state_dict(name, seed=3)
+        model, pre = hf.build_model(name, sd), hf.make_preprocess(name)
+        with torch.inference_mode():
+            h = model(pixel_values=torch.stack([pre(Image.fromarray(p)) for p in patches])).last_hidden_state
+            want = torch.cat([h[:, 0], h[:, 5:].mean(1)], dim=-1).numpy()
+            wrong = torch.cat([h[:, 0], h[:, 1:].mean(1)], dim=-1).numpy()          # what a head that keeps the registers would give
+        ext = B200FeatureExtractor(name, sd, input_patch=P, max_batch=4)
+        got = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, torch.from_numpy(rows).cuda()).cpu().numpy()
+        ext.cleanup()
+        assert got.shape == want.shape == (n, 768)
+        for half in (slice(0, 384), slice(384, 768)):
+            r = np.linalg.norm(got[:, half] - want[:, half], axis=1) / np.linalg.norm(want[:, half], axis=1)
+            assert r.max() < 1e-3, r
+        assert (np.linalg.norm(wrong - want, axis=1) / np.linalg.norm(want, axis=1)).min() > 5e-3    # the test can tell the two apart
+    finally:
+        for d in (wt.DINOV2_SPECS, wt.DINOV2_REGISTERS, d2.DINOV2_CONFIGS, d2.DINOV2_REGISTERS, FAMILY_RECIPES):
+            d.pop(name, None)

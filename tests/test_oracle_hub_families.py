@@ -9,7 +9,7 @@ import torch.nn.functional as F
 from oracle import hub_families as hf
 from oracle import resize_aa
 
-FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny"]
+FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny", "hibou_test_tiny", "openmidnight_test_tiny"]
 
 
 def _patch(P, seed=0):
@@ -51,6 +51,10 @@ def _engine_forward(x, w, *, patch, layers, heads, d, mlp, swiglu, eps, pool):
     B = x.shape[0]
     t = F.conv2d(x, w["conv_proj.weight"], w["conv_proj.bias"], stride=patch).reshape(B, d, -1).permute(0, 2, 1)
     t = torch.cat([w["class_token"].expand(B, -1, -1), t], dim=1) + w["encoder.pos_embedding"]
+    lead = 1
+    if "register_tokens" in w:      # engine layout: [class + pos_0 ; registers ; patches + pos]
+        lead += w["register_tokens"].shape[0]
+        t = torch.cat([t[:, :1], w["register_tokens"][None].expand(B, -1, -1), t[:, 1:]], dim=1)
     for i in range(layers):
         p = f"encoder.layers.encoder_layer_{i}."
         y = F.layer_norm(t, (d,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], eps=eps)
@@ -67,12 +71,13 @@ def _engine_forward(x, w, *, patch, layers, heads, d, mlp, swiglu, eps, pool):
             h = F.gelu(h)
         t = t + h @ w[p + "mlp.3.weight"].T + w[p + "mlp.3.bias"]
     t = F.layer_norm(t, (d,), w["encoder.ln.weight"], w["encoder.ln.bias"], eps=eps)
-    return torch.cat([t[:, 0], t[:, 1:].mean(1)], dim=-1) if pool == 1 else t[:, 0]
+    return torch.cat([t[:, 0], t[:, lead:].mean(1)], dim=-1) if pool == 1 else t[:, 0]
 
 
 @pytest.mark.parametrize("name", FAMILIES)
 def test_recipe_and_converted_weights_reproduce_transformers(name):
-    from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, HF_VIT_CONFIGS, convert_dinov2_state_dict, convert_hf_vit_state_dict
+    from atlaspatch_b200.dinov2 import (DINOV2_CONFIGS, DINOV2_REGISTERS, HF_VIT_CONFIGS, convert_dinov2_state_dict,
+                                        convert_hf_vit_state_dict)
     from atlaspatch_b200.encoder import FAMILY_RECIPES, IMAGENET_MEAN, IMAGENET_STD
 
     r = FAMILY_RECIPES[name]
@@ -81,7 +86,7 @@ def test_recipe_and_converted_weights_reproduce_transformers(name):
     want = hf.extract_features(patches, sd, name)
     if name in DINOV2_CONFIGS:
         patch, layers, heads, d, mlp, swiglu = DINOV2_CONFIGS[name]
-        w = convert_dinov2_state_dict(sd, layers=layers, swiglu=swiglu, image_size=224, patch=patch)
+        w = convert_dinov2_state_dict(sd, layers=layers, swiglu=swiglu, image_size=224, patch=patch, registers=DINOV2_REGISTERS.get(name, 0))
     else:
         (patch, layers, heads, d, mlp), swiglu = HF_VIT_CONFIGS[name], False
         w = convert_hf_vit_state_dict(sd, layers=layers)
@@ -106,3 +111,50 @@ def test_full_size_configs_have_the_published_shapes():
     for name in ("midnight", "phikon_v1", "phikon_v2"):
         cfg = DINOV2_CONFIGS.get(name) or HF_VIT_CONFIGS[name]
         assert cfg[3] // cfg[2] == 64 and 224 % cfg[0] == 0 and (224 // cfg[0]) ** 2 + 1 <= 257      # what the attention kernels cover
+
+
+def hf_to_fb_names(sd, layers, swiglu):
+    """Inverse of atlaspatch_b200.dinov2.fb_to_hf_dinov2_names, written independently from the facebookresearch/dinov2 module tree
+    (DinoVisionTransformer: cls_token, pos_embed, register_tokens, patch_embed.proj, blocks.i.{norm1, attn.qkv, attn.proj, ls1, norm2,
+    mlp.{fc1, fc2 | w12, w3}, ls2}, norm): the key layout torch.hub's dinov2_vitg14_reg holds in openmidnight.py:49-63."""
+    out = {"cls_token": sd["embeddings.cls_token"], "pos_embed": sd["embeddings.position_embeddings"],
+           "mask_token": sd["embeddings.mask_token"], "patch_embed.proj.weight": sd["embeddings.patch_embeddings.projection.weight"],
+           "patch_embed.proj.bias": sd["embeddings.patch_embeddings.projection.bias"], "norm.weight": sd["layernorm.weight"],
+           "norm.bias": sd["layernorm.bias"]}
+    if "embeddings.register_tokens" in sd:
+        out["register_tokens"] = sd["embeddings.register_tokens"]
+    for i in range(layers):
+        a, b = f"encoder.layer.{i}.", f"blocks.{i}."
+        for k in ("weight", "bias"):
+            out[b + f"norm1.{k}"], out[b + f"norm2.{k}"] = sd[a + f"norm1.{k}"], sd[a + f"norm2.{k}"]
+            out[b + f"attn.qkv.{k}"] = torch.cat([sd[a + f"attention.attention.{n}.{k}"] for n in ("query", "key", "value")], dim=0)
+            out[b + f"attn.proj.{k}"] = sd[a + f"attention.output.dense.{k}"]
+            if swiglu:
+                out[b + f"mlp.w12.{k}"], out[b + f"mlp.w3.{k}"] = sd[a + f"mlp.weights_in.{k}"], sd[a + f"mlp.weights_out.{k}"]
+            else:
+                out[b + f"mlp.fc1.{k}"], out[b + f"mlp.fc2.{k}"] = sd[a + f"mlp.fc1.{k}"], sd[a + f"mlp.fc2.{k}"]
+        out[b + "ls1.gamma"], out[b + "ls2.gamma"] = sd[a + "layer_scale1.lambda1"], sd[a + "layer_scale2.lambda1"]
+    return out
+
+
+@pytest.mark.parametrize("name", ["openmidnight_test_tiny", "hibou_test_tiny"])
+def test_facebook_key_layout_converts_to_the_same_tensors(name):
+    from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, DINOV2_REGISTERS, convert_dinov2_state_dict
+
+    patch, layers, heads, d, mlp, swiglu = DINOV2_CONFIGS[name]
+    sd = hf.state_dict(name, seed=8)
+    kw = dict(layers=layers, swiglu=swiglu, image_size=224, patch=patch, registers=DINOV2_REGISTERS[name])
+    a = convert_dinov2_state_dict(sd, **kw)
+    b = convert_dinov2_state_dict(hf_to_fb_names(sd, layers, swiglu), **kw)
+    assert a.keys() == b.keys() and "register_tokens" in a and a["register_tokens"].shape == (4, d)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_register_checkpoints_need_the_input_grid():
+    from atlaspatch_b200.dinov2 import convert_dinov2_state_dict
+    from atlaspatch_b200.weights import dinov2_state_dict
+
+    sd = dinov2_state_dict("hibou_test_tiny", seed=0, image_size=518)     # 37 x 37 grid: would need the antialiased interpolation
+    with pytest.raises(ValueError, match="position grid"):
+        convert_dinov2_state_dict(sd, layers=2, swiglu=False, image_size=224, patch=14, registers=4)
