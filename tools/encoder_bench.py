@@ -1,6 +1,6 @@
 """Device-timed throughput of any registered encoder on an HBM-resident synthetic slide (embed_coords fast path).
 
-    python tools/encoder_bench.py dinov2_large 224 [n_patches] [max_batch] [fast|strict]
+    python tools/encoder_bench.py dinov2_large|hibou_l|midnight|phikon_v2|... 224 [n_patches] [max_batch] [fast|strict]
 """
 import json
 import sys
@@ -20,7 +20,14 @@ name, P = sys.argv[1], int(sys.argv[2])
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 1016
 mb = int(sys.argv[4]) if len(sys.argv) > 4 else 127
 precision = sys.argv[5] if len(sys.argv) > 5 else "fast"     # "fast" | "strict" (B200FeatureExtractor precision preset)
-if name.startswith("dinov2"):
+from atlaspatch_b200.encoder import FAMILY_RECIPES  # noqa: E402
+
+# hub families: same FLOPs as the architecture they share (+ 4 register tokens: 261 / 257 of the per-token work)
+GFLOP.update({"midnight": 598.78, "openmidnight": 598.78 * 261 / 257, "phikon_v1": 35.13, "phikon_v2": 123.11, "hibou_l": 162.02 * 261 / 257,
+              "hibou_b": 46.7 * 261 / 257})
+if name in FAMILY_RECIPES:
+    from oracle.hub_families import state_dict as make_sd
+elif name.startswith("dinov2"):
     from oracle.dinov2_hf import dinov2_state_dict as make_sd
 else:
     from oracle.weights import vit_state_dict as make_sd
