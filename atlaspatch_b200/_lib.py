@@ -20,7 +20,8 @@ class VitDesc(C.Structure):
     _fields_ = [("image_size", C.c_int), ("patch", C.c_int), ("layers", C.c_int), ("heads", C.c_int),
                 ("hidden", C.c_int), ("mlp", C.c_int), ("input_patch", C.c_int), ("max_batch", C.c_int), ("precise_layers", C.c_int),
                 ("ln_eps", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3),
-                ("preprocess", C.c_int), ("resize_to", C.c_int), ("mlp_kind", C.c_int), ("pool", C.c_int), ("registers", C.c_int)]
+                ("preprocess", C.c_int), ("resize_to", C.c_int), ("mlp_kind", C.c_int), ("pool", C.c_int), ("registers", C.c_int),
+                ("pre_ln", C.c_int), ("proj_dim", C.c_int)]
 
 
 class Sam2Desc(C.Structure):

@@ -49,6 +49,9 @@ struct ap_encoder {
     std::vector<void*> allocs;
     // packed weights
     __half* w_pe = nullptr;
+    float *preln_g = nullptr, *preln_b = nullptr, *b_proj = nullptr;   // CLIP: LayerNorm after the embeddings; zero bias of the projection
+    __half *w_proj = nullptr, *yc_proj = nullptr;                       // visual projection [proj_dim, 2 D] (hi | lo), its A operand [images, 2 D]
+    GemmPlan p_proj;
     float *b_pe = nullptr, *cls = nullptr, *regs = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
     GemmPlan p_pe;
     AttnPlan p_attn;
@@ -216,6 +219,19 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
         ex.lead_tokens = e->lead;
         if ((rc = ap_gemm_run(ctx, &p, e->b_pe, nullptr, e->x, &ex, st))) return rc;
     }
+    // CLIP (modeling_clip.py CLIPVisionTransformer: hidden = pre_layrnorm(embeddings)): the residual stream itself is normalised, in
+    // place (each warp holds its row in registers); layer 0 then runs its own LayerNorm kernel (finalize: fold1 = false)
+    if (e->d.pre_ln && (rc = ap_layernorm_run(ctx, e->x, D, e->preln_g, e->preln_b, e->d.ln_eps, nullptr, e->x, rows, D, st))) return rc;
+    // final LayerNorm of the class rows (row stride xs) -> fp32 features, or -> [hi | lo] fp16 and through the bias-free visual projection
+    // (CLIPModel.get_image_features: visual_projection(post_layernorm(hidden[:, 0])), three-product split GEMM = fp32-like precision)
+    auto head = [&](const float* xsrc, int64_t xs) -> int {
+        if (e->d.proj_dim <= 0) return ap_layernorm_run(ctx, xsrc, xs, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
+        int r2 = ap_layernorm_run(ctx, xsrc, xs, e->lnf_g, e->lnf_b, e->d.ln_eps, e->yc_proj, nullptr, nb, D, st, 2 * D, 1);
+        if (r2) return r2;
+        GemmPlan pp = e->p_proj;
+        pp.M = nb;
+        return ap_gemm_run(ctx, &pp, e->b_proj, nullptr, out_feats, nullptr, st);
+    };
     for (size_t li = 0; li < e->layers.size(); ++li) {
         auto& L = e->layers[li];
         GemmPlan p;
@@ -240,7 +256,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
             if ((rc = ap_gemm_run(ctx, &p, L.b_1, nullptr, e->hc, nullptr, st))) return rc;
             p = L.pc_2; p.M = nb;
             if ((rc = ap_gemm_run(ctx, &p, L.b_2, e->xc, e->xc, nullptr, st))) return rc;
-            return ap_layernorm_run(ctx, e->xc, D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
+            return head(e->xc, D);
         }
         if (L.asplit & 2) {   // out_proj reads [hi | lo] attention outputs (finalize only sets this bit with the tcgen05 kernel)
             if ((rc = ap_attention_tc_run(ctx, &e->p_attn, e->y2s, nb, T1, e->d.heads, st, 2 * D, 1))) return rc;
@@ -261,7 +277,7 @@ int forward_chunk(ap_encoder* e, const uint8_t* slide, int64_t W, int64_t H, int
     if (e->d.pool == 1)   // final LayerNorm on every token, then [class || mean of the patch tokens] (midnight.py:57-61)
         return ap_cls_mean_pool_run(ctx, e->x, nb, T1, e->lead, D, e->lnf_g, e->lnf_b, e->d.ln_eps, out_feats, st);
     // final LayerNorm on the class-token rows only -> fp32 features
-    return ap_layernorm_run(ctx, e->x, static_cast<int64_t>(T1) * D, e->lnf_g, e->lnf_b, e->d.ln_eps, nullptr, out_feats, nb, D, st);
+    return head(e->x, static_cast<int64_t>(T1) * D);
 }
 
 }  // namespace
@@ -273,12 +289,14 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     AP_REQUIRE(ctx, desc->preprocess >= 0 && desc->preprocess <= 3, "encoder: unknown preprocess %d", desc->preprocess);
     AP_REQUIRE(ctx, desc->registers >= 0 && desc->registers <= 8, "encoder: registers %d unsupported (0..8)", desc->registers);
     AP_REQUIRE(ctx, desc->pool == 0 || desc->pool == 1, "encoder: unknown pool %d (0 class token, 1 [class || mean of patch tokens])", desc->pool);
-    AP_REQUIRE(ctx, desc->mlp_kind == 0 || desc->mlp_kind == 1, "encoder: unknown mlp_kind %d", desc->mlp_kind);
+    AP_REQUIRE(ctx, desc->mlp_kind >= 0 && desc->mlp_kind <= 2, "encoder: unknown mlp_kind %d", desc->mlp_kind);
+    AP_REQUIRE(ctx, desc->proj_dim >= 0 && desc->proj_dim % 128 == 0 && (desc->proj_dim == 0 || desc->pool == 0),
+               "encoder: proj_dim %d unsupported (multiple of 128, class-token head only)", desc->proj_dim);
     AP_REQUIRE(ctx, desc->patch == 16 || desc->patch == 32 || (desc->preprocess >= 1 && desc->patch >= 4 && desc->patch <= 32),
                "encoder: conv patch %d unsupported (16 / 32 with the crop preprocess, 4..32 with the resizing preprocesses)", desc->patch);
     AP_REQUIRE(ctx, desc->preprocess == 0 || desc->resize_to >= desc->image_size, "encoder: resize_to %d < image_size %d", desc->resize_to,
                desc->image_size);
-    AP_REQUIRE(ctx, desc->mlp_kind == 0 || (2 * desc->mlp) % 256 == 0, "encoder: SwiGLU needs 2 * mlp %% 256 == 0 (mlp %d)", desc->mlp);
+    AP_REQUIRE(ctx, desc->mlp_kind != 1 || (2 * desc->mlp) % 256 == 0, "encoder: SwiGLU needs 2 * mlp %% 256 == 0 (mlp %d)", desc->mlp);
     AP_REQUIRE(ctx, desc->image_size % desc->patch == 0, "encoder: image %d not a multiple of patch %d", desc->image_size, desc->patch);
     AP_REQUIRE(ctx, desc->hidden % desc->heads == 0 && desc->hidden / desc->heads == 64,
                "encoder: head_dim must be 64 (hidden %d, heads %d)", desc->hidden, desc->heads);
@@ -291,7 +309,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     e->d = *desc;
     const int g = desc->image_size / desc->patch;
     e->tokens = g * g;
-    e->out_dim = desc->pool == 1 ? 2 * desc->hidden : desc->hidden;
+    e->out_dim = desc->proj_dim > 0 ? desc->proj_dim : desc->pool == 1 ? 2 * desc->hidden : desc->hidden;
     e->lead = 1 + desc->registers;
     e->kpe = 3 * desc->patch * desc->patch;
     e->kpe_pad = (e->kpe + 63) / 64 * 64;
@@ -389,6 +407,16 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
         AP_GET(g, "encoder.ln.weight", D)
         AP_GET(b, "encoder.ln.bias", D)
         if ((rc = upload_f32(e, &e->cls, *c))) return rc;
+        if (e->d.pre_ln) {
+            AP_GET(pg, "encoder.pre_ln.weight", D)
+            AP_GET(pb, "encoder.pre_ln.bias", D)
+            if ((rc = upload_f32(e, &e->preln_g, *pg)) || (rc = upload_f32(e, &e->preln_b, *pb))) return rc;
+        }
+        if (e->d.proj_dim > 0) {
+            AP_GET(wp, "head.proj.weight", (size_t)e->d.proj_dim * D)
+            std::vector<float> zb(e->d.proj_dim, 0.0f);
+            if ((rc = upload_f16_split(e, &e->w_proj, wp->data(), e->d.proj_dim, D)) || (rc = upload_f32(e, &e->b_proj, zb))) return rc;
+        }
         if (e->d.registers > 0) {
             AP_GET(r, "register_tokens", (size_t)e->d.registers * D)
             if ((rc = upload_f32(e, &e->regs, *r))) return rc;
@@ -429,7 +457,7 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
             const int aw = ctx->precise_aw_layers >= 0 ? ctx->precise_aw_layers : (e->d.layers > 32 ? 8 : 0);
             L.asplit = (i < e->precise_layers && i < aw && a_ok) ? (pm & 7) : 0;
         }
-        L.fold1 = e->fold_ln && !(L.asplit & 1);
+        L.fold1 = e->fold_ln && !(L.asplit & 1) && !(i == 0 && e->d.pre_ln);   // after the in-place pre-LayerNorm the producers' fp16 copy / statistics of x are stale
         L.fold2 = e->fold_ln && !(L.asplit & 4);
         std::vector<float> wq(*wqkv), bq(*bqkv), wf(*w1), bf1(*b1);
         if (L.fold1) fold_ln_affine(wq, bq, *ln1g, *ln1b, (size_t)3 * D, D);
@@ -476,6 +504,10 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
     if ((rc = dev_alloc(e, (void**)&e->yc_attn, rows_c * D * 2)) || (rc = dev_alloc(e, (void**)&e->yc_ln, rows_c * D * 2)) ||
         (rc = dev_alloc(e, (void**)&e->hc, rows_c * M * 2)) || (rc = dev_alloc(e, (void**)&e->xc, rows_c * D * 4)))
         return rc;
+    if (e->d.proj_dim > 0) {
+        if ((rc = dev_alloc(e, (void**)&e->yc_proj, rows_c * 2 * D * 2))) return rc;
+        AP_CHECK_CUDA(ctx, cudaMemset(e->yc_proj, 0, rows_c * 2 * D * 2));
+    }
     AP_CHECK_CUDA(ctx, cudaMemset(e->yc_attn, 0, rows_c * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->yc_ln, 0, rows_c * D * 2));
     AP_CHECK_CUDA(ctx, cudaMemset(e->hc, 0, rows_c * M * 2));
@@ -489,7 +521,8 @@ extern "C" int ap_encoder_finalize(ap_encoder* e) {
 
     // ---- GEMM plans (TMA descriptors over the fixed workspaces / weights) ------------------------------
     if ((rc = ap_gemm_plan(ctx, &e->p_pe, e->a_pe, e->w_pe, MB * T, D, 2 * Kp, AP_EPI_BIAS_F32, Kp))) return rc;
-    const int epi1 = e->d.mlp_kind == 1 ? AP_EPI_BIAS_SWIGLU_F16 : AP_EPI_BIAS_GELU_F16;
+    if (e->d.proj_dim > 0 && (rc = ap_gemm_plan_split(ctx, &e->p_proj, e->yc_proj, e->w_proj, MB, e->d.proj_dim, D, AP_EPI_BIAS_F32, AP_SPLIT_AW))) return rc;
+    const int epi1 = e->d.mlp_kind == 1 ? AP_EPI_BIAS_SWIGLU_F16 : e->d.mlp_kind == 2 ? AP_EPI_BIAS_QGELU_F16 : AP_EPI_BIAS_GELU_F16;
     for (auto& L : e->layers) {
         const int sq = (L.split & 1) ? 2 : 1, so = (L.split & 2) ? 2 : 1, s1 = (L.split & 4) ? 2 : 1, s2 = (L.split & 8) ? 2 : 1;
         auto mode = [&](int bit) { return ((L.asplit & bit) ? AP_SPLIT_A : 0) | ((L.split & bit) ? AP_SPLIT_W : 0); };

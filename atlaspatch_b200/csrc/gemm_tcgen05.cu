@@ -289,6 +289,10 @@ __device__ __forceinline__ void epilogue_stage_f16(const uint32_t (&r)[32], uint
         if (EPI == AP_EPI_BIAS_GELU_F16) {
             gelu_erf2(v[0], v[1]); gelu_erf2(v[2], v[3]); gelu_erf2(v[4], v[5]); gelu_erf2(v[6], v[7]);
         }
+        if (EPI == AP_EPI_BIAS_QGELU_F16) {   // CLIP's QuickGELU: x sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x))
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = v[k] * rcp_approx(1.0f + ex2_approx(-2.4554669595930157f * v[k]));
+        }
         *reinterpret_cast<uint4*>(stg + stg_off(lane, half_sel * 4 + j)) =
             make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
     }
@@ -474,7 +478,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     else ptx::mbar_arrive_relaxed(&tempty_bar[as]);
                 }
             };
-            if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16 || EPI == AP_EPI_BIAS_SWIGLU_F16) {
+            if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16 || EPI == AP_EPI_BIAS_QGELU_F16 || EPI == AP_EPI_BIAS_SWIGLU_F16) {
                 // lane = accumulator row; its LayerNorm statistics are fetched (L2) while this tile's MMAs are still running
                 const LnRow ln = ln_row_coeffs(ep, row_base + lane, M);
                 const bool owns = lane * 4 < COLS_PER_WARP;   // BN = 128: 64 columns per warp, lanes 16..31 hold nothing
@@ -532,7 +536,7 @@ template <int CG, int BN, int EPI>
 int launch(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream_t stream) {
     // fp16 outputs leave through TMA stores: box = 32 rows x 64 halfs (one staged tile), 128B swizzle, rows clipped at M
     CUtensorMap map_out{};
-    if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16 || EPI == AP_EPI_BIAS_SWIGLU_F16) {
+    if (EPI == AP_EPI_BIAS_F16 || EPI == AP_EPI_BIAS_GELU_F16 || EPI == AP_EPI_BIAS_QGELU_F16 || EPI == AP_EPI_BIAS_SWIGLU_F16) {
         const int n_out = EPI == AP_EPI_BIAS_SWIGLU_F16 ? p->N / 2 : p->N;
         int rc = ap_make_tmap_f16_2d(ctx, &map_out, ep.out, (uint64_t)p->M, (uint64_t)n_out, (uint64_t)n_out, 32, 64);
         if (rc) return rc;
@@ -561,6 +565,7 @@ int dispatch_epi(ap_ctx* ctx, const GemmPlan* p, const EpiParams& ep, cudaStream
     switch (p->epilogue) {
         case AP_EPI_BIAS_F16: return launch<CG, BN, AP_EPI_BIAS_F16>(ctx, p, ep, stream);
         case AP_EPI_BIAS_GELU_F16: return launch<CG, BN, AP_EPI_BIAS_GELU_F16>(ctx, p, ep, stream);
+        case AP_EPI_BIAS_QGELU_F16: return launch<CG, BN, AP_EPI_BIAS_QGELU_F16>(ctx, p, ep, stream);
         case AP_EPI_BIAS_RESID_F32: return launch<CG, BN, AP_EPI_BIAS_RESID_F32>(ctx, p, ep, stream);
         case AP_EPI_BIAS_F32: return launch<CG, BN, AP_EPI_BIAS_F32>(ctx, p, ep, stream);
         case AP_EPI_BIAS_SWIGLU_F16:
@@ -603,7 +608,7 @@ namespace {
 int plan_common(ap_ctx* ctx, GemmPlan* plan, const void* A, const void* W, int M, int N, int epilogue, int Kw) {
     const int K = plan->K, Ka = plan->Ka;
     AP_REQUIRE(ctx, N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
-    AP_REQUIRE(ctx, epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
+    AP_REQUIRE(ctx, epilogue >= 0 && epilogue <= 5, "gemm: unknown epilogue %d", epilogue);
     AP_REQUIRE(ctx, epilogue != AP_EPI_BIAS_SWIGLU_F16 || N % 256 == 0, "gemm: SwiGLU epilogue needs N %% 256 == 0 (N=%d)", N);
     (void)K;
     plan->M = M; plan->N = N; plan->epilogue = epilogue;

@@ -37,6 +37,15 @@ DINOV2_CONFIGS = {
     "hibou_test_tiny": (14, 2, 4, 256, 1024, False),
     "openmidnight_test_tiny": (14, 2, 6, 384, 1024, True),
 }
+# name -> (patch, layers, heads, hidden, mlp, projection): image towers of transformers CLIPModel checkpoints (models/patch/plip.py:34,
+# quilt.py:12-16,56): pre-LayerNorm after the embeddings, QuickGELU MLP, bias-free visual projection of the class token
+HF_CLIP_CONFIGS = {
+    "plip": (32, 12, 12, 768, 3072, 512),
+    "quilt_b_32": (32, 12, 12, 768, 3072, 512),
+    "quilt_b_16": (16, 12, 12, 768, 3072, 512),
+    "plip_test_tiny": (32, 2, 4, 256, 512, 128),
+    "quilt_b_16_test_tiny": (16, 2, 4, 256, 512, 128),
+}
 DINOV2_REGISTERS = {"hibou_b": 4, "hibou_l": 4, "openmidnight": 4, "hibou_test_tiny": 4, "openmidnight_test_tiny": 4}
 # name -> (patch, layers, heads, hidden, mlp): transformers ViTModel checkpoints (owkin/phikon, models/patch/phikon.py:41-44)
 HF_VIT_CONFIGS = {
@@ -188,4 +197,32 @@ def fb_to_hf_dinov2_names(sd: Mapping[str, object], *, layers: int, swiglu: bool
         pairs = (("mlp.w12", "mlp.weights_in"), ("mlp.w3", "mlp.weights_out")) if swiglu else (("mlp.fc1", "mlp.fc1"), ("mlp.fc2", "mlp.fc2"))
         for a, b in pairs:
             out[d + b + ".weight"], out[d + b + ".bias"] = sd[s + a + ".weight"], sd[s + a + ".bias"]
+    return out
+
+
+def convert_hf_clip_state_dict(sd: Mapping[str, object], *, layers: int) -> dict[str, np.ndarray]:
+    """transformers CLIPModel names (`CLIPModel.from_pretrained("vinid/plip")`, models/patch/plip.py:34; text tower ignored) -> engine
+    names.  CLIPVisionEmbeddings: bias-free patch convolution, class_embedding + position_embedding; pre_layrnorm -> "encoder.pre_ln";
+    q / k / v projections stacked into in_proj (the 1 / sqrt(head_dim) scale is the attention kernel's); post_layernorm ->
+    "encoder.ln"; visual_projection -> "head.proj.weight"."""
+    v = "vision_model."
+    out: dict[str, np.ndarray] = {}
+    w = _np(sd[v + "embeddings.patch_embedding.weight"])
+    out["conv_proj.weight"] = w
+    out["conv_proj.bias"] = np.zeros((w.shape[0],), dtype=np.float32)
+    out["class_token"] = _np(sd[v + "embeddings.class_embedding"]).reshape(1, 1, -1)
+    pos = _np(sd[v + "embeddings.position_embedding.weight"])
+    out["encoder.pos_embedding"] = pos.reshape(1, pos.shape[-2], pos.shape[-1])
+    out["encoder.pre_ln.weight"], out["encoder.pre_ln.bias"] = _np(sd[v + "pre_layrnorm.weight"]), _np(sd[v + "pre_layrnorm.bias"])
+    out["encoder.ln.weight"], out["encoder.ln.bias"] = _np(sd[v + "post_layernorm.weight"]), _np(sd[v + "post_layernorm.bias"])
+    out["head.proj.weight"] = _np(sd["visual_projection.weight"])
+    for i in range(layers):
+        s, d = v + f"encoder.layers.{i}.", f"encoder.layers.encoder_layer_{i}."
+        out[d + "ln_1.weight"], out[d + "ln_1.bias"] = _np(sd[s + "layer_norm1.weight"]), _np(sd[s + "layer_norm1.bias"])
+        out[d + "ln_2.weight"], out[d + "ln_2.bias"] = _np(sd[s + "layer_norm2.weight"]), _np(sd[s + "layer_norm2.bias"])
+        out[d + "self_attention.in_proj_weight"] = np.concatenate([_np(sd[s + f"self_attn.{n}.weight"]) for n in ("q_proj", "k_proj", "v_proj")], axis=0)
+        out[d + "self_attention.in_proj_bias"] = np.concatenate([_np(sd[s + f"self_attn.{n}.bias"]) for n in ("q_proj", "k_proj", "v_proj")], axis=0)
+        out[d + "self_attention.out_proj.weight"], out[d + "self_attention.out_proj.bias"] = _np(sd[s + "self_attn.out_proj.weight"]), _np(sd[s + "self_attn.out_proj.bias"])
+        out[d + "mlp.0.weight"], out[d + "mlp.0.bias"] = _np(sd[s + "mlp.fc1.weight"]), _np(sd[s + "mlp.fc1.bias"])
+        out[d + "mlp.3.weight"], out[d + "mlp.3.bias"] = _np(sd[s + "mlp.fc2.weight"]), _np(sd[s + "mlp.fc2.bias"])
     return out

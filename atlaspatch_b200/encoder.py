@@ -13,7 +13,8 @@ from typing import Mapping, Sequence
 import numpy as np
 
 from atlaspatch_b200._lib import Context, VitDesc, current_stream_ptr
-from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, DINOV2_REGISTERS, HF_VIT_CONFIGS, convert_dinov2_state_dict, convert_hf_vit_state_dict
+from atlaspatch_b200.dinov2 import (DINOV2_CONFIGS, DINOV2_REGISTERS, HF_CLIP_CONFIGS, HF_VIT_CONFIGS, convert_dinov2_state_dict,
+                                    convert_hf_clip_state_dict, convert_hf_vit_state_dict)
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -34,6 +35,8 @@ VIT_CONFIGS = {
 #   pool: 0 class token, 1 [class || mean of patch tokens]
 _HALF = (0.5, 0.5, 0.5)
 _HIBOU_MEAN, _HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
+_CLIP_MEAN, _CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+_CLIP = dict(preprocess=1, resize_to=224, mean=_CLIP_MEAN, std=_CLIP_STD, pool=0, ln_eps=1e-5, default_patch=224)
 FAMILY_RECIPES = {
     # kaiko-ai/midnight (models/patch/midnight.py:15-25,55-61): torchvision Resize(224) on the PIL patch, CenterCrop(224),
     # Normalize(0.5, 0.5); feature = cat(last_hidden_state[:, 0], last_hidden_state[:, 1:].mean(1)) -> 3072
@@ -55,13 +58,21 @@ FAMILY_RECIPES = {
     # mean / std; facebookresearch dinov2_vitg14_reg (4 register tokens, SwiGLU), feature = class token
     "openmidnight": dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
     "openmidnight_test_tiny": dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
+    # vinid/plip, wisdomik/QuiltNet-B-32 / -B-16 (models/patch/plip.py:34-35,56, quilt.py:56-60): transformers CLIPModel +
+    # CLIPProcessor (fast image processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature =
+    # get_image_features = visual_projection(post_layernorm(class token)) -> 512
+    "plip": _CLIP, "quilt_b_32": _CLIP, "quilt_b_16": _CLIP, "plip_test_tiny": _CLIP, "quilt_b_16_test_tiny": _CLIP,
 }
 
 
-def vit_state_dict_names(layers: int, registers: int = 0) -> list[str]:
+def vit_state_dict_names(layers: int, registers: int = 0, pre_ln: bool = False, proj: bool = False) -> list[str]:
     names = ["conv_proj.weight", "conv_proj.bias", "class_token", "encoder.pos_embedding", "encoder.ln.weight", "encoder.ln.bias"]
     if registers:
         names.append("register_tokens")
+    if pre_ln:
+        names += ["encoder.pre_ln.weight", "encoder.pre_ln.bias"]
+    if proj:
+        names.append("head.proj.weight")
     for i in range(layers):
         p = f"encoder.layers.encoder_layer_{i}."
         names += [p + s for s in ("ln_1.weight", "ln_1.bias", "self_attention.in_proj_weight", "self_attention.in_proj_bias",
@@ -90,11 +101,14 @@ class B200FeatureExtractor:
         folded): max 8.7e-4 on the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log), 21.1 k against 24.1 k patches/s."""
         if precision not in ("fast", "strict"):
             raise ValueError("precision must be 'fast' or 'strict'")
-        preprocess, resize_to, mlp_kind, pool, ln_eps, registers = 0, 0, 0, 0, 1e-6, 0
+        preprocess, resize_to, mlp_kind, pool, ln_eps, registers, pre_ln, proj_dim = 0, 0, 0, 0, 1e-6, 0, 0, 0
         mean, std = IMAGENET_MEAN, IMAGENET_STD
         recipe = FAMILY_RECIPES.get(name, {}) if config is None else {}
-        if config is None and (name in DINOV2_CONFIGS or name in HF_VIT_CONFIGS):
-            if name in DINOV2_CONFIGS:
+        if config is None and (name in DINOV2_CONFIGS or name in HF_VIT_CONFIGS or name in HF_CLIP_CONFIGS):
+            if name in HF_CLIP_CONFIGS:
+                (patch, layers, heads, hidden, mlp, proj_dim), swiglu, pre_ln = HF_CLIP_CONFIGS[name], False, 1
+                state_dict = convert_hf_clip_state_dict(state_dict, layers=layers)
+            elif name in DINOV2_CONFIGS:
                 patch, layers, heads, hidden, mlp, swiglu = DINOV2_CONFIGS[name]
                 registers = DINOV2_REGISTERS.get(name, 0)
                 state_dict = convert_dinov2_state_dict(state_dict, layers=layers, swiglu=swiglu, image_size=image_size, patch=patch,
@@ -102,14 +116,14 @@ class B200FeatureExtractor:
             else:
                 (patch, layers, heads, hidden, mlp), swiglu = HF_VIT_CONFIGS[name], False
                 state_dict = convert_hf_vit_state_dict(state_dict, layers=layers)
-            preprocess, resize_to, mlp_kind = recipe.get("preprocess", 1), recipe.get("resize_to", 256), int(swiglu)
+            preprocess, resize_to, mlp_kind = recipe.get("preprocess", 1), recipe.get("resize_to", 256), (2 if name in HF_CLIP_CONFIGS else int(swiglu))
             pool, ln_eps = recipe.get("pool", 0), recipe.get("ln_eps", 1e-6)
             mean, std = recipe.get("mean", IMAGENET_MEAN), recipe.get("std", IMAGENET_STD)
             input_patch = recipe.get("default_patch", 224) if input_patch is None else input_patch
         else:
             cfg = config or VIT_CONFIGS.get(name)
             if cfg is None:
-                raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS) + sorted(DINOV2_CONFIGS) + sorted(HF_VIT_CONFIGS)}")
+                raise KeyError(f"Unknown B200 encoder '{name}'. Available: {sorted(VIT_CONFIGS) + sorted(DINOV2_CONFIGS) + sorted(HF_VIT_CONFIGS) + sorted(HF_CLIP_CONFIGS)}")
             patch, layers, heads, hidden, mlp = cfg
             input_patch = 256 if input_patch is None else input_patch
             if int(input_patch) != 256:
@@ -118,7 +132,7 @@ class B200FeatureExtractor:
                 preprocess, resize_to = 2, 256
         self._patch, self._grid = int(patch), int(image_size) // int(patch)
         self.name = registry_name or name   # H5 dataset name: features/<name> (services/storage.py:250-337)
-        self.embedding_dim = int(hidden) * (2 if pool == 1 else 1)
+        self.embedding_dim = int(proj_dim) if proj_dim else int(hidden) * (2 if pool == 1 else 1)
         self._mean = tuple(float(m) for m in mean)
         self.input_patch = int(input_patch)
         self.max_batch = int(max_batch)
@@ -129,12 +143,12 @@ class B200FeatureExtractor:
         desc = VitDesc(image_size=image_size, patch=patch, layers=layers, heads=heads, hidden=hidden, mlp=mlp,
                        input_patch=input_patch, max_batch=max_batch, precise_layers=precise_layers, ln_eps=ln_eps,
                        mean=(C.c_float * 3)(*mean), std=(C.c_float * 3)(*std), preprocess=preprocess,
-                       resize_to=resize_to, mlp_kind=mlp_kind, pool=pool, registers=registers)
+                       resize_to=resize_to, mlp_kind=mlp_kind, pool=pool, registers=registers, pre_ln=pre_ln, proj_dim=proj_dim)
         h = C.c_void_p()
         self.ctx.check(lib.ap_encoder_create(self.ctx.handle, C.byref(desc), C.byref(h)))
         self._h = h
         try:
-            for key in vit_state_dict_names(layers, registers):
+            for key in vit_state_dict_names(layers, registers, bool(pre_ln), bool(proj_dim)):
                 if key not in state_dict:
                     raise KeyError(f"state_dict is missing '{key}'")
                 t = state_dict[key]

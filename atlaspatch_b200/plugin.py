@@ -67,7 +67,10 @@ _HUB = {"midnight": "kaiko-ai/midnight",        # models/patch/midnight.py:12,44
         "phikon_v2": "owkin/phikon-v2",         # models/patch/phikon.py:90-92    AutoModel (Dinov2Model ViT-L/16) -> 1024
         "hibou_b": "histai/hibou-B",            # models/patch/hibou.py:12-15,54  AutoModel(trust_remote_code): DINOv2 + 4 registers -> 768
         "hibou_l": "histai/hibou-L",            #                                 -> 1024
-        "openmidnight": "SophontAI/OpenMidnight"}   # models/patch/openmidnight.py:49-63  torch.hub dinov2_vitg14_reg + checkpoint -> 1536
+        "openmidnight": "SophontAI/OpenMidnight",   # models/patch/openmidnight.py:49-63  torch.hub dinov2_vitg14_reg + checkpoint -> 1536
+        "plip": "vinid/plip",                   # models/patch/plip.py:34         CLIPModel (ViT-B/32), get_image_features -> 512
+        "quilt_b_32": "wisdomik/QuiltNet-B-32",  # models/patch/quilt.py:12-16,56  CLIPModel (ViT-B/32 / ViT-B/16) -> 512
+        "quilt_b_16": "wisdomik/QuiltNet-B-16"}
 
 
 def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
@@ -90,6 +93,10 @@ def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtracto
         checkpoint = torch.load(hf_hub_download(repo_id=_HUB[name], filename="teacher_checkpoint_load.pt"), map_location="cpu")
         model.pos_embed = torch.nn.parameter.Parameter(checkpoint["pos_embed"])
         model.load_state_dict(checkpoint)
+    elif name == "plip" or name.startswith("quilt"):
+        from transformers import CLIPModel
+
+        model = CLIPModel.from_pretrained(_HUB[name])
     elif name.startswith("hibou"):
         from transformers import AutoModel
 

@@ -196,6 +196,58 @@ def hf_vit_state_dict(name: str, seed: int = 0, image_size: int = 224) -> dict[s
     return sd
 
 
+# ---- transformers CLIPModel key layout, image tower + visual projection (vinid/plip: atlas_patch/models/patch/plip.py:34;
+#      wisdomik/QuiltNet-B-32 / -B-16: quilt.py:12-16,56) ----
+HF_CLIP_SPECS = {
+    # name: (patch, layers, heads, hidden, mlp, projection)
+    "plip": (32, 12, 12, 768, 3072, 512),
+    "quilt_b_32": (32, 12, 12, 768, 3072, 512),
+    "quilt_b_16": (16, 12, 12, 768, 3072, 512),
+    "plip_test_tiny": (32, 2, 4, 256, 512, 128),
+    "quilt_b_16_test_tiny": (16, 2, 4, 256, 512, 128),
+}
+
+
+def hf_clip_state_dict(name: str, seed: int = 0, image_size: int = 224) -> dict[str, torch.Tensor]:
+    """Seeded weights of the image side of transformers' CLIPModel (vision_model.* + visual_projection.weight)."""
+    patch, layers, heads, d, mlp, proj = HF_CLIP_SPECS[name]
+    rng = np.random.default_rng(seed)
+    g = image_size // patch
+
+    def normal(shape, std):
+        return torch.from_numpy((rng.standard_normal(shape, dtype=np.float32) * np.float32(std)))
+
+    def uniform(shape, bound):
+        return torch.from_numpy(rng.uniform(-bound, bound, shape).astype(np.float32))
+
+    v = "vision_model."
+    sd: dict[str, torch.Tensor] = {}
+    sd[v + "embeddings.class_embedding"] = normal((d,), 0.02)
+    sd[v + "embeddings.patch_embedding.weight"] = normal((d, 3, patch, patch), math.sqrt(1.0 / (3 * patch * patch)))
+    sd[v + "embeddings.position_embedding.weight"] = normal((g * g + 1, d), 0.02)
+    sd[v + "pre_layrnorm.weight"] = 1.0 + normal((d,), 0.1)
+    sd[v + "pre_layrnorm.bias"] = normal((d,), 0.05)
+    for i in range(layers):
+        p = v + f"encoder.layers.{i}."
+        sd[p + "layer_norm1.weight"] = 1.0 + normal((d,), 0.1)
+        sd[p + "layer_norm1.bias"] = normal((d,), 0.05)
+        for nm in ("q_proj", "k_proj", "v_proj"):
+            sd[p + f"self_attn.{nm}.weight"] = uniform((d, d), math.sqrt(6.0 / (d + 3 * d)))
+            sd[p + f"self_attn.{nm}.bias"] = normal((d,), 0.02)
+        sd[p + "self_attn.out_proj.weight"] = uniform((d, d), math.sqrt(1.0 / d))
+        sd[p + "self_attn.out_proj.bias"] = normal((d,), 0.02)
+        sd[p + "layer_norm2.weight"] = 1.0 + normal((d,), 0.1)
+        sd[p + "layer_norm2.bias"] = normal((d,), 0.05)
+        sd[p + "mlp.fc1.weight"] = uniform((mlp, d), math.sqrt(6.0 / (d + mlp)))
+        sd[p + "mlp.fc1.bias"] = normal((mlp,), 0.02)
+        sd[p + "mlp.fc2.weight"] = uniform((d, mlp), math.sqrt(6.0 / (d + mlp)))
+        sd[p + "mlp.fc2.bias"] = normal((d,), 0.02)
+    sd[v + "post_layernorm.weight"] = 1.0 + normal((d,), 0.1)
+    sd[v + "post_layernorm.bias"] = normal((d,), 0.05)
+    sd["visual_projection.weight"] = uniform((proj, d), math.sqrt(3.0 / d))
+    return sd
+
+
 # ---- SAM2 (transformers Sam2Model key layout; 'tiny' = the model the reference ships, 'large' = BASELINE.json configs[2]) ----
 def sam2_config(variant: str = "tiny"):
     """'tiny' = the model the reference ships (configs/sam2.1_hiera_t.yaml); 'large' = BASELINE.json configs[2] (Hiera-L)."""

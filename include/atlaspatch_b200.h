@@ -152,7 +152,9 @@ typedef struct ap_vit_desc {
     int resize_to;    /* 256 (preprocess 1, 2); 224 (preprocess 3) */
     int mlp_kind;     /* 0: Linear - GELU - Linear, mlp = hidden features;
                          1: SwiGLU (Dinov2SwiGLUFFN): "mlp.0" = weights_in with 2 * mlp rows interleaved as AP_EPI_BIAS_SWIGLU_F16
-                            expects, "mlp.3" = weights_out [hidden, mlp] */
+                            expects, "mlp.3" = weights_out [hidden, mlp];
+                         2: Linear - QuickGELU (x sigmoid(1.702 x)) - Linear: OpenAI CLIP checkpoints (atlas_patch/models/patch/plip.py:34,
+                            quilt.py:56 via transformers CLIPModel) */
     int pool;         /* 0: feature = final LayerNorm of the class token (torchvision heads -> Identity, base.py:100; transformers
                             last_hidden_state[:, 0], dinov2.py:60-62), hidden floats per patch;
                          1: [class || mean of the patch tokens] of the final-LayerNorm'd sequence, 2 * hidden floats per patch
@@ -161,6 +163,11 @@ typedef struct ap_vit_desc {
     int registers;    /* register tokens between the class token and the patch tokens ("register_tokens" [registers, hidden], no
                          position embedding: transformers Dinov2WithRegistersEmbeddings; hibou.py, openmidnight.py:49, the reg4 timm
                          models of hoptimus.py): sequence = 1 + registers + (image_size / patch)^2 <= 272.  0 = none */
+    int pre_ln;       /* 1: LayerNorm ("encoder.pre_ln.weight / bias") on the embedded sequence before the first layer (CLIP's
+                         pre_layrnorm, transformers modeling_clip.py CLIPVisionTransformer) */
+    int proj_dim;     /* > 0: feature = "head.proj.weight" [proj_dim, hidden] x final LayerNorm of the class token, no bias
+                         (CLIPModel.get_image_features = visual_projection(pooler_output): plip.py:56, quilt.py:60); multiple of 128.
+                         0: no projection */
 } ap_vit_desc;
 
 int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encoder** out_enc);
@@ -229,6 +236,7 @@ int ap_sam2_debug_copy(ap_sam2* s, const char* buffer_name, float* host_out, int
 #define AP_EPI_BIAS_SWIGLU_F16 4 /* out fp16 [M, N/2] = silu(g) * v, (g, v) = acc + bias in 16-column blocks: columns
                                     32b..32b+15 hold the gates and 32b+16..32b+31 the values of outputs 16b..16b+15
                                     (Dinov2SwiGLUFFN with weights_in rows interleaved); N % 256 == 0 */
+#define AP_EPI_BIAS_QGELU_F16 5  /* out fp16 = v sigmoid(1.702 v), v = acc + bias (CLIP's QuickGELU: transformers activations.QuickGELUActivation) */
 /* out[M,N] = epilogue(A[M,K] (fp16, row-major) x W[N,K]^T (fp16, row-major)); tcgen05/TMEM/TMA.
  * K % 64 == 0, N % 128 == 0. */
 int ap_gemm_f16(ap_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,

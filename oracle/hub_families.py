@@ -15,6 +15,10 @@
   checkpoint's 224 px position grid, torchvision `Resize((224, 224)) -> ToTensor -> Normalize(ImageNet)`, feature = model(x) = the
   class token after the final LayerNorm.  facebookresearch/dinov2 is not importable offline; Dinov2WithRegistersModel is the same
   architecture under transformers' key names (atlaspatch_b200/dinov2.py: fb_to_hf_dinov2_names maps one layout onto the other).
+* `plip`, `quilt_b_32`, `quilt_b_16` (plip.py:34-35,56; quilt.py:12-16,56-60): transformers `CLIPModel` + `CLIPProcessor` (fast image
+  processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature = `get_image_features(pixel_values=x)` =
+  visual_projection(post_layernorm(class token)) -> 512.  transformers 4.x returns that tensor (what the reference's forward_fn
+  hands on); transformers >= 5 returns the vision ModelOutput with the projected features in `pooler_output` -- same numbers.
 
 There is no network: the oracle builds the classes those hub files resolve to, from the published contents of their config.json /
 preprocessor_config.json (restated from memory of the public repos -- parity of the *settings* is unpinned; parity of the
@@ -27,16 +31,17 @@ from typing import Sequence
 import numpy as np
 import torch
 
-from atlaspatch_b200.weights import (DINOV2_PATCH, DINOV2_REGISTERS, DINOV2_SPECS, HF_VIT_SPECS, dinov2_state_dict,  # noqa: F401
-                                     hf_vit_state_dict)
+from atlaspatch_b200.weights import (DINOV2_PATCH, DINOV2_REGISTERS, DINOV2_SPECS, HF_CLIP_SPECS, HF_VIT_SPECS,  # noqa: F401
+                                     dinov2_state_dict, hf_clip_state_dict, hf_vit_state_dict)
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 HIBOU_MEAN, HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
+CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
 
 
 def _family(name: str) -> str:
-    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight"):
+    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight", "plip", "quilt"):
         if name.startswith(fam):
             return fam
     raise KeyError(name)
@@ -46,6 +51,8 @@ def state_dict(name: str, seed: int = 0) -> dict[str, torch.Tensor]:
     """Seeded weights in the key layout of the model class the reference loads (224 px position grids)."""
     if _family(name) == "phikon_v1":
         return hf_vit_state_dict(name, seed=seed, image_size=224)
+    if _family(name) in ("plip", "quilt"):
+        return hf_clip_state_dict(name, seed=seed, image_size=224)
     return dinov2_state_dict(name, seed=seed, image_size=224)
 
 
@@ -58,6 +65,18 @@ def build_model(name: str, sd: dict[str, torch.Tensor]):
         cfg = ViTConfig(hidden_size=d, num_hidden_layers=layers, num_attention_heads=heads, intermediate_size=mlp, patch_size=patch,
                         image_size=224, hidden_act="gelu", layer_norm_eps=1e-12, qkv_bias=True)
         model = ViTModel(cfg, add_pooling_layer=False).eval()
+    elif fam in ("plip", "quilt"):
+        from transformers import CLIPConfig, CLIPModel, CLIPTextConfig, CLIPVisionConfig
+
+        patch, layers, heads, d, mlp, proj = HF_CLIP_SPECS[name]
+        vc = CLIPVisionConfig(hidden_size=d, intermediate_size=mlp, num_hidden_layers=layers, num_attention_heads=heads, image_size=224,
+                              patch_size=patch, hidden_act="quick_gelu", layer_norm_eps=1e-5, projection_dim=proj)
+        tc = CLIPTextConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, vocab_size=100,
+                            max_position_embeddings=16, projection_dim=proj)         # the text tower is not on the path: kept minimal
+        model = CLIPModel(CLIPConfig(text_config=tc.to_dict(), vision_config=vc.to_dict(), projection_dim=proj)).eval()
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith(("text_model.", "text_projection.", "logit_scale")) for k in missing), (missing, unexpected)
+        return model
     else:
         from transformers import Dinov2Config, Dinov2Model, Dinov2WithRegistersConfig, Dinov2WithRegistersModel
 
@@ -88,7 +107,11 @@ def make_preprocess(name: str):
                                    transforms.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])
     import transformers
 
-    if fam == "hibou":
+    if fam in ("plip", "quilt"):
+        proc = transformers.CLIPImageProcessor(do_resize=True, size={"shortest_edge": 224}, resample=3, do_center_crop=True,
+                                               crop_size={"height": 224, "width": 224}, do_rescale=True, rescale_factor=1 / 255,
+                                               do_normalize=True, image_mean=list(CLIP_MEAN), image_std=list(CLIP_STD), do_convert_rgb=True)
+    elif fam == "hibou":
         proc = transformers.BitImageProcessor(do_resize=True, size={"shortest_edge": 224}, resample=3, do_center_crop=True,
                                               crop_size={"height": 224, "width": 224}, do_rescale=True, rescale_factor=1 / 255,
                                               do_normalize=True, image_mean=list(HIBOU_MEAN), image_std=list(HIBOU_STD), do_convert_rgb=True)
@@ -112,7 +135,7 @@ def pixels(name: str, patch: np.ndarray) -> np.ndarray:
         return ra.vit_preset_pixels(patch, resize_to=224, crop=224)
     if fam == "openmidnight":
         return ra.resize_pil_bilinear(patch, 224, 224)
-    if fam in ("phikon_v2", "hibou"):
+    if fam in ("phikon_v2", "hibou", "plip", "quilt"):
         return ra.dinov2_pixels(patch, resize_to=224, crop=224) if patch.shape[0] != 224 else patch
     return ra.hf_vit_pixels(patch, 224)
 
@@ -128,11 +151,15 @@ def extract_features(patches: Sequence[np.ndarray], sd: dict[str, torch.Tensor],
     outs = []
     for i in range(0, len(patches), batch_size):
         x = torch.stack([pre(Image.fromarray(np.asarray(p))) for p in patches[i:i + batch_size]])
+        if _family(name) in ("plip", "quilt"):
+            out = model.get_image_features(pixel_values=x)                     # plip.py:56, quilt.py:60
+            outs.append(out if isinstance(out, torch.Tensor) else out.pooler_output)
+            continue
         out = model(pixel_values=x)
         h = out.last_hidden_state
         if _family(name) == "hibou":
             outs.append(out.pooler_output)                                     # hibou.py:67-69
         else:
             outs.append(torch.cat([h[:, 0], h[:, 1:].mean(1)], dim=-1) if cls_mean else h[:, 0])
-    d = model.config.hidden_size * (2 if cls_mean else 1)
+    d = getattr(model.config, "projection_dim", None) or model.config.hidden_size * (2 if cls_mean else 1)
     return torch.cat(outs).to(torch.float32).numpy() if outs else np.empty((0, d), dtype=np.float32)

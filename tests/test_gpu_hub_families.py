@@ -1,6 +1,7 @@
 """GPU: hub encoder families of SURVEY.md section 8(f) rank 4 on the DINOv2 / ViT kernels through the C ABI -- midnight ([class || mean
 of patch tokens] head, Pillow BILINEAR preset, atlas_patch/models/patch/midnight.py), phikon_v1 (transformers ViTModel + uint8
-bilinear-antialias processor, phikon.py:41-56) and phikon_v2 (Dinov2Model ViT-L/16 + bicubic processor, phikon.py:90-105):
+bilinear-antialias processor, phikon.py:41-56), phikon_v2 (Dinov2Model ViT-L/16 + bicubic processor, phikon.py:90-105), hibou /
+openmidnight (4 register tokens) and the CLIP image towers of plip / quilt (pre-LayerNorm, QuickGELU, visual projection):
 preprocess pixels bit-exact vs the integer restatements (pinned on the CPU against the reference's own preprocess objects),
 features within 1e-3 relative of transformers' models run in fp32 on the CPU with the same seeded weights."""
 import numpy as np
@@ -22,7 +23,9 @@ def _slide():
                                     ("phikon_v1_test_tiny", 224), ("phikon_v1_test_tiny", 256), ("phikon_v1_test_tiny", 300),
                                     ("phikon_v2_test_tiny", 224), ("phikon_v2_test_tiny", 256),
                                     ("hibou_test_tiny", 224), ("hibou_test_tiny", 256),                  # 4 register tokens: 261-token sequence
-                                    ("openmidnight_test_tiny", 224), ("openmidnight_test_tiny", 512)])
+                                    ("openmidnight_test_tiny", 224), ("openmidnight_test_tiny", 512),
+                                    # CLIP towers: pre-LayerNorm, QuickGELU, 128-wide visual projection (ViT-B/32: 50 tokens; B/16: 197)
+                                    ("plip_test_tiny", 224), ("plip_test_tiny", 256), ("quilt_b_16_test_tiny", 256)])
 def test_tiny_family_pixels_bit_exact_and_features(name, P):
     import torch
 
@@ -44,14 +47,13 @@ def test_tiny_family_pixels_bit_exact_and_features(name, P):
         sd_in = hf_to_fb_names(sd, 2, True)
     ext = B200FeatureExtractor(name, sd_in, input_patch=P, max_batch=4)         # 9 patches -> three forward chunks
     pool = FAMILY_RECIPES[name]["pool"]
-    assert ext.embedding_dim == sd["layernorm.weight"].numel() * (2 if pool == 1 else 1)
     rows_dev = torch.from_numpy(rows).cuda()
     pix = ext.preprocess_pixels(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows_dev[-4:])
     for i in range(4):
         assert np.array_equal(pix[i], hf.pixels(name, patches[n - 4 + i])), i
     want = hf.extract_features(patches, sd, name)
     got = ext.embed_coords(wsi.device_image, wsi.w, wsi.h, wsi.pitch, rows_dev).cpu().numpy()
-    assert got.shape == want.shape
+    assert got.shape == want.shape == (n, ext.embedding_dim)
     rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
     print(name, P, "rel err per row:", rel)
     assert rel.max() < 1e-3, rel

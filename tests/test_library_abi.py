@@ -33,7 +33,7 @@ def test_every_header_symbol_is_exported(lib):
 
     from atlaspatch_b200._lib import Sam2Desc, VitDesc
 
-    assert lib.ap_sizeof(b"ap_vit_desc") == C.sizeof(VitDesc) == 84
+    assert lib.ap_sizeof(b"ap_vit_desc") == C.sizeof(VitDesc) == 92
     assert lib.ap_sizeof(b"ap_sam2_desc") == C.sizeof(Sam2Desc)
     assert lib.ap_sizeof(b"nope") == -1
     doc = (ROOT / "INTEGRATION.md").read_text()

@@ -9,7 +9,8 @@ import torch.nn.functional as F
 from oracle import hub_families as hf
 from oracle import resize_aa
 
-FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny", "hibou_test_tiny", "openmidnight_test_tiny"]
+FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny", "hibou_test_tiny", "openmidnight_test_tiny",
+            "plip_test_tiny", "quilt_b_16_test_tiny"]
 
 
 def _patch(P, seed=0):
@@ -44,7 +45,7 @@ def test_pixels_match_the_reference_preprocess(name, P):
     assert np.abs(got - want).max() < 2e-6
 
 
-def _engine_forward(x, w, *, patch, layers, heads, d, mlp, swiglu, eps, pool):
+def _engine_forward(x, w, *, patch, layers, heads, d, mlp, swiglu, eps, pool, quick_gelu=False):
     """The engine's tensor layout (torchvision names) evaluated with plain torch ops."""
     from atlaspatch_b200.dinov2 import SWIGLU_BLOCK
 
@@ -55,6 +56,8 @@ def _engine_forward(x, w, *, patch, layers, heads, d, mlp, swiglu, eps, pool):
     if "register_tokens" in w:      # engine layout: [class + pos_0 ; registers ; patches + pos]
         lead += w["register_tokens"].shape[0]
         t = torch.cat([t[:, :1], w["register_tokens"][None].expand(B, -1, -1), t[:, 1:]], dim=1)
+    if "encoder.pre_ln.weight" in w:
+        t = F.layer_norm(t, (d,), w["encoder.pre_ln.weight"], w["encoder.pre_ln.bias"], eps=eps)
     for i in range(layers):
         p = f"encoder.layers.encoder_layer_{i}."
         y = F.layer_norm(t, (d,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], eps=eps)
@@ -67,24 +70,32 @@ def _engine_forward(x, w, *, patch, layers, heads, d, mlp, swiglu, eps, pool):
         if swiglu:
             h = h.reshape(B, -1, mlp // SWIGLU_BLOCK, 2, SWIGLU_BLOCK)
             h = (F.silu(h[..., 0, :]) * h[..., 1, :]).reshape(B, -1, mlp)
+        elif quick_gelu:
+            h = h * torch.sigmoid(1.702 * h)
         else:
             h = F.gelu(h)
         t = t + h @ w[p + "mlp.3.weight"].T + w[p + "mlp.3.bias"]
     t = F.layer_norm(t, (d,), w["encoder.ln.weight"], w["encoder.ln.bias"], eps=eps)
+    if "head.proj.weight" in w:
+        return t[:, 0] @ w["head.proj.weight"].T
     return torch.cat([t[:, 0], t[:, lead:].mean(1)], dim=-1) if pool == 1 else t[:, 0]
 
 
 @pytest.mark.parametrize("name", FAMILIES)
 def test_recipe_and_converted_weights_reproduce_transformers(name):
-    from atlaspatch_b200.dinov2 import (DINOV2_CONFIGS, DINOV2_REGISTERS, HF_VIT_CONFIGS, convert_dinov2_state_dict,
-                                        convert_hf_vit_state_dict)
+    from atlaspatch_b200.dinov2 import (DINOV2_CONFIGS, DINOV2_REGISTERS, HF_CLIP_CONFIGS, HF_VIT_CONFIGS, convert_dinov2_state_dict,
+                                        convert_hf_clip_state_dict, convert_hf_vit_state_dict)
     from atlaspatch_b200.encoder import FAMILY_RECIPES, IMAGENET_MEAN, IMAGENET_STD
 
     r = FAMILY_RECIPES[name]
     sd = hf.state_dict(name, seed=4)
+    out_dim = None
     patches = [_patch(256, seed=s) for s in range(3)]
     want = hf.extract_features(patches, sd, name)
-    if name in DINOV2_CONFIGS:
+    if name in HF_CLIP_CONFIGS:
+        (patch, layers, heads, d, mlp, out_dim), swiglu = HF_CLIP_CONFIGS[name], False
+        w = convert_hf_clip_state_dict(sd, layers=layers)
+    elif name in DINOV2_CONFIGS:
         patch, layers, heads, d, mlp, swiglu = DINOV2_CONFIGS[name]
         w = convert_dinov2_state_dict(sd, layers=layers, swiglu=swiglu, image_size=224, patch=patch, registers=DINOV2_REGISTERS.get(name, 0))
     else:
@@ -95,8 +106,8 @@ def test_recipe_and_converted_weights_reproduce_transformers(name):
     x = np.stack([(hf.pixels(name, p).astype(np.float32) / 255.0 - mean) / std for p in patches]).transpose(0, 3, 1, 2)
     with torch.inference_mode():
         got = _engine_forward(torch.from_numpy(np.ascontiguousarray(x)), w, patch=patch, layers=layers, heads=heads, d=d, mlp=mlp,
-                              swiglu=swiglu, eps=r["ln_eps"], pool=r["pool"]).numpy()
-    assert got.shape == want.shape == (3, d * (2 if r["pool"] == 1 else 1))
+                              swiglu=swiglu, eps=r["ln_eps"], pool=r["pool"], quick_gelu=name in HF_CLIP_CONFIGS).numpy()
+    assert got.shape == want.shape == (3, out_dim or d * (2 if r["pool"] == 1 else 1))
     rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
     assert rel.max() < 2e-5, rel
 
