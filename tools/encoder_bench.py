@@ -24,7 +24,7 @@ from atlaspatch_b200.encoder import FAMILY_RECIPES  # noqa: E402
 
 # hub families: same FLOPs as the architecture they share (+ 4 register tokens: 261 / 257 of the per-token work)
 GFLOP.update({"midnight": 598.78, "openmidnight": 598.78 * 261 / 257, "phikon_v1": 35.13, "phikon_v2": 123.11, "hibou_l": 162.02 * 261 / 257,
-              "hibou_b": 46.7 * 261 / 257})
+              "hibou_b": 46.7 * 261 / 257, "plip": 8.8, "quilt_b_32": 8.8, "quilt_b_16": 35.2})
 if name in FAMILY_RECIPES:
     from oracle.hub_families import state_dict as make_sd
 elif name.startswith("dinov2"):
