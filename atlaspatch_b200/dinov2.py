@@ -36,6 +36,11 @@ DINOV2_CONFIGS = {
     "openmidnight": (14, 40, 24, 1536, 4096, True),
     "hibou_test_tiny": (14, 2, 4, 256, 1024, False),
     "openmidnight_test_tiny": (14, 2, 6, 384, 1024, True),
+    # bioptimus/H-optimus-0 / -1 (models/patch/hoptimus.py:53-58,98-132): timm vit_giant_patch14_reg4_dinov2 = the same ViT-g/14 with
+    # 4 registers and a packed SwiGLU, class-token feature (1 536)
+    "h_optimus_0": (14, 40, 24, 1536, 4096, True),
+    "h_optimus_1": (14, 40, 24, 1536, 4096, True),
+    "h_optimus_test_tiny": (14, 2, 6, 384, 1024, True),
 }
 # name -> (patch, layers, heads, hidden, mlp, projection): image towers of transformers CLIPModel checkpoints (models/patch/plip.py:34,
 # quilt.py:12-16,56): pre-LayerNorm after the embeddings, QuickGELU MLP, bias-free visual projection of the class token
@@ -46,7 +51,8 @@ HF_CLIP_CONFIGS = {
     "plip_test_tiny": (32, 2, 4, 256, 512, 128),
     "quilt_b_16_test_tiny": (16, 2, 4, 256, 512, 128),
 }
-DINOV2_REGISTERS = {"hibou_b": 4, "hibou_l": 4, "openmidnight": 4, "hibou_test_tiny": 4, "openmidnight_test_tiny": 4}
+DINOV2_REGISTERS = {"hibou_b": 4, "hibou_l": 4, "openmidnight": 4, "hibou_test_tiny": 4, "openmidnight_test_tiny": 4,
+                    "h_optimus_0": 4, "h_optimus_1": 4, "h_optimus_test_tiny": 4}
 # name -> (patch, layers, heads, hidden, mlp): transformers ViTModel checkpoints (owkin/phikon, models/patch/phikon.py:41-44)
 HF_VIT_CONFIGS = {
     "phikon_v1": (16, 12, 12, 768, 3072),
@@ -177,13 +183,22 @@ def convert_hf_vit_state_dict(sd: Mapping[str, object], *, layers: int) -> dict[
 def fb_to_hf_dinov2_names(sd: Mapping[str, object], *, layers: int, swiglu: bool) -> dict[str, object]:
     """facebookresearch/dinov2 DinoVisionTransformer keys (what torch.hub's dinov2_vitg14_reg holds after models/patch/
     openmidnight.py:49-63 loads the checkpoint into it; block_chunks = 0 as the hub entry points build it) -> transformers names.
-    Same tensors, same arithmetic: qkv rows are [q ; k ; v], SwiGLUFFNFused.w12 = weights_in (gate half first), w3 = weights_out."""
-    out: dict[str, object] = {"embeddings.cls_token": sd["cls_token"], "embeddings.position_embeddings": sd["pos_embed"],
+    Same tensors, same arithmetic: qkv rows are [q ; k ; v], SwiGLUFFNFused.w12 = weights_in (gate half first), w3 = weights_out.
+    timm's VisionTransformer (`vit_giant_patch14_reg4_dinov2` of bioptimus/H-optimus-0 / -1, models/patch/hoptimus.py:53-58) uses the
+    same module tree with three differences, accepted here: `reg_token` for the registers, SwiGLUPacked's `mlp.fc1` / `mlp.fc2`
+    for w12 / w3 (x1, x2 = fc1(x).chunk(2); fc2(silu(x1) * x2)), and -- with no_embed_class -- a `pos_embed` without the class row
+    (the class and register tokens get no position: a zero row is put in front)."""
+    pos = _np(sd["pos_embed"])
+    pos = pos.reshape(1, pos.shape[-2], pos.shape[-1])
+    if int(round((pos.shape[1] - 1) ** 0.5)) ** 2 != pos.shape[1] - 1:      # timm no_embed_class: rows = patches only
+        pos = np.concatenate([np.zeros((1, 1, pos.shape[-1]), dtype=np.float32), pos], axis=1)
+    out: dict[str, object] = {"embeddings.cls_token": sd["cls_token"], "embeddings.position_embeddings": pos,
                               "embeddings.patch_embeddings.projection.weight": sd["patch_embed.proj.weight"],
                               "embeddings.patch_embeddings.projection.bias": sd["patch_embed.proj.bias"],
                               "layernorm.weight": sd["norm.weight"], "layernorm.bias": sd["norm.bias"]}
-    if "register_tokens" in sd:
-        out["embeddings.register_tokens"] = sd["register_tokens"]
+    for key in ("register_tokens", "reg_token"):
+        if key in sd:
+            out["embeddings.register_tokens"] = sd[key]
     for i in range(layers):
         s, d = f"blocks.{i}.", f"encoder.layer.{i}."
         for a, b in (("norm1", "norm1"), ("norm2", "norm2"), ("attn.proj", "attention.output.dense")):
@@ -194,7 +209,11 @@ def fb_to_hf_dinov2_names(sd: Mapping[str, object], *, layers: int, swiglu: bool
             out[d + f"attention.attention.{n}.weight"] = qkv_w[j * D:(j + 1) * D]
             out[d + f"attention.attention.{n}.bias"] = qkv_b[j * D:(j + 1) * D]
         out[d + "layer_scale1.lambda1"], out[d + "layer_scale2.lambda1"] = sd[s + "ls1.gamma"], sd[s + "ls2.gamma"]
-        pairs = (("mlp.w12", "mlp.weights_in"), ("mlp.w3", "mlp.weights_out")) if swiglu else (("mlp.fc1", "mlp.fc1"), ("mlp.fc2", "mlp.fc2"))
+        if swiglu:
+            packed = (s + "mlp.w12.weight") not in sd                  # timm SwiGLUPacked
+            pairs = (("mlp.fc1" if packed else "mlp.w12", "mlp.weights_in"), ("mlp.fc2" if packed else "mlp.w3", "mlp.weights_out"))
+        else:
+            pairs = (("mlp.fc1", "mlp.fc1"), ("mlp.fc2", "mlp.fc2"))
         for a, b in pairs:
             out[d + b + ".weight"], out[d + b + ".bias"] = sd[s + a + ".weight"], sd[s + a + ".bias"]
     return out

@@ -36,6 +36,8 @@ VIT_CONFIGS = {
 _HALF = (0.5, 0.5, 0.5)
 _HIBOU_MEAN, _HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
 _CLIP_MEAN, _CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+_HOPT = dict(preprocess=2, resize_to=224, mean=(0.707223, 0.578729, 0.703617), std=(0.211883, 0.230117, 0.177517), pool=0, ln_eps=1e-6,
+             default_patch=224)
 _CLIP = dict(preprocess=1, resize_to=224, mean=_CLIP_MEAN, std=_CLIP_STD, pool=0, ln_eps=1e-5, default_patch=224)
 FAMILY_RECIPES = {
     # kaiko-ai/midnight (models/patch/midnight.py:15-25,55-61): torchvision Resize(224) on the PIL patch, CenterCrop(224),
@@ -58,6 +60,8 @@ FAMILY_RECIPES = {
     # mean / std; facebookresearch dinov2_vitg14_reg (4 register tokens, SwiGLU), feature = class token
     "openmidnight": dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
     "openmidnight_test_tiny": dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
+    # bioptimus/H-optimus-0 / -1 (models/patch/hoptimus.py:14-31): torchvision Resize((224, 224)) on the PIL patch, the models' own mean / std
+    "h_optimus_0": _HOPT, "h_optimus_1": _HOPT, "h_optimus_test_tiny": _HOPT,
     # vinid/plip, wisdomik/QuiltNet-B-32 / -B-16 (models/patch/plip.py:34-35,56, quilt.py:56-60): transformers CLIPModel +
     # CLIPProcessor (fast image processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature =
     # get_image_features = visual_projection(post_layernorm(class token)) -> 512

@@ -70,7 +70,9 @@ _HUB = {"midnight": "kaiko-ai/midnight",        # models/patch/midnight.py:12,44
         "openmidnight": "SophontAI/OpenMidnight",   # models/patch/openmidnight.py:49-63  torch.hub dinov2_vitg14_reg + checkpoint -> 1536
         "plip": "vinid/plip",                   # models/patch/plip.py:34         CLIPModel (ViT-B/32), get_image_features -> 512
         "quilt_b_32": "wisdomik/QuiltNet-B-32",  # models/patch/quilt.py:12-16,56  CLIPModel (ViT-B/32 / ViT-B/16) -> 512
-        "quilt_b_16": "wisdomik/QuiltNet-B-16"}
+        "quilt_b_16": "wisdomik/QuiltNet-B-16",
+        "h_optimus_0": "hf-hub:bioptimus/H-optimus-0",   # models/patch/hoptimus.py:53-58,98-132  timm ViT-g/14 reg4 -> 1536
+        "h_optimus_1": "hf-hub:bioptimus/H-optimus-1"}
 
 
 def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
@@ -93,6 +95,10 @@ def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtracto
         checkpoint = torch.load(hf_hub_download(repo_id=_HUB[name], filename="teacher_checkpoint_load.pt"), map_location="cpu")
         model.pos_embed = torch.nn.parameter.Parameter(checkpoint["pos_embed"])
         model.load_state_dict(checkpoint)
+    elif name.startswith("h_optimus"):      # hoptimus.py:53-58; the state_dict stays in timm's key layout
+        import timm
+
+        model = timm.create_model(_HUB[name], pretrained=True, init_values=1e-5, dynamic_img_size=False)
     elif name == "plip" or name.startswith("quilt"):
         from transformers import CLIPModel
 

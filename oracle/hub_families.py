@@ -15,6 +15,9 @@
   checkpoint's 224 px position grid, torchvision `Resize((224, 224)) -> ToTensor -> Normalize(ImageNet)`, feature = model(x) = the
   class token after the final LayerNorm.  facebookresearch/dinov2 is not importable offline; Dinov2WithRegistersModel is the same
   architecture under transformers' key names (atlaspatch_b200/dinov2.py: fb_to_hf_dinov2_names maps one layout onto the other).
+* `h_optimus_0`, `h_optimus_1` (hoptimus.py:14-31,53-58): timm `vit_giant_patch14_reg4_dinov2` (ViT-g/14, 4 registers, packed SwiGLU,
+  no_embed_class) with torchvision `Resize((224, 224)) -> ToTensor -> Normalize(own mean / std)`, feature = the class token.  timm is
+  not in this image; the architecture is Dinov2WithRegistersModel's, and fb_to_hf_dinov2_names accepts timm's key names.
 * `plip`, `quilt_b_32`, `quilt_b_16` (plip.py:34-35,56; quilt.py:12-16,56-60): transformers `CLIPModel` + `CLIPProcessor` (fast image
   processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature = `get_image_features(pixel_values=x)` =
   visual_projection(post_layernorm(class token)) -> 512.  transformers 4.x returns that tensor (what the reference's forward_fn
@@ -37,11 +40,12 @@ from atlaspatch_b200.weights import (DINOV2_PATCH, DINOV2_REGISTERS, DINOV2_SPEC
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 HIBOU_MEAN, HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
+HOPT_MEAN, HOPT_STD = (0.707223, 0.578729, 0.703617), (0.211883, 0.230117, 0.177517)
 CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
 
 
 def _family(name: str) -> str:
-    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight", "plip", "quilt"):
+    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight", "h_optimus", "plip", "quilt"):
         if name.startswith(fam):
             return fam
     raise KeyError(name)
@@ -100,11 +104,11 @@ def make_preprocess(name: str):
 
         return transforms.Compose([transforms.Resize(224), transforms.CenterCrop(224), transforms.ToTensor(),
                                    transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
-    if fam == "openmidnight":                               # openmidnight.py:17-30
+    if fam in ("openmidnight", "h_optimus"):                # openmidnight.py:17-30, hoptimus.py:14-31
         from torchvision import transforms
 
-        return transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
-                                   transforms.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])
+        mean, std = (IMAGENET_MEAN, IMAGENET_STD) if fam == "openmidnight" else (HOPT_MEAN, HOPT_STD)
+        return transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(), transforms.Normalize(mean=list(mean), std=list(std))])
     import transformers
 
     if fam in ("plip", "quilt"):
@@ -133,7 +137,7 @@ def pixels(name: str, patch: np.ndarray) -> np.ndarray:
     fam = _family(name)
     if fam == "midnight":
         return ra.vit_preset_pixels(patch, resize_to=224, crop=224)
-    if fam == "openmidnight":
+    if fam in ("openmidnight", "h_optimus"):
         return ra.resize_pil_bilinear(patch, 224, 224)
     if fam in ("phikon_v2", "hibou", "plip", "quilt"):
         return ra.dinov2_pixels(patch, resize_to=224, crop=224) if patch.shape[0] != 224 else patch

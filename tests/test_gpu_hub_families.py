@@ -23,7 +23,7 @@ def _slide():
                                     ("phikon_v1_test_tiny", 224), ("phikon_v1_test_tiny", 256), ("phikon_v1_test_tiny", 300),
                                     ("phikon_v2_test_tiny", 224), ("phikon_v2_test_tiny", 256),
                                     ("hibou_test_tiny", 224), ("hibou_test_tiny", 256),                  # 4 register tokens: 261-token sequence
-                                    ("openmidnight_test_tiny", 224), ("openmidnight_test_tiny", 512),
+                                    ("openmidnight_test_tiny", 224), ("openmidnight_test_tiny", 512), ("h_optimus_test_tiny", 256),
                                     # CLIP towers: pre-LayerNorm, QuickGELU, 128-wide visual projection (ViT-B/32: 50 tokens; B/16: 197)
                                     ("plip_test_tiny", 224), ("plip_test_tiny", 256), ("quilt_b_16_test_tiny", 256)])
 def test_tiny_family_pixels_bit_exact_and_features(name, P):
@@ -45,6 +45,11 @@ def test_tiny_family_pixels_bit_exact_and_features(name, P):
         from tests.test_oracle_hub_families import hf_to_fb_names
 
         sd_in = hf_to_fb_names(sd, 2, True)
+    if name.startswith("h_optimus"):        # timm's key layout (hoptimus.py:53-58), no position on the class token
+        from tests.test_oracle_hub_families import hf_to_timm_names
+
+        sd["embeddings.position_embeddings"][:, 0] = 0.0
+        sd_in = hf_to_timm_names(sd, 2, True)
     ext = B200FeatureExtractor(name, sd_in, input_patch=P, max_batch=4)         # 9 patches -> three forward chunks
     pool = FAMILY_RECIPES[name]["pool"]
     rows_dev = torch.from_numpy(rows).cuda()

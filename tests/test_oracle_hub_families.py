@@ -10,7 +10,7 @@ from oracle import hub_families as hf
 from oracle import resize_aa
 
 FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny", "hibou_test_tiny", "openmidnight_test_tiny",
-            "plip_test_tiny", "quilt_b_16_test_tiny"]
+            "plip_test_tiny", "quilt_b_16_test_tiny", "h_optimus_test_tiny"]
 
 
 def _patch(P, seed=0):
@@ -146,6 +146,38 @@ def hf_to_fb_names(sd, layers, swiglu):
                 out[b + f"mlp.fc1.{k}"], out[b + f"mlp.fc2.{k}"] = sd[a + f"mlp.fc1.{k}"], sd[a + f"mlp.fc2.{k}"]
         out[b + "ls1.gamma"], out[b + "ls2.gamma"] = sd[a + "layer_scale1.lambda1"], sd[a + "layer_scale2.lambda1"]
     return out
+
+
+def hf_to_timm_names(sd, layers, swiglu):
+    """timm VisionTransformer keys of vit_giant_patch14_reg4_dinov2 (hoptimus.py:53-58), written from timm's module tree: like
+    facebookresearch's, but `reg_token`, SwiGLUPacked `mlp.fc1 / fc2`, and (no_embed_class) a pos_embed without the class row -- the
+    class row of the transformers layout must therefore be zero for the two to mean the same thing."""
+    out = hf_to_fb_names(sd, layers, swiglu)
+    out.pop("mask_token")
+    if "register_tokens" in out:
+        out["reg_token"] = out.pop("register_tokens")
+    assert float(out["pos_embed"][:, 0].abs().max()) == 0.0
+    out["pos_embed"] = out["pos_embed"][:, 1:]
+    for i in range(layers):
+        for k in ("weight", "bias"):
+            if swiglu:
+                out[f"blocks.{i}.mlp.fc1.{k}"], out[f"blocks.{i}.mlp.fc2.{k}"] = out.pop(f"blocks.{i}.mlp.w12.{k}"), out.pop(f"blocks.{i}.mlp.w3.{k}")
+    return out
+
+
+def test_timm_key_layout_converts_to_the_same_tensors():
+    from atlaspatch_b200.dinov2 import DINOV2_CONFIGS, DINOV2_REGISTERS, convert_dinov2_state_dict
+
+    name = "h_optimus_test_tiny"
+    patch, layers, heads, d, mlp, swiglu = DINOV2_CONFIGS[name]
+    sd = hf.state_dict(name, seed=8)
+    sd["embeddings.position_embeddings"][:, 0] = 0.0                      # no_embed_class: the class token carries no position
+    kw = dict(layers=layers, swiglu=swiglu, image_size=224, patch=patch, registers=DINOV2_REGISTERS[name])
+    a = convert_dinov2_state_dict(sd, **kw)
+    b = convert_dinov2_state_dict(hf_to_timm_names(sd, layers, swiglu), **kw)
+    assert a.keys() == b.keys() and b["encoder.pos_embedding"].shape == (1, 257, d) and not b["encoder.pos_embedding"][0, 0].any()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
 
 
 @pytest.mark.parametrize("name", ["openmidnight_test_tiny", "hibou_test_tiny"])
