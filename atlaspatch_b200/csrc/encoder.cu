@@ -286,7 +286,7 @@ extern "C" int ap_encoder_create(ap_ctx* ctx, const ap_vit_desc* desc, ap_encode
     if (!ctx || !desc || !out_enc) return AP_EINVAL;
     DeviceGuard guard(ctx);
     *out_enc = nullptr;
-    AP_REQUIRE(ctx, desc->preprocess >= 0 && desc->preprocess <= 3, "encoder: unknown preprocess %d", desc->preprocess);
+    AP_REQUIRE(ctx, desc->preprocess >= 0 && desc->preprocess <= 4, "encoder: unknown preprocess %d", desc->preprocess);
     AP_REQUIRE(ctx, desc->registers >= 0 && desc->registers <= 8, "encoder: registers %d unsupported (0..8)", desc->registers);
     AP_REQUIRE(ctx, desc->pool == 0 || desc->pool == 1, "encoder: unknown pool %d (0 class token, 1 [class || mean of patch tokens])", desc->pool);
     AP_REQUIRE(ctx, desc->mlp_kind >= 0 && desc->mlp_kind <= 2, "encoder: unknown mlp_kind %d", desc->mlp_kind);

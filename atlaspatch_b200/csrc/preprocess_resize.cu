@@ -102,13 +102,16 @@ double cubic_aa(double x) {  // Keys cubic, a = -0.5 (ATen HelperInterpCubic::aa
 //           coefficients (torchvision's ImageClassification preset on the PIL image the reference hands it; crop offset
 //           int(round((n_out - image) / 2.0)) as torchvision's center_crop computes it);
 //   kind 2: ATen's uint8 bilinear with antialias (triangle, support 1; int16 weights with the precision rule of kind 0): what
-//           transformers' ViTImageProcessorFast runs for `resample = 2` checkpoints (atlas_patch/models/patch/phikon.py:15-21,46).
+//           transformers' ViTImageProcessorFast runs for `resample = 2` checkpoints (atlas_patch/models/patch/phikon.py:15-21,46);
+//   kind 3: Pillow's BICUBIC (Keys cubic a = -0.5, support 2) with Pillow's fixed 22-bit coefficients and torchvision's crop offset:
+//           torchvision `Resize(256, BICUBIC) -> CenterCrop(224)` on the PIL patch (atlas_patch/models/patch/gigapath.py:17-26).
 int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, int kind, std::vector<int32_t>& tap_min, std::vector<int32_t>& tap_cnt,
                            std::vector<int32_t>& tap_w, int* max_taps, int* precision) {
     AP_REQUIRE(ctx, n_in > 0 && n_out >= image && image > 0, "resize tables: bad sizes %d -> %d crop %d", n_in, n_out, image);
-    AP_REQUIRE(ctx, kind >= 0 && kind <= 2, "resize tables: unknown filter kind %d", kind);
+    AP_REQUIRE(ctx, kind >= 0 && kind <= 3, "resize tables: unknown filter kind %d", kind);
+    const bool cubic = kind == 0 || kind == 3, pillow = kind == 1 || kind == 3;
     const double scale = static_cast<double>(n_in) / n_out;
-    const double fsup = kind == 0 ? 2.0 : 1.0;
+    const double fsup = cubic ? 2.0 : 1.0;
     const double support = scale >= 1.0 ? fsup * scale : fsup;
     const double invscale = scale >= 1.0 ? 1.0 / scale : 1.0;
     std::vector<std::vector<double>> ws(n_out);
@@ -126,7 +129,7 @@ int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, int kind
         ws[i].resize(xsize);
         for (int j = 0; j < xsize; ++j) {
             const double t = (j + xmin - center + 0.5) * invscale;
-            ws[i][j] = kind == 0 ? cubic_aa(t) : std::max(0.0, 1.0 - std::fabs(t));
+            ws[i][j] = cubic ? cubic_aa(t) : std::max(0.0, 1.0 - std::fabs(t));
             total += ws[i][j];
         }
         for (int j = 0; j < xsize; ++j) {
@@ -137,13 +140,13 @@ int ap_build_resize_tables(ap_ctx* ctx, int n_in, int n_out, int image, int kind
         if (xsize > taps) taps = xsize;
     }
     int prec = 22;                         // Pillow: PRECISION_BITS = 32 - 8 - 2
-    if (kind != 1)
+    if (!pillow)
         for (prec = 0; prec < 22; ++prec) {
             const int next = static_cast<int>(0.5 + wt_max * (1 << (prec + 1)));
             if (next >= (1 << 15)) break;
         }
     // transformers center_crop: top = (h - crop) // 2; torchvision center_crop: int(round((h - crop) / 2.0)) (half to even)
-    const int off = kind != 1 ? (n_out - image) / 2 : static_cast<int>(std::nearbyint((n_out - image) / 2.0));
+    const int off = !pillow ? (n_out - image) / 2 : static_cast<int>(std::nearbyint((n_out - image) / 2.0));
     tap_min.assign(image, 0);
     tap_cnt.assign(image, 0);
     tap_w.assign(static_cast<size_t>(image) * taps, 0);

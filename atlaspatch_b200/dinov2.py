@@ -41,6 +41,12 @@ DINOV2_CONFIGS = {
     "h_optimus_0": (14, 40, 24, 1536, 4096, True),
     "h_optimus_1": (14, 40, 24, 1536, 4096, True),
     "h_optimus_test_tiny": (14, 2, 6, 384, 1024, True),
+    # timm ViTs with LayerScale whose preprocess the reference spells out: AI4Pathology/PathOrchestra (models/patch/pathorchestra.py:38-58,
+    # ViT-L/16) and prov-gigapath/prov-gigapath (gigapath.py:17-26,46: vit_giant_patch14_dinov2 with patch 16, packed SwiGLU)
+    "pathorchestra": (16, 24, 16, 1024, 4096, False),
+    "prov_gigapath": (16, 40, 24, 1536, 4096, True),
+    "pathorchestra_test_tiny": (16, 2, 4, 256, 1024, False),
+    "prov_gigapath_test_tiny": (16, 2, 6, 384, 1024, True),
 }
 # name -> (patch, layers, heads, hidden, mlp, projection): image towers of transformers CLIPModel checkpoints (models/patch/plip.py:34,
 # quilt.py:12-16,56): pre-LayerNorm after the embeddings, QuickGELU MLP, bias-free visual projection of the class token

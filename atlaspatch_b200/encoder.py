@@ -31,13 +31,15 @@ VIT_CONFIGS = {
 
 # Hub encoders of the reference that run on the same kernels with their own preprocess / head.  The
 # processor settings are the published contents of each repo's preprocessor_config.json (no network here: restated, not fetched).
-#   preprocess: ap_vit_desc.preprocess (1 ATen uint8 bicubic-antialias, 2 Pillow BILINEAR, 3 ATen uint8 bilinear-antialias)
+#   preprocess: ap_vit_desc.preprocess (1 ATen uint8 bicubic-antialias, 2 Pillow BILINEAR, 3 ATen uint8 bilinear-antialias, 4 Pillow BICUBIC)
 #   pool: 0 class token, 1 [class || mean of patch tokens]
 _HALF = (0.5, 0.5, 0.5)
 _HIBOU_MEAN, _HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
 _CLIP_MEAN, _CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
 _HOPT = dict(preprocess=2, resize_to=224, mean=(0.707223, 0.578729, 0.703617), std=(0.211883, 0.230117, 0.177517), pool=0, ln_eps=1e-6,
              default_patch=224)
+_PORCH = dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224)
+_GIGA = dict(preprocess=4, resize_to=256, pool=0, ln_eps=1e-6, default_patch=256)
 _CLIP = dict(preprocess=1, resize_to=224, mean=_CLIP_MEAN, std=_CLIP_STD, pool=0, ln_eps=1e-5, default_patch=224)
 FAMILY_RECIPES = {
     # kaiko-ai/midnight (models/patch/midnight.py:15-25,55-61): torchvision Resize(224) on the PIL patch, CenterCrop(224),
@@ -62,6 +64,10 @@ FAMILY_RECIPES = {
     "openmidnight_test_tiny": dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224),
     # bioptimus/H-optimus-0 / -1 (models/patch/hoptimus.py:14-31): torchvision Resize((224, 224)) on the PIL patch, the models' own mean / std
     "h_optimus_0": _HOPT, "h_optimus_1": _HOPT, "h_optimus_test_tiny": _HOPT,
+    # AI4Pathology/PathOrchestra (models/patch/pathorchestra.py:52-58): torchvision Resize(224) on the PIL patch, ImageNet mean / std
+    "pathorchestra": _PORCH, "pathorchestra_test_tiny": _PORCH,
+    # prov-gigapath (models/patch/gigapath.py:17-26): torchvision Resize(256, BICUBIC) -> CenterCrop(224) on the PIL patch, ImageNet
+    "prov_gigapath": _GIGA, "prov_gigapath_test_tiny": _GIGA,
     # vinid/plip, wisdomik/QuiltNet-B-32 / -B-16 (models/patch/plip.py:34-35,56, quilt.py:56-60): transformers CLIPModel +
     # CLIPProcessor (fast image processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature =
     # get_image_features = visual_projection(post_layernorm(class token)) -> 512

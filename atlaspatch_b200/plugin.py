@@ -72,7 +72,9 @@ _HUB = {"midnight": "kaiko-ai/midnight",        # models/patch/midnight.py:12,44
         "quilt_b_32": "wisdomik/QuiltNet-B-32",  # models/patch/quilt.py:12-16,56  CLIPModel (ViT-B/32 / ViT-B/16) -> 512
         "quilt_b_16": "wisdomik/QuiltNet-B-16",
         "h_optimus_0": "hf-hub:bioptimus/H-optimus-0",   # models/patch/hoptimus.py:53-58,98-132  timm ViT-g/14 reg4 -> 1536
-        "h_optimus_1": "hf-hub:bioptimus/H-optimus-1"}
+        "h_optimus_1": "hf-hub:bioptimus/H-optimus-1",
+        "pathorchestra": "hf-hub:AI4Pathology/PathOrchestra",   # models/patch/pathorchestra.py:38-43  timm ViT-L/16 -> 1024
+        "prov_gigapath": "hf_hub:prov-gigapath/prov-gigapath"}  # models/patch/gigapath.py:12,46       timm ViT-g/16 -> 1536
 
 
 def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
@@ -99,6 +101,14 @@ def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtracto
         import timm
 
         model = timm.create_model(_HUB[name], pretrained=True, init_values=1e-5, dynamic_img_size=False)
+    elif name == "pathorchestra":           # pathorchestra.py:38-43
+        import timm
+
+        model = timm.create_model(_HUB[name], pretrained=True, init_values=1e-5, dynamic_img_size=True)
+    elif name == "prov_gigapath":           # gigapath.py:46
+        import timm
+
+        model = timm.create_model(_HUB[name], pretrained=True)
     elif name == "plip" or name.startswith("quilt"):
         from transformers import CLIPModel
 

@@ -91,9 +91,14 @@ DINOV2_SPECS = {
     "h_optimus_0": (40, 24, 1536, True),        # hoptimus.py: timm vit_giant_patch14_reg4_dinov2
     "h_optimus_1": (40, 24, 1536, True),
     "h_optimus_test_tiny": (2, 6, 384, True),
+    "pathorchestra": (24, 16, 1024, False),     # pathorchestra.py: timm ViT-L/16 with LayerScale
+    "prov_gigapath": (40, 24, 1536, True),      # gigapath.py: timm ViT-g/16, packed SwiGLU
+    "pathorchestra_test_tiny": (2, 4, 256, False),
+    "prov_gigapath_test_tiny": (2, 6, 384, True),
 }
 PATCH = 14
-DINOV2_PATCH = {"phikon_v2": 16, "phikon_v2_test_tiny": 16}   # conv patch where it is not 14
+DINOV2_PATCH = {"phikon_v2": 16, "phikon_v2_test_tiny": 16, "pathorchestra": 16, "prov_gigapath": 16, "pathorchestra_test_tiny": 16,
+                "prov_gigapath_test_tiny": 16}   # conv patch where it is not 14
 DINOV2_REGISTERS = {"hibou_b": 4, "hibou_l": 4, "openmidnight": 4, "hibou_test_tiny": 4, "openmidnight_test_tiny": 4,
                     "h_optimus_0": 4, "h_optimus_1": 4, "h_optimus_test_tiny": 4}
 

@@ -148,7 +148,9 @@ typedef struct ap_vit_desc {
                             no resize and uses preprocess 0;
                          3: transformers ViTImageProcessorFast with resample = 2 (atlas_patch/models/patch/phikon.py:15-21,46 for
                             owkin/phikon): uint8 bilinear-antialias resize (ATen's separable uint8 kernel, triangle filter) of the
-                            input_patch^2 patch to resize_to^2, centre crop to image_size (none when equal), rescale + normalise */
+                            input_patch^2 patch to resize_to^2, centre crop to image_size (none when equal), rescale + normalise;
+                         4: as 2 with Pillow's BICUBIC filter: torchvision Resize(resize_to, BICUBIC) -> CenterCrop(image_size) on the PIL
+                            patch (atlas_patch/models/patch/gigapath.py:17-26) */
     int resize_to;    /* 256 (preprocess 1, 2); 224 (preprocess 3) */
     int mlp_kind;     /* 0: Linear - GELU - Linear, mlp = hidden features;
                          1: SwiGLU (Dinov2SwiGLUFFN): "mlp.0" = weights_in with 2 * mlp rows interleaved as AP_EPI_BIAS_SWIGLU_F16

@@ -18,6 +18,9 @@
 * `h_optimus_0`, `h_optimus_1` (hoptimus.py:14-31,53-58): timm `vit_giant_patch14_reg4_dinov2` (ViT-g/14, 4 registers, packed SwiGLU,
   no_embed_class) with torchvision `Resize((224, 224)) -> ToTensor -> Normalize(own mean / std)`, feature = the class token.  timm is
   not in this image; the architecture is Dinov2WithRegistersModel's, and fb_to_hf_dinov2_names accepts timm's key names.
+* `pathorchestra` (pathorchestra.py:38-58) and `prov_gigapath` (gigapath.py:17-26,46): timm ViT-L/16 / ViT-g/16 (packed SwiGLU) with
+  LayerScale = Dinov2Model's architecture at patch 16; torchvision `Resize(224)` resp. `Resize(256, BICUBIC) -> CenterCrop(224)` on the
+  PIL patch, ImageNet mean / std, feature = the class token (timm global_pool "token").
 * `plip`, `quilt_b_32`, `quilt_b_16` (plip.py:34-35,56; quilt.py:12-16,56-60): transformers `CLIPModel` + `CLIPProcessor` (fast image
   processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature = `get_image_features(pixel_values=x)` =
   visual_projection(post_layernorm(class token)) -> 512.  transformers 4.x returns that tensor (what the reference's forward_fn
@@ -45,7 +48,7 @@ CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.261302
 
 
 def _family(name: str) -> str:
-    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight", "h_optimus", "plip", "quilt"):
+    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight", "h_optimus", "pathorchestra", "prov_gigapath", "plip", "quilt"):
         if name.startswith(fam):
             return fam
     raise KeyError(name)
@@ -104,6 +107,12 @@ def make_preprocess(name: str):
 
         return transforms.Compose([transforms.Resize(224), transforms.CenterCrop(224), transforms.ToTensor(),
                                    transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
+    if fam in ("pathorchestra", "prov_gigapath"):           # pathorchestra.py:52-58, gigapath.py:17-26
+        from torchvision import transforms
+
+        head = ([transforms.Resize(224)] if fam == "pathorchestra" else
+                [transforms.Resize(256, interpolation=transforms.InterpolationMode.BICUBIC), transforms.CenterCrop(224)])
+        return transforms.Compose(head + [transforms.ToTensor(), transforms.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)])
     if fam in ("openmidnight", "h_optimus"):                # openmidnight.py:17-30, hoptimus.py:14-31
         from torchvision import transforms
 
@@ -137,8 +146,10 @@ def pixels(name: str, patch: np.ndarray) -> np.ndarray:
     fam = _family(name)
     if fam == "midnight":
         return ra.vit_preset_pixels(patch, resize_to=224, crop=224)
-    if fam in ("openmidnight", "h_optimus"):
+    if fam in ("openmidnight", "h_optimus", "pathorchestra"):
         return ra.resize_pil_bilinear(patch, 224, 224)
+    if fam == "prov_gigapath":
+        return ra.vit_preset_pixels(patch, resize_to=256, crop=224, mode="bicubic")
     if fam in ("phikon_v2", "hibou", "plip", "quilt"):
         return ra.dinov2_pixels(patch, resize_to=224, crop=224) if patch.shape[0] != 224 else patch
     return ra.hf_vit_pixels(patch, 224)

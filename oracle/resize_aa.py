@@ -96,18 +96,20 @@ def dinov2_pixels(patch: np.ndarray, resize_to: int = 256, crop: int = 224) -> n
 PIL_PRECISION_BITS = 22
 
 
-def pil_bilinear_weights(n_in: int, n_out: int):
-    """precompute_coeffs + normalize_coeffs_8bpc: (xmin[n_out], xsize[n_out], list of int64 weight arrays)."""
+def pil_bilinear_weights(n_in: int, n_out: int, mode: str = "bilinear"):
+    """precompute_coeffs + normalize_coeffs_8bpc: (xmin[n_out], xsize[n_out], list of int64 weight arrays).  mode "bicubic": Pillow's
+    bicubic_filter (Keys cubic a = -0.5, support 2) through the same coefficient arithmetic (gigapath.py:17-26)."""
+    filt, half = ((lambda t: max(0.0, 1.0 - abs(t))), 1.0) if mode == "bilinear" else (_cubic, 2.0)
     scale = n_in / n_out
     filterscale = max(scale, 1.0)
-    support = 1.0 * filterscale
+    support = half * filterscale
     ss = 1.0 / filterscale
     xmins, sizes, ws = [], [], []
     for i in range(n_out):
         center = (i + 0.5) * scale
         xmin = max(int(center - support + 0.5), 0)
         xmax = min(int(center + support + 0.5), n_in) - xmin
-        w = np.array([max(0.0, 1.0 - abs((x + xmin - center + 0.5) * ss)) for x in range(xmax)], dtype=np.float64)
+        w = np.array([filt((x + xmin - center + 0.5) * ss) for x in range(xmax)], dtype=np.float64)
         tot = float(w.sum())
         if tot != 0.0:
             w = w / tot
@@ -117,9 +119,9 @@ def pil_bilinear_weights(n_in: int, n_out: int):
     return np.asarray(xmins), np.asarray(sizes), ws
 
 
-def _resize_axis_pil(a: np.ndarray, n_out: int, axis: int) -> np.ndarray:
+def _resize_axis_pil(a: np.ndarray, n_out: int, axis: int, mode: str = "bilinear") -> np.ndarray:
     a = np.moveaxis(a, axis, 0).astype(np.int64)
-    xmins, sizes, ws = pil_bilinear_weights(a.shape[0], n_out)
+    xmins, sizes, ws = pil_bilinear_weights(a.shape[0], n_out, mode)
     out = np.empty((n_out,) + a.shape[1:], dtype=np.int64)
     for i in range(n_out):
         acc = np.tensordot(ws[i], a[xmins[i]:xmins[i] + sizes[i]], axes=(0, 0)) + (1 << (PIL_PRECISION_BITS - 1))
@@ -127,14 +129,14 @@ def _resize_axis_pil(a: np.ndarray, n_out: int, axis: int) -> np.ndarray:
     return np.moveaxis(out, 0, axis).astype(np.uint8)
 
 
-def resize_pil_bilinear(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    """PIL.Image.fromarray(img).resize((out_w, out_h), BILINEAR) for HWC uint8: horizontal pass first, then vertical."""
-    t = _resize_axis_pil(img, out_w, 1) if img.shape[1] != out_w else img
-    return _resize_axis_pil(t, out_h, 0) if img.shape[0] != out_h else t
+def resize_pil_bilinear(img: np.ndarray, out_h: int, out_w: int, mode: str = "bilinear") -> np.ndarray:
+    """PIL.Image.fromarray(img).resize((out_w, out_h), BILINEAR | BICUBIC) for HWC uint8: horizontal pass first, then vertical."""
+    t = _resize_axis_pil(img, out_w, 1, mode) if img.shape[1] != out_w else img
+    return _resize_axis_pil(t, out_h, 0, mode) if img.shape[0] != out_h else t
 
 
-def vit_preset_pixels(patch: np.ndarray, resize_to: int = 256, crop: int = 224) -> np.ndarray:
+def vit_preset_pixels(patch: np.ndarray, resize_to: int = 256, crop: int = 224, mode: str = "bilinear") -> np.ndarray:
     """uint8 (crop, crop, 3) the torchvision preset normalises for a square PIL patch of any size."""
-    r = resize_pil_bilinear(patch, resize_to, resize_to) if patch.shape[0] != resize_to else patch
+    r = resize_pil_bilinear(patch, resize_to, resize_to, mode) if patch.shape[0] != resize_to else patch
     o = int(round((resize_to - crop) / 2.0))
     return r[o:o + crop, o:o + crop]

@@ -24,6 +24,8 @@ def _slide():
                                     ("phikon_v2_test_tiny", 224), ("phikon_v2_test_tiny", 256),
                                     ("hibou_test_tiny", 224), ("hibou_test_tiny", 256),                  # 4 register tokens: 261-token sequence
                                     ("openmidnight_test_tiny", 224), ("openmidnight_test_tiny", 512), ("h_optimus_test_tiny", 256),
+                                    ("pathorchestra_test_tiny", 256),                                    # timm keys, Pillow BILINEAR to 224
+                                    ("prov_gigapath_test_tiny", 224), ("prov_gigapath_test_tiny", 256), ("prov_gigapath_test_tiny", 512),  # Pillow BICUBIC
                                     # CLIP towers: pre-LayerNorm, QuickGELU, 128-wide visual projection (ViT-B/32: 50 tokens; B/16: 197)
                                     ("plip_test_tiny", 224), ("plip_test_tiny", 256), ("quilt_b_16_test_tiny", 256)])
 def test_tiny_family_pixels_bit_exact_and_features(name, P):
@@ -45,6 +47,15 @@ def test_tiny_family_pixels_bit_exact_and_features(name, P):
         from tests.test_oracle_hub_families import hf_to_fb_names
 
         sd_in = hf_to_fb_names(sd, 2, True)
+    if name.startswith(("pathorchestra", "prov_gigapath")):     # timm's key layout with a class position (no_embed_class = False)
+        from tests.test_oracle_hub_families import hf_to_fb_names
+
+        sd_in = hf_to_fb_names(sd, 2, name.startswith("prov_gigapath"))
+        sd_in.pop("mask_token")
+        if name.startswith("prov_gigapath"):
+            for i in range(2):
+                for k in ("weight", "bias"):
+                    sd_in[f"blocks.{i}.mlp.fc1.{k}"], sd_in[f"blocks.{i}.mlp.fc2.{k}"] = sd_in.pop(f"blocks.{i}.mlp.w12.{k}"), sd_in.pop(f"blocks.{i}.mlp.w3.{k}")
     if name.startswith("h_optimus"):        # timm's key layout (hoptimus.py:53-58), no position on the class token
         from tests.test_oracle_hub_families import hf_to_timm_names
 

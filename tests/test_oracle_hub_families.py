@@ -10,7 +10,7 @@ from oracle import hub_families as hf
 from oracle import resize_aa
 
 FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny", "hibou_test_tiny", "openmidnight_test_tiny",
-            "plip_test_tiny", "quilt_b_16_test_tiny", "h_optimus_test_tiny"]
+            "plip_test_tiny", "quilt_b_16_test_tiny", "h_optimus_test_tiny", "pathorchestra_test_tiny", "prov_gigapath_test_tiny"]
 
 
 def _patch(P, seed=0):
