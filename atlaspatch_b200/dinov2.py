@@ -56,6 +56,13 @@ HF_CLIP_CONFIGS = {
     "quilt_b_16": (16, 12, 12, 768, 3072, 512),
     "plip_test_tiny": (32, 2, 4, 256, 512, 128),
     "quilt_b_16_test_tiny": (16, 2, 4, 256, 512, 128),
+    # OpenAI CLIP ViTs through open_clip (models/patch/clip.py:15-17: ViT-B-32 / ViT-B-16 / ViT-L-14, pretrained "openai"); ViT-L/14 is
+    # the other reading of BASELINE.json configs[3]'s "ViT-L/14".  ViT-L-14-336 (577 tokens) and the ResNets are not on these kernels
+    "clip_vit_b_32": (32, 12, 12, 768, 3072, 512),
+    "clip_vit_b_16": (16, 12, 12, 768, 3072, 512),
+    "clip_vit_l_14": (14, 24, 16, 1024, 4096, 768),
+    "clip_vit_b_32_test_tiny": (32, 2, 4, 256, 512, 128),
+    "clip_vit_l_14_test_tiny": (14, 2, 4, 256, 512, 128),
 }
 DINOV2_REGISTERS = {"hibou_b": 4, "hibou_l": 4, "openmidnight": 4, "hibou_test_tiny": 4, "openmidnight_test_tiny": 4,
                     "h_optimus_0": 4, "h_optimus_1": 4, "h_optimus_test_tiny": 4}
@@ -229,7 +236,10 @@ def convert_hf_clip_state_dict(sd: Mapping[str, object], *, layers: int) -> dict
     """transformers CLIPModel names (`CLIPModel.from_pretrained("vinid/plip")`, models/patch/plip.py:34; text tower ignored) -> engine
     names.  CLIPVisionEmbeddings: bias-free patch convolution, class_embedding + position_embedding; pre_layrnorm -> "encoder.pre_ln";
     q / k / v projections stacked into in_proj (the 1 / sqrt(head_dim) scale is the attention kernel's); post_layernorm ->
-    "encoder.ln"; visual_projection -> "head.proj.weight"."""
+    "encoder.ln"; visual_projection -> "head.proj.weight".  open_clip's key layout (`visual.conv1`, `visual.transformer.resblocks.i` ...,
+    what models/patch/clip.py:36-40 holds) is accepted too."""
+    if "visual.conv1.weight" in sd:
+        sd = openclip_to_hf_clip_names(sd, layers=layers)
     v = "vision_model."
     out: dict[str, np.ndarray] = {}
     w = _np(sd[v + "embeddings.patch_embedding.weight"])
@@ -250,4 +260,27 @@ def convert_hf_clip_state_dict(sd: Mapping[str, object], *, layers: int) -> dict
         out[d + "self_attention.out_proj.weight"], out[d + "self_attention.out_proj.bias"] = _np(sd[s + "self_attn.out_proj.weight"]), _np(sd[s + "self_attn.out_proj.bias"])
         out[d + "mlp.0.weight"], out[d + "mlp.0.bias"] = _np(sd[s + "mlp.fc1.weight"]), _np(sd[s + "mlp.fc1.bias"])
         out[d + "mlp.3.weight"], out[d + "mlp.3.bias"] = _np(sd[s + "mlp.fc2.weight"]), _np(sd[s + "mlp.fc2.bias"])
+    return out
+
+
+def openclip_to_hf_clip_names(sd: Mapping[str, object], *, layers: int) -> dict[str, object]:
+    """open_clip CLIP.visual (VisionTransformer) keys -> transformers CLIPModel names.  Same tensors: nn.MultiheadAttention's
+    in_proj rows are [q ; k ; v]; `visual.proj` is stored [width, output_dim] and applied as `pooled @ proj`, i.e. the transpose of
+    visual_projection.weight."""
+    v = "vision_model."
+    out: dict[str, object] = {v + "embeddings.class_embedding": sd["visual.class_embedding"],
+                              v + "embeddings.patch_embedding.weight": sd["visual.conv1.weight"],
+                              v + "embeddings.position_embedding.weight": sd["visual.positional_embedding"],
+                              "visual_projection.weight": np.ascontiguousarray(_np(sd["visual.proj"]).T)}
+    for a, b in (("visual.ln_pre", "pre_layrnorm"), ("visual.ln_post", "post_layernorm")):
+        out[v + b + ".weight"], out[v + b + ".bias"] = sd[a + ".weight"], sd[a + ".bias"]
+    for i in range(layers):
+        s, d = f"visual.transformer.resblocks.{i}.", v + f"encoder.layers.{i}."
+        w, b = _np(sd[s + "attn.in_proj_weight"]), _np(sd[s + "attn.in_proj_bias"])
+        D = w.shape[1]
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            out[d + f"self_attn.{n}.weight"], out[d + f"self_attn.{n}.bias"] = w[j * D:(j + 1) * D], b[j * D:(j + 1) * D]
+        for a2, b2 in (("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"), ("attn.out_proj", "self_attn.out_proj"), ("mlp.c_fc", "mlp.fc1"),
+                       ("mlp.c_proj", "mlp.fc2")):
+            out[d + b2 + ".weight"], out[d + b2 + ".bias"] = sd[s + a2 + ".weight"], sd[s + a2 + ".bias"]
     return out

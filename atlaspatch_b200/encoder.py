@@ -38,6 +38,7 @@ _HIBOU_MEAN, _HIBOU_STD = (0.7068, 0.5755, 0.722), (0.195, 0.2316, 0.1816)
 _CLIP_MEAN, _CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
 _HOPT = dict(preprocess=2, resize_to=224, mean=(0.707223, 0.578729, 0.703617), std=(0.211883, 0.230117, 0.177517), pool=0, ln_eps=1e-6,
              default_patch=224)
+_OCLIP = dict(preprocess=4, resize_to=224, mean=_CLIP_MEAN, std=_CLIP_STD, pool=0, ln_eps=1e-5, default_patch=224)
 _PORCH = dict(preprocess=2, resize_to=224, pool=0, ln_eps=1e-6, default_patch=224)
 _GIGA = dict(preprocess=4, resize_to=256, pool=0, ln_eps=1e-6, default_patch=256)
 _CLIP = dict(preprocess=1, resize_to=224, mean=_CLIP_MEAN, std=_CLIP_STD, pool=0, ln_eps=1e-5, default_patch=224)
@@ -72,6 +73,10 @@ FAMILY_RECIPES = {
     # CLIPProcessor (fast image processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature =
     # get_image_features = visual_projection(post_layernorm(class token)) -> 512
     "plip": _CLIP, "quilt_b_32": _CLIP, "quilt_b_16": _CLIP, "plip_test_tiny": _CLIP, "quilt_b_16_test_tiny": _CLIP,
+    # OpenAI CLIP through open_clip (models/patch/clip.py:36-40,58): open_clip's eval transform = torchvision Resize(224, BICUBIC) ->
+    # CenterCrop(224) on the PIL patch (Pillow BICUBIC), CLIP mean / std; feature = encode_image = ln_post(class token) @ visual.proj
+    "clip_vit_b_32": _OCLIP, "clip_vit_b_16": _OCLIP, "clip_vit_l_14": _OCLIP, "clip_vit_b_32_test_tiny": _OCLIP,
+    "clip_vit_l_14_test_tiny": _OCLIP,
 }
 
 

@@ -74,7 +74,8 @@ _HUB = {"midnight": "kaiko-ai/midnight",        # models/patch/midnight.py:12,44
         "h_optimus_0": "hf-hub:bioptimus/H-optimus-0",   # models/patch/hoptimus.py:53-58,98-132  timm ViT-g/14 reg4 -> 1536
         "h_optimus_1": "hf-hub:bioptimus/H-optimus-1",
         "pathorchestra": "hf-hub:AI4Pathology/PathOrchestra",   # models/patch/pathorchestra.py:38-43  timm ViT-L/16 -> 1024
-        "prov_gigapath": "hf_hub:prov-gigapath/prov-gigapath"}  # models/patch/gigapath.py:12,46       timm ViT-g/16 -> 1536
+        "prov_gigapath": "hf_hub:prov-gigapath/prov-gigapath",  # models/patch/gigapath.py:12,46       timm ViT-g/16 -> 1536
+        "clip_vit_b_32": "ViT-B-32", "clip_vit_b_16": "ViT-B-16", "clip_vit_l_14": "ViT-L-14"}   # models/patch/clip.py:15-17  open_clip, "openai"
 
 
 def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
@@ -101,6 +102,10 @@ def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtracto
         import timm
 
         model = timm.create_model(_HUB[name], pretrained=True, init_values=1e-5, dynamic_img_size=False)
+    elif name.startswith("clip_vit"):       # clip.py:36-40; the state_dict stays in open_clip's key layout
+        import open_clip
+
+        model, _, _ = open_clip.create_model_and_transforms(_HUB[name], pretrained="openai")
     elif name == "pathorchestra":           # pathorchestra.py:38-43
         import timm
 

@@ -214,6 +214,11 @@ HF_CLIP_SPECS = {
     "quilt_b_16": (16, 12, 12, 768, 3072, 512),
     "plip_test_tiny": (32, 2, 4, 256, 512, 128),
     "quilt_b_16_test_tiny": (16, 2, 4, 256, 512, 128),
+    "clip_vit_b_32": (32, 12, 12, 768, 3072, 512),      # clip.py:15-17 (open_clip, pretrained "openai")
+    "clip_vit_b_16": (16, 12, 12, 768, 3072, 512),
+    "clip_vit_l_14": (14, 24, 16, 1024, 4096, 768),
+    "clip_vit_b_32_test_tiny": (32, 2, 4, 256, 512, 128),
+    "clip_vit_l_14_test_tiny": (14, 2, 4, 256, 512, 128),
 }
 
 

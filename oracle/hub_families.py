@@ -25,6 +25,10 @@
   processor: shortest_edge 224 bicubic, crop 224, OpenAI CLIP mean / std), feature = `get_image_features(pixel_values=x)` =
   visual_projection(post_layernorm(class token)) -> 512.  transformers 4.x returns that tensor (what the reference's forward_fn
   hands on); transformers >= 5 returns the vision ModelOutput with the projected features in `pooler_output` -- same numbers.
+* `clip_vit_b_32`, `clip_vit_b_16`, `clip_vit_l_14` (clip.py:15-17,36-40,58): OpenAI CLIP through open_clip; the eval transform
+  open_clip builds is torchvision `Resize(224, BICUBIC) -> CenterCrop(224) -> ToTensor -> Normalize(CLIP mean / std)` on the PIL patch,
+  feature = `encode_image` = ln_post(class token) @ visual.proj.  open_clip is not in this image; transformers' CLIPModel is the same
+  network (the OpenAI checkpoints converted), and atlaspatch_b200/dinov2.py: openclip_to_hf_clip_names maps open_clip's keys onto it.
 
 There is no network: the oracle builds the classes those hub files resolve to, from the published contents of their config.json /
 preprocessor_config.json (restated from memory of the public repos -- parity of the *settings* is unpinned; parity of the
@@ -48,7 +52,7 @@ CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.261302
 
 
 def _family(name: str) -> str:
-    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight", "h_optimus", "pathorchestra", "prov_gigapath", "plip", "quilt"):
+    for fam in ("midnight", "phikon_v2", "phikon_v1", "hibou", "openmidnight", "h_optimus", "pathorchestra", "prov_gigapath", "plip", "quilt", "clip_vit"):
         if name.startswith(fam):
             return fam
     raise KeyError(name)
@@ -58,7 +62,7 @@ def state_dict(name: str, seed: int = 0) -> dict[str, torch.Tensor]:
     """Seeded weights in the key layout of the model class the reference loads (224 px position grids)."""
     if _family(name) == "phikon_v1":
         return hf_vit_state_dict(name, seed=seed, image_size=224)
-    if _family(name) in ("plip", "quilt"):
+    if _family(name) in ("plip", "quilt", "clip_vit"):
         return hf_clip_state_dict(name, seed=seed, image_size=224)
     return dinov2_state_dict(name, seed=seed, image_size=224)
 
@@ -72,7 +76,7 @@ def build_model(name: str, sd: dict[str, torch.Tensor]):
         cfg = ViTConfig(hidden_size=d, num_hidden_layers=layers, num_attention_heads=heads, intermediate_size=mlp, patch_size=patch,
                         image_size=224, hidden_act="gelu", layer_norm_eps=1e-12, qkv_bias=True)
         model = ViTModel(cfg, add_pooling_layer=False).eval()
-    elif fam in ("plip", "quilt"):
+    elif fam in ("plip", "quilt", "clip_vit"):
         from transformers import CLIPConfig, CLIPModel, CLIPTextConfig, CLIPVisionConfig
 
         patch, layers, heads, d, mlp, proj = HF_CLIP_SPECS[name]
@@ -107,6 +111,11 @@ def make_preprocess(name: str):
 
         return transforms.Compose([transforms.Resize(224), transforms.CenterCrop(224), transforms.ToTensor(),
                                    transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
+    if fam == "clip_vit":                                   # open_clip.transform.image_transform(is_train=False) for "openai" weights
+        from torchvision import transforms
+
+        return transforms.Compose([transforms.Resize(224, interpolation=transforms.InterpolationMode.BICUBIC), transforms.CenterCrop(224),
+                                   transforms.ToTensor(), transforms.Normalize(mean=CLIP_MEAN, std=CLIP_STD)])
     if fam in ("pathorchestra", "prov_gigapath"):           # pathorchestra.py:52-58, gigapath.py:17-26
         from torchvision import transforms
 
@@ -150,6 +159,8 @@ def pixels(name: str, patch: np.ndarray) -> np.ndarray:
         return ra.resize_pil_bilinear(patch, 224, 224)
     if fam == "prov_gigapath":
         return ra.vit_preset_pixels(patch, resize_to=256, crop=224, mode="bicubic")
+    if fam == "clip_vit":
+        return ra.vit_preset_pixels(patch, resize_to=224, crop=224, mode="bicubic")
     if fam in ("phikon_v2", "hibou", "plip", "quilt"):
         return ra.dinov2_pixels(patch, resize_to=224, crop=224) if patch.shape[0] != 224 else patch
     return ra.hf_vit_pixels(patch, 224)
@@ -166,7 +177,7 @@ def extract_features(patches: Sequence[np.ndarray], sd: dict[str, torch.Tensor],
     outs = []
     for i in range(0, len(patches), batch_size):
         x = torch.stack([pre(Image.fromarray(np.asarray(p))) for p in patches[i:i + batch_size]])
-        if _family(name) in ("plip", "quilt"):
+        if _family(name) in ("plip", "quilt", "clip_vit"):
             out = model.get_image_features(pixel_values=x)                     # plip.py:56, quilt.py:60
             outs.append(out if isinstance(out, torch.Tensor) else out.pooler_output)
             continue

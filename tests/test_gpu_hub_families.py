@@ -27,7 +27,9 @@ def _slide():
                                     ("pathorchestra_test_tiny", 256),                                    # timm keys, Pillow BILINEAR to 224
                                     ("prov_gigapath_test_tiny", 224), ("prov_gigapath_test_tiny", 256), ("prov_gigapath_test_tiny", 512),  # Pillow BICUBIC
                                     # CLIP towers: pre-LayerNorm, QuickGELU, 128-wide visual projection (ViT-B/32: 50 tokens; B/16: 197)
-                                    ("plip_test_tiny", 224), ("plip_test_tiny", 256), ("quilt_b_16_test_tiny", 256)])
+                                    ("plip_test_tiny", 224), ("plip_test_tiny", 256), ("quilt_b_16_test_tiny", 256),
+                                    # OpenAI CLIP through open_clip: Pillow BICUBIC preprocess, open_clip key layout; L/14 = 257 tokens
+                                    ("clip_vit_b_32_test_tiny", 224), ("clip_vit_l_14_test_tiny", 256)])
 def test_tiny_family_pixels_bit_exact_and_features(name, P):
     import torch
 
@@ -56,6 +58,10 @@ def test_tiny_family_pixels_bit_exact_and_features(name, P):
             for i in range(2):
                 for k in ("weight", "bias"):
                     sd_in[f"blocks.{i}.mlp.fc1.{k}"], sd_in[f"blocks.{i}.mlp.fc2.{k}"] = sd_in.pop(f"blocks.{i}.mlp.w12.{k}"), sd_in.pop(f"blocks.{i}.mlp.w3.{k}")
+    if name.startswith("clip_vit"):         # open_clip's key layout (clip.py:36-40)
+        from tests.test_oracle_hub_families import hf_to_openclip_names
+
+        sd_in = hf_to_openclip_names(sd, 2)
     if name.startswith("h_optimus"):        # timm's key layout (hoptimus.py:53-58), no position on the class token
         from tests.test_oracle_hub_families import hf_to_timm_names
 

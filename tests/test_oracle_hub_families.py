@@ -10,7 +10,8 @@ from oracle import hub_families as hf
 from oracle import resize_aa
 
 FAMILIES = ["midnight_test_tiny", "phikon_v2_test_tiny", "phikon_v1_test_tiny", "hibou_test_tiny", "openmidnight_test_tiny",
-            "plip_test_tiny", "quilt_b_16_test_tiny", "h_optimus_test_tiny", "pathorchestra_test_tiny", "prov_gigapath_test_tiny"]
+            "plip_test_tiny", "quilt_b_16_test_tiny", "h_optimus_test_tiny", "pathorchestra_test_tiny", "prov_gigapath_test_tiny",
+            "clip_vit_b_32_test_tiny", "clip_vit_l_14_test_tiny"]
 
 
 def _patch(P, seed=0):
@@ -201,3 +202,36 @@ def test_register_checkpoints_need_the_input_grid():
     sd = dinov2_state_dict("hibou_test_tiny", seed=0, image_size=518)     # 37 x 37 grid: would need the antialiased interpolation
     with pytest.raises(ValueError, match="position grid"):
         convert_dinov2_state_dict(sd, layers=2, swiglu=False, image_size=224, patch=14, registers=4)
+
+
+def hf_to_openclip_names(sd, layers):
+    """open_clip's CLIP.visual key layout (open_clip/transformer.py VisionTransformer: conv1, class_embedding, positional_embedding,
+    ln_pre, transformer.resblocks.i.{ln_1, attn (nn.MultiheadAttention), ln_2, mlp.c_fc, mlp.c_proj}, ln_post, proj [width, out]),
+    written from that module tree: what models/patch/clip.py:36-40 holds."""
+    v = "vision_model."
+    out = {"visual.class_embedding": sd[v + "embeddings.class_embedding"], "visual.conv1.weight": sd[v + "embeddings.patch_embedding.weight"],
+           "visual.positional_embedding": sd[v + "embeddings.position_embedding.weight"],
+           "visual.proj": sd["visual_projection.weight"].T.contiguous()}
+    for a, b in (("pre_layrnorm", "visual.ln_pre"), ("post_layernorm", "visual.ln_post")):
+        out[b + ".weight"], out[b + ".bias"] = sd[v + a + ".weight"], sd[v + a + ".bias"]
+    for i in range(layers):
+        a, b = v + f"encoder.layers.{i}.", f"visual.transformer.resblocks.{i}."
+        for k in ("weight", "bias"):
+            out[b + f"attn.in_proj_{k}"] = torch.cat([sd[a + f"self_attn.{n}.{k}"] for n in ("q_proj", "k_proj", "v_proj")], dim=0)
+            for x, y in (("layer_norm1", "ln_1"), ("layer_norm2", "ln_2"), ("self_attn.out_proj", "attn.out_proj"), ("mlp.fc1", "mlp.c_fc"),
+                         ("mlp.fc2", "mlp.c_proj")):
+                out[b + f"{y}.{k}"] = sd[a + f"{x}.{k}"]
+    return out
+
+
+def test_open_clip_key_layout_converts_to_the_same_tensors():
+    from atlaspatch_b200.dinov2 import HF_CLIP_CONFIGS, convert_hf_clip_state_dict
+
+    name = "clip_vit_l_14_test_tiny"
+    layers = HF_CLIP_CONFIGS[name][1]
+    sd = hf.state_dict(name, seed=8)
+    a = convert_hf_clip_state_dict(sd, layers=layers)
+    b = convert_hf_clip_state_dict(hf_to_openclip_names(sd, layers), layers=layers)
+    assert a.keys() == b.keys() and a["head.proj.weight"].shape == (128, 256)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
