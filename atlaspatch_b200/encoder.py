@@ -149,6 +149,9 @@ class B200FeatureExtractor:
         self.name = registry_name or name   # H5 dataset name: features/<name> (services/storage.py:250-337)
         self.embedding_dim = int(proj_dim) if proj_dim else int(hidden) * (2 if pool == 1 else 1)
         self._mean = tuple(float(m) for m in mean)
+        # the device path resamples reads larger than the patch (40x slide at 20x: cv2.resize, feature_embedding.py:93-95) only in front of
+        # the crop preprocess; the resizing preprocesses take reads of exactly input_patch (services.py falls back to host reads otherwise)
+        self.supports_large_reads = preprocess == 0
         self.input_patch = int(input_patch)
         self.max_batch = int(max_batch)
         self.ctx = Context.get(device)

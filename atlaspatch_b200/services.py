@@ -126,7 +126,11 @@ class B200FeatureEmbeddingService:
         name = self.extractor.name
         if result.num_patches == 0:
             result.features[name] = np.empty((0, self.extractor.embedding_dim), dtype=np.float32)
-        elif hasattr(wsi, "device_image") and result.coords_device is not None:
+        elif (hasattr(wsi, "device_image") and result.coords_device is not None and
+              (int(result.coords[0, 2]) == int(getattr(self.extractor, "input_patch", result.coords[0, 2]))
+               or getattr(self.extractor, "supports_large_reads", True))):
+            # (an extractor whose CUDA preprocess resizes -- DINOv2 / hub families -- reads exactly its patch size on the device; a larger
+            # read goes through the reference-style host path below, cv2.resize included)
             _require_level0(result.coords, "embed_features")
             rows = result.coords_device.contiguous()
             if sharded:

@@ -55,3 +55,24 @@ def test_device_paths_refuse_rows_on_other_pyramid_levels():
     _require_level0(np.array([[0, 0, 256, 256, 0]], np.int32), "x")
     with pytest.raises(NotImplementedError, match="level > 0"):
         _require_level0(np.array([[0, 0, 256, 256, 0], [0, 0, 256, 256, 1]], np.int32), "x")
+
+
+def test_large_reads_with_a_resizing_extractor_take_the_host_path():
+    """A device-resident slide read at 2 x the patch size: the crop-preprocess extractors resample on the device, the families whose CUDA
+    preprocess already resizes (DINOv2 / hub encoders) go through the reference's host sequence (read, cv2.resize, extract_batch)."""
+    coords = np.array([[0, 0, 448, 448, 0], [448, 0, 448, 448, 0]], dtype=np.int32)
+
+    class _DevWSI(_HostWSI):
+        device_image, w, h, pitch = object(), 4096, 4096, 4096 * 3
+
+    class _Resizing(_Recorder):
+        input_patch, supports_large_reads = 224, False
+
+        def embed_coords(self, *a, **k):
+            raise AssertionError("device path must not be taken for reads larger than the patch")
+
+    res = ExtractionResult(slide=Slide(Path("x.svs")), h5_path=None, num_patches=2, coords=coords, patch_size_level0=448)
+    res.coords_device = object()
+    wsi, ext = _DevWSI(), _Resizing()
+    out = B200FeatureEmbeddingService(ext, ExtractionConfig(patch_size=224, target_magnification=20)).embed_features(res, wsi=wsi)
+    assert out.features["rec"].shape == (2, 4) and len(wsi.reads) == 2 and all(p.shape == (224, 224, 3) for p in ext.patches)
