@@ -1,4 +1,6 @@
-"""DINOv2 encoders (`dinov2_large`, `dinov2_giant`; reference: atlas_patch/models/patch/dinov2.py) on the B200 engine.
+"""DINOv2 encoders (`dinov2_large`, `dinov2_giant`; reference: atlas_patch/models/patch/dinov2.py) on the B200 engine, and the key maps of
+the other hub families that share its kernels (bottom of the file: transformers ViTModel and CLIPModel, facebookresearch / timm DINOv2-style
+ViTs, open_clip's CLIP.visual).
 
 Host-side weight preparation only: transformers' Dinov2Model state_dict (what `AutoModel.from_pretrained` gives the
 reference, dinov2.py:50) is renamed to the engine's tensor names, with

@@ -101,7 +101,10 @@ class B200FeatureExtractor:
 
     torchvision ViTs (models/patch/vit.py) take a torchvision state_dict and the ImageClassification preset (centre crop);
     `dinov2_*` (models/patch/dinov2.py) take a transformers Dinov2Model state_dict and the BitImageProcessorFast preprocess
-    (bicubic-antialias resize to 256, centre crop 224).  `input_patch` is the --patch-size of the run (the size of the patches
+    (bicubic-antialias resize to 256, centre crop 224).  The hub families of FAMILY_RECIPES (midnight, phikon, hibou, openmidnight,
+    h_optimus, pathorchestra, prov_gigapath, plip / quilt, OpenAI CLIP) take the state_dict of the model class the reference loads, in that
+    class's own key layout (transformers, facebookresearch dinov2, timm, open_clip), and run their preprocess, register tokens and head
+    ([class || mean], visual projection) in the CUDA path.  `input_patch` is the --patch-size of the run (the size of the patches
     handed to extract_batch / cut by embed_coords)."""
 
     def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int | None = None, image_size: int = 224,
