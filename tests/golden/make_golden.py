@@ -136,7 +136,7 @@ def main() -> None:
     (OUT / "versions.json").write_text(json.dumps(versions, indent=1) + "\n")
 
 
-if __name__ == "__main__" and not ({"--sam2", "--sam2-large", "--filter", "--dinov2", "--thumb-general", "--vit-resize"} & set(sys.argv)):
+if __name__ == "__main__" and not ({"--sam2", "--sam2-large", "--filter", "--dinov2", "--thumb-general", "--vit-resize", "--hub"} & set(sys.argv)):
     os.environ.setdefault("OMP_NUM_THREADS", "8")
     main()
 
@@ -266,3 +266,65 @@ def make_vit_resize_golden() -> None:
 
 if __name__ == "__main__" and "--vit-resize" in sys.argv:
     make_vit_resize_golden()
+
+
+def make_hub_golden() -> None:
+    """Features of the hub encoder families on three seeded 256 px patches, tiny seeded configs, fp32 CPU.  Where the reference's own
+    extractor class can run with only its hub call replaced (tests/test_ref_hub_families.py: Midnight, Phikon, PhikonV2, HibouEncoder,
+    PLIPExtractor, QuiltNet, PathOrchestraEncoder, HOptimus0, ProvGigaPathExtractor) the rows come from THAT class; openmidnight
+    (torch.hub + checkpoint file) and the open_clip CLIP towers come from the oracle (oracle/hub_families.py), and `source_<name>` says which."""
+    import importlib
+    from unittest import mock
+
+    import timm
+    import torch
+
+    from oracle import hub_families as hf
+    from tests import test_ref_hub_families as T
+
+    cpu = T.CPU
+    patches = T._patches()
+    out = {}
+
+    def token_model(model):
+        class _Token(torch.nn.Module):
+            def forward(self, x):
+                return model(pixel_values=x).last_hidden_state[:, 0]
+        return _Token()
+
+    via_class = {
+        "midnight_test_tiny": ("midnight", "Midnight", {}, "hf"),
+        "phikon_v1_test_tiny": ("phikon", "Phikon", {}, "hf+proc"),
+        "phikon_v2_test_tiny": ("phikon", "PhikonV2", {}, "hf+proc"),
+        "hibou_test_tiny": ("hibou", "HibouEncoder", dict(name="hibou_b", model_id="histai/hibou-B", embedding_dim=256), "hf+proc"),
+        "plip_test_tiny": ("plip", "PLIPExtractor", {}, "clip"),
+        "quilt_b_16_test_tiny": ("quilt", "QuiltNet", dict(name="quilt_b_16", model_id="wisdomik/QuiltNet-B-16"), "clip"),
+        "pathorchestra_test_tiny": ("pathorchestra", "PathOrchestraEncoder", {}, "timm"),
+        "h_optimus_test_tiny": ("hoptimus", "HOptimus0", {}, "timm"),
+        "prov_gigapath_test_tiny": ("gigapath", "ProvGigaPathExtractor", {}, "timm"),
+    }
+    for name in ["midnight_test_tiny", "phikon_v1_test_tiny", "phikon_v2_test_tiny", "hibou_test_tiny", "openmidnight_test_tiny",
+                 "h_optimus_test_tiny", "pathorchestra_test_tiny", "prov_gigapath_test_tiny", "plip_test_tiny", "quilt_b_16_test_tiny",
+                 "clip_vit_b_32_test_tiny", "clip_vit_l_14_test_tiny"]:
+        sd = hf.state_dict(name, seed=21)
+        if name in via_class:
+            module, cls, kw, how = via_class[name]
+            klass = getattr(importlib.import_module(f"atlas_patch.models.patch.{module}"), cls)
+            model = hf.build_model(name, sd)
+            if how == "timm":
+                with mock.patch.object(timm, "create_model", lambda *a, m=model, **k: token_model(m), create=True):
+                    ext = klass(**kw, **cpu)
+            else:
+                with T._hub(T._Clip4x(model) if how == "clip" else model, None if how == "hf" else T._Processor(name)):
+                    ext = klass(**kw, **cpu)
+            feats, src = ext.extract_batch(patches, batch_size=2), f"reference class {module}.{cls}"
+        else:
+            feats, src = hf.extract_features(patches, sd, name), "oracle/hub_families.py (reference loader not runnable offline)"
+        out[f"feats_{name}"] = feats.astype(np.float32)
+        out[f"source_{name}"] = np.array(src)
+        print(f"{name}: {feats.shape} <- {src}")
+    np.savez_compressed(OUT / "hub_families.npz", **out)
+
+
+if __name__ == "__main__" and "--hub" in sys.argv:
+    make_hub_golden()

@@ -235,3 +235,21 @@ def test_open_clip_key_layout_converts_to_the_same_tensors():
     assert a.keys() == b.keys() and a["head.proj.weight"].shape == (128, 256)
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_oracle_reproduces_the_committed_golden_features():
+    """tests/golden/hub_families.npz (make_golden.py --hub): rows produced by the reference's own extractor classes where they can run
+    offline (hub call replaced), by the oracle otherwise.  The live oracle must reproduce every row."""
+    from pathlib import Path
+
+    from tests.test_ref_hub_families import _patches
+
+    g = np.load(Path(__file__).parent / "golden" / "hub_families.npz")
+    names = [k[len("feats_"):] for k in g.files if k.startswith("feats_")]
+    assert len(names) == 12 and sum("reference class" in str(g[f"source_{n}"]) for n in names) == 9
+    patches = _patches()
+    for name in names:
+        want = g[f"feats_{name}"]
+        got = hf.extract_features(patches, hf.state_dict(name, seed=21), name)
+        assert got.shape == want.shape, name
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), (name, np.abs(got - want).max())
