@@ -101,14 +101,33 @@ def _bicubic_matrix(n_in: int, n_out: int) -> np.ndarray:
     return m
 
 
-def interpolate_pos_embedding(pos: np.ndarray, grid_out: int) -> np.ndarray:
-    """(1 + g*g, D) -> (1 + grid_out^2, D); identity when the grids match (modeling_dinov2.py interpolate_pos_encoding)."""
+def _bicubic_aa_matrix(n_in: int, n_out: int) -> np.ndarray:
+    """(n_out, n_in) matrix of torch.nn.functional.interpolate(mode="bicubic", antialias=True, align_corners=False) along one axis for
+    float tensors (ATen _compute_indices_weights_aa: Keys cubic a = -0.5, support 2 max(scale, 1), weights normalised)."""
+    scale = n_in / n_out
+    support = 2.0 * scale if scale >= 1.0 else 2.0
+    invscale = 1.0 / scale if scale >= 1.0 else 1.0
+    a = -0.5
+    m = np.zeros((n_out, n_in), dtype=np.float64)
+    for i in range(n_out):
+        center = scale * (i + 0.5)
+        xmin = max(int(center - support + 0.5), 0)
+        xsize = min(int(center + support + 0.5), n_in) - xmin
+        t = np.abs((np.arange(xsize) + xmin - center + 0.5) * invscale)
+        w = np.where(t < 1.0, ((a + 2.0) * t - (a + 3.0)) * t * t + 1.0, np.where(t < 2.0, (((t - 5.0) * t + 8.0) * t - 4.0) * a, 0.0))
+        m[i, xmin:xmin + xsize] = w / w.sum()
+    return m
+
+
+def interpolate_pos_embedding(pos: np.ndarray, grid_out: int, antialias: bool = False) -> np.ndarray:
+    """(1 + g*g, D) -> (1 + grid_out^2, D); identity when the grids match (modeling_dinov2.py interpolate_pos_encoding).  antialias:
+    the register-token models' variant (modeling_dinov2_with_registers.py, facebookresearch dinov2 `interpolate_antialias=True`)."""
     n = pos.shape[0] - 1
     g = int(round(n ** 0.5))
     assert g * g == n, "position embedding is not a square grid"
     if g == grid_out:
         return pos.astype(np.float32)
-    m = _bicubic_matrix(g, grid_out)
+    m = _bicubic_aa_matrix(g, grid_out) if antialias else _bicubic_matrix(g, grid_out)
     grid = pos[1:].astype(np.float64).reshape(g, g, -1)
     out = np.einsum("yi,xj,ijd->yxd", m, m, grid)
     return np.concatenate([pos[:1].astype(np.float32), out.reshape(grid_out * grid_out, -1).astype(np.float32)], axis=0)
@@ -130,17 +149,15 @@ def convert_dinov2_state_dict(sd: Mapping[str, object], *, layers: int, swiglu: 
     sd = {k[len("dinov2."):] if k.startswith("dinov2.") else k: v for k, v in sd.items()}
     out: dict[str, np.ndarray] = {}
     if registers:
-        # Dinov2WithRegistersEmbeddings: [class + pos_0 ; registers (no position) ; patches + pos]; its position interpolation is the
-        # antialiased one, which is not restated here: the checkpoints this serves (224 px, 16 x 16 grid) need none
-        n_pos = _np(sd["embeddings.position_embeddings"]).shape[-2] - 1
-        if n_pos != (image_size // patch) ** 2:
-            raise ValueError(f"register-token checkpoints must carry the {image_size // patch}^2 position grid of the input (got {n_pos} positions)")
+        # Dinov2WithRegistersEmbeddings: [class + pos_0 ; registers (no position) ; patches + pos]; a position grid of another
+        # resolution (OpenMidnight's checkpoint carries its training grid: openmidnight.py:58-61) is interpolated with antialiasing
         out["register_tokens"] = _np(sd["embeddings.register_tokens"]).reshape(registers, -1)
     out["conv_proj.weight"] = _np(sd["embeddings.patch_embeddings.projection.weight"])
     out["conv_proj.bias"] = _np(sd["embeddings.patch_embeddings.projection.bias"])
     out["class_token"] = _np(sd["embeddings.cls_token"]).reshape(1, 1, -1)
     pos = _np(sd["embeddings.position_embeddings"])
-    out["encoder.pos_embedding"] = interpolate_pos_embedding(pos.reshape(pos.shape[-2], pos.shape[-1]), image_size // patch)[None]
+    out["encoder.pos_embedding"] = interpolate_pos_embedding(pos.reshape(pos.shape[-2], pos.shape[-1]), image_size // patch,
+                                                             antialias=registers > 0)[None]
     out["encoder.ln.weight"] = _np(sd["layernorm.weight"])
     out["encoder.ln.bias"] = _np(sd["layernorm.bias"])
     for i in range(layers):

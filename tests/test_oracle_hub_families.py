@@ -195,46 +195,35 @@ def test_facebook_key_layout_converts_to_the_same_tensors(name):
         assert np.array_equal(a[k], b[k]), k
 
 
-def test_register_checkpoints_need_the_input_grid():
-    from atlaspatch_b200.dinov2 import convert_dinov2_state_dict
+def test_register_checkpoints_interpolate_their_position_grid_with_antialiasing():
+    """OpenMidnight's checkpoint carries the position grid of its training resolution (openmidnight.py:58-61: "from 392 to 224"); the
+    register-token models interpolate it with antialias=True (modeling_dinov2_with_registers.py, facebookresearch dinov2
+    interpolate_antialias).  The converted 16 x 16 grid must reproduce transformers' forward on a 224 px input."""
+    from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
+
+    from atlaspatch_b200.dinov2 import _bicubic_aa_matrix, convert_dinov2_state_dict
     from atlaspatch_b200.weights import dinov2_state_dict
 
-    sd = dinov2_state_dict("hibou_test_tiny", seed=0, image_size=518)     # 37 x 37 grid: would need the antialiased interpolation
-    with pytest.raises(ValueError, match="position grid"):
-        convert_dinov2_state_dict(sd, layers=2, swiglu=False, image_size=224, patch=14, registers=4)
-
-
-def hf_to_openclip_names(sd, layers):
-    """open_clip's CLIP.visual key layout (open_clip/transformer.py VisionTransformer: conv1, class_embedding, positional_embedding,
-    ln_pre, transformer.resblocks.i.{ln_1, attn (nn.MultiheadAttention), ln_2, mlp.c_fc, mlp.c_proj}, ln_post, proj [width, out]),
-    written from that module tree: what models/patch/clip.py:36-40 holds."""
-    v = "vision_model."
-    out = {"visual.class_embedding": sd[v + "embeddings.class_embedding"], "visual.conv1.weight": sd[v + "embeddings.patch_embedding.weight"],
-           "visual.positional_embedding": sd[v + "embeddings.position_embedding.weight"],
-           "visual.proj": sd["visual_projection.weight"].T.contiguous()}
-    for a, b in (("pre_layrnorm", "visual.ln_pre"), ("post_layernorm", "visual.ln_post")):
-        out[b + ".weight"], out[b + ".bias"] = sd[v + a + ".weight"], sd[v + a + ".bias"]
-    for i in range(layers):
-        a, b = v + f"encoder.layers.{i}.", f"visual.transformer.resblocks.{i}."
-        for k in ("weight", "bias"):
-            out[b + f"attn.in_proj_{k}"] = torch.cat([sd[a + f"self_attn.{n}.{k}"] for n in ("q_proj", "k_proj", "v_proj")], dim=0)
-            for x, y in (("layer_norm1", "ln_1"), ("layer_norm2", "ln_2"), ("self_attn.out_proj", "attn.out_proj"), ("mlp.fc1", "mlp.c_fc"),
-                         ("mlp.fc2", "mlp.c_proj")):
-                out[b + f"{y}.{k}"] = sd[a + f"{x}.{k}"]
-    return out
-
-
-def test_open_clip_key_layout_converts_to_the_same_tensors():
-    from atlaspatch_b200.dinov2 import HF_CLIP_CONFIGS, convert_hf_clip_state_dict
-
-    name = "clip_vit_l_14_test_tiny"
-    layers = HF_CLIP_CONFIGS[name][1]
-    sd = hf.state_dict(name, seed=8)
-    a = convert_hf_clip_state_dict(sd, layers=layers)
-    b = convert_hf_clip_state_dict(hf_to_openclip_names(sd, layers), layers=layers)
-    assert a.keys() == b.keys() and a["head.proj.weight"].shape == (128, 256)
-    for k in a:
-        assert np.array_equal(a[k], b[k]), k
+    for n_in, n_out in ((28, 16), (37, 16), (10, 16)):
+        x = torch.from_numpy(np.random.default_rng(n_in).standard_normal((1, 3, n_in, n_in)).astype(np.float32))
+        ref = F.interpolate(x, size=(n_out, n_out), mode="bicubic", antialias=True, align_corners=False)[0].numpy()
+        m = _bicubic_aa_matrix(n_in, n_out)
+        assert np.abs(np.einsum("yi,xj,cij->cyx", m, m, x[0].numpy().astype(np.float64)) - ref).max() < 1e-5
+    name = "openmidnight_test_tiny"
+    sd = dinov2_state_dict(name, seed=0, image_size=392)                   # 28 x 28 grid
+    cfg = Dinov2WithRegistersConfig(hidden_size=384, num_hidden_layers=2, num_attention_heads=6, mlp_ratio=4, patch_size=14, image_size=392,
+                                    use_swiglu_ffn=True, layer_norm_eps=1e-6, qkv_bias=True, layerscale_value=1.0, num_register_tokens=4)
+    model = Dinov2WithRegistersModel(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    x = torch.from_numpy(np.random.default_rng(1).standard_normal((2, 3, 224, 224)).astype(np.float32))
+    with torch.inference_mode():
+        want = model(pixel_values=x).last_hidden_state[:, 0].numpy()
+        w = convert_dinov2_state_dict(sd, layers=2, swiglu=True, image_size=224, patch=14, registers=4)
+        assert w["encoder.pos_embedding"].shape == (1, 257, 384)
+        w = {k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}
+        got = _engine_forward(x, w, patch=14, layers=2, heads=6, d=384, mlp=1024, swiglu=True, eps=1e-6, pool=0).numpy()
+    rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert rel.max() < 2e-5, rel
 
 
 def test_oracle_reproduces_the_committed_golden_features():
