@@ -242,3 +242,23 @@ def test_oracle_reproduces_the_committed_golden_features():
         got = hf.extract_features(patches, hf.state_dict(name, seed=21), name)
         assert got.shape == want.shape, name
         assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), (name, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("name", FAMILIES)
+def test_extractor_host_side_runs_up_to_the_device_init(name):
+    """B200FeatureExtractor's host side (recipe lookup, key map, derived attributes) for every family, up to the point where the library
+    is asked for a device: without a GPU that must fail loudly (no CPU fallback), with the attributes of the family already in place."""
+    import torch
+
+    from atlaspatch_b200._lib import AtlasB200Error
+    from atlaspatch_b200.encoder import FAMILY_RECIPES, B200FeatureExtractor
+
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    ext = B200FeatureExtractor.__new__(B200FeatureExtractor)
+    with pytest.raises(AtlasB200Error, match="no CUDA device"):
+        ext.__init__(name, hf.state_dict(name, seed=1), input_patch=256, max_batch=4)
+    ext._h = None
+    want = hf.extract_features([_patch(256)], hf.state_dict(name, seed=1), name).shape[1]
+    assert ext.embedding_dim == want and ext.input_patch == 256
+    assert ext.supports_large_reads is (FAMILY_RECIPES[name]["preprocess"] == 0)
