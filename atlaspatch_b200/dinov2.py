@@ -240,7 +240,8 @@ def fb_to_hf_dinov2_names(sd: Mapping[str, object], *, layers: int, swiglu: bool
         for j, n in enumerate(("query", "key", "value")):
             out[d + f"attention.attention.{n}.weight"] = qkv_w[j * D:(j + 1) * D]
             out[d + f"attention.attention.{n}.bias"] = qkv_b[j * D:(j + 1) * D]
-        out[d + "layer_scale1.lambda1"], out[d + "layer_scale2.lambda1"] = sd[s + "ls1.gamma"], sd[s + "ls2.gamma"]
+        ones = np.ones((D,), dtype=np.float32)                          # timm ViTs built without init_values carry no LayerScale
+        out[d + "layer_scale1.lambda1"], out[d + "layer_scale2.lambda1"] = sd.get(s + "ls1.gamma", ones), sd.get(s + "ls2.gamma", ones)
         if swiglu:
             packed = (s + "mlp.w12.weight") not in sd                  # timm SwiGLUPacked
             pairs = (("mlp.fc1" if packed else "mlp.w12", "mlp.weights_in"), ("mlp.fc2" if packed else "mlp.w3", "mlp.weights_out"))

@@ -109,7 +109,7 @@ class B200FeatureExtractor:
 
     def __init__(self, name: str, state_dict: Mapping[str, "object"], *, input_patch: int | None = None, image_size: int = 224,
                  max_batch: int = 254, device: int = 0, config: tuple | None = None, registry_name: str | None = None,
-                 precise_layers: int = -1, precision: str = "fast"):
+                 precise_layers: int = -1, precision: str = "fast", arch: tuple | None = None, recipe: dict | None = None):
         """max_batch: patches per forward chunk = size of the activation workspaces (ViT-B/16: ~1 GB at 254).  Larger chunks amortise
         launch gaps and the tails of the HBM-bound residual GEMMs: 127 -> 254 -> 508 patches gave 22.9 -> 24.1 -> 24.9 k patches/s for
         ViT-B/16 (bench.py uses 508), +2-5 % for ViT-L / DINOv2.
@@ -119,11 +119,21 @@ class B200FeatureExtractor:
         folded): max 8.7e-4 on the same 1 024-row survey (profiles/r02_vit_b_16_precision_survey.log), 21.1 k against 24.1 k patches/s."""
         if precision not in ("fast", "strict"):
             raise ValueError("precision must be 'fast' or 'strict'")
+        if (arch is None) != (recipe is None):
+            raise ValueError("arch and recipe are given together")
         preprocess, resize_to, mlp_kind, pool, ln_eps, registers, pre_ln, proj_dim = 0, 0, 0, 0, 1e-6, 0, 0, 0
         mean, std = IMAGENET_MEAN, IMAGENET_STD
-        recipe = FAMILY_RECIPES.get(name, {}) if config is None else {}
-        if config is None and (name in DINOV2_CONFIGS or name in HF_VIT_CONFIGS or name in HF_CLIP_CONFIGS):
-            if name in HF_CLIP_CONFIGS:
+        if recipe is None:
+            recipe = FAMILY_RECIPES.get(name, {}) if config is None else {}
+        if config is None and (arch is not None or name in DINOV2_CONFIGS or name in HF_VIT_CONFIGS or name in HF_CLIP_CONFIGS):
+            if arch is not None:
+                # a DINOv2-layout ViT (pre-LayerNorm blocks, optional LayerScale / SwiGLU / register tokens) described by the caller:
+                # (patch, layers, heads, hidden, mlp, swiglu, registers) + a FAMILY_RECIPES-style recipe.  plugin.py derives both from a
+                # timm model object and its data config for the timm-loaded families (uni, h0_mini, lunit)
+                patch, layers, heads, hidden, mlp, swiglu, registers = arch
+                state_dict = convert_dinov2_state_dict(state_dict, layers=layers, swiglu=swiglu, image_size=image_size, patch=patch,
+                                                       registers=registers)
+            elif name in HF_CLIP_CONFIGS:
                 (patch, layers, heads, hidden, mlp, proj_dim), swiglu, pre_ln = HF_CLIP_CONFIGS[name], False, 1
                 state_dict = convert_hf_clip_state_dict(state_dict, layers=layers)
             elif name in DINOV2_CONFIGS:

@@ -131,6 +131,73 @@ def _build_hub(name: str, device, patch_size: int | None) -> B200FeatureExtracto
     return B200FeatureExtractor(name, model.state_dict(), input_patch=patch, device=idx, registry_name=f"b200_{name}")
 
 
+# ---- timm-loaded ViTs whose evaluation transform comes from the checkpoint's data config ---------------------------------------------
+# (models/patch/uni.py:30-45,80-110, hoptimus.py:141-161 H0-mini, lunit.py:46-60): nothing about them is restated here -- the
+# architecture is read off the timm model object and the preprocess off timm's resolved data config at load time.
+_TIMM = {"uni_v1": ("hf-hub:MahmoodLab/uni", 0), "uni_v2": ("hf-hub:MahmoodLab/UNI2-h", 0), "h0_mini": ("hf-hub:bioptimus/H0-mini", 1),
+         "lunit_vit_small_patch16_dino": ("hf-hub:1aurent/vit_small_patch16_224.lunit_dino", 0)}   # name -> (hub id, pool)
+
+
+def recipe_from_timm_data_config(cfg, *, pool: int = 0) -> tuple[dict, int]:
+    """timm.data.create_transform(**cfg) for evaluation (transforms_factory.transforms_imagenet_eval) applied to a SQUARE PIL patch:
+    Resize(floor(img / crop_pct), interpolation) -> CenterCrop(img) -> ToTensor -> Normalize(mean, std); for a square image the
+    'center', 'squash' and 'border' crop modes coincide.  Returns (recipe for B200FeatureExtractor, image size).  PIL's BILINEAR /
+    BICUBIC are the two filters the CUDA preprocess restates bit for bit (ap_vit_desc.preprocess 2 / 4)."""
+    import math
+
+    size = tuple(cfg["input_size"])
+    img = int(size[-1])
+    if int(size[-2]) != img:
+        raise ValueError(f"timm data config: input_size {size} is not square")
+    kind = {"bilinear": 2, "bicubic": 4}.get(cfg.get("interpolation", "bilinear"))
+    if kind is None:
+        raise ValueError(f"timm data config: interpolation '{cfg.get('interpolation')}' has no CUDA restatement (bilinear, bicubic)")
+    if cfg.get("crop_border_pixels"):
+        raise ValueError("timm data config: crop_border_pixels is not supported")
+    scale = int(math.floor(img / (cfg.get("crop_pct") or 0.875)))         # timm's DEFAULT_CROP_PCT
+    if scale < img:
+        raise ValueError(f"timm data config: crop_pct {cfg.get('crop_pct')} > 1 pads instead of cropping; not supported")
+    return dict(preprocess=kind, resize_to=scale, mean=tuple(float(m) for m in cfg["mean"]), std=tuple(float(v) for v in cfg["std"]),
+                pool=int(pool), ln_eps=1e-6, default_patch=img), img
+
+
+def arch_from_timm_vit(model) -> tuple:
+    """(patch, layers, heads, hidden, mlp, swiglu, registers) of a timm VisionTransformer, read off the module tree."""
+    blk = model.blocks[0]
+    patch = model.patch_embed.patch_size
+    patch = int(patch[0] if isinstance(patch, (tuple, list)) else patch)
+    fc1_out, fc2_in = int(blk.mlp.fc1.out_features), int(blk.mlp.fc2.in_features)
+    return (patch, len(model.blocks), int(blk.attn.num_heads), int(model.embed_dim), fc2_in, fc1_out == 2 * fc2_in,
+            int(getattr(model, "num_reg_tokens", 0) or 0))
+
+
+def _build_timm(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
+    import os
+
+    import timm
+    import torch
+
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("atlaspatch_b200 encoders need a CUDA device (B200); no CPU fallback exists")
+    hub_id, pool = _TIMM[name]
+    if name == "uni_v1":                    # uni.py:30-36
+        model = timm.create_model(hub_id, pretrained=True, init_values=1e-5, dynamic_img_size=True, num_classes=0)
+    elif name == "uni_v2":                  # uni.py:80-99
+        model = timm.create_model(hub_id, pretrained=True, img_size=224, patch_size=14, depth=24, num_heads=24, init_values=1e-5, embed_dim=1536,
+                                  mlp_ratio=2.66667 * 2, num_classes=0, no_embed_class=True, mlp_layer=timm.layers.SwiGLUPacked,
+                                  act_layer=torch.nn.SiLU, reg_tokens=8, dynamic_img_size=True)
+    elif name == "h0_mini":                 # hoptimus.py:141-146
+        model = timm.create_model(hub_id, pretrained=True, mlp_layer=timm.layers.SwiGLUPacked, act_layer=torch.nn.SiLU)
+    else:                                   # lunit.py:46-49
+        model = timm.create_model(hub_id, pretrained=True)
+    cfg = timm.data.resolve_data_config(model.pretrained_cfg, model=model)      # uni.py:42, hoptimus.py:155, lunit.py:58
+    recipe, image_size = recipe_from_timm_data_config(cfg, pool=pool)
+    idx = torch.device(device).index or 0
+    patch = int(patch_size or os.environ.get("ATLASPATCH_B200_PATCH_SIZE", image_size))
+    return B200FeatureExtractor(name, model.state_dict(), input_patch=patch, image_size=image_size, device=idx, registry_name=f"b200_{name}",
+                                arch=arch_from_timm_vit(model), recipe=recipe)
+
+
 def resolve_feature_dtype(device, precision: str):
     """services/feature_embedding.py:28-39: the reference's dtype policy (float16 is downgraded to float32 on CPU devices)."""
     import torch
@@ -153,3 +220,5 @@ def register_feature_extractors(registry, device, dtype, num_workers) -> None:
         registry.register(f"b200_{name}", lambda n=name: _build_dinov2(n, device, None))
     for name in _HUB:
         registry.register(f"b200_{name}", lambda n=name: _build_hub(n, device, None))
+    for name in _TIMM:
+        registry.register(f"b200_{name}", lambda n=name: _build_timm(n, device, None))

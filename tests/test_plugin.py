@@ -13,7 +13,8 @@ NAMES = {"b200_vit_b_16", "b200_vit_l_16", "b200_vit_b_32", "b200_vit_l_32", "b2
          "b200_dinov2_large", "b200_dinov2_giant", "b200_midnight", "b200_phikon_v1", "b200_phikon_v2", "b200_hibou_b", "b200_hibou_l",
          "b200_openmidnight", "b200_plip", "b200_quilt_b_32", "b200_quilt_b_16", "b200_h_optimus_0",
          "b200_h_optimus_1", "b200_pathorchestra", "b200_prov_gigapath",
-         "b200_clip_vit_b_32", "b200_clip_vit_b_16", "b200_clip_vit_l_14"}
+         "b200_clip_vit_b_32", "b200_clip_vit_b_16", "b200_clip_vit_l_14",
+         "b200_uni_v1", "b200_uni_v2", "b200_h0_mini", "b200_lunit_vit_small_patch16_dino"}
 
 
 def _reference():
