@@ -262,3 +262,19 @@ def test_extractor_host_side_runs_up_to_the_device_init(name):
     want = hf.extract_features([_patch(256)], hf.state_dict(name, seed=1), name).shape[1]
     assert ext.embedding_dim == want and ext.input_patch == 256
     assert ext.supports_large_reads is (FAMILY_RECIPES[name]["preprocess"] == 0)
+
+
+def test_clip_recipe_equals_the_processor_class_defaults():
+    """The CLIP checkpoints' preprocessor_config.json (vinid/plip, wisdomik/QuiltNet-*) cannot be fetched here; they are the defaults of
+    transformers' CLIPImageProcessor (the OpenAI CLIP values), which this pins the recipe and the oracle to."""
+    import transformers
+
+    from atlaspatch_b200.encoder import FAMILY_RECIPES
+
+    p = transformers.CLIPImageProcessor()
+    r = FAMILY_RECIPES["plip"]
+    assert dict(p.size) == {"shortest_edge": 224} and dict(p.crop_size) == {"height": 224, "width": 224} and int(p.resample) == 3
+    assert p.do_resize and p.do_center_crop and p.do_rescale and p.do_normalize and abs(p.rescale_factor - 1 / 255) < 1e-12
+    assert np.allclose(p.image_mean, r["mean"], atol=0, rtol=0) and np.allclose(p.image_std, r["std"], atol=0, rtol=0)
+    assert r["resize_to"] == 224 and r["preprocess"] == 1
+    assert np.allclose(p.image_mean, hf.CLIP_MEAN, atol=0, rtol=0) and np.allclose(p.image_std, hf.CLIP_STD, atol=0, rtol=0)
