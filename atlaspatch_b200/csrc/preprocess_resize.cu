@@ -186,3 +186,18 @@ int ap_preprocess_resize_run(ap_ctx* ctx, const uint8_t* slide, int64_t W, int64
     AP_CHECK_LAUNCH(ctx, "preprocess_resize_kernel");
     return AP_OK;
 }
+
+extern "C" int ap_resize_tap_tables(int filter, int n_in, int n_out, int image, int32_t* tap_min, int32_t* tap_cnt, int32_t* tap_w,
+                                    int taps_capacity, int* max_taps, int* precision) {
+    if (!tap_min || !tap_cnt || !tap_w || !max_taps || !precision) return AP_EINVAL;
+    std::vector<int32_t> tmin, tcnt, tw;
+    int rc = ap_build_resize_tables(nullptr, n_in, n_out, image, filter, tmin, tcnt, tw, max_taps, precision);
+    if (rc) return rc;
+    if (*max_taps > taps_capacity) return AP_EINVAL;
+    for (int o = 0; o < image; ++o) {
+        tap_min[o] = tmin[o];
+        tap_cnt[o] = tcnt[o];
+        for (int j = 0; j < taps_capacity; ++j) tap_w[static_cast<size_t>(o) * taps_capacity + j] = j < *max_taps ? tw[static_cast<size_t>(o) * *max_taps + j] : 0;
+    }
+    return AP_OK;
+}

@@ -189,6 +189,13 @@ int ap_encoder_embedding_dim(const ap_encoder* enc);
  * (ap_vit_desc.preprocess = 1) only takes read_size == input_patch. */
 int ap_encoder_embed_coords(ap_encoder* enc, const uint8_t* slide_dev, int64_t W, int64_t H, int64_t pitch,
                             const int32_t* coords_dev, int64_t n, int read_size, float* out_features_dev, void* stream);
+/* Host-only (no device, no context): the integer tap tables the resizing preprocesses run from, for the `image` output indices that
+ * survive the centre crop of an n_in -> n_out resize.  filter = ap_vit_desc.preprocess - 1 (0 ATen uint8 bicubic-antialias, 1 Pillow
+ * BILINEAR, 2 ATen uint8 bilinear-antialias, 3 Pillow BICUBIC).  tap_min / tap_cnt: [image]; tap_w: [image * taps_capacity], row o
+ * holds tap_cnt[o] weights; *max_taps = widest row, *precision = the shift of both passes.  AP_EINVAL when taps_capacity is too
+ * small (*max_taps then says how much is needed).  What CPU tests compare against the reference libraries' own coefficients. */
+int ap_resize_tap_tables(int filter, int n_in, int n_out, int image, int32_t* tap_min, int32_t* tap_cnt, int32_t* tap_w,
+                         int taps_capacity, int* max_taps, int* precision);
 /* a12 alone (used by the parity tests): run only the patch read + preprocess of n <= max_batch coordinates and copy the fp16
  * im2col rows the patch-embedding GEMM consumes to out_dev [n * tokens, *out_cols]: value = (pixel - round(255 mean_c)) / 256 at
  * column c * patch^2 + ky * patch + kx (exact in fp16), columns >= 3 * patch^2 are zero padding. */
