@@ -58,6 +58,7 @@ _SIGNATURES = {
     "ap_encoder_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "ap_encoder_finalize": (C.c_int, [_P]),
     "ap_encoder_embedding_dim": (C.c_int, [_P]),
+    "ap_linear_tap_tables": (C.c_int, [C.c_int, C.c_int, _I32P, C.POINTER(C.c_int16)]),
     "ap_resize_tap_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _I32P, _I32P, _I32P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ap_encoder_embed_coords": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int, _P, _P]),
     "ap_encoder_preprocess": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int, _P, C.POINTER(C.c_int64), _P]),

@@ -689,3 +689,14 @@ extern "C" int ap_attention_f16(ap_ctx* ctx, const void* qkv_dev, void* out_dev,
     return ap_attention_run(ctx, static_cast<const __half*>(qkv_dev), static_cast<__half*>(out_dev), B, S, heads,
                             static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int ap_linear_tap_tables(int n_src, int n_dst, int32_t* taps, int16_t* weights) {
+    if (!taps || !weights) return AP_EINVAL;
+    std::vector<int32_t> t;
+    std::vector<int16_t> w;
+    int rc = ap_build_linear_tables(nullptr, n_src, n_dst, t, w);
+    if (rc) return rc;
+    std::copy(t.begin(), t.end(), taps);
+    std::copy(w.begin(), w.end(), weights);
+    return AP_OK;
+}

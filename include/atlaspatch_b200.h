@@ -196,6 +196,10 @@ int ap_encoder_embed_coords(ap_encoder* enc, const uint8_t* slide_dev, int64_t W
  * small (*max_taps then says how much is needed).  What CPU tests compare against the reference libraries' own coefficients. */
 int ap_resize_tap_tables(int filter, int n_in, int n_out, int image, int32_t* tap_min, int32_t* tap_cnt, int32_t* tap_w,
                          int taps_capacity, int* max_taps, int* precision);
+/* Host-only: OpenCV's 8-bit INTER_LINEAR taps of an n_src -> n_dst down-scale (the cv2.resize of reads larger than the patch,
+ * feature_embedding.py:93-95), as the crop preprocess and the content filter use them: taps[2 d], taps[2 d + 1] = the two source
+ * indices of output d, weights[2 d], weights[2 d + 1] their coefficients in units of 1 / 2048.  n_src > n_dst. */
+int ap_linear_tap_tables(int n_src, int n_dst, int32_t* taps, int16_t* weights);
 /* a12 alone (used by the parity tests): run only the patch read + preprocess of n <= max_batch coordinates and copy the fp16
  * im2col rows the patch-embedding GEMM consumes to out_dev [n * tokens, *out_cols]: value = (pixel - round(255 mean_c)) / 256 at
  * column c * patch^2 + ky * patch + kx (exact in fp16), columns >= 3 * patch^2 are zero padding. */

@@ -57,6 +57,16 @@ def shrink_bilinear(rgb: np.ndarray, r: int) -> np.ndarray:
     return ((a[k::r, k::r] + a[k::r, k + 1::r] + a[k + 1::r, k::r] + a[k + 1::r, k + 1::r] + 2) >> 2).astype(np.uint8)
 
 
+def linear_taps(n_src: int, n_dst: int):
+    """OpenCV's 8-bit INTER_LINEAR taps of one axis before any border rule: (first source index s[n_dst], weight of s, weight of s + 1),
+    weights in units of 1 / 2048 (resize_linear_u8 below applies the same arithmetic and is pinned against cv2 itself)."""
+    scale = 1.0 / (n_dst / n_src)
+    f = ((np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    return s, np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int64), np.rint(f * np.float32(2048)).astype(np.int64)
+
+
 def resize_linear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     """cv2.resize(img, (out_w, out_h)) with the default INTER_LINEAR on uint8, any ratio (OpenCV resize.cpp, 8-bit path):
     per axis fx = float32((d + 0.5) * scale - 0.5), scale = 1 / (n_dst / n_src) in float64; s = floor(fx); fx -= s; on x the

@@ -52,3 +52,23 @@ def test_capacity_and_arguments_are_checked(lib):
     assert rc != 0 and max_taps > 4                     # tells how much room is needed
     assert _tables(lib, 7, 224, 256, 224)[0] != 0       # unknown filter
     assert _tables(lib, 0, 224, 200, 224)[0] != 0       # crop larger than the resized image
+
+
+@pytest.mark.parametrize("n_src,n_dst", [(512, 256), (257, 256), (320, 256), (384, 256), (683, 256), (768, 256), (1024, 256), (2048, 256),
+                                         (448, 224), (300, 224), (1000, 224), (513, 512)])
+def test_cv2_linear_taps_equal_the_opencv_arithmetic(lib, n_src, n_dst):
+    """The taps of the cv2.resize the reference applies to reads larger than the patch (40x / 80x slides at 20x), against the
+    restatement that tests/test_oracle_filter.py pins to cv2 itself."""
+    from oracle.patch_filter import linear_taps
+
+    taps, w = np.zeros(2 * n_dst, np.int32), np.zeros(2 * n_dst, np.int16)
+    assert lib.ap_linear_tap_tables(n_src, n_dst, taps.ctypes.data_as(C.POINTER(C.c_int32)), w.ctypes.data_as(C.POINTER(C.c_int16))) == 0
+    s, a0, a1 = linear_taps(n_src, n_dst)
+    assert np.array_equal(taps[0::2], s) and np.array_equal(taps[1::2], s + 1)
+    assert np.array_equal(w[0::2], a0) and np.array_equal(w[1::2], a1) and np.all(w[0::2].astype(int) + w[1::2] == 2048)
+    assert s.min() >= 0 and s.max() + 1 <= n_src - 1      # down-scaling never leaves the source: no border rule is needed
+
+
+def test_cv2_linear_taps_refuse_up_scaling(lib):
+    taps, w = np.zeros(8, np.int32), np.zeros(8, np.int16)
+    assert lib.ap_linear_tap_tables(200, 256, taps.ctypes.data_as(C.POINTER(C.c_int32)), w.ctypes.data_as(C.POINTER(C.c_int16))) != 0
