@@ -1,5 +1,6 @@
 // Non-GEMM kernels of the encoder forward: patch crop -> fp16 im2col (preprocess), class-token rows,
 // LayerNorm, multi-head attention.  All fp32 statistics / softmax; fp16 only as tensor-core operands.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
