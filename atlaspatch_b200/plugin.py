@@ -174,11 +174,12 @@ def arch_from_timm_vit(model) -> tuple:
 def _build_timm(name: str, device, patch_size: int | None) -> B200FeatureExtractor:
     import os
 
-    import timm
     import torch
 
     if torch.device(device).type != "cuda":
         raise RuntimeError("atlaspatch_b200 encoders need a CUDA device (B200); no CPU fallback exists")
+    import timm
+
     hub_id, pool = _TIMM[name]
     if name == "uni_v1":                    # uni.py:30-36
         model = timm.create_model(hub_id, pretrained=True, init_values=1e-5, dynamic_img_size=True, num_classes=0)

@@ -69,6 +69,14 @@ def test_builders_refuse_cpu_devices():
         _build("vit_b_16", "cpu")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _build_dinov2("dinov2_large", "cpu", 224)
+    from atlaspatch_b200.plugin import _HUB, _TIMM, _build_hub, _build_timm
+
+    for name in _HUB:                       # refused before any hub / timm / open_clip import is attempted
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            _build_hub(name, "cpu", None)
+    for name in _TIMM:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            _build_timm(name, "cpu", None)
 
 
 def test_dtype_policy_matches_the_reference():
