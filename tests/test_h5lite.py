@@ -155,3 +155,56 @@ def test_h5py_reads_h5lite_file_and_back(tmp_path):
         f.attrs["n"] = 3
     with h5.File(q, "r") as f:
         assert np.array_equal(f["coords"][...], coords) and f.attrs["wsi_path"] == "abc" and f.attrs["n"] == 3
+
+
+def test_property_append_sequences_round_trip(tmp_path):
+    """Property test (hypothesis): the container's write pattern -- an extendable (N, D) dataset grown by resize + slice writes in batches
+    of any size (services/storage.py:279-337 appends 32 rows at a time), closed and reopened in append mode in between, any chunking,
+    int32 / float32 / S-string rows, attributes of every kind the container uses -- reads back exactly, through the independent reader."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    counter = [0]
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(d=st.integers(1, 9), chunk_rows=st.integers(1, 40), batches=st.lists(st.integers(0, 70), min_size=0, max_size=6),
+           kind=st.sampled_from(["int32", "float32", "S17"]), reopen_at=st.integers(0, 6), seed=st.integers(0, 2 ** 16),
+           label=st.text(alphabet=st.characters(blacklist_categories=("Cs",), blacklist_characters="\x00"), max_size=12))
+    def run(d, chunk_rows, batches, kind, reopen_at, seed, label):
+        counter[0] += 1
+        p = tmp_path / f"p{counter[0]}.h5"
+        rng = np.random.default_rng(seed)
+        dt = np.dtype(kind)
+        shape_tail = () if dt.kind == "S" else (d,)
+
+        def rows(n):
+            if dt.kind == "S":
+                return np.array([("r%d_%d" % (seed, rng.integers(0, 10 ** 6))).encode() for _ in range(n)], dtype=dt).reshape((n,))
+            a = rng.integers(-2 ** 31, 2 ** 31 - 1, (n, d)) if dt.kind == "i" else rng.standard_normal((n, d)) * 1e3
+            return a.astype(dt)
+
+        want = rows(0)
+        f = h5.File(p, "w")
+        ds = f.create_dataset("x", shape=(0,) + shape_tail, maxshape=(None,) + shape_tail, chunks=(chunk_rows,) + shape_tail, dtype=dt)
+        f.attrs["label"], f.attrs["n"], f.attrs["ratio"] = label, np.int64(len(batches)), 0.25
+        for i, n in enumerate(batches):
+            if i == reopen_at:                          # close and come back in append mode, like a second extractor appending features
+                f.close()
+                f = h5.File(p, "a")
+                ds = f["x"]
+            new = rows(n)
+            ds.resize(ds.shape[0] + n, axis=0)
+            if n:
+                ds[ds.shape[0] - n:] = new
+            want = np.concatenate([want, new], axis=0)
+        f.close()
+        with h5.File(p, "r") as g:
+            got = g["x"]
+            assert got.shape == want.shape and got.dtype == dt and got.chunks == (chunk_rows,) + shape_tail
+            assert np.array_equal(got[...], want)
+            if want.shape[0]:
+                k = int(rng.integers(0, want.shape[0]))
+                assert np.array_equal(got[k], want[k]) and np.array_equal(got[k:k + 5], want[k:k + 5])
+            assert g.attrs["label"] == label and g.attrs["n"] == len(batches) and g.attrs["ratio"] == 0.25
+
+    run()
